@@ -1,0 +1,152 @@
+// gae.cu — GAE reverse-time scan (gae(), ppo.jl:48-73) + returns (ppo.jl:181).
+//
+// Purely bandwidth-bound: per (env, step) it reads value 4 B + reward 4 B + done 1 B and writes
+// advantage 4 B + return 4 B = 17 B. One thread owns VEC consecutive envs and walks t from the
+// end; every row access is a coalesced, streaming (evict-first) 128-bit load/store across the
+// warp. The recurrence is serial in t but the loads are not: each thread prefetches U rows into
+// registers before it touches the dependent Float64 chain, so U x 36 B per thread are in flight.
+// values[t+1] is carried in a register, never re-read.
+//
+// The recurrence runs in Float64 exactly as the reference's promotion rules dictate
+// (nonterm = 1.0 .- terminals and gae = 0.0 are Float64, ppo.jl:63,65) and uses _rn intrinsics
+// so that no mul+add is contracted: results are bit-identical to the oracle.
+#include "kernels.h"
+
+namespace {
+
+template <int VEC> struct Vec;
+template <> struct Vec<1> {
+  using F = float;
+  using B = unsigned char;
+};
+template <> struct Vec<4> {
+  using F = float4;
+  using B = uchar4;
+};
+
+__device__ __forceinline__ void unpack(float v, float o[1]) { o[0] = v; }
+__device__ __forceinline__ void unpack(float4 v, float o[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(unsigned char v, unsigned char o[1]) { o[0] = v; }
+__device__ __forceinline__ void unpack(uchar4 v, unsigned char o[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void pack(const float i[1], float& v) { v = i[0]; }
+__device__ __forceinline__ void pack(const float i[4], float4& v) { v = make_float4(i[0], i[1], i[2], i[3]); }
+
+template <int MODE, int VEC, int U>
+__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards,
+                                                  const unsigned char* __restrict__ dones,
+                                                  const float* __restrict__ next_value,
+                                                  const unsigned char* __restrict__ next_done,
+                                                  float* __restrict__ adv, float* __restrict__ ret, int T,
+                                                  long long N, float gamma, float gl) {
+  using VF = typename Vec<VEC>::F;
+  using VB = typename Vec<VEC>::B;
+  const long long nv = N / VEC;  // vectors per row
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const VF* vv = reinterpret_cast<const VF*>(values);
+  const VF* rr = reinterpret_cast<const VF*>(rewards);
+  const VB* dd = reinterpret_cast<const VB*>(dones);
+  VF* av = reinterpret_cast<VF*>(adv);
+  VF* rv = reinterpret_cast<VF*>(ret);
+  const double g = (double)gamma, gld = (double)gl;
+
+  double gae[VEC];
+  float vnext[VEC];
+  unsigned char dnext[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; k++) gae[k] = 0.0;
+  int t_hi;
+  if (MODE == CRL_GAE_REF_COMPAT) {
+    // Q1: the loop at ppo.jl:66 starts at T-1 (1-based); adv[T] is never written: define it as 0.
+    const VF vl = __ldcs(vv + (long long)(T - 1) * nv + i);
+    unpack(vl, vnext);
+    unpack(T > 1 ? __ldcs(dd + (long long)(T - 1) * nv + i) : VB(), dnext);
+    float z[VEC], rl[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k++) { z[k] = 0.0f; rl[k] = 0.0f + vnext[k]; }
+    VF o;
+    pack(z, o);
+    __stcs(av + (long long)(T - 1) * nv + i, o);
+    pack(rl, o);
+    __stcs(rv + (long long)(T - 1) * nv + i, o);
+    t_hi = T - 2;
+  } else {
+    unpack(reinterpret_cast<const VF*>(next_value)[i], vnext);
+    unpack(reinterpret_cast<const VB*>(next_done)[i], dnext);
+    t_hi = T - 1;
+  }
+
+  for (int t0 = t_hi; t0 >= 0; t0 -= U) {
+    VF v[U], r[U];
+    VB d[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 - u;
+      if (t >= 0) {
+        v[u] = __ldcs(vv + (long long)t * nv + i);
+        r[u] = __ldcs(rr + (long long)t * nv + i);
+        if (t > 0) d[u] = __ldcs(dd + (long long)t * nv + i);  // dones[0] is never used
+        else d[u] = VB();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 - u;
+      if (t >= 0) {
+        float vf[VEC], rf[VEC], af[VEC], rt[VEC];
+        unsigned char df[VEC];
+        unpack(v[u], vf);
+        unpack(r[u], rf);
+        unpack(d[u], df);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+          const double nonterm = dnext[k] ? 0.0 : 1.0;  // 1.0 - terminals[t+1]
+          const double delta =
+              __dsub_rn(__dadd_rn((double)rf[k], __dmul_rn(__dmul_rn(g, nonterm), (double)vnext[k])), (double)vf[k]);
+          gae[k] = __dadd_rn(delta, __dmul_rn(__dmul_rn(gld, nonterm), gae[k]));
+          af[k] = (float)gae[k];
+          rt[k] = __fadd_rn(af[k], vf[k]);
+          vnext[k] = vf[k];
+          dnext[k] = df[k];
+        }
+        VF o;
+        pack(af, o);
+        __stcs(av + (long long)t * nv + i, o);
+        pack(rt, o);
+        __stcs(rv + (long long)t * nv + i, o);
+      }
+    }
+  }
+}
+
+template <int MODE>
+cudaError_t launch_mode(const float* values, const float* rewards, const uint8_t* dones, const float* next_value,
+                        const uint8_t* next_done, float* adv, float* ret, int T, long long N, float gamma, float gl,
+                        cudaStream_t s) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; };
+  const bool vec_ok = (N % 4 == 0) && al16(values) && al16(rewards) && al16(adv) && al16(ret) && al4(dones) &&
+                      (MODE == CRL_GAE_REF_COMPAT || (al16(next_value) && al4(next_done)));
+  // vectorise only when there are enough threads to fill the machine several times over
+  if (vec_ok && N / 4 >= 148LL * 1024) {
+    const long long nv = N / 4;
+    gae_kernel<MODE, 4, 8><<<(unsigned)((nv + 127) / 128), 128, 0, s>>>(values, rewards, dones, next_value, next_done,
+                                                                       adv, ret, T, N, gamma, gl);
+  } else {
+    gae_kernel<MODE, 1, 16><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(values, rewards, dones, next_value, next_done,
+                                                                       adv, ret, T, N, gamma, gl);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gae(const float* values, const float* rewards, const uint8_t* dones, const float* next_value,
+                       const uint8_t* next_done, float* adv, float* ret, int T, long long N, float gamma,
+                       float lambda, int mode, cudaStream_t s) {
+  if (N == 0) return cudaSuccess;
+  const float gl = gamma * lambda;  // Float32 product first (γ * λ * ..., ppo.jl:68)
+  if (mode == CRL_GAE_REF_COMPAT)
+    return launch_mode<CRL_GAE_REF_COMPAT>(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, gl, s);
+  return launch_mode<CRL_GAE_FIXED>(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, gl, s);
+}

@@ -1,0 +1,132 @@
+// kernels.h — host-visible launchers of the sm_100a kernels (internal; the public ABI is
+// include/cleanrl_cuda.h).
+#pragma once
+#include "common.cuh"
+
+struct RolloutArgs {
+  const float* params;
+  const DevState* ds;
+  unsigned long long seed;
+  int env_id_base;
+  int N, T, max_steps;
+  // env state (in/out)
+  float* env_state;
+  int* env_t;
+  double* ep_return;
+  int* ep_length;
+  uint32_t* reset_count;
+  float* next_obs;
+  uint8_t* next_done;
+  float* next_value;
+  // rollout buffer (out)
+  float* state;
+  void* action;
+  float* logprob;
+  float* reward;
+  float* value;
+  uint8_t* terminal;
+  // optional injected noise (device copies)
+  const double* action_noise;
+  const float* reset_noise;
+  // episode records
+  EpisodeBuf* eb;
+  crl_episode* records;
+  int ep_capacity;
+};
+
+// where the minibatch sample indices come from: an explicit device array, or the
+// Philox-keyed Feistel permutation evaluated in registers (no index array in memory).
+struct IdxSrc {
+  const int32_t* arr;  // device int32[M] or nullptr
+  uint32_t start;      // offset of this minibatch inside the epoch permutation
+  uint32_t B;          // batch size (permutation domain)
+  int half_bits;
+  uint32_t epoch, rank;
+  unsigned long long seed;
+  const DevState* ds;  // update_index lives on the device
+};
+
+struct MbFinal {
+  float adv_mean, adv_std, s_unclipped, min_vlc;
+  double M_global;
+  unsigned long long cnt;  // #{i : s > (clip_i - R_i)^2}, ppo.jl:236 (Q5)
+};
+
+struct UpdateArgs {
+  int env_kind;
+  const float* params;
+  IdxSrc idx;
+  int M;  // local minibatch size
+  // flattened rollout data (ppo.jl:184-189)
+  const float* states;
+  const void* actions;
+  const float* logprobs;
+  const float* advantages;
+  const float* returns;
+  const float* values;
+  float clip_coef, ent_coeff, v_coef;
+  // scratch
+  float* vnew;           // [M]
+  MbScalars* parts;      // per-CTA partial sums written by mb_stats
+  int n_parts_cap;
+  const MbScalars* parts_in;  // what mb_count reduces (local parts, or the all-gathered ranks)
+  int n_parts_in;
+  MbFinal* fin;
+  int world;
+  float* gpart;          // [grid][P] per-CTA partial gradients
+  double* spart;         // [grid][4] per-CTA partial loss sums
+  int grid_loss;
+  double* gsum;          // [P + 4] reduced gradient (+ loss sums) in double: the allreduce buffer
+};
+
+struct AdamArgs {
+  int env_kind;
+  float* params;
+  const double* gsum;  // [P+4] reduced sums (double), or nullptr to read gf
+  const float* gf;     // [P] Float32 gradient (raw entry point)
+  double grad_scale;   // 1, or 1/world with CRL_FLAG_LOCAL_STATS
+  double stat_ranks;   // ranks whose loss sums were added into gsum[P..] when M_global is local
+  float* grads_out;    // [P] un-clipped Float32 gradient (may be nullptr)
+  float* m;
+  float* v;
+  double* beta_pow;    // [n_arrays][2]
+  const DevState* ds;  // lr read from device when lr_host < 0
+  double lr_host;
+  float clip_norm;
+  float ent_coeff, v_coef;
+  double M_global;
+  int A;
+  double* stats_out;   // 4 doubles: loss, pg_loss, v_loss, entropy_loss (may be nullptr)
+};
+
+// per-device opt-in to large dynamic shared memory; call once per device outside stream capture
+cudaError_t kernels_init_rollout();
+cudaError_t kernels_init_update();
+cudaError_t launch_episode_buf_init(EpisodeBuf* eb, cudaStream_t s);
+cudaError_t launch_rollout(int env_kind, const RolloutArgs& a, cudaStream_t s);
+cudaError_t launch_env_step_raw(int env_kind, float* state, int* t, const void* action, float* reward,
+                                uint8_t* done, long long n, int max_steps, cudaStream_t s);
+cudaError_t launch_policy_forward_raw(int env_kind, const float* params, const float* obs, float* out_policy,
+                                      float* logp, float* value, long long n, cudaStream_t s);
+cudaError_t launch_gae(const float* values, const float* rewards, const uint8_t* dones, const float* next_value,
+                       const uint8_t* next_done, float* adv, float* ret, int T, long long N, float gamma,
+                       float lambda, int mode, cudaStream_t s);
+
+int mb_stats_grid(int M, int sm_count);
+int loss_grad_grid(int M, int sm_count);
+cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
+cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
+cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
+cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);
+cudaError_t launch_loss_finalize(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
+                                 float v_coef, double* stats_out, cudaStream_t s);
+cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cudaStream_t s);
+cudaError_t launch_env_reset(int env_kind, int N, unsigned long long seed, int env_id_base, float* env_state,
+                             int* env_t, double* ep_return, int* ep_length, uint32_t* reset_count, float* next_obs,
+                             uint8_t* next_done, cudaStream_t s);
+cudaError_t launch_env_refresh(int env_kind, int N, const float* env_state, float* next_obs, uint8_t* next_done,
+                               cudaStream_t s);
+cudaError_t launch_advance(DevState* ds, unsigned long long d_policy_step, unsigned long long d_update, cudaStream_t s);
+cudaError_t launch_fill_perm(int32_t* out, uint32_t B, unsigned long long seed, unsigned long long update_index,
+                             uint32_t epoch, uint32_t rank, cudaStream_t s);

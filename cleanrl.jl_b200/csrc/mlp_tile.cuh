@@ -1,0 +1,138 @@
+// mlp_tile.cuh — register-tiled FFMA layers over a tile of samples held in shared memory.
+//
+// A CTA of 256 threads owns a tile of S samples. Activations live in shared memory
+// feature-major: act[row][s], row = net*64 + neuron, row stride S_PAD = S + 4 floats (the +4
+// makes row-strided float4 accesses hit distinct banks). Each thread owns a TS x TS register
+// tile (TS neurons x TS samples). Lane mapping inside a warp: q_lo = lane % 8 picks the neuron
+// chunk, p_lo = lane / 8 picks the sample chunk, so a warp-wide float4 weight load touches one
+// contiguous 128 B line (8 distinct q_lo, broadcast over p_lo) and a float4 activation load
+// touches 64 B (4 distinct p_lo, broadcast over q_lo): one shared-memory wavefront each.
+//
+// Weight matrices are used exactly as Flux stores them: W (out,in) column-major = k-major
+// [in][out] (see common.cuh), so the forward layer needs no transposition.
+#pragma once
+#include "common.cuh"
+#include "device_math.cuh"
+
+#define CRL_THREADS 256
+
+// Geometry of one tile configuration.
+//   TS   thread tile edge (4 or 8)
+//   NETS 2 = actor+critic side by side (rows 0..127), 1 = a single net (rows 0..63)
+template <int TS_, int NETS_> struct TileGeom {
+  static constexpr int TS = TS_, NETS = NETS_;
+  static constexpr int QN = CRL_H / TS;        // neuron groups per net
+  static constexpr int QG = NETS * QN;         // neuron groups total
+  static constexpr int PG = CRL_THREADS / QG;  // sample groups
+  static constexpr int S = PG * TS;            // samples per tile
+  static constexpr int S_PAD = S + 4;
+  static constexpr int NC = TS / 4;            // float4 chunks per thread edge
+  static constexpr int ROWS = NETS * CRL_H;
+  static constexpr int PH = PG / 4;            // warps along the sample axis
+  static_assert(QG % 8 == 0 && PG % 4 == 0, "warp = 4 sample groups x 8 neuron groups");
+  static_assert((QG / 8) * PH == CRL_THREADS / 32, "warp grid must cover the CTA");
+};
+
+template <class G> struct ThreadCoord {
+  int p, q, net;
+  int jb[G::NC];  // neuron base of each float4 chunk (within the net)
+  int sb[G::NC];  // sample base of each float4 chunk
+  __device__ ThreadCoord() {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q_lo = lane & 7, p_lo = lane >> 3;
+    const int q_hi = w / G::PH, p_hi = w % G::PH;
+    p = p_hi * 4 + p_lo;
+    q = q_hi * 8 + q_lo;
+    net = q / G::QN;
+    const int qin = q % G::QN;
+    if (G::TS == 8) {
+#pragma unroll
+      for (int c = 0; c < G::NC; c++) { jb[c] = 4 * qin + 32 * c; sb[c] = 4 * p + (G::S / 2) * c; }
+    } else {
+      jb[0] = 4 * qin;
+      sb[0] = 4 * p;
+    }
+  }
+};
+
+__device__ __forceinline__ float f4_get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+#define EPI_BIAS_TANH 0   // out = tanh_fast(acc + bias)                         (forward)
+#define EPI_DTANH 1       // out = acc * (1 - out_old^2), in place over h        (backward)
+
+// One dense layer for this thread's tile:  acc[j][s] = sum_k Wt[k][j] * in[k][s].
+//   Wt   shared, [K][64] for this thread's net (k-major)
+//   in   shared, row 0 of this net's input block (row stride S_PAD)
+//   out  shared, row 0 of this net's output block
+template <class G, int K, int EPI>
+__device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float* __restrict__ Wt,
+                                           const float* __restrict__ bias, const float* __restrict__ in,
+                                           float* __restrict__ out) {
+  constexpr int TS = G::TS, NC = G::NC, SP = G::S_PAD;
+  float acc[TS][TS];
+#pragma unroll
+  for (int j = 0; j < TS; j++)
+#pragma unroll
+    for (int s = 0; s < TS; s++) acc[j][s] = 0.0f;
+#pragma unroll 4
+  for (int k = 0; k < K; k++) {
+    float4 w[NC], a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      w[c] = *reinterpret_cast<const float4*>(Wt + k * CRL_H + tc.jb[c]);
+      a[c] = *reinterpret_cast<const float4*>(in + k * SP + tc.sb[c]);
+    }
+#pragma unroll
+    for (int j = 0; j < TS; j++)
+#pragma unroll
+      for (int s = 0; s < TS; s++) acc[j][s] = fmaf(f4_get(w[j / 4], j % 4), f4_get(a[s / 4], s % 4), acc[j][s]);
+  }
+#pragma unroll
+  for (int j = 0; j < TS; j++) {
+    const int row = tc.jb[j / 4] + (j % 4);
+    float b = 0.0f;
+    if (EPI == EPI_BIAS_TANH) b = bias[row];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      float4* dst = reinterpret_cast<float4*>(out + row * SP + tc.sb[c]);
+      float4 o;
+      if (EPI == EPI_BIAS_TANH) {
+        o.x = tanh_fast(acc[j][4 * c + 0] + b);
+        o.y = tanh_fast(acc[j][4 * c + 1] + b);
+        o.z = tanh_fast(acc[j][4 * c + 2] + b);
+        o.w = tanh_fast(acc[j][4 * c + 3] + b);
+      } else {
+        const float4 h = *dst;
+        o.x = acc[j][4 * c + 0] * (1.0f - h.x * h.x);
+        o.y = acc[j][4 * c + 1] * (1.0f - h.y * h.y);
+        o.z = acc[j][4 * c + 2] * (1.0f - h.z * h.z);
+        o.w = acc[j][4 * c + 3] * (1.0f - h.w * h.w);
+      }
+      *dst = o;
+    }
+  }
+}
+
+// Shared-memory image of the parameters: each net copied to a 16-byte aligned base so the
+// float4 weight loads are legal (the flat vector puts the critic at an odd offset).
+template <int ENV> struct SmemParams {
+  using E = EnvTraits<ENV>;
+  static constexpr int ACTOR = 0;
+  static constexpr int CRITIC = (E::NET_A + 3) & ~3;
+  static constexpr int LOGSTD = CRITIC + ((E::NET_C + 3) & ~3);
+  static constexpr int SIZE = LOGSTD + 4;
+};
+
+template <int ENV>
+__device__ __forceinline__ void load_params(const float* __restrict__ g, float* __restrict__ sp) {
+  using E = EnvTraits<ENV>;
+  using SP = SmemParams<ENV>;
+  for (int i = threadIdx.x; i < E::NET_A; i += blockDim.x) sp[SP::ACTOR + i] = g[i];
+  for (int i = threadIdx.x; i < E::NET_C; i += blockDim.x) sp[SP::CRITIC + i] = g[E::NET_A + i];
+  if (E::CONT && threadIdx.x < E::A) sp[SP::LOGSTD + threadIdx.x] = g[E::NET_A + E::NET_C + threadIdx.x];
+}
+
+// base of net `net` inside the smem parameter image, and its head width
+template <int ENV> __device__ __forceinline__ int net_base(int net) {
+  return net == 0 ? SmemParams<ENV>::ACTOR : SmemParams<ENV>::CRITIC;
+}

@@ -1,0 +1,470 @@
+// rollout.cu — persistent rollout kernel (replaces the loop ppo.jl:123-166) and the raw
+// env-step / policy-forward entry points.
+//
+// One launch runs all T steps. A CTA of 256 threads owns 32 envs for the whole rollout: the
+// policy weights are constant during a rollout and nothing couples envs, so no
+// grid-wide synchronisation is needed. Per step: the two 64-64 MLPs are evaluated for the 32
+// envs as register-tiled FFMA layers out of shared memory (weights staged once per launch),
+// then warp 0 (one lane per env) samples the action, steps the env in registers, writes the
+// [T][N] rollout buffer with coalesced stores (state as one float4 per (t,n)), and resets
+// finished envs on the spot.
+#include "kernels.h"
+#include "mlp_tile.cuh"
+
+namespace {
+
+constexpr int RE = 32;  // envs per CTA
+
+template <int ENV> struct RolloutSmem {
+  using G = TileGeom<4, 2>;
+  using E = EnvTraits<ENV>;
+  static constexpr int SP = G::S_PAD;
+  static constexpr int PARAMS = 0;
+  static constexpr int X = PARAMS + SmemParams<ENV>::SIZE;
+  static constexpr int H1 = X + CRL_MAXD * SP;
+  static constexpr int H2 = H1 + G::ROWS * SP;
+  static constexpr int OUT = H2 + G::ROWS * SP;
+  static constexpr int FLOATS = OUT + 4 * RE;
+  static constexpr size_t BYTES = FLOATS * sizeof(float);
+};
+
+// both nets forward for the 32 samples whose observations sit in xs; heads -> so[o][e]
+// (o < A: actor logits/mean, o == A: critic value)
+template <int ENV>
+__device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc, float* smem) {
+  using G = TileGeom<4, 2>;
+  using E = EnvTraits<ENV>;
+  using SM = RolloutSmem<ENV>;
+  constexpr int SP = G::S_PAD;
+  float* sp = smem + SM::PARAMS;
+  float* xs = smem + SM::X;
+  float* h1 = smem + SM::H1;
+  float* h2 = smem + SM::H2;
+  float* so = smem + SM::OUT;
+  const float* np = sp + net_base<ENV>(tc.net);
+  using NO = NetOff<E::D, 1>;  // W1,B1,W2,B2,W3 offsets do not depend on the head width
+  tile_layer<G, E::D, EPI_BIAS_TANH>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
+  __syncthreads();
+  tile_layer<G, CRL_H, EPI_BIAS_TANH>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
+  __syncthreads();
+  if (threadIdx.x < RE * (E::A + 1)) {
+    const int o = threadIdx.x / RE, e = threadIdx.x % RE;
+    float acc = 0.0f;
+    if (o < E::A) {
+      const float* a = sp + SmemParams<ENV>::ACTOR;
+      const float* W3 = a + NetOff<E::D, E::A>::W3;
+#pragma unroll 8
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(W3[k * E::A + o], h2[k * SP + e], acc);
+      acc += a[NetOff<E::D, E::A>::B3 + o];
+    } else {
+      const float* c = sp + SmemParams<ENV>::CRITIC;
+      const float* W3 = c + NetOff<E::D, 1>::W3;
+#pragma unroll 8
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(W3[k], h2[(CRL_H + k) * SP + e], acc);
+      acc += c[NetOff<E::D, 1>::B3];
+    }
+    so[o * RE + e] = acc;
+  }
+  __syncthreads();
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
+  using G = TileGeom<4, 2>;
+  using E = EnvTraits<ENV>;
+  using SM = RolloutSmem<ENV>;
+  constexpr int SP = G::S_PAD;
+  constexpr int D = E::D, A = E::A, S = E::S;
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem + SM::PARAMS;
+  float* xs = smem + SM::X;
+  float* so = smem + SM::OUT;
+  const ThreadCoord<G> tc;
+
+  load_params<ENV>(a.params, sp);
+  for (int i = threadIdx.x; i < CRL_MAXD * SP; i += blockDim.x) xs[i] = 0.0f;
+
+  const int e = threadIdx.x;  // env lane, meaningful for warp 0
+  const long long n = (long long)blockIdx.x * RE + e;
+  const bool owner = threadIdx.x < RE;
+  const bool valid = owner && n < a.N;
+  const unsigned long long step0 = a.ds->policy_step;
+  const uint32_t gid = (uint32_t)(a.env_id_base + (int)n);
+
+  float st[S];
+  float obs[D];
+  int env_t = 0, ep_len = 0;
+  double ep_ret = 0.0;
+  uint32_t resets = 0;
+  bool done_flag = false;  // Q3: ppo.jl:170 — is_terminated(env) after reset! is false
+  // per-thread episode aggregates
+  unsigned long long agg_n = 0;
+  double agg_ret = 0.0, agg_len = 0.0, agg_max = -INFINITY;
+
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < S; i++) st[i] = a.env_state[n * S + i];
+    env_t = a.env_t[n];
+    ep_len = a.ep_length[n];
+    ep_ret = a.ep_return[n];
+    resets = a.reset_count[n];
+  } else {
+#pragma unroll
+    for (int i = 0; i < S; i++) st[i] = 0.0f;
+  }
+  __syncthreads();
+  if (owner) {
+    env_obs<ENV>(st, obs);  // Q3: ppo.jl:169 — state(env) refreshed (post-reset state)
+#pragma unroll
+    for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
+  }
+  __syncthreads();
+
+  for (int t = 0; t < a.T; t++) {
+    forward32<ENV>(tc, smem);  // ends with a barrier; so[] is ready
+    if (owner) {
+      const long long b = (long long)t * a.N + n;
+      ep_len += 1;  // ppo.jl:125
+      const float value = so[A * RE + e];
+      float logprob;
+      int act_i = 0;
+      float act_f = 0.0f;
+      if (!E::CONT) {
+        // get_action, ppo.jl:22-29: softmax / logsoftmax [NNlib], then
+        // StatsBase.sample(Weights(p)): t = rand()*sum(p); walk cw += p[i] while cw < t.
+        float z[A], p[A], lp[A];
+#pragma unroll
+        for (int k = 0; k < A; k++) z[k] = so[k * RE + e];
+        float m = z[0];
+#pragma unroll
+        for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+        float ex[A], sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
+        const float ls = logf(sum);
+        float psum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < A; k++) {
+          p[k] = __fdiv_rn(ex[k], sum);
+          lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+          psum = __fadd_rn(psum, p[k]);
+        }
+        double u = 0.0;
+        if (valid) u = a.action_noise ? a.action_noise[b] : rng_action_uniform(a.seed, gid, step0 + (unsigned long long)t);
+        const double tt = __dmul_rn(u, (double)psum);
+        float cw = p[0];
+        int i = 0;
+#pragma unroll
+        for (int k = 1; k < A; k++) {
+          if ((double)cw < tt && i == k - 1) { i = k; cw = __fadd_rn(cw, p[k]); }
+        }
+        act_i = i;
+        logprob = lp[0];
+#pragma unroll
+        for (int k = 1; k < A; k++) logprob = (i == k) ? lp[k] : logprob;
+      } else {
+        // Gaussian head (CleanRL-Python convention; the reference has none)
+        float zn[2] = {0.0f, 0.0f};
+        if (valid) {
+          if (a.action_noise) { for (int k = 0; k < A; k++) zn[k] = (float)a.action_noise[b * A + k]; }
+          else rng_action_normals(a.seed, gid, step0 + (unsigned long long)t, zn);
+        }
+        float lps = 0.0f;
+#pragma unroll
+        for (int k = 0; k < A; k++) {
+          const float mean = so[k * RE + e];
+          const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
+          const float sd = expf(logstd);
+          const float ak = __fadd_rn(mean, __fmul_rn(sd, zn[k]));
+          const float diff = __fsub_rn(ak, mean);
+          const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+          lps = __fadd_rn(lps, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
+          if (k == 0) act_f = ak;
+          if (valid) reinterpret_cast<float*>(a.action)[b * A + k] = ak;
+        }
+        logprob = lps;
+      }
+      if (valid) {
+        // Buffer.add!, ppo.jl:133-140: state = next_obs, terminal = next_done (previous step)
+        if (D == 4) {
+          reinterpret_cast<float4*>(a.state)[b] = make_float4(obs[0], obs[1], obs[2], obs[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < D; k++) a.state[b * D + k] = obs[k];
+        }
+        if (!E::CONT) reinterpret_cast<int32_t*>(a.action)[b] = act_i;
+        a.logprob[b] = logprob;
+        a.value[b] = value;
+        a.terminal[b] = done_flag ? 1 : 0;
+      }
+      // env(action), ppo.jl:130
+      float r;
+      bool dn;
+      if (ENV == CRL_ENV_CARTPOLE) cartpole_step(st, env_t, act_i, a.max_steps, r, dn);
+      else pendulum_step(st, env_t, act_f, a.max_steps, r, dn);
+      env_obs<ENV>(st, obs);  // ppo.jl:143 — copied BEFORE reset! (Q2: stale terminal obs)
+      done_flag = dn;         // ppo.jl:144
+      ep_ret += (double)r;    // ppo.jl:145
+      if (valid) {
+        a.reward[b] = r;  // ppo.jl:132
+        if (dn) {         // ppo.jl:147-165
+          const unsigned int slot = atomicAdd(&a.eb->count, 1u);
+          if (slot < (unsigned int)a.ep_capacity) {
+            crl_episode rec;
+            rec.step = t; rec.env = (int)n; rec.length = ep_len; rec._pad = 0; rec.episode_return = ep_ret;
+            a.records[slot] = rec;
+          }
+          agg_n += 1; agg_ret += ep_ret; agg_len += (double)ep_len; agg_max = fmax(agg_max, ep_ret);
+          ep_ret = 0.0;
+          ep_len = 0;
+          float u4[4];
+          if (a.reset_noise) {
+            const float4 v = reinterpret_cast<const float4*>(a.reset_noise)[b];
+            u4[0] = v.x; u4[1] = v.y; u4[2] = v.z; u4[3] = v.w;
+          } else {
+            rng_reset_uniforms(a.seed, gid, resets, u4);
+          }
+          resets += 1;
+          env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
+    }
+    __syncthreads();
+  }
+
+  // Bootstrap value for GAE: next_values = critic(state(env)) with the refreshed (post-reset)
+  // observation, ppo.jl:169-171. The weights cannot change between here and crl_gae.
+  float obs_last[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) obs_last[k] = obs[k];
+  if (owner) {
+    float fresh[D];
+    env_obs<ENV>(st, fresh);
+#pragma unroll
+    for (int k = 0; k < D; k++) xs[k * SP + e] = fresh[k];
+  }
+  __syncthreads();
+  forward32<ENV>(tc, smem);
+  if (valid) {
+    a.next_value[n] = so[A * RE + e];
+#pragma unroll
+    for (int i = 0; i < S; i++) a.env_state[n * S + i] = st[i];
+    a.env_t[n] = env_t;
+    a.ep_length[n] = ep_len;
+    a.ep_return[n] = ep_ret;
+    a.reset_count[n] = resets;
+#pragma unroll
+    for (int k = 0; k < D; k++) a.next_obs[n * D + k] = obs_last[k];
+    a.next_done[n] = done_flag ? 1 : 0;
+  }
+  if (threadIdx.x < 32) {
+    const double sr = warp_sum(agg_ret), sl = warp_sum(agg_len), mx = warp_max(agg_max);
+    unsigned long long cn = agg_n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
+    if (threadIdx.x == 0 && cn > 0) {
+      atomicAdd(&a.eb->n_episodes, cn);
+      atomicAdd(&a.eb->sum_return, sr);
+      atomicAdd(&a.eb->sum_length, sl);
+      unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.eb->max_return);
+      unsigned long long old = *addr, assumed;
+      do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) >= mx) break;
+        old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
+      } while (assumed != old);
+    }
+  }
+}
+
+// ---- raw kernels (parity tests) --------------------------------------------------------
+template <int ENV>
+__global__ void env_step_raw_kernel(float* state, int* t, const void* action, float* reward, uint8_t* done,
+                                    long long n, int max_steps) {
+  constexpr int S = EnvTraits<ENV>::S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float st[S];
+#pragma unroll
+  for (int k = 0; k < S; k++) st[k] = state[i * S + k];
+  int tt = t[i];
+  float r;
+  bool dn;
+  if (ENV == CRL_ENV_CARTPOLE) cartpole_step(st, tt, reinterpret_cast<const int32_t*>(action)[i], max_steps, r, dn);
+  else pendulum_step(st, tt, reinterpret_cast<const float*>(action)[i], max_steps, r, dn);
+#pragma unroll
+  for (int k = 0; k < S; k++) state[i * S + k] = st[k];
+  t[i] = tt;
+  reward[i] = r;
+  done[i] = dn ? 1 : 0;
+}
+
+// same tile code as the rollout: 32 observations per CTA
+template <int ENV>
+__global__ void __launch_bounds__(CRL_THREADS) policy_forward_raw_kernel(const float* params, const float* obs,
+                                                                         float* out_policy, float* logp,
+                                                                         float* value, long long n) {
+  using G = TileGeom<4, 2>;
+  using E = EnvTraits<ENV>;
+  using SM = RolloutSmem<ENV>;
+  constexpr int SP = G::S_PAD;
+  constexpr int D = E::D, A = E::A;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem + SM::X;
+  float* so = smem + SM::OUT;
+  const ThreadCoord<G> tc;
+  load_params<ENV>(params, smem + SM::PARAMS);
+  const int e = threadIdx.x;
+  const long long i = (long long)blockIdx.x * RE + e;
+  if (e < RE) {
+#pragma unroll
+    for (int k = 0; k < D; k++) xs[k * SP + e] = i < n ? obs[i * D + k] : 0.0f;
+  }
+  __syncthreads();
+  forward32<ENV>(tc, smem);
+  if (e < RE && i < n) {
+    float z[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) { z[k] = so[k * RE + e]; out_policy[i * A + k] = z[k]; }
+    value[i] = so[A * RE + e];
+    if (!E::CONT) {
+      float m = z[0];
+#pragma unroll
+      for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < A; k++) sum = __fadd_rn(sum, expf(__fsub_rn(z[k], m)));
+      const float ls = logf(sum);
+#pragma unroll
+      for (int k = 0; k < A; k++) logp[i * A + k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+    }
+  }
+}
+
+template <int ENV> cudaError_t launch_rollout_t(const RolloutArgs& a, cudaStream_t s) {
+  const int grid = (a.N + RE - 1) / RE;
+  rollout_kernel<ENV><<<grid, CRL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int ENV>
+cudaError_t launch_policy_forward_t(const float* params, const float* obs, float* out_policy, float* logp,
+                                    float* value, long long n, cudaStream_t s) {
+  const long long grid = (n + RE - 1) / RE;
+  if (grid == 0) return cudaSuccess;
+  policy_forward_raw_kernel<ENV><<<(unsigned)grid, CRL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(params, obs, out_policy,
+                                                                                              logp, value, n);
+  return cudaGetLastError();
+}
+
+__global__ void episode_buf_init_kernel(EpisodeBuf* eb) {
+  eb->count = 0; eb->_pad = 0; eb->n_episodes = 0ull; eb->sum_return = 0.0; eb->sum_length = 0.0;
+  eb->max_return = -INFINITY;
+}
+
+template <int ENV> cudaError_t init_attrs_t() {
+  cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)RolloutSmem<ENV>::BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(policy_forward_raw_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)RolloutSmem<ENV>::BYTES);
+}
+
+}  // namespace
+
+// opt in to > 48 KB dynamic shared memory (per device; must run outside stream capture)
+cudaError_t kernels_init_rollout() {
+  cudaError_t e = init_attrs_t<CRL_ENV_CARTPOLE>();
+  if (e != cudaSuccess) return e;
+  return init_attrs_t<CRL_ENV_PENDULUM>();
+}
+
+cudaError_t launch_episode_buf_init(EpisodeBuf* eb, cudaStream_t s) {
+  episode_buf_init_kernel<<<1, 1, 0, s>>>(eb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(int env_kind, const RolloutArgs& a, cudaStream_t s) {
+  return env_kind == CRL_ENV_CARTPOLE ? launch_rollout_t<CRL_ENV_CARTPOLE>(a, s) : launch_rollout_t<CRL_ENV_PENDULUM>(a, s);
+}
+
+cudaError_t launch_env_step_raw(int env_kind, float* state, int* t, const void* action, float* reward,
+                                uint8_t* done, long long n, int max_steps, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (env_kind == CRL_ENV_CARTPOLE)
+    env_step_raw_kernel<CRL_ENV_CARTPOLE><<<grid, 128, 0, s>>>(state, t, action, reward, done, n, max_steps);
+  else
+    env_step_raw_kernel<CRL_ENV_PENDULUM><<<grid, 128, 0, s>>>(state, t, action, reward, done, n, max_steps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_policy_forward_raw(int env_kind, const float* params, const float* obs, float* out_policy,
+                                      float* logp, float* value, long long n, cudaStream_t s) {
+  return env_kind == CRL_ENV_CARTPOLE
+             ? launch_policy_forward_t<CRL_ENV_CARTPOLE>(params, obs, out_policy, logp, value, n, s)
+             : launch_policy_forward_t<CRL_ENV_PENDULUM>(params, obs, out_policy, logp, value, n, s);
+}
+
+// ---- env reset / refresh (ppo.jl:112-115) ------------------------------------------------
+namespace {
+template <int ENV>
+__global__ void env_reset_kernel(int N, unsigned long long seed, int env_id_base, float* env_state, int* env_t,
+                                 double* ep_return, int* ep_length, uint32_t* reset_count, float* next_obs,
+                                 uint8_t* next_done) {
+  constexpr int S = EnvTraits<ENV>::S, D = EnvTraits<ENV>::D;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float u4[4], st[S], obs[D];
+  const uint32_t k = reset_count[n];
+  rng_reset_uniforms(seed, (uint32_t)(env_id_base + n), k, u4);
+  int t;
+  env_reset<ENV>(st, t, u4);
+  env_obs<ENV>(st, obs);
+#pragma unroll
+  for (int i = 0; i < S; i++) env_state[n * S + i] = st[i];
+#pragma unroll
+  for (int i = 0; i < D; i++) next_obs[n * D + i] = obs[i];
+  env_t[n] = t;
+  reset_count[n] = k + 1;
+  next_done[n] = 0;
+  ep_return[n] = 0.0;
+  ep_length[n] = 0;
+}
+template <int ENV>
+__global__ void env_refresh_kernel(int N, const float* env_state, float* next_obs, uint8_t* next_done) {
+  constexpr int S = EnvTraits<ENV>::S, D = EnvTraits<ENV>::D;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float st[S], obs[D];
+#pragma unroll
+  for (int i = 0; i < S; i++) st[i] = env_state[n * S + i];
+  env_obs<ENV>(st, obs);
+#pragma unroll
+  for (int i = 0; i < D; i++) next_obs[n * D + i] = obs[i];
+  next_done[n] = 0;
+}
+}  // namespace
+
+cudaError_t launch_env_reset(int env_kind, int N, unsigned long long seed, int env_id_base, float* env_state,
+                             int* env_t, double* ep_return, int* ep_length, uint32_t* reset_count, float* next_obs,
+                             uint8_t* next_done, cudaStream_t s) {
+  const int grid = (N + 127) / 128;
+  if (env_kind == CRL_ENV_CARTPOLE)
+    env_reset_kernel<CRL_ENV_CARTPOLE><<<grid, 128, 0, s>>>(N, seed, env_id_base, env_state, env_t, ep_return, ep_length,
+                                                           reset_count, next_obs, next_done);
+  else
+    env_reset_kernel<CRL_ENV_PENDULUM><<<grid, 128, 0, s>>>(N, seed, env_id_base, env_state, env_t, ep_return, ep_length,
+                                                           reset_count, next_obs, next_done);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_env_refresh(int env_kind, int N, const float* env_state, float* next_obs, uint8_t* next_done,
+                               cudaStream_t s) {
+  const int grid = (N + 127) / 128;
+  if (env_kind == CRL_ENV_CARTPOLE) env_refresh_kernel<CRL_ENV_CARTPOLE><<<grid, 128, 0, s>>>(N, env_state, next_obs, next_done);
+  else env_refresh_kernel<CRL_ENV_PENDULUM><<<grid, 128, 0, s>>>(N, env_state, next_obs, next_done);
+  return cudaGetLastError();
+}

@@ -1,0 +1,793 @@
+// update.cu — the clipped-surrogate minibatch update (ppo.jl:191-252) as five kernels:
+//
+//   mb_stats    critic forward over the minibatch -> v_new[M] + per-CTA sums for the three
+//               minibatch-global scalars the reference's loss needs before any gradient exists:
+//               mean/std of the advantages (ppo.jl:221) and s = mean(newvalue .- R.^2) (ppo.jl:232,
+//               quirk Q5), plus min_i (clip_i - R_i)^2 to short-cut the count below.
+//   mb_count    finalises those scalars and counts #{i : s > (clip_i - R_i)^2} (ppo.jl:236).
+//   loss_grad   fused forward (actor+critic) + loss + full backward for tiles of 128 samples;
+//               every 64x64 contraction is a register-tiled FFMA GEMM out of shared memory;
+//               weight gradients stay in registers for the whole kernel.
+//   grad_reduce sums the per-CTA partial gradients in a fixed order (deterministic) into the
+//               double-precision buffer that is also the NCCL allreduce payload.
+//   clip_adam   Flux.Optimiser(ClipNorm(0.5), Adam) per parameter array (ppo.jl:93,250).
+//
+// FP32 FFMA throughout (no TF32): results are within fp32 rounding of the oracle.
+#include "kernels.h"
+#include "mlp_tile.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ int sample_index(const IdxSrc& ix, const uint32_t* keys, int m) {
+  if (ix.arr) return ix.arr[m];
+  return (int)perm_index(ix.start + (uint32_t)m, ix.B, ix.half_bits, keys);
+}
+
+// value-loss pieces of ppo.jl:234-235, evaluated identically in all three kernels
+__device__ __forceinline__ void value_clip(float v, float V, float R, float c, float& vc_minus_R, float& vlc,
+                                           bool& inside) {
+  const float dv = __fsub_rn(v, V);
+  const float cl = dv < -c ? -c : (dv > c ? c : dv);
+  const float vc = __fadd_rn(V, cl);
+  vc_minus_R = __fsub_rn(vc, R);
+  vlc = __fmul_rn(vc_minus_R, vc_minus_R);
+  inside = dv >= -c && dv <= c;
+}
+
+template <int NW> __device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) s += red[w];
+  return s;
+}
+
+// ------------------------------------------------------------------ mb_stats
+template <int ENV> struct StatsSmem {
+  using G = TileGeom<8, 1>;
+  using E = EnvTraits<ENV>;
+  static constexpr int SP = G::S_PAD;
+  static constexpr int PARAMS = 0;
+  static constexpr int X = (E::NET_C + 3) & ~3;
+  static constexpr int H1 = X + CRL_MAXD * SP;
+  static constexpr int H2 = H1 + CRL_H * SP;
+  static constexpr int KEYS = H2 + CRL_H * SP;
+  static constexpr int RED = KEYS + 8;  // 16 doubles
+  static constexpr int FLOATS = RED + 32;
+  static constexpr size_t BYTES = FLOATS * sizeof(float);
+};
+
+template <int ENV>
+__global__ void __launch_bounds__(CRL_THREADS, 1) mb_stats_kernel(UpdateArgs a) {
+  using G = TileGeom<8, 1>;
+  using E = EnvTraits<ENV>;
+  using SM = StatsSmem<ENV>;
+  using NO = NetOff<E::D, 1>;
+  constexpr int SP = G::S_PAD, S = G::S, D = E::D;
+  extern __shared__ __align__(16) float smem[];
+  float* cp = smem + SM::PARAMS;
+  float* xs = smem + SM::X;
+  float* h1 = smem + SM::H1;
+  float* h2 = smem + SM::H2;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SM::KEYS);
+  double* red = reinterpret_cast<double*>(smem + SM::RED);
+  const ThreadCoord<G> tc;
+  for (int i = threadIdx.x; i < E::NET_C; i += blockDim.x) cp[i] = a.params[E::NET_A + i];
+  if (threadIdx.x == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.fin->cnt = 0ull;
+  __syncthreads();
+
+  double s_adv = 0.0, s_adv2 = 0.0, s_s = 0.0;
+  float mn = INFINITY;
+  const int tid = threadIdx.x;
+  for (int m0 = blockIdx.x * S; m0 < a.M; m0 += gridDim.x * S) {
+    const int m = m0 + tid;
+    const bool valid = m < a.M;
+    float adv = 0.0f, R = 0.0f, V = 0.0f;
+    float x[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) x[k] = 0.0f;
+    if (valid) {
+      const int b = sample_index(a.idx, keys, m);
+      if (D == 4) {
+        const float4 v4 = reinterpret_cast<const float4*>(a.states)[b];
+        x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[D - 1] = v4.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) x[k] = a.states[(long long)b * D + k];
+      }
+      adv = a.advantages[b];
+      R = a.returns[b];
+      V = a.values[b];
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) xs[k * SP + tid] = x[k];
+    __syncthreads();
+    tile_layer<G, D, EPI_BIAS_TANH>(tc, cp + NO::W1, cp + NO::B1, xs, h1);
+    __syncthreads();
+    tile_layer<G, CRL_H, EPI_BIAS_TANH>(tc, cp + NO::W2, cp + NO::B2, h1, h2);
+    __syncthreads();
+    float v = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < CRL_H; k++) v = fmaf(cp[NO::W3 + k], h2[k * SP + tid], v);
+    v += cp[NO::B3];
+    if (valid) {
+      a.vnew[m] = v;
+      const double ad = (double)adv;
+      s_adv += ad;
+      s_adv2 += ad * ad;
+      s_s += (double)__fsub_rn(v, __fmul_rn(R, R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
+      float d, vlc;
+      bool inside;
+      value_clip(v, V, R, a.clip_coef, d, vlc, inside);
+      mn = fminf(mn, vlc);
+    }
+  }
+  const double t_adv = block_sum<8>(s_adv, red);
+  const double t_adv2 = block_sum<8>(s_adv2, red);
+  const double t_s = block_sum<8>(s_s, red);
+  mn = warp_min(mn);
+  __shared__ float mred[8];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m8 = mred[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) m8 = fminf(m8, mred[w]);
+    MbScalars o;
+    o.sum_adv = t_adv; o.sum_adv2 = t_adv2; o.sum_s = t_s; o.min_vlc = m8; o._pad = 0.0f;
+    a.parts[blockIdx.x] = o;
+  }
+}
+
+// ------------------------------------------------------------------ mb_count
+template <int DUMMY>
+__global__ void __launch_bounds__(CRL_THREADS) mb_count_kernel(UpdateArgs a) {
+  __shared__ double red[8];
+  __shared__ float mred[8];
+  __shared__ uint32_t keys[8];
+  double s_adv = 0.0, s_adv2 = 0.0, s_s = 0.0;
+  float mn = INFINITY;
+  for (int i = threadIdx.x; i < a.n_parts_in; i += blockDim.x) {
+    const MbScalars p = a.parts_in[i];
+    s_adv += p.sum_adv; s_adv2 += p.sum_adv2; s_s += p.sum_s; mn = fminf(mn, p.min_vlc);
+  }
+  // fixed-order (deterministic) reduction: lanes -> warps -> block
+  const double t_adv = block_sum<8>(s_adv, red);
+  const double t_adv2 = block_sum<8>(s_adv2, red);
+  const double t_s = block_sum<8>(s_s, red);
+  mn = warp_min(mn);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = mn;
+  if (threadIdx.x == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
+  __syncthreads();
+  float m8 = mred[0];
+#pragma unroll
+  for (int w = 1; w < 8; w++) m8 = fminf(m8, mred[w]);
+  const double Mg = (double)a.M * (double)a.world;
+  const double mean = t_adv / Mg;
+  double var = (t_adv2 - Mg * mean * mean) / (Mg - 1.0);  // corrected std, ppo.jl:221
+  if (var < 0.0) var = 0.0;
+  const float mean_f = (float)mean, std_f = (float)sqrt(var), s_f = (float)(t_s / Mg);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.fin->adv_mean = mean_f; a.fin->adv_std = std_f; a.fin->s_unclipped = s_f; a.fin->min_vlc = m8;
+    a.fin->M_global = Mg;
+  }
+  if (!(s_f > m8)) return;  // common case: the scalar never wins the max, count is 0
+  unsigned int c = 0;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += gridDim.x * blockDim.x) {
+    const int b = sample_index(a.idx, keys, m);
+    float d, vlc;
+    bool inside;
+    value_clip(a.vnew[m], a.values[b], a.returns[b], a.clip_coef, d, vlc, inside);
+    c += (s_f > vlc) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&a.fin->cnt, (unsigned long long)c);
+}
+
+// ------------------------------------------------------------------ loss_grad
+template <int ENV> struct LossSmem {
+  using G = TileGeom<8, 2>;
+  using E = EnvTraits<ENV>;
+  static constexpr int SP = G::S_PAD, S = G::S;
+  static constexpr int PARAMS = 0;
+  static constexpr int W2T = PARAMS + SmemParams<ENV>::SIZE;  // [2][64][64], [net][j][k]
+  static constexpr int X = W2T + 2 * CRL_H * CRL_H;
+  static constexpr int H1 = X + CRL_MAXD * SP;
+  static constexpr int H2 = H1 + G::ROWS * SP;
+  static constexpr int ZO = H2 + G::ROWS * SP;  // z[A][S] then v[S]
+  static constexpr int DOUT = ZO + 3 * S;       // dz[A][S] then dv[S]
+  static constexpr int KEYS = DOUT + 3 * S;
+  static constexpr int RED = KEYS + 8;
+  static constexpr int FLOATS = RED + 32;
+  static constexpr size_t BYTES = FLOATS * sizeof(float);
+  static_assert(BYTES <= 227 * 1024, "loss_grad shared memory exceeds 227 KB");
+};
+
+template <int ENV>
+__global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a) {
+  using G = TileGeom<8, 2>;
+  using E = EnvTraits<ENV>;
+  using SM = LossSmem<ENV>;
+  using NO = NetOff<E::D, 1>;
+  using NA = NetOff<E::D, E::A>;
+  constexpr int SP = G::S_PAD, S = G::S, D = E::D, A = E::A;
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem + SM::PARAMS;
+  float* w2t = smem + SM::W2T;
+  float* xs = smem + SM::X;
+  float* h1 = smem + SM::H1;
+  float* h2 = smem + SM::H2;
+  float* zo = smem + SM::ZO;
+  float* dout = smem + SM::DOUT;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SM::KEYS);
+  double* red = reinterpret_cast<double*>(smem + SM::RED);
+  const ThreadCoord<G> tc;
+  const int tid = threadIdx.x;
+
+  load_params<ENV>(a.params, sp);
+  if (tid == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
+  __syncthreads();
+  // W2T[net][j][k] = W2(j,k): the k-major operand of the dh1 = W2^T dz2 contraction
+  for (int i = tid; i < 2 * CRL_H * CRL_H; i += blockDim.x) {
+    const int net = i / (CRL_H * CRL_H), r = i % (CRL_H * CRL_H), j = r / CRL_H, k = r % CRL_H;
+    w2t[i] = sp[net_base<ENV>(net) + NO::W2 + k * CRL_H + j];
+  }
+  const float mean_f = a.fin->adv_mean, std_f = a.fin->adv_std, s_f = a.fin->s_unclipped;
+  const double Mg = a.fin->M_global;
+  const double cnt_over_M = (double)a.fin->cnt / Mg;
+  const float c = a.clip_coef;
+  const float lo_c = 1.0f - c, hi_c = 1.0f + c;
+  __syncthreads();
+
+  // persistent per-thread gradient accumulators (live for the whole kernel)
+  float gW2[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) gW2[i][j] = 0.0f;
+  float gW3 = 0.0f, gb3 = 0.0f;             // head phase owner (tid < 64*(A+1))
+  float gW1[D], gb12 = 0.0f;                // row-sum phase: tid<128: dW1 + db1; tid>=128: db2
+#pragma unroll
+  for (int k = 0; k < D; k++) gW1[k] = 0.0f;
+  double st_pg = 0.0, st_vmax = 0.0, st_ent = 0.0, g_logstd[A];
+#pragma unroll
+  for (int k = 0; k < A; k++) g_logstd[k] = 0.0;
+
+  // phase-specific coordinates
+  const int w_net = tid >> 7;          // dW2 phase: warps 0-3 actor, 4-7 critic
+  const int w_jq = tid & 7;            // j rows jq + 8*i2
+  const int w_kq = (tid & 127) >> 3;   // k rows kq + 16*i
+
+  for (int m0 = blockIdx.x * S; m0 < a.M; m0 += gridDim.x * S) {
+    // ---- P0 gather (threads 0..127 own one sample each for the scalar phases)
+    float s_adv = 0.0f, s_oldlp = 0.0f, s_R = 0.0f, s_V = 0.0f, s_actf[A];
+    int s_act = 0;
+    bool valid = false;
+#pragma unroll
+    for (int k = 0; k < A; k++) s_actf[k] = 0.0f;
+    if (tid < S) {
+      const int m = m0 + tid;
+      valid = m < a.M;
+      float x[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) x[k] = 0.0f;
+      if (valid) {
+        const int b = sample_index(a.idx, keys, m);
+        if (D == 4) {
+          const float4 v4 = reinterpret_cast<const float4*>(a.states)[b];
+          x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[D - 1] = v4.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < D; k++) x[k] = a.states[(long long)b * D + k];
+        }
+        s_adv = a.advantages[b];
+        s_oldlp = a.logprobs[b];
+        s_R = a.returns[b];
+        s_V = a.values[b];
+        if (E::CONT) {
+#pragma unroll
+          for (int k = 0; k < A; k++) s_actf[k] = reinterpret_cast<const float*>(a.actions)[(long long)b * A + k];
+        } else {
+          s_act = reinterpret_cast<const int32_t*>(a.actions)[b];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < D; k++) xs[k * SP + tid] = x[k];
+    }
+    __syncthreads();
+    // ---- P1/P2 forward, both nets (logprob_actions ppo.jl:35 and critic ppo.jl:214)
+    {
+      const float* np = sp + net_base<ENV>(tc.net);
+      tile_layer<G, D, EPI_BIAS_TANH>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
+      __syncthreads();
+      tile_layer<G, CRL_H, EPI_BIAS_TANH>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
+      __syncthreads();
+    }
+    // ---- P3 heads
+    {
+      const int s = tid & (S - 1);
+      if (tid < S) {
+        const float* ap = sp + SmemParams<ENV>::ACTOR;
+        float acc[A];
+#pragma unroll
+        for (int o = 0; o < A; o++) acc[o] = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < CRL_H; k++) {
+          const float h = h2[k * SP + s];
+#pragma unroll
+          for (int o = 0; o < A; o++) acc[o] = fmaf(ap[NA::W3 + k * A + o], h, acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < A; o++) zo[o * S + s] = acc[o] + ap[NA::B3 + o];
+      } else {
+        const float* cp = sp + SmemParams<ENV>::CRITIC;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < CRL_H; k++) acc = fmaf(cp[NO::W3 + k], h2[(CRL_H + k) * SP + s], acc);
+        zo[A * S + s] = acc + cp[NO::B3];
+      }
+    }
+    __syncthreads();
+    // ---- P4 per-sample loss and its gradient w.r.t. the head outputs (ppo.jl:213-243)
+    if (tid < S) {
+      const int s = tid;
+      float dz[A], dv = 0.0f;
+#pragma unroll
+      for (int k = 0; k < A; k++) dz[k] = 0.0f;
+      if (valid) {
+        float z[A];
+#pragma unroll
+        for (int k = 0; k < A; k++) z[k] = zo[k * S + s];
+        const float v = zo[A * S + s];
+        // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
+        const double adv_n = (double)__fsub_rn(s_adv, mean_f) / ((double)std_f + 1e-8);
+        float newlp, p[A], lp[A];
+        double ent_sum = 0.0;
+        if (!E::CONT) {
+          float m = z[0];
+#pragma unroll
+          for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+          float ex[A], sum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
+          const float ls = logf(sum);
+          newlp = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            p[k] = __fdiv_rn(ex[k], sum);
+            lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+            ent_sum += (double)(-__fmul_rn(p[k], lp[k]));  // ppo.jl:42 (Q4: A x M matrix)
+            if (k == s_act) newlp = lp[k];
+          }
+        } else {
+          float acc = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
+            const float sd = expf(logstd);
+            const float diff = __fsub_rn(s_actf[k], z[k]);
+            const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+            acc = __fadd_rn(acc, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
+            ent_sum += (double)__fadd_rn(__fadd_rn(0.5f, 0.9189385332046727f), logstd);
+            p[k] = 0.0f; lp[k] = 0.0f;
+          }
+          newlp = acc;
+        }
+        const float logratio = __fsub_rn(newlp, s_oldlp);  // ppo.jl:224
+        const float ratio = expf(logratio);                // ppo.jl:225
+        const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
+        const double pg1 = -adv_n * (double)ratio;  // ppo.jl:226
+        const double pg2 = -adv_n * (double)rc;     // ppo.jl:227
+        double pgm, dratio;
+        if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
+        else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
+        st_pg += pgm;
+        const double g_lp = dratio * (double)ratio / Mg;
+        // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
+        float d_vcR, vlc;
+        bool inside;
+        value_clip(v, s_V, s_R, c, d_vcR, vlc, inside);
+        const bool s_wins = s_f > vlc;
+        st_vmax += (double)(s_wins ? s_f : vlc);
+        double dv_d = cnt_over_M;
+        if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
+        dv = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
+        st_ent += ent_sum;
+        const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);
+        if (!E::CONT) {
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            double d = g_lp * ((k == s_act ? 1.0 : 0.0) - (double)p[k]);
+            d += ent_scale * (double)p[k] * ((double)lp[k] + ent_sum);
+            dz[k] = (float)d;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            const float sd = expf(sp[SmemParams<ENV>::LOGSTD + k]);
+            const double diff = (double)__fsub_rn(s_actf[k], z[k]);
+            const double var = (double)sd * (double)sd;
+            dz[k] = (float)(g_lp * diff / var);
+            g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < A; k++) dout[k * S + s] = dz[k];
+      dout[A * S + s] = dv;
+    }
+    __syncthreads();
+    // ---- P5 head backward: dW3 += h2 * dout^T, db3 += sum dout
+    if (tid < CRL_H * (A + 1)) {
+      const int o = tid / CRL_H, k = tid % CRL_H;
+      const float* hrow = h2 + ((o < A ? 0 : CRL_H) + k) * SP;
+      const float* drow = dout + o * S;
+      float acc = 0.0f, bacc = 0.0f;
+#pragma unroll 4
+      for (int s = 0; s < S; s += 4) {
+        const float4 h = *reinterpret_cast<const float4*>(hrow + s);
+        const float4 d = *reinterpret_cast<const float4*>(drow + s);
+        acc = fmaf(h.x, d.x, acc); acc = fmaf(h.y, d.y, acc); acc = fmaf(h.z, d.z, acc); acc = fmaf(h.w, d.w, acc);
+        bacc += (d.x + d.y) + (d.z + d.w);
+      }
+      gW3 += acc;
+      gb3 += bacc;
+    }
+    __syncthreads();
+    // ---- P6 dz2 = (W3^T dout) .* (1 - h2^2), in place over this thread's own h2 tile
+    {
+      float* hb = h2 + tc.net * CRL_H * SP;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int row = tc.jb[j / 4] + (j % 4);
+        float w3[A];
+        if (tc.net == 0) {
+#pragma unroll
+          for (int o = 0; o < A; o++) w3[o] = sp[SmemParams<ENV>::ACTOR + NA::W3 + row * A + o];
+        } else {
+          w3[0] = sp[SmemParams<ENV>::CRITIC + NO::W3 + row];
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          float4* hp = reinterpret_cast<float4*>(hb + row * SP + tc.sb[cc]);
+          const float4 h = *hp;
+          float4 dh;
+          if (tc.net == 0) {
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < A; o++) {
+              const float4 d = *reinterpret_cast<const float4*>(dout + o * S + tc.sb[cc]);
+              acc4.x = fmaf(w3[o], d.x, acc4.x); acc4.y = fmaf(w3[o], d.y, acc4.y);
+              acc4.z = fmaf(w3[o], d.z, acc4.z); acc4.w = fmaf(w3[o], d.w, acc4.w);
+            }
+            dh = acc4;
+          } else {
+            const float4 d = *reinterpret_cast<const float4*>(dout + A * S + tc.sb[cc]);
+            dh = make_float4(w3[0] * d.x, w3[0] * d.y, w3[0] * d.z, w3[0] * d.w);
+          }
+          float4 o4;
+          o4.x = dh.x * (1.0f - h.x * h.x); o4.y = dh.y * (1.0f - h.y * h.y);
+          o4.z = dh.z * (1.0f - h.z * h.z); o4.w = dh.w * (1.0f - h.w * h.w);
+          *hp = o4;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- P7 dW2 += dz2 * h1^T (per net): 4 k-rows x 8 j-rows per thread, reduce over samples
+    {
+      const float* h1b = h1 + w_net * CRL_H * SP;
+      const float* d2b = h2 + w_net * CRL_H * SP;
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+#pragma unroll 2
+      for (int s = 0; s < S; s += 4) {
+        float4 hk[4], dj[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) hk[i] = *reinterpret_cast<const float4*>(h1b + (w_kq + 16 * i) * SP + s);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dj[j] = *reinterpret_cast<const float4*>(d2b + (w_jq + 8 * j) * SP + s);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            acc[i][j] = fmaf(hk[i].x, dj[j].x, acc[i][j]);
+            acc[i][j] = fmaf(hk[i].y, dj[j].y, acc[i][j]);
+            acc[i][j] = fmaf(hk[i].z, dj[j].z, acc[i][j]);
+            acc[i][j] = fmaf(hk[i].w, dj[j].w, acc[i][j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) gW2[i][j] += acc[i][j];
+    }
+    __syncthreads();
+    // ---- P8 dz1 = (W2^T dz2) .* (1 - h1^2), in place over h1
+    tile_layer<G, CRL_H, EPI_DTANH>(tc, w2t + tc.net * CRL_H * CRL_H, nullptr, h2 + tc.net * CRL_H * SP,
+                                    h1 + tc.net * CRL_H * SP);
+    __syncthreads();
+    // ---- P9 row sums: tid<128: db1[row], dW1[k][row]; tid>=128: db2[row]
+    {
+      const int row = tid & 127;
+      const float* src = (tid < 128 ? h1 : h2) + row * SP;
+      float bacc = 0.0f, wacc[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) wacc[k] = 0.0f;
+#pragma unroll 4
+      for (int s = 0; s < S; s += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(src + s);
+        bacc += (d.x + d.y) + (d.z + d.w);
+        if (tid < 128) {
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xs + k * SP + s);
+            wacc[k] = fmaf(x4.x, d.x, wacc[k]); wacc[k] = fmaf(x4.y, d.y, wacc[k]);
+            wacc[k] = fmaf(x4.z, d.z, wacc[k]); wacc[k] = fmaf(x4.w, d.w, wacc[k]);
+          }
+        }
+      }
+      gb12 += bacc;
+#pragma unroll
+      for (int k = 0; k < D; k++) gW1[k] += wacc[k];
+    }
+    __syncthreads();
+  }
+
+  // ---- write this CTA's partial gradient (every element of [0,P) exactly once)
+  float* gp = a.gpart + (long long)blockIdx.x * E::P;
+  {
+    const int nb = w_net == 0 ? 0 : E::NET_A;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) gp[nb + NO::W2 + (w_jq + 8 * j) + CRL_H * (w_kq + 16 * i)] = gW2[i][j];
+  }
+  if (tid < CRL_H * (A + 1)) {
+    const int o = tid / CRL_H, k = tid % CRL_H;
+    if (o < A) {
+      gp[NA::W3 + o + A * k] = gW3;
+      if (k == 0) gp[NA::B3 + o] = gb3;
+    } else {
+      gp[E::NET_A + NO::W3 + k] = gW3;
+      if (k == 0) gp[E::NET_A + NO::B3] = gb3;
+    }
+  }
+  {
+    const int row = tid & 127, net = row >> 6, j = row & 63;
+    const int nb = net == 0 ? 0 : E::NET_A;
+    if (tid < 128) {
+      gp[nb + NO::B1 + j] = gb12;
+#pragma unroll
+      for (int k = 0; k < D; k++) gp[nb + NO::W1 + j + CRL_H * k] = gW1[k];
+    } else {
+      gp[nb + NO::B2 + j] = gb12;
+    }
+  }
+  const double t_pg = block_sum<8>(st_pg, red);
+  const double t_vm = block_sum<8>(st_vmax, red);
+  const double t_en = block_sum<8>(st_ent, red);
+  double t_ls[A];
+#pragma unroll
+  for (int k = 0; k < A; k++) t_ls[k] = block_sum<8>(g_logstd[k], red);
+  if (tid == 0) {
+    double* spp = a.spart + (long long)blockIdx.x * 4;
+    spp[0] = t_pg; spp[1] = t_vm; spp[2] = t_en; spp[3] = 0.0;
+    if (E::CONT) {
+#pragma unroll
+      for (int k = 0; k < A; k++) gp[E::NET_A + E::NET_C + k] = (float)t_ls[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ grad_reduce
+__global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double* __restrict__ spart, int grid, int P,
+                                   double* __restrict__ gsum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < P) {
+    double s = 0.0;
+    for (int c = 0; c < grid; c++) s += (double)gpart[(long long)c * P + e];
+    gsum[e] = s;
+  } else if (e < P + 4) {
+    double s = 0.0;
+    for (int c = 0; c < grid; c++) s += spart[(long long)c * 4 + (e - P)];
+    gsum[e] = s;
+  }
+}
+
+// loss scalars from the reduced sums (ppo.jl:228,237,242,243)
+__device__ __forceinline__ void finalize_stats(const double* sums, double Mg, int A, float ent_coeff, float v_coef,
+                                               double* out) {
+  const double pg = sums[0] / Mg;                                   // ppo.jl:228
+  const double vl = 0.5 * (double)(float)(sums[1] / Mg);            // ppo.jl:237
+  const double en = (double)(float)(sums[2] / ((double)A * Mg));    // ppo.jl:242
+  out[0] = pg - (double)__fmul_rn(ent_coeff, (float)en) + (double)v_coef * vl;  // ppo.jl:243
+  out[1] = pg;
+  out[2] = vl;
+  out[3] = en;
+}
+__device__ __forceinline__ float load_grad(const AdamArgs& a, int e) {
+  return a.gsum ? (float)(a.gsum[e] * a.grad_scale) : a.gf[e];
+}
+
+// raw path: Float32 gradient + loss scalars out of the double sums
+__global__ void loss_finalize_kernel(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
+                                     float v_coef, double* stats_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < P) grads_out[e] = (float)gsum[e];
+  if (e == 0 && stats_out) finalize_stats(gsum + P, Mg, A, ent_coeff, v_coef, stats_out);
+}
+
+// reduce the per-CTA partial sums of mb_stats to one record (multi-GPU all-gather payload)
+__global__ void stats_pack_kernel(const MbScalars* parts, int n, MbScalars* out) {
+  __shared__ double red[8];
+  __shared__ float mred[8];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  float mn = INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const MbScalars p = parts[i];
+    s0 += p.sum_adv; s1 += p.sum_adv2; s2 += p.sum_s; mn = fminf(mn, p.min_vlc);
+  }
+  s0 = block_sum<8>(s0, red); s1 = block_sum<8>(s1, red); s2 = block_sum<8>(s2, red);
+  mn = warp_min(mn);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m8 = mred[0];
+    for (int w = 1; w < 8; w++) m8 = fminf(m8, mred[w]);
+    MbScalars o;
+    o.sum_adv = s0; o.sum_adv2 = s1; o.sum_s = s2; o.min_vlc = m8; o._pad = 0.0f;
+    *out = o;
+  }
+}
+
+// ------------------------------------------------------------------ clip + Adam
+// Flux.Optimiser(ClipNorm(thresh), Adam(η)) [Flux 0.13.4], one CTA per parameter array.
+__global__ void __launch_bounds__(CRL_THREADS) clip_adam_kernel(AdamArgs a) {
+  __shared__ double red[8];
+  Layout L;
+  make_layout(a.env_kind, &L);
+  const int i = blockIdx.x;
+  const int o = L.off[i], n = L.size[i];
+  double ss = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double g = (double)load_grad(a, o + k);  // the Float32 gradient array Zygote returns
+    ss += g * g;
+  }
+  ss = block_sum<8>(ss, red);
+  const float nrm = (float)sqrt(ss);  // norm(Δ::Array{Float32})::Float32
+  const bool clip = (double)nrm > (double)a.clip_norm;
+  const double scale = clip ? (double)a.clip_norm / (double)nrm : 1.0;
+  const double lr = a.lr_host >= 0.0 ? a.lr_host : a.ds->lr;
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float g = load_grad(a, o + k);
+    if (a.grads_out) a.grads_out[o + k] = g;
+    float d = g;
+    if (clip) d = (float)__dmul_rn((double)d, scale);  // rmul!(Δ, thresh/nrm)
+    const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[o + k]), __dmul_rn(1.0 - b1, (double)d));
+    const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[o + k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
+    a.m[o + k] = mt;
+    a.v[o + k] = vt;
+    const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - bp2)), eps);
+    const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - bp1), den), lr);
+    a.params[o + k] = __fsub_rn(a.params[o + k], step);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.beta_pow[2 * i] = bp1 * b1;
+    a.beta_pow[2 * i + 1] = bp2 * b2;
+    if (i == 0 && a.stats_out && a.gsum)
+      finalize_stats(a.gsum + L.P, a.M_global * a.stat_ranks, a.A, a.ent_coeff, a.v_coef, a.stats_out);
+  }
+}
+
+__global__ void advance_kernel(DevState* ds, unsigned long long dstep, unsigned long long dupd) {
+  ds->policy_step += dstep;
+  ds->update_index += dupd;
+}
+
+__global__ void fill_perm_kernel(int32_t* out, uint32_t B, int half_bits, unsigned long long seed,
+                                 unsigned long long update_index, uint32_t epoch, uint32_t rank) {
+  __shared__ uint32_t keys[8];
+  if (threadIdx.x == 0) perm_keys(seed, update_index, epoch, rank, keys);
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+    out[i] = (int32_t)perm_index(i, B, half_bits, keys);
+}
+
+template <typename K> cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+int mb_stats_grid(int M, int sm_count) {
+  const int tiles = (M + 255) / 256;
+  return tiles < sm_count ? (tiles < 1 ? 1 : tiles) : sm_count;
+}
+int loss_grad_grid(int M, int sm_count) {
+  const int tiles = (M + 127) / 128;
+  return tiles < sm_count ? (tiles < 1 ? 1 : tiles) : sm_count;
+}
+
+cudaError_t kernels_init_update() {
+  cudaError_t e = set_smem(mb_stats_kernel<CRL_ENV_CARTPOLE>, StatsSmem<CRL_ENV_CARTPOLE>::BYTES);
+  if (e != cudaSuccess) return e;
+  e = set_smem(mb_stats_kernel<CRL_ENV_PENDULUM>, StatsSmem<CRL_ENV_PENDULUM>::BYTES);
+  if (e != cudaSuccess) return e;
+  e = set_smem(loss_grad_kernel<CRL_ENV_CARTPOLE>, LossSmem<CRL_ENV_CARTPOLE>::BYTES);
+  if (e != cudaSuccess) return e;
+  return set_smem(loss_grad_kernel<CRL_ENV_PENDULUM>, LossSmem<CRL_ENV_PENDULUM>::BYTES);
+}
+
+cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s) {
+  if (a.env_kind == CRL_ENV_CARTPOLE)
+    mb_stats_kernel<CRL_ENV_CARTPOLE><<<grid, CRL_THREADS, StatsSmem<CRL_ENV_CARTPOLE>::BYTES, s>>>(a);
+  else
+    mb_stats_kernel<CRL_ENV_PENDULUM><<<grid, CRL_THREADS, StatsSmem<CRL_ENV_PENDULUM>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s) {
+  int grid = (a.M + 1023) / 1024;
+  if (grid < 1) grid = 1;
+  if (grid > 148) grid = 148;
+  mb_count_kernel<0><<<grid, CRL_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s) {
+  if (a.env_kind == CRL_ENV_CARTPOLE)
+    loss_grad_kernel<CRL_ENV_CARTPOLE><<<a.grid_loss, CRL_THREADS, LossSmem<CRL_ENV_CARTPOLE>::BYTES, s>>>(a);
+  else
+    loss_grad_kernel<CRL_ENV_PENDULUM><<<a.grid_loss, CRL_THREADS, LossSmem<CRL_ENV_PENDULUM>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s) {
+  const int grid = (P + 4 + 255) / 256;
+  grad_reduce_kernel<<<grid, 256, 0, s>>>(a.gpart, a.spart, a.grid_loss, P, a.gsum);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s) {
+  Layout L;
+  if (!make_layout(a.env_kind, &L)) return cudaErrorInvalidValue;
+  clip_adam_kernel<<<L.n_arrays, CRL_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss_finalize(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
+                                 float v_coef, double* stats_out, cudaStream_t s) {
+  loss_finalize_kernel<<<(P + 255) / 256, 256, 0, s>>>(gsum, P, grads_out, Mg, A, ent_coeff, v_coef, stats_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cudaStream_t s) {
+  stats_pack_kernel<<<1, CRL_THREADS, 0, s>>>(parts, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_advance(DevState* ds, unsigned long long d_policy_step, unsigned long long d_update, cudaStream_t s) {
+  advance_kernel<<<1, 1, 0, s>>>(ds, d_policy_step, d_update);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_perm(int32_t* out, uint32_t B, unsigned long long seed, unsigned long long update_index,
+                             uint32_t epoch, uint32_t rank, cudaStream_t s) {
+  fill_perm_kernel<<<64, 256, 0, s>>>(out, B, perm_half_bits(B), seed, update_index, epoch, rank);
+  return cudaGetLastError();
+}
