@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — PPO env-steps/s end to end (BASELINE.json metric) + GAE achieved HBM GB/s.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+A "step" is one PPO update: rollout of T=128 steps over the local envs, GAE, and
+update_epochs x num_minibatches clipped-surrogate minibatch updates (ppo.jl:117-253).
+Workload at N=1 = BASELINE.json configs[1]: CartPole, 4096 envs x 128 steps, 64-64 MLPs, the
+reference's default 4 epochs x 4 minibatches. Weak scaling: every GPU owns 4096 envs.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ENVS_PER_GPU = 4096
+NUM_STEPS = 128
+NUM_MINIBATCHES = 4
+UPDATE_EPOCHS = 4
+FWD_FLOP = 17_792          # actor 8,960 + critic 8,832 FLOP per sample
+UPDATE_FLOP = 53_376       # forward + backward per sample per epoch
+METRIC = "ppo_env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--env", default="CartPole", choices=["CartPole", "Pendulum"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gae-n", type=int, default=1 << 20, help="envs in the GAE HBM measurement (T=128)")
+    ap.add_argument("--local-stats", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "PPO %s, %d vectorized envs x %d steps per GPU, 64-64 MLP, %d epochs x %d minibatches "
+                        "(BASELINE.json configs[1] per GPU)" % (args.env, args.envs_per_gpu, NUM_STEPS, UPDATE_EPOCHS,
+                                                                NUM_MINIBATCHES),
+            "env": args.env, "num_envs_per_gpu": args.envs_per_gpu, "num_envs_global": args.envs_per_gpu * world,
+            "num_steps": NUM_STEPS, "batch_per_gpu": args.envs_per_gpu * NUM_STEPS,
+            "update_epochs": UPDATE_EPOCHS, "num_minibatches": NUM_MINIBATCHES, "gae_mode": "ref_compat",
+            "parallelism": "envs sharded over %d GPU(s), NCCL gradient allreduce per minibatch" % world if world > 1
+            else "single GPU"}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """samples SM clock and throttle reasons with NVML during the timed region"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+        alt = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+               "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k in names:
+                    bit = getattr(nv, names[k], None) or getattr(nv, alt[k], 0)
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nv and self.thread.is_alive():
+            self.thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_ppo_throughput(env_kind, n_envs, steps, warmup, threads):
+    """times the C restatement of the reference's PPO (oracle, -O3 -mavx2 build) on the host cores"""
+    from cleanrl_jl_b200 import _abi, networks
+    from oracle.oracle import OracleLib
+    fast = False
+    try:
+        flags = open("/proc/cpuinfo").read()
+        fast = " avx2" in flags and " fma" in flags
+    except Exception:
+        pass
+    olib = OracleLib(fast=fast)
+    olib.set_threads(threads)
+    cfg = _abi.make_config(env_kind=env_kind, num_envs=n_envs, num_steps=NUM_STEPS, num_minibatches=NUM_MINIBATCHES,
+                           update_epochs=UPDATE_EPOCHS, seed=1)
+    o = olib.create(cfg)
+    d = olib.dims(env_kind)
+    o.set_params(networks.init_params(env_kind == 1, d["D"], d["A"], seed=1))
+    o.env_reset()
+    lr = 2.5e-4
+    for _ in range(warmup):
+        o.train_update(lr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.train_update(lr)
+    dt = time.perf_counter() - t0
+    o.close()
+    return n_envs * NUM_STEPS * steps / dt, dt / steps, "avx2" if fast else "sse2"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from cleanrl_jl_b200 import _abi
+    kind = _abi.CRL_ENV_CARTPOLE if args.env == "CartPole" else _abi.CRL_ENV_PENDULUM
+    cores = os.cpu_count() or 1
+    # calibrate on a small sample, then size the per-step sample so the run ends within ~150 s
+    rate, _, build = cpu_ppo_throughput(kind, 256, 1, 1, cores)
+    budget = 150.0
+    per_step = rate * budget / max(args.steps + args.warmup, 1)
+    n_envs = int(min(args.envs_per_gpu * max(args.gpus, 1), max(64, per_step // NUM_STEPS)))
+    n_envs = max(4, (n_envs // 4) * 4)
+    value, sec_per_step, build = cpu_ppo_throughput(kind, n_envs, args.steps, args.warmup, cores)
+    sample = "%d envs x %d steps per update (%d env-steps), %d epochs x %d minibatches, %d updates timed" % (
+        n_envs, NUM_STEPS, n_envs * NUM_STEPS, UPDATE_EPOCHS, NUM_MINIBATCHES, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference's multi-threaded CPU PPO (oracle/ppo_oracle.c, %s build); "
+                                 "Julia is not installed in this image so the Julia original cannot be timed" % build},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def gae_roofline(torch, lib_mod, N, T=NUM_STEPS):
+    """GAE at a working set far larger than L2 (2.29 GB at N=2^20): achieved HBM GB/s."""
+    lib = lib_mod.load()
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    v = torch.randn((T, N), device="cuda", generator=g)
+    r = torch.randn((T, N), device="cuda", generator=g)
+    d = (torch.rand((T, N), device="cuda", generator=g) < 0.01).to(torch.uint8)
+    nv = torch.randn(N, device="cuda", generator=g)
+    nd = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    adv = torch.empty((T, N), device="cuda")
+    ret = torch.empty((T, N), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    def launch():
+        lib_mod.check(lib.crl_gae_raw(lib_mod.ptr(v), lib_mod.ptr(r), lib_mod.ptr(d), lib_mod.ptr(nv), lib_mod.ptr(nd),
+                                      lib_mod.ptr(adv), lib_mod.ptr(ret), T, N, 0.99, 0.95, 0, stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 17 * T * N + 5 * N
+    return nbytes / (ms * 1e-3) / 1e9, ms, nbytes
+
+
+def run_ours(args):
+    import torch
+    from cleanrl_jl_b200 import _abi, _lib, networks, parallel
+    from cleanrl_jl_b200.config import PPOConfig
+    from cleanrl_jl_b200.handle import PPOHandle, comm_unique_id
+    from cleanrl_jl_b200.ppo import ppo, make_crl_config
+    from cleanrl_jl_b200 import logger as Logger
+
+    rank, local_rank, world = parallel.dist_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kind = _abi.CRL_ENV_CARTPOLE if args.env == "CartPole" else _abi.CRL_ENV_PENDULUM
+    n_local = args.envs_per_gpu
+    pcfg = PPOConfig(total_timesteps=10 ** 12, num_steps=NUM_STEPS, num_envs=n_local * world,
+                     num_minibatches=NUM_MINIBATCHES, update_epochs=UPDATE_EPOCHS, env_id=args.env, seed=1,
+                     local_stats=args.local_stats)
+    cfg = make_crl_config(pcfg, n_local, local_rank, world, rank, rank * n_local)
+    h = PPOHandle(cfg)
+    if world > 1:
+        h.comm_init(parallel.exchange_unique_id(comm_unique_id))
+    h.set_params(networks.init_params(kind == 1, h.d["D"], h.d["A"], seed=1))
+    h.env_reset()
+    lr = float(np.float32(2.5e-4))
+    B_local = n_local * NUM_STEPS
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if h.h:
+            h.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        h.train_update(lr)
+    barrier()
+    stream = torch.cuda.ExternalStream(h.stream())
+    sampler = ClockSampler(local_rank)
+    launches0 = h.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        h.train_update(lr)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1))
+    launches = h.kernel_launches() - launches0
+    value = args.steps * B_local * world / (ms_total * 1e-3)
+    stats, agg = h.fetch_update()
+
+    # ---- per-kernel device time (CUDA events on the handle's stream, graphs off for this pass)
+    h.profile(True)
+    prof_updates = 5
+    for _ in range(prof_updates):
+        h.train_update(lr)
+    kt = h.profile_read()
+    h.profile(False)
+    total_k = sum(v["ms"] for v in kt.values()) or 1.0
+    kernels = {k: {"ms_per_update": v["ms"] / prof_updates, "launches_per_update": v["launches"] / prof_updates,
+                   "share": v["ms"] / total_k} for k, v in kt.items() if v["launches"]}
+    lg = kt["loss_grad"]
+    M_local = B_local // NUM_MINIBATCHES
+    lg_ms = lg["ms"] / max(lg["launches"], 1)
+    flops = UPDATE_FLOP * M_local
+    peaks = measured_peaks()
+    sm_max = (clocks.get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    roofline = {"kernel": "loss_grad_kernel", "bound": "fp32",
+                "achieved": flops / (lg_ms * 1e-3) / 1e12 if lg_ms else None, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": (flops / (lg_ms * 1e-3) / 1e12 / fp32_peak) if lg_ms else None, "traffic": None,
+                "avg_launch_ms": lg_ms, "share_of_step": kernels.get("loss_grad", {}).get("share"),
+                "algorithmic": "%d FLOP/sample x %d samples per launch" % (UPDATE_FLOP, M_local),
+                "peak_source": "derived FP32 FFMA peak: 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json has no fp32 "
+                               "figure); FFMA path, no tensor cores, so neither 'hbm' nor 'tensor' applies"}
+
+    # ---- GAE HBM roofline (the metric's second half) on rank 0
+    roofline_gae = None
+    if rank == 0:
+        try:
+            gbs, gms, nbytes = gae_roofline(torch, _lib, args.gae_n)
+            hbm = (peaks or {}).get("hbm_gbs")
+            peak = hbm or 6650.0
+            roofline_gae = {"kernel": "gae_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                            "frac": gbs / peak, "traffic": None, "avg_launch_ms": gms, "bytes_per_launch": nbytes,
+                            "workload": "T=128, N=%d envs, %.2f GB > 126 MB L2" % (args.gae_n, nbytes / 1e9),
+                            "peak_source": "of measured (MEASURED_PEAKS.json hbm_gbs)" if hbm else "of fallback 6.65 TB/s"}
+        except Exception as e:  # pragma: no cover
+            roofline_gae = {"error": repr(e)}
+    h.close()
+
+    # ---- e2e: the public ppo(config) call, wall clock as the reference defines it (ppo.jl:111,148)
+    e2e_updates = max(10, min(args.steps, 200))
+    tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
+    logger = Logger.make_logger("bench", to_terminal=False, to_tensorboard=True, log_dir=tmp) if rank == 0 else None
+    pcfg2 = PPOConfig(total_timesteps=e2e_updates * B_local * world, num_steps=NUM_STEPS, num_envs=n_local * world,
+                      num_minibatches=NUM_MINIBATCHES, update_epochs=UPDATE_EPOCHS, env_id=args.env, seed=1,
+                      local_stats=args.local_stats)
+    barrier()
+    res = ppo(pcfg2, logger=logger, device=local_rank)
+    e2e_s = parallel.max_over_ranks(res["elapsed_s"])
+    e2e = {"value": res["global_step"] / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": res["h2d_bytes"] / res["num_updates"], "d2h_bytes_per_step": res["d2h_bytes"] / res["num_updates"],
+           "updates": res["num_updates"], "wall_s": e2e_s,
+           "note": "ppo(config) public API: parameter upload, per-update lr upload, per-update loss/episode statistics "
+                   "read-back and logging inside the timed region; envs live on the device so there is no per-step input copy"}
+    if logger:
+        logger.close()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, _, build = cpu_ppo_throughput(kind, 256, 1, 1, cores)
+        n_s = int(min(n_local, max(64, (rate * 15.0) // NUM_STEPS)))
+        n_s = max(4, (n_s // 4) * 4)
+        v, spu, build = cpu_ppo_throughput(kind, n_s, 1, 0, cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "1 PPO update of %d envs x %d steps (%d env-steps, 4 epochs x 4 minibatches), %.1f s" % (
+                            n_s, NUM_STEPS, n_s * NUM_STEPS, spu),
+                        "note": "C restatement of the reference's multi-threaded CPU PPO (%s build); not the Julia program" % build}
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world),
+                                                                l2="not flushed: every step regenerates its 16.5 MB rollout buffer on the device "
+                                                                   "(L2-resident in production too); the GAE roofline uses a 2.29 GB input"),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gae": roofline_gae,
+            "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "last_loss": float(stats[-1, 0]), "episodes_last_update": int(agg.count),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

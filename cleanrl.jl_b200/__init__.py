@@ -1,0 +1,32 @@
+"""cleanrl.jl_b200 — B200-native PPO hot path of sash-a/CleanRL.jl behind a C ABI.
+
+Host-side mirror of the reference's Julia interface (Python stands in for Julia, which is not
+available in this image): PPOConfig / ppo() (ppo.jl), ConfigParser.argparse_struct
+(config_parser.jl), Logger.make_logger (logger.jl), Networks.make_actor_critic (networks.jl).
+All compute happens in libcleanrl_cuda.so (csrc/, sm_100a); importing this package loads
+nothing — the library is dlopen'ed on first use and there is no CPU fallback.
+"""
+from . import _abi  # noqa: F401
+from .config import PPOConfig, argparse_struct  # noqa: F401
+
+__all__ = ["PPOConfig", "argparse_struct", "ppo", "PPOHandle", "Networks", "Logger", "ConfigParser"]
+
+
+def __getattr__(name):
+    # lazy: keep `import cleanrl_jl_b200` free of ctypes/torch side effects
+    if name == "ppo":
+        from .ppo import ppo
+        return ppo
+    if name == "PPOHandle":
+        from .handle import PPOHandle
+        return PPOHandle
+    if name == "Networks":
+        from . import networks
+        return networks
+    if name == "Logger":
+        from . import logger
+        return logger
+    if name == "ConfigParser":
+        from . import config
+        return config
+    raise AttributeError(name)

@@ -1,0 +1,37 @@
+"""Short, graph-free workload for ncu: 2 PPO updates at BASELINE configs[1] (CartPole, 4096 envs
+x 128 steps) and one GAE launch at N=2^20 (2.29 GB). Used by the ncu recipes in profiles/README.md."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["CRL_NO_GRAPH"] = "1"
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from cleanrl_jl_b200 import _abi, _lib, networks  # noqa: E402
+from cleanrl_jl_b200.handle import PPOHandle  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.cuda.set_device(0)
+if what in ("all", "ppo"):
+    cfg = _abi.make_config(num_envs=4096, num_steps=128, num_minibatches=4, update_epochs=4, seed=1)
+    h = PPOHandle(cfg)
+    h.set_params(networks.init_params(False, 4, 2, seed=1))
+    h.env_reset()
+    for _ in range(2):
+        h.train_update(2.5e-4)
+    h.sync()
+    h.close()
+if what in ("all", "gae"):
+    T, N = 128, 1 << 20
+    lib = _lib.load()
+    v = torch.randn((T, N), device="cuda")
+    r = torch.randn((T, N), device="cuda")
+    d = (torch.rand((T, N), device="cuda") < 0.01).to(torch.uint8)
+    adv = torch.empty((T, N), device="cuda")
+    ret = torch.empty((T, N), device="cuda")
+    for _ in range(2):
+        _lib.check(lib.crl_gae_raw(_lib.ptr(v), _lib.ptr(r), _lib.ptr(d), None, None, _lib.ptr(adv), _lib.ptr(ret),
+                                   T, N, 0.99, 0.95, 0, None))
+    torch.cuda.synchronize()
+print("profile target done")
