@@ -57,6 +57,8 @@ class OracleLib:
         L.orc_policy_forward_raw.argtypes = [C.c_int32] + [C.c_void_p] * 5 + [C.c_int64]
         L.orc_ppo_loss_raw.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + \
             [C.c_float] * 3 + [C.c_void_p] * 3
+        L.orc_ppo_loss_phase.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + \
+            [C.c_float] * 3 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_clip_adam_raw.argtypes = [C.c_int32] + [C.c_void_p] * 5 + [C.c_double, C.c_float]
         L.orc_create.argtypes = [C.POINTER(_abi.crl_config), C.POINTER(C.c_void_p)]
         for f in ("orc_destroy", "orc_env_reset", "orc_gae"):
@@ -183,6 +185,23 @@ class OracleLib:
                                        clip_coef, ent_coeff, v_coef, _ptr(grads), _ptr(stats), _ptr(vnew))
         assert rc == 0, rc
         return grads, stats, vnew
+
+    def ppo_loss_phase(self, env_kind, params, idx, states, actions, logprobs, advantages, returns, values,
+                       clip_coef, ent_coeff, v_coef, phase, io, vnew):
+        """one phase of the loss on one shard; io (8 doubles) and vnew are updated in place"""
+        d = self.dims(env_kind)
+        params = np.ascontiguousarray(params, np.float32)
+        idx = np.ascontiguousarray(idx, np.int32)
+        states = np.ascontiguousarray(states, np.float32)
+        actions = np.ascontiguousarray(actions, np.int32 if env_kind == _abi.CRL_ENV_CARTPOLE else np.float32)
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (logprobs, advantages, returns, values)]
+        grads = np.zeros(d["P"], np.float64)
+        assert io.dtype == np.float64 and io.size == 8 and vnew.dtype == np.float32 and vnew.size == idx.size
+        rc = self.lib.orc_ppo_loss_phase(env_kind, _ptr(params), _ptr(idx), idx.shape[0], _ptr(states), _ptr(actions),
+                                         _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]),
+                                         clip_coef, ent_coeff, v_coef, phase, _ptr(io), _ptr(vnew), _ptr(grads))
+        assert rc == 0, rc
+        return grads
 
     def clip_adam_raw(self, env_kind, params, grads, m, v, beta_pow, lr, clip_norm):
         params = np.array(params, np.float32, copy=True)

@@ -683,6 +683,7 @@ typedef struct {
   double adv_mean_f, adv_std_f; /* Float32 results held in double */
   float s_unclipped;
   double inv_cnt_term; /* cnt / M */
+  double Mg;           /* normalising minibatch size (= M, or world*M when sharded) */
   int phase;
   /* per-thread partials */
   double* part; /* [threads][P + 8] */
@@ -768,7 +769,7 @@ static void loss_range(int64_t lo, int64_t hi, int tid, void* argp) {
       if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
       else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
       sl[SL_PG] += pgm;
-      g_lp = dratio * (double)ratio / (double)a->M;
+      g_lp = dratio * (double)ratio / a->Mg;
       /* value loss, Q5 */
       float R = a->returns[b], V = a->values[b];
       float dvv = v - V;
@@ -779,10 +780,10 @@ static void loss_range(int64_t lo, int64_t hi, int tid, void* argp) {
       sl[SL_VMAX] += (double)vmax;
       double dv_d = a->inv_cnt_term; /* (1/M) * cnt: every v_new_j feeds s */
       if (!(a->s_unclipped > vlc) && dvv >= -c && dvv <= c) dv_d += 2.0 * (double)(vc - R);
-      float dv = (float)((double)a->v_coef * 0.5 / (double)a->M * dv_d);
+      float dv = (float)((double)a->v_coef * 0.5 / a->Mg * dv_d);
       sl[SL_ENT] += ent_sum;
       /* back through the heads */
-      const double ent_scale = (double)a->ent_coeff / ((double)A * (double)a->M);
+      const double ent_scale = (double)a->ent_coeff / ((double)A * a->Mg);
       if (!L.continuous) {
         int act = ((const int32_t*)a->actions)[b];
         double Hs = ent_sum;
@@ -833,7 +834,7 @@ int orc_ppo_loss_raw(int32_t env_kind, const float* params, const int32_t* idx, 
   memset(&a, 0, sizeof(a));
   a.env_kind = env_kind; a.params = params; a.idx = idx; a.M = M; a.states = states; a.actions = actions;
   a.logprobs = logprobs; a.advantages = advantages; a.returns = returns; a.values = values;
-  a.clip_coef = clip_coef; a.ent_coeff = ent_coeff; a.v_coef = v_coef; a.P = L.P;
+  a.clip_coef = clip_coef; a.ent_coeff = ent_coeff; a.v_coef = v_coef; a.P = L.P; a.Mg = (double)M;
   a.vnew = vnew_out ? vnew_out : (float*)malloc(4 * (size_t)M);
   a.part = (double*)calloc((size_t)nt * W, 8);
   double* tot = (double*)calloc(W, 8);
@@ -869,6 +870,43 @@ int orc_ppo_loss_raw(int32_t env_kind, const float* params, const int32_t* idx, 
   if (!vnew_out) free(a.vnew);
   free(a.part);
   free(tot);
+  return 0;
+}
+
+/* One phase of the same closure on ONE SHARD of a minibatch that is split over several ranks
+ * (SURVEY §8e): the three minibatch-global scalars are exchanged between phases by the caller
+ * (tests/test_dist_gloo.py does it with gloo; the CUDA library with NCCL).
+ *   phase 0: out io[0..2] = local Σadv, Σadv², Σ(v_new - R²); fills vnew[M]
+ *   phase 1: in io[3] = s (global); out io[4] = local #{s > (clip-R)²}
+ *   phase 2: in io[3] = s, io[4] = global count, io[5] = adv mean, io[6] = adv std, io[7] = global M;
+ *            out grads[P] (local sums, double), io[0..2] = local Σpg, Σvmax, Σentropy */
+int orc_ppo_loss_phase(int32_t env_kind, const float* params, const int32_t* idx, int32_t M, const float* states,
+                       const void* actions, const float* logprobs, const float* advantages, const float* returns,
+                       const float* values, float clip_coef, float ent_coeff, float v_coef, int32_t phase, double* io,
+                       float* vnew, double* grads) {
+  layout_t L;
+  if (make_layout(env_kind, &L) || M < 1 || phase < 0 || phase > 2) return CRL_ERR_INVALID;
+  int W = L.P + SL_N;
+  loss_args a;
+  memset(&a, 0, sizeof(a));
+  a.env_kind = env_kind; a.params = params; a.idx = idx; a.M = M; a.states = states; a.actions = actions;
+  a.logprobs = logprobs; a.advantages = advantages; a.returns = returns; a.values = values;
+  a.clip_coef = clip_coef; a.ent_coeff = ent_coeff; a.v_coef = v_coef; a.P = L.P; a.vnew = vnew; a.phase = phase;
+  a.part = (double*)calloc((size_t)W, 8);
+  a.s_unclipped = (float)io[3];
+  a.adv_mean_f = io[5]; a.adv_std_f = io[6]; a.Mg = io[7];
+  a.inv_cnt_term = phase == 2 ? io[4] / io[7] : 0.0;
+  int save = g_threads;
+  g_threads = 1;
+  parallel_for(M, loss_range, &a);
+  g_threads = save;
+  if (phase == 0) { io[0] = a.part[L.P + SL_SUM_ADV]; io[1] = a.part[L.P + SL_SUM_ADV2]; io[2] = a.part[L.P + SL_SUM_S]; }
+  else if (phase == 1) io[4] = a.part[L.P + SL_CNT];
+  else {
+    for (int k = 0; k < L.P; k++) grads[k] = a.part[k];
+    io[0] = a.part[L.P + SL_PG]; io[1] = a.part[L.P + SL_VMAX]; io[2] = a.part[L.P + SL_ENT];
+  }
+  free(a.part);
   return 0;
 }
 
