@@ -276,7 +276,10 @@ def run_ours(args):
                    "share": v["ms"] / total_k} for k, v in kt.items() if v["launches"]}
     lg = kt["loss_grad"]
     M_local = B_local // NUM_MINIBATCHES
-    lg_ms = lg["ms"] / max(lg["launches"], 1)
+    # the speculative path launches loss_grad twice per minibatch; the second (verification) launch exits at
+    # once unless the speculation failed, so the time is attributed to the epochs*minibatches real launches
+    real_launches = prof_updates * UPDATE_EPOCHS * NUM_MINIBATCHES
+    lg_ms = lg["ms"] / real_launches
     flops = UPDATE_FLOP * M_local
     peaks = measured_peaks()
     sm_max = (clocks.get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0)

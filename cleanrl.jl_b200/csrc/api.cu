@@ -109,8 +109,8 @@ struct crl_ctx {
   float* vnew;
   MbScalars *parts, *parts_send, *parts_recv;
   MbFinal* fin;
-  float* gpart;
-  double *spart, *gsum, *stats_dev;
+  float *gpart, *mpart;
+  double *spart, *gsum, *stats_dev, *advparts;
   int32_t *idx_dev, *perm_dev;
   int grid_stats, grid_loss;
   // injected noise (lazy)
@@ -255,8 +255,9 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
   A_(dalloc(&c->vnew, c->M)); A_(dalloc(&c->parts, c->sm_count)); A_(dalloc(&c->parts_send, 1));
   A_(dalloc(&c->parts_recv, cfg->world_size)); A_(dalloc(&c->fin, 1));
   A_(dalloc(&c->gpart, (size_t)c->sm_count * L.P)); A_(dalloc(&c->spart, (size_t)c->sm_count * 4));
-  A_(dalloc(&c->gsum, L.P + 4));
+  A_(dalloc(&c->gsum, L.P + 4)); A_(dalloc(&c->mpart, c->sm_count));
   const size_t nmb = (size_t)std::max(1, cfg->update_epochs) * cfg->num_minibatches;
+  A_(dalloc(&c->advparts, nmb * ADV_CHUNKS * 2));
   A_(dalloc(&c->stats_dev, nmb * 4)); A_(dalloc(&c->idx_dev, B)); A_(dalloc(&c->perm_dev, (size_t)std::max(1, cfg->update_epochs) * B));
   {
     cudaError_t e1 = cudaMallocHost(reinterpret_cast<void**>(&c->stats_host), nmb * sizeof(crl_loss_stats));
@@ -286,7 +287,7 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
   void* ptrs[] = {c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
                   c->ep_length, c->reset_count, c->next_obs, c->next_done, c->next_value, c->state, c->action, c->logprob,
                   c->reward, c->value, c->advantage, c->ret, c->terminal, c->eb, c->records, c->vnew, c->parts,
-                  c->parts_send, c->parts_recv, c->fin, c->gpart, c->spart, c->gsum, c->stats_dev, c->idx_dev,
+                  c->parts_send, c->parts_recv, c->fin, c->gpart, c->mpart, c->advparts, c->spart, c->gsum, c->stats_dev, c->idx_dev,
                   c->perm_dev, c->action_noise_dev, c->reset_noise_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->stats_host) cudaFreeHost(c->stats_host);
@@ -460,7 +461,23 @@ static IdxSrc idx_array(crl_ctx* c, const int32_t* arr) {
 
 // one minibatch: mb_stats -> [all-gather] -> mb_count -> [allreduce cnt] -> loss_grad -> grad_reduce
 // -> [allreduce grads] -> clip_adam. lr_host < 0 reads lr from DevState.
-static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host, double* stats_slot) {
+static int enqueue_adv_stats(crl_ctx* c, const int32_t* arr_base, int M, int nmb, int n_sets) {
+  AdvStatsArgs aa;
+  aa.idx.arr = nullptr; aa.idx.start = 0; aa.idx.B = (uint32_t)c->B; aa.idx.half_bits = perm_half_bits((uint32_t)c->B);
+  aa.idx.epoch = 0; aa.idx.rank = (uint32_t)c->cfg.rank; aa.idx.seed = c->cfg.seed; aa.idx.ds = c->ds;
+  aa.arr_base = arr_base; aa.B = c->B; aa.M = M; aa.nmb = nmb; aa.n_sets = n_sets;
+  aa.advantages = c->advantage; aa.advparts = c->advparts;
+  KernelScope ks(c, CRL_K_MB_STATS);
+  CK(launch_adv_stats(aa, c->stream));
+  return CRL_OK;
+}
+
+// one minibatch. Single GPU (speculative, no critic pre-pass):
+//   loss_grad(SPEC) -> grad_reduce(+verify) -> [mb_count -> loss_grad(EXACT) -> grad_reduce: exit at once unless the
+//   speculation failed] -> clip_adam.   `set` indexes the advantage sums written by enqueue_adv_stats.
+// Multi GPU (exact global statistics): mb_stats -> all-gather -> mb_count -> allreduce(cnt) -> loss_grad(EXACT) ->
+//   grad_reduce -> allreduce(grads) -> clip_adam.          lr_host < 0 reads lr from DevState.
+static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host, double* stats_slot, int set) {
   const bool multi = c->cfg.world_size > 1;
   const bool local_stats = (c->cfg.flags & CRL_FLAG_LOCAL_STATS) != 0;
   if (multi && !c->comm) return fail(CRL_ERR_STATE, "world_size > 1 but crl_comm_init was not called");
@@ -474,8 +491,19 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.grid_loss = loss_grad_grid(M, c->sm_count);
   ua.parts_in = c->parts; ua.n_parts_in = gs; ua.fin = c->fin; ua.world = 1;
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
+  ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
   const bool exchange = multi && !local_stats;
   if (exchange) { ua.parts_in = c->parts_recv; ua.n_parts_in = c->cfg.world_size; ua.world = c->cfg.world_size; }
+  if (!multi) {
+    ua.mode = LG_SPEC;
+    { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
+    { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
+    ua.fixup = 1;
+    { KernelScope ks(c, CRL_K_MB_COUNT); CK(launch_mb_count(ua, c->stream)); }
+    ua.mode = LG_EXACT;
+    { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
+    { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
+  } else {
   {
     KernelScope ks(c, CRL_K_MB_STATS);
     CK(launch_mb_stats(ua, gs, c->stream));
@@ -504,10 +532,11 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
     KernelScope ks(c, CRL_K_GRAD_REDUCE);
     CK(launch_grad_reduce(ua, c->L.P, c->stream));
   }
-  if (multi) {
+  {
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4, ncclFloat64, ncclSum, c->comm, c->stream));
   }
+  }  // multi
   AdamArgs aa;
   aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.gsum = c->gsum; aa.gf = nullptr;
   aa.grad_scale = (multi && local_stats) ? 1.0 / c->cfg.world_size : 1.0;
@@ -535,7 +564,8 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(use_device(c));
   CK(cudaMemcpyAsync(c->idx_dev, idx, 4 * (size_t)M, cudaMemcpyHostToDevice, c->stream));
-  CKRC(enqueue_minibatch(c, idx_array(c, c->idx_dev), M, lr, c->stats_dev));
+  if (c->cfg.world_size == 1) CKRC(enqueue_adv_stats(c, c->idx_dev, M, 1, 1));
+  CKRC(enqueue_minibatch(c, idx_array(c, c->idx_dev), M, lr, c->stats_dev, 0));
   double s4[4];
   CK(cudaMemcpyAsync(s4, c->stats_dev, sizeof(s4), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -545,10 +575,12 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
 
 static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host) {
   int k = 0;
+  if (c->cfg.world_size == 1)
+    CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, c->cfg.update_epochs * c->cfg.num_minibatches));
   for (int e = 0; e < c->cfg.update_epochs; e++) {  // ppo.jl:193
     for (int start = 0; start < c->B; start += c->M) {  // ppo.jl:197
       IdxSrc ix = perm_dev ? idx_array(c, perm_dev + (size_t)e * c->B + start) : idx_perm(c, e, start);
-      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k));
+      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k, k));
       k++;
     }
   }
@@ -821,8 +853,8 @@ struct RawScratch {
   float* vnew = nullptr;
   MbScalars* parts = nullptr;
   MbFinal* fin = nullptr;
-  float* gpart = nullptr;
-  double *spart = nullptr, *gsum = nullptr;
+  float *gpart = nullptr, *mpart = nullptr;
+  double *spart = nullptr, *gsum = nullptr, *advparts = nullptr;
   DevState* ds = nullptr;
 };
 static RawScratch g_raw;
@@ -842,7 +874,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
   cudaStream_t s = (cudaStream_t)stream;
   if (g_raw.device != dev || g_raw.M < M) {
     CK(cudaDeviceSynchronize());
-    void* old[] = {g_raw.vnew, g_raw.parts, g_raw.fin, g_raw.gpart, g_raw.spart, g_raw.gsum, g_raw.ds};
+    void* old[] = {g_raw.vnew, g_raw.parts, g_raw.fin, g_raw.gpart, g_raw.spart, g_raw.gsum, g_raw.ds, g_raw.mpart, g_raw.advparts};
     for (void* p : old) if (p) cudaFree(p);
     g_raw = RawScratch();
     cudaDeviceProp prop;
@@ -851,6 +883,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
     CKRC(dalloc(&g_raw.vnew, M)); CKRC(dalloc(&g_raw.parts, g_raw.sm)); CKRC(dalloc(&g_raw.fin, 1));
     CKRC(dalloc(&g_raw.gpart, (size_t)g_raw.sm * CRL_H * (CRL_H + 16) * 2)); CKRC(dalloc(&g_raw.spart, (size_t)g_raw.sm * 4));
     CKRC(dalloc(&g_raw.gsum, (size_t)CRL_H * (CRL_H + 16) * 2)); CKRC(dalloc(&g_raw.ds, 1));
+    CKRC(dalloc(&g_raw.mpart, g_raw.sm)); CKRC(dalloc(&g_raw.advparts, ADV_CHUNKS * 2));
     g_raw.device = dev; g_raw.M = M;
   }
   UpdateArgs ua;
@@ -863,8 +896,18 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
   const int gs = mb_stats_grid(M, g_raw.sm);
   ua.parts_in = g_raw.parts; ua.n_parts_in = gs; ua.fin = g_raw.fin; ua.world = 1;
   ua.gpart = g_raw.gpart; ua.spart = g_raw.spart; ua.grid_loss = loss_grad_grid(M, g_raw.sm); ua.gsum = g_raw.gsum;
-  CK(launch_mb_stats(ua, gs, s));
+  (void)gs;
+  AdvStatsArgs as;
+  as.idx = ua.idx; as.arr_base = idx; as.B = M; as.M = M; as.nmb = 1; as.n_sets = 1; as.advantages = advantages;
+  as.advparts = g_raw.advparts;
+  ua.advparts = g_raw.advparts; ua.mpart = g_raw.mpart;
+  CK(launch_adv_stats(as, s));
+  ua.mode = LG_SPEC; ua.fixup = 0;
+  CK(launch_loss_grad(ua, s));
+  CK(launch_grad_reduce(ua, L.P, s));
+  ua.fixup = 1;
   CK(launch_mb_count(ua, s));
+  ua.mode = LG_EXACT;
   CK(launch_loss_grad(ua, s));
   CK(launch_grad_reduce(ua, L.P, s));
   CK(launch_loss_finalize(g_raw.gsum, L.P, grads_out, (double)M, L.A, ent_coeff, v_coef, stats_out, s));

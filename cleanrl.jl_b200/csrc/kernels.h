@@ -50,6 +50,21 @@ struct MbFinal {
   float adv_mean, adv_std, s_unclipped, min_vlc;
   double M_global;
   unsigned long long cnt;  // #{i : s > (clip_i - R_i)^2}, ppo.jl:236 (Q5)
+  int need_fixup;          // speculative pass found s > min (clip_i - R_i)^2: redo with the exact terms
+  int _pad;
+};
+
+#define LG_EXACT 0  // minibatch scalars (mean, std, s, count) are known: fin is valid
+#define LG_SPEC 1   // speculate that the scalar s never wins the max (ppo.jl:236); verify afterwards
+#define ADV_CHUNKS 32
+
+// per-minibatch advantage sums for a whole update (they do not depend on the parameters)
+struct AdvStatsArgs {
+  IdxSrc idx;               // seed / ds / rank / B / half_bits (epoch and start are derived per set)
+  const int32_t* arr_base;  // device permutations [epochs][B] (or one index list), nullptr = device permutation
+  int B, M, nmb, n_sets;
+  const float* advantages;
+  double* advparts;         // [n_sets][ADV_CHUNKS][2] = (sum adv, sum adv^2)
 };
 
 struct UpdateArgs {
@@ -77,6 +92,10 @@ struct UpdateArgs {
   double* spart;         // [grid][4] per-CTA partial loss sums
   int grid_loss;
   double* gsum;          // [P + 4] reduced gradient (+ loss sums) in double: the allreduce buffer
+  int mode;              // LG_EXACT | LG_SPEC
+  int fixup;             // 1: this launch is the verification re-run; exits at once unless fin->need_fixup
+  const double* advparts;  // [ADV_CHUNKS][2] of this minibatch (LG_SPEC)
+  float* mpart;          // [grid] per-CTA min (clip_i - R_i)^2 (LG_SPEC)
 };
 
 struct AdamArgs {
@@ -114,6 +133,7 @@ cudaError_t launch_gae(const float* values, const float* rewards, const uint8_t*
 
 int mb_stats_grid(int M, int sm_count);
 int loss_grad_grid(int M, int sm_count);
+cudaError_t launch_adv_stats(const AdvStatsArgs& a, cudaStream_t s);
 cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);

@@ -151,6 +151,25 @@ __global__ void __launch_bounds__(CRL_THREADS) mb_count_kernel(UpdateArgs a) {
   __shared__ double red[8];
   __shared__ float mred[8];
   __shared__ uint32_t keys[8];
+  if (a.fixup) {
+    // verification re-run of the speculative path: fin already holds s; count only if it is needed
+    if (!a.fin->need_fixup) return;
+    if (threadIdx.x == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
+    __syncthreads();
+    const float s_fx = a.fin->s_unclipped;
+    unsigned int cf = 0;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += gridDim.x * blockDim.x) {
+      const int b = sample_index(a.idx, keys, m);
+      float d, vlc;
+      bool inside;
+      value_clip(a.vnew[m], a.values[b], a.returns[b], a.clip_coef, d, vlc, inside);
+      cf += (s_fx > vlc) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cf += __shfl_xor_sync(0xffffffffu, cf, o);
+    if ((threadIdx.x & 31) == 0 && cf) atomicAdd(&a.fin->cnt, (unsigned long long)cf);
+    return;
+  }
   double s_adv = 0.0, s_adv2 = 0.0, s_s = 0.0;
   float mn = INFINITY;
   for (int i = threadIdx.x; i < a.n_parts_in; i += blockDim.x) {
@@ -177,6 +196,7 @@ __global__ void __launch_bounds__(CRL_THREADS) mb_count_kernel(UpdateArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.fin->adv_mean = mean_f; a.fin->adv_std = std_f; a.fin->s_unclipped = s_f; a.fin->min_vlc = m8;
     a.fin->M_global = Mg;
+    a.fin->need_fixup = 0;
   }
   if (!(s_f > m8)) return;  // common case: the scalar never wins the max, count is 0
   unsigned int c = 0;
@@ -231,6 +251,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   double* red = reinterpret_cast<double*>(smem + SM::RED);
   const ThreadCoord<G> tc;
   const int tid = threadIdx.x;
+  if (a.fixup && !a.fin->need_fixup) return;  // speculation held: nothing to redo
 
   load_params<ENV>(a.params, sp);
   if (tid == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
@@ -240,9 +261,27 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     const int net = i / (CRL_H * CRL_H), r = i % (CRL_H * CRL_H), j = r / CRL_H, k = r % CRL_H;
     w2t[i] = sp[net_base<ENV>(net) + NO::W2 + k * CRL_H + j];
   }
-  const float mean_f = a.fin->adv_mean, std_f = a.fin->adv_std, s_f = a.fin->s_unclipped;
-  const double Mg = a.fin->M_global;
-  const double cnt_over_M = (double)a.fin->cnt / Mg;
+  const bool spec = a.mode == LG_SPEC;
+  float mean_f, std_f, s_f;
+  double Mg, cnt_over_M;
+  if (spec) {
+    // advantage mean / corrected std of this minibatch from the per-update pre-pass (ppo.jl:221);
+    // s is unknown yet: assume it never wins the max (checked by grad_reduce afterwards)
+    double sa = 0.0, sa2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < ADV_CHUNKS; i++) { sa += a.advparts[2 * i]; sa2 += a.advparts[2 * i + 1]; }
+    Mg = (double)a.M * (double)a.world;
+    const double mean = sa / Mg;
+    double var = (sa2 - Mg * mean * mean) / (Mg - 1.0);
+    if (var < 0.0) var = 0.0;
+    mean_f = (float)mean; std_f = (float)sqrt(var); s_f = 0.0f; cnt_over_M = 0.0;
+  } else {
+    mean_f = a.fin->adv_mean; std_f = a.fin->adv_std; s_f = a.fin->s_unclipped;
+    Mg = a.fin->M_global;
+    cnt_over_M = (double)a.fin->cnt / Mg;
+  }
+  double st_s = 0.0;
+  float st_min = INFINITY;
   const float c = a.clip_coef;
   const float lo_c = 1.0f - c, hi_c = 1.0f + c;
   __syncthreads();
@@ -395,8 +434,13 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         float d_vcR, vlc;
         bool inside;
         value_clip(v, s_V, s_R, c, d_vcR, vlc, inside);
-        const bool s_wins = s_f > vlc;
+        const bool s_wins = !spec && s_f > vlc;
         st_vmax += (double)(s_wins ? s_f : vlc);
+        if (spec) {
+          st_s += (double)__fsub_rn(v, __fmul_rn(s_R, s_R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
+          st_min = fminf(st_min, vlc);
+          a.vnew[m0 + s] = v;
+        }
         double dv_d = cnt_over_M;
         if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
         dv = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
@@ -577,12 +621,23 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   const double t_pg = block_sum<8>(st_pg, red);
   const double t_vm = block_sum<8>(st_vmax, red);
   const double t_en = block_sum<8>(st_ent, red);
+  const double t_ss = block_sum<8>(st_s, red);
+  __shared__ float mred_s[8];
+  st_min = warp_min(st_min);
+  __syncthreads();
+  if ((tid & 31) == 0) mred_s[tid >> 5] = st_min;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; w++) mred_s[0] = fminf(mred_s[0], mred_s[w]);
+  }
   double t_ls[A];
 #pragma unroll
   for (int k = 0; k < A; k++) t_ls[k] = block_sum<8>(g_logstd[k], red);
   if (tid == 0) {
     double* spp = a.spart + (long long)blockIdx.x * 4;
-    spp[0] = t_pg; spp[1] = t_vm; spp[2] = t_en; spp[3] = 0.0;
+    spp[0] = t_pg; spp[1] = t_vm; spp[2] = t_en; spp[3] = t_ss;
+    if (spec) a.mpart[blockIdx.x] = mred_s[0];
     if (E::CONT) {
 #pragma unroll
       for (int k = 0; k < A; k++) gp[E::NET_A + E::NET_C + k] = (float)t_ls[k];
@@ -591,17 +646,81 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
 }
 
 // ------------------------------------------------------------------ grad_reduce
-__global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double* __restrict__ spart, int grid, int P,
-                                   double* __restrict__ gsum) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// Sums the per-CTA partials in a fixed order (deterministic): 64 elements per block, the partials
+// split over 4 thread groups so ~37 independent loads are in flight per thread. The extra last
+// block verifies the speculation of LG_SPEC: s = mean(v_new - R^2) must not exceed
+// min_i (clip_i - R_i)^2, otherwise the exact kernels that follow redo the minibatch.
+__global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
+  __shared__ double sh[4][64];
+  if (a.fixup && !a.fin->need_fixup) return;
+  const int grid = a.grid_loss;
+  if (blockIdx.x == gridDim.x - 1) {
+    if (a.mode != LG_SPEC || a.fixup) return;
+    __shared__ double red[8];
+    __shared__ float mred[8];
+    double ss = 0.0;
+    float mn = INFINITY;
+    for (int c = threadIdx.x; c < grid; c += blockDim.x) { ss += a.spart[(long long)c * 4 + 3]; mn = fminf(mn, a.mpart[c]); }
+    ss = warp_sum(ss);
+    mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; mred[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      float m8 = mred[0];
+      for (int w = 0; w < 8; w++) { tot += red[w]; m8 = fminf(m8, mred[w]); }
+      double sa = 0.0, sa2 = 0.0;
+      for (int i = 0; i < ADV_CHUNKS; i++) { sa += a.advparts[2 * i]; sa2 += a.advparts[2 * i + 1]; }
+      const double Mg = (double)a.M * (double)a.world;
+      const double mean = sa / Mg;
+      double var = (sa2 - Mg * mean * mean) / (Mg - 1.0);
+      if (var < 0.0) var = 0.0;
+      const float s_f = (float)(tot / Mg);
+      a.fin->adv_mean = (float)mean; a.fin->adv_std = (float)sqrt(var); a.fin->s_unclipped = s_f; a.fin->min_vlc = m8;
+      a.fin->M_global = Mg; a.fin->cnt = 0ull; a.fin->need_fixup = (s_f > m8) ? 1 : 0;
+    }
+    return;
+  }
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;
+  double s = 0.0;
   if (e < P) {
-    double s = 0.0;
-    for (int c = 0; c < grid; c++) s += (double)gpart[(long long)c * P + e];
-    gsum[e] = s;
+#pragma unroll 8
+    for (int c = g; c < grid; c += 4) s += (double)a.gpart[(long long)c * P + e];
   } else if (e < P + 4) {
-    double s = 0.0;
-    for (int c = 0; c < grid; c++) s += spart[(long long)c * 4 + (e - P)];
-    gsum[e] = s;
+    for (int c = g; c < grid; c += 4) s += a.spart[(long long)c * 4 + (e - P)];
+  }
+  sh[g][el] = s;
+  __syncthreads();
+  if (g == 0 && e < P + 4) a.gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+}
+
+// advantage sums of every minibatch of an update in one launch: grid (ADV_CHUNKS, n_sets)
+__global__ void __launch_bounds__(256) adv_stats_kernel(AdvStatsArgs a) {
+  __shared__ double red[8];
+  __shared__ uint32_t keys[8];
+  const int set = blockIdx.y, epoch = set / a.nmb, start = (set % a.nmb) * a.M;
+  IdxSrc ix = a.idx;
+  ix.epoch = (uint32_t)epoch;
+  ix.start = (uint32_t)start;
+  ix.arr = a.arr_base ? a.arr_base + (long long)epoch * a.B + start : nullptr;
+  if (threadIdx.x == 0 && !ix.arr) perm_keys(ix.seed, ix.ds->update_index, ix.epoch, ix.rank, keys);
+  __syncthreads();
+  const int per = (a.M + ADV_CHUNKS - 1) / ADV_CHUNKS;
+  const int lo = blockIdx.x * per, hi = min(a.M, lo + per);
+  double sa = 0.0, sa2 = 0.0;
+#pragma unroll 4
+  for (int m = lo + threadIdx.x; m < hi; m += blockDim.x) {
+    const double ad = (double)a.advantages[sample_index(ix, keys, m)];
+    sa += ad;
+    sa2 += ad * ad;
+  }
+  sa = block_sum<8>(sa, red);
+  sa2 = block_sum<8>(sa2, red);
+  if (threadIdx.x == 0) {
+    double* o = a.advparts + ((long long)set * ADV_CHUNKS + blockIdx.x) * 2;
+    o[0] = sa;
+    o[1] = sa2;
   }
 }
 
@@ -654,8 +773,8 @@ __global__ void stats_pack_kernel(const MbScalars* parts, int n, MbScalars* out)
 
 // ------------------------------------------------------------------ clip + Adam
 // Flux.Optimiser(ClipNorm(thresh), Adam(η)) [Flux 0.13.4], one CTA per parameter array.
-__global__ void __launch_bounds__(CRL_THREADS) clip_adam_kernel(AdamArgs a) {
-  __shared__ double red[8];
+__global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
+  __shared__ double red[32];
   Layout L;
   make_layout(a.env_kind, &L);
   const int i = blockIdx.x;
@@ -665,7 +784,7 @@ __global__ void __launch_bounds__(CRL_THREADS) clip_adam_kernel(AdamArgs a) {
     const double g = (double)load_grad(a, o + k);  // the Float32 gradient array Zygote returns
     ss += g * g;
   }
-  ss = block_sum<8>(ss, red);
+  ss = block_sum<32>(ss, red);
   const float nrm = (float)sqrt(ss);  // norm(Δ::Array{Float32})::Float32
   const bool clip = (double)nrm > (double)a.clip_norm;
   const double scale = clip ? (double)a.clip_norm / (double)nrm : 1.0;
@@ -758,15 +877,21 @@ cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s) {
-  const int grid = (P + 4 + 255) / 256;
-  grad_reduce_kernel<<<grid, 256, 0, s>>>(a.gpart, a.spart, a.grid_loss, P, a.gsum);
+  const int grid = (P + 4 + 63) / 64 + 1;  // + the verification block
+  grad_reduce_kernel<<<grid, 256, 0, s>>>(a, P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adv_stats(const AdvStatsArgs& a, cudaStream_t s) {
+  if (a.n_sets < 1) return cudaSuccess;
+  adv_stats_kernel<<<dim3(ADV_CHUNKS, a.n_sets), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s) {
   Layout L;
   if (!make_layout(a.env_kind, &L)) return cudaErrorInvalidValue;
-  clip_adam_kernel<<<L.n_arrays, CRL_THREADS, 0, s>>>(a);
+  clip_adam_kernel<<<L.n_arrays, 1024, 0, s>>>(a);
   return cudaGetLastError();
 }
 
