@@ -1,0 +1,219 @@
+# CleanRLCuda.jl — `ccall` binding of libcleanrl_cuda.so (include/cleanrl_cuda.h) and the drop-in
+# `ppo(config)` that replaces src/algorithms/ppo.jl:75-254 of sash-a/CleanRL.jl.
+#
+# STATUS: this file is the reference-side binding a maintainer would add. Julia is not installed
+# in the build image (nor on the GPU boxes), so it has NOT been executed; the Python package next
+# to it (cleanrl.jl_b200/*.py) is the executed, tested host side and is a line-for-line mirror of
+# the control flow below. Keep the two in sync.
+#
+# Usage inside the reference repo:
+#   include("utils/CleanRLCuda.jl")          # after logger.jl / networks.jl in src/CleanRL.jl
+#   CleanRL.CleanRLCuda.ppo(PPOConfig(num_envs=4096, num_steps=128))
+module CleanRLCuda
+
+using Random: shuffle
+
+const LIB = get(ENV, "CLEANRL_CUDA_LIB", "libcleanrl_cuda.so")
+
+const CRL_ENV_CARTPOLE = Int32(0)
+const CRL_ENV_PENDULUM = Int32(1)
+const CRL_GAE_REF_COMPAT = Int32(0)
+const CRL_GAE_FIXED = Int32(1)
+
+# field ids for crl_read_field / crl_write_field
+const F_STATE, F_ACTION, F_LOGPROB, F_REWARD, F_TERMINAL, F_VALUE, F_ADVANTAGE, F_RETURN = Int32.(0:7)
+
+# mirror of `struct crl_config` (88 bytes, seed at offset 80; same field order; checked by struct_size)
+struct CrlConfig
+  struct_size::Int32
+  env_kind::Int32
+  num_envs::Int32
+  num_steps::Int32
+  num_minibatches::Int32
+  update_epochs::Int32
+  max_episode_steps::Int32
+  gae_mode::Int32
+  device::Int32
+  world_size::Int32
+  rank::Int32
+  env_id_base::Int32
+  episode_capacity::Int32
+  flags::UInt32
+  gamma::Float32
+  gae_lambda::Float32
+  clip_coef::Float32
+  ent_coeff::Float32
+  v_coef::Float32
+  clip_norm::Float32
+  seed::UInt64
+end
+
+struct LossStats            # crl_loss_stats, the "Training Statistics" record (ppo.jl:247)
+  loss::Float64
+  pg_loss::Float64
+  v_loss::Float64
+  entropy_loss::Float64
+end
+
+struct Episode              # crl_episode, one "Episode Statistics" record (ppo.jl:152-157)
+  step::Int32
+  env::Int32
+  length::Int32
+  _pad::Int32
+  episode_return::Float64
+end
+
+struct EpisodeAgg
+  count::Int64
+  sum_return::Float64
+  sum_length::Float64
+  max_return::Float64
+  dropped::Int64
+end
+
+last_error() = unsafe_string(ccall((:crl_last_error, LIB), Cstring, ()))
+check(rc::Integer) = rc == 0 ? nothing : error("libcleanrl_cuda error $rc: $(last_error())")
+
+mutable struct Handle
+  ptr::Ptr{Cvoid}
+  cfg::CrlConfig
+  function Handle(cfg::CrlConfig)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:crl_create, LIB), Cint, (Ref{CrlConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+    h = new(out[], cfg)
+    finalizer(h -> (h.ptr != C_NULL && ccall((:crl_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+    h
+  end
+end
+
+function make_config(config; env_kind=CRL_ENV_CARTPOLE, num_envs=config.num_envs, device=0, world_size=1, rank=0,
+                     env_id_base=0, max_steps=500, gae_mode=CRL_GAE_REF_COMPAT, seed=UInt64(1))
+  CrlConfig(Int32(sizeof(CrlConfig)), env_kind, num_envs, config.num_steps, config.num_minibatches,
+            config.update_epochs, max_steps, gae_mode, device, world_size, rank, env_id_base, 0, UInt32(0),
+            config.gamma, config.gae_lambda, config.clip_coef, config.ent_coeff, config.v_coef, 0.5f0, seed)
+end
+
+# Flux.params(actor, critic) order (ppo.jl:196); each W is already (out,in) column-major in Flux,
+# which is exactly the flat layout the library expects: no transposition.
+flat_params(actor, critic) = reduce(vcat, [vec(Float32.(p)) for p in Iterators.flatten((Flux_params(actor), Flux_params(critic)))])
+Flux_params(chain) = reduce(vcat, [[l.weight, l.bias] for l in chain.layers])
+
+function set_params!(h::Handle, p::Vector{Float32})
+  GC.@preserve p check(ccall((:crl_set_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, p, length(p)))
+end
+function get_params(h::Handle, n::Integer)
+  p = Vector{Float32}(undef, n)
+  GC.@preserve p check(ccall((:crl_get_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, p, n))
+  p
+end
+
+env_reset!(h::Handle) = check(ccall((:crl_env_reset, LIB), Cint, (Ptr{Cvoid},), h.ptr))
+rollout!(h::Handle) = check(ccall((:crl_rollout, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float32}), h.ptr, C_NULL, C_NULL))
+gae!(h::Handle) = check(ccall((:crl_gae, LIB), Cint, (Ptr{Cvoid},), h.ptr))
+train_update!(h::Handle, lr::Float64) = check(ccall((:crl_train_update, LIB), Cint, (Ptr{Cvoid}, Float64), h.ptr, lr))
+
+# perms: Matrix{Int32} (B, update_epochs) of 1-BASED indices as shuffle(1:B) produces (ppo.jl:191-194);
+# the C ABI is 0-based, so subtract 1 here.
+function update_epochs!(h::Handle, perms::Union{Nothing,Matrix{Int32}}, lr::Float64)
+  n = h.cfg.update_epochs * h.cfg.num_minibatches
+  stats = Vector{LossStats}(undef, n)
+  if perms === nothing
+    GC.@preserve stats check(ccall((:crl_update_epochs, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Float64, Ptr{LossStats}),
+                                   h.ptr, C_NULL, lr, stats))
+  else
+    p0 = perms .- Int32(1)
+    GC.@preserve p0 stats check(ccall((:crl_update_epochs, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Float64, Ptr{LossStats}),
+                                      h.ptr, p0, lr, stats))
+  end
+  stats
+end
+
+function fetch_update(h::Handle)
+  n = h.cfg.update_epochs * h.cfg.num_minibatches
+  stats = Vector{LossStats}(undef, n)
+  agg = Ref(EpisodeAgg(0, 0.0, 0.0, 0.0, 0))
+  GC.@preserve stats check(ccall((:crl_fetch_update, LIB), Cint, (Ptr{Cvoid}, Ptr{LossStats}, Ref{EpisodeAgg}), h.ptr, stats, agg))
+  stats, agg[]
+end
+
+function pop_episodes(h::Handle, max_records::Integer=1 << 20)
+  recs = Vector{Episode}(undef, max_records)
+  n = Ref{Int32}(0)
+  agg = Ref(EpisodeAgg(0, 0.0, 0.0, 0.0, 0))
+  GC.@preserve recs check(ccall((:crl_pop_episodes, LIB), Cint, (Ptr{Cvoid}, Ptr{Episode}, Int32, Ref{Int32}, Ref{EpisodeAgg}),
+                                h.ptr, recs, max_records, n, agg))
+  resize!(recs, n[]), agg[]
+end
+
+# rb.data.*-shaped views: Julia column-major (D,N,T) == the library's [T][N][D], so a plain copy
+function read_field(h::Handle, field::Int32, ::Type{T}, dims...) where {T}
+  a = Array{T}(undef, dims...)
+  GC.@preserve a check(ccall((:crl_read_field, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Csize_t), h.ptr, field, a, sizeof(a)))
+  a
+end
+
+# gae(values, rewards, terminals, γ, λ) with the reference's signature (ppo.jl:48): one env, values [0,k],
+# rewards [1,k], terminals [0,k]. Runs crl_gae_raw on device copies made with CUDA.jl.
+# (Needs `using CUDA`; left as the call shape only because CUDA.jl is a declared but unused dependency of
+# the reference, Project.toml:9.)
+#   crl_gae_raw(values[1:k], rewards, terminals[1:k], values[k+1:k+1], terminals[k+1:k+1], adv, ret, k, 1, γ, λ, mode, C_NULL)
+
+"""
+    ppo(config::PPOConfig = PPOConfig(); actor, critic, logger_info)
+
+Drop-in for `CleanRL.ppo` (ppo.jl:75). Same config struct, same `@info` record names and keys.
+`actor`/`critic` are the Flux chains from `Networks.make_actor_critic` (networks.jl:36-49); they are used
+only to initialise the device parameters.
+"""
+function ppo(config; actor, critic, log_episodes::Bool=false)
+  nt = config.num_envs                                            # ppo.jl:76
+  h = Handle(make_config(config))
+  p = flat_params(actor, critic)                                  # ppo.jl:85-87,196
+  set_params!(h, p)
+  batch_size = config.num_steps * nt                              # ppo.jl:89
+  num_updates = config.total_timesteps ÷ batch_size               # ppo.jl:91
+  global_step = 0                                                 # ppo.jl:106
+  last_log_step = 0
+  start_time = time()                                             # ppo.jl:111
+  env_reset!(h)                                                   # ppo.jl:112-115
+  for update in 1:num_updates                                     # ppo.jl:117
+    lr_now = Float64(config.lr)
+    if config.anneal_lr
+      frac = 1.0 - (update - 1.0) / num_updates                   # ppo.jl:119
+      lr_now = frac * config.lr                                   # ppo.jl:120
+    end
+    step_base = global_step
+    if log_episodes
+      rollout!(h)                                                 # ppo.jl:123-166 in one launch
+      recs, _ = pop_episodes(h)
+      for r in recs                                               # (step, env) order == ppo.jl:149
+        gs = step_base + (r.step + 1) * nt
+        steps_per_sec = trunc(gs / (time() - start_time))         # ppo.jl:148
+        log_step_inc = last_log_step == 0 ? 0 : gs - last_log_step
+        @info "Episode Statistics" episode_return = r.episode_return episode_length = Float64(r.length) global_step = gs steps_per_sec log_step_increment = log_step_inc
+        last_log_step = gs
+      end
+      global_step += batch_size
+      gae!(h)                                                     # ppo.jl:169-181
+      stats = update_epochs!(h, nothing, lr_now)                  # ppo.jl:191-252 (device permutation)
+    else
+      train_update!(h, lr_now)                                    # whole update, one CUDA-graph launch
+      global_step += batch_size
+      stats, agg = fetch_update(h)
+      if agg.count > 0
+        steps_per_sec = trunc(global_step / (time() - start_time))
+        log_step_inc = last_log_step == 0 ? 0 : global_step - last_log_step
+        @info "Episode Statistics" episode_return = agg.sum_return / agg.count episode_length = agg.sum_length / agg.count global_step steps_per_sec log_step_increment = log_step_inc
+        last_log_step = global_step
+      end
+    end
+    for s in stats                                                # ppo.jl:246-248
+      log_step_inc = last_log_step == 0 ? 0 : global_step - last_log_step
+      @info "Training Statistics" loss = s.loss pg_loss = s.pg_loss v_loss = s.v_loss entropy_loss = s.entropy_loss log_step_increment = log_step_inc
+      last_log_step = global_step
+    end
+  end
+  get_params(h, length(p))
+end
+
+end # module
