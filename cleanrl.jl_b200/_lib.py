@@ -47,6 +47,7 @@ SIGNATURES = {
     "crl_device_permutation": (C.c_int, [V, I64, I32, V]),
     "crl_train_update": (C.c_int, [V, F64]),
     "crl_fetch_update": (C.c_int, [V, V, V]),
+    "crl_fetch_update_at": (C.c_int, [V, I32, V, V]),
     "crl_read_field": (C.c_int, [V, I32, V, C.c_size_t]),
     "crl_write_field": (C.c_int, [V, I32, V, C.c_size_t]),
     "crl_pop_episodes": (C.c_int, [V, V, I32, V, V]),

@@ -117,8 +117,10 @@ struct crl_ctx {
   double* action_noise_dev;
   float* reset_noise_dev;
   // pinned host mirrors
-  crl_loss_stats* stats_host;
-  EpisodeBuf* eb_host;
+  crl_loss_stats* stats_host[2];  // double-buffered so the host can log update u-1 while update u runs
+  EpisodeBuf* eb_host[2];
+  cudaEvent_t fetch_ev[2];
+  uint64_t update_seq;            // number of crl_train_update calls so far
   double* lr_host;
   // graph
   cudaGraphExec_t graph_exec;
@@ -260,12 +262,16 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
   A_(dalloc(&c->advparts, nmb * ADV_CHUNKS * 2));
   A_(dalloc(&c->stats_dev, nmb * 4)); A_(dalloc(&c->idx_dev, B)); A_(dalloc(&c->perm_dev, (size_t)std::max(1, cfg->update_epochs) * B));
   {
-    cudaError_t e1 = cudaMallocHost(reinterpret_cast<void**>(&c->stats_host), nmb * sizeof(crl_loss_stats));
-    cudaError_t e2 = cudaMallocHost(reinterpret_cast<void**>(&c->eb_host), sizeof(EpisodeBuf));
-    cudaError_t e3 = cudaMallocHost(reinterpret_cast<void**>(&c->lr_host), sizeof(double));
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { crl_destroy(c); return fail(CRL_ERR_CUDA, "cudaMallocHost failed"); }
-    memset(c->stats_host, 0, nmb * sizeof(crl_loss_stats));
-    memset(c->eb_host, 0, sizeof(EpisodeBuf));
+    cudaError_t e3 = cudaMallocHost(reinterpret_cast<void**>(&c->lr_host), 16 * sizeof(double));
+    bool ok = e3 == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&c->stats_host[i]), nmb * sizeof(crl_loss_stats)) == cudaSuccess;
+      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&c->eb_host[i]), sizeof(EpisodeBuf)) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming) == cudaSuccess;
+      if (ok) { memset(c->stats_host[i], 0, nmb * sizeof(crl_loss_stats)); memset(c->eb_host[i], 0, sizeof(EpisodeBuf)); }
+    }
+    if (!ok) { crl_destroy(c); return fail(CRL_ERR_CUDA, "pinned host allocation failed"); }
+    c->update_seq = 0;
   }
 #undef A_
   // Flux keeps (β1, β2) as the initial power state of every array
@@ -290,8 +296,11 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
                   c->parts_send, c->parts_recv, c->fin, c->gpart, c->mpart, c->advparts, c->spart, c->gsum, c->stats_dev, c->idx_dev,
                   c->perm_dev, c->action_noise_dev, c->reset_noise_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (c->stats_host) cudaFreeHost(c->stats_host);
-  if (c->eb_host) cudaFreeHost(c->eb_host);
+  for (int i = 0; i < 2; i++) {
+    if (c->stats_host[i]) cudaFreeHost(c->stats_host[i]);
+    if (c->eb_host[i]) cudaFreeHost(c->eb_host[i]);
+    if (c->fetch_ev[i]) cudaEventDestroy(c->fetch_ev[i]);
+  }
   if (c->lr_host) cudaFreeHost(c->lr_host);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -628,10 +637,6 @@ static int enqueue_train_update(crl_ctx* c) {
     KernelScope ks(c, CRL_K_OTHER);
     CK(launch_advance(c->ds, (unsigned long long)c->T, 1ull, c->stream));
   }
-  const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
-  static_assert(sizeof(crl_loss_stats) == 4 * sizeof(double), "crl_loss_stats must be 4 doubles");
-  if (nmb) CK(cudaMemcpyAsync(c->stats_host, c->stats_dev, nmb * sizeof(crl_loss_stats), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->eb_host, c->eb, sizeof(EpisodeBuf), cudaMemcpyDeviceToHost, c->stream));
   return CRL_OK;
 }
 
@@ -663,26 +668,43 @@ extern "C" CRL_API int crl_train_update(crl_ctx* c, double lr) {
     CK(cudaGraphLaunch(c->graph_exec, c->stream));
     c->launches += c->graph_kernels;
   }
+  {
+    // results of this update -> pinned slot (update_seq & 1); the event lets the host fetch update u-1
+    // while update u is still running (crl_fetch_update_at with lag = 1)
+    const int slot = (int)(c->update_seq & 1);
+    const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
+    static_assert(sizeof(crl_loss_stats) == 4 * sizeof(double), "crl_loss_stats must be 4 doubles");
+    if (nmb) CK(cudaMemcpyAsync(c->stats_host[slot], c->stats_dev, nmb * sizeof(crl_loss_stats), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->eb_host[slot], c->eb, sizeof(EpisodeBuf), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->fetch_ev[slot], c->stream));
+    c->update_seq += 1;
+  }
   c->rolled = true;
   c->gae_done = true;
   c->have_update = true;
   return CRL_OK;
 }
 
-extern "C" CRL_API int crl_fetch_update(crl_ctx* c, crl_loss_stats* stats, crl_episode_agg* agg) {
+extern "C" CRL_API int crl_fetch_update_at(crl_ctx* c, int32_t lag, crl_loss_stats* stats, crl_episode_agg* agg) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
-  if (!c->have_update) return fail(CRL_ERR_STATE, "crl_fetch_update called before crl_train_update");
+  if (lag < 0 || lag > 1) return fail(CRL_ERR_INVALID, "lag must be 0 (latest update) or 1 (the one before)");
+  if (!c->have_update || c->update_seq < (uint64_t)lag + 1) return fail(CRL_ERR_STATE, "no such update has been enqueued yet");
   CKRC(use_device(c));
-  CK(cudaStreamSynchronize(c->stream));
+  const int slot = (int)((c->update_seq - 1 - (uint64_t)lag) & 1);
+  CK(cudaEventSynchronize(c->fetch_ev[slot]));
   const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
-  if (stats && nmb) memcpy(stats, c->stats_host, nmb * sizeof(crl_loss_stats));
+  if (stats && nmb) memcpy(stats, c->stats_host[slot], nmb * sizeof(crl_loss_stats));
   if (agg) {
-    const EpisodeBuf& e = *c->eb_host;
+    const EpisodeBuf& e = *c->eb_host[slot];
     agg->count = (int64_t)e.n_episodes; agg->sum_return = e.sum_return; agg->sum_length = e.sum_length;
     agg->max_return = e.max_return;
     agg->dropped = e.count > (unsigned)c->ep_capacity ? (int64_t)(e.count - c->ep_capacity) : 0;
   }
   return CRL_OK;
+}
+
+extern "C" CRL_API int crl_fetch_update(crl_ctx* c, crl_loss_stats* stats, crl_episode_agg* agg) {
+  return crl_fetch_update_at(c, 0, stats, agg);
 }
 
 // ------------------------------------------------------------------ data access

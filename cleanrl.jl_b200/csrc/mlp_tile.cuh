@@ -57,6 +57,12 @@ template <class G> struct ThreadCoord {
 
 __device__ __forceinline__ float f4_get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+// Column swizzle of the activation tiles: physical column = s ^ act_swz(row). With the 132-float row stride
+// the 8 lanes of a quarter-warp that store rows 4*q_lo + j land on only two bank groups (4-way conflict on every
+// float4 store); XOR-ing the column with 4*((row >> 3) & 3) spreads them over all eight. The XOR is a multiple of
+// 4 below 16, so float4 accesses stay aligned and inside their 16-float group.
+__device__ __forceinline__ int act_swz(int row) { return ((row >> 3) & 3) << 2; }
+
 #define EPI_BIAS_TANH 0   // out = tanh_fast(acc + bias)                         (forward)
 #define EPI_DTANH 1       // out = acc * (1 - out_old^2), in place over h        (backward)
 
@@ -64,7 +70,7 @@ __device__ __forceinline__ float f4_get(const float4& v, int i) { return i == 0 
 //   Wt   shared, [K][64] for this thread's net (k-major)
 //   in   shared, row 0 of this net's input block (row stride S_PAD)
 //   out  shared, row 0 of this net's output block
-template <class G, int K, int EPI>
+template <class G, int K, int EPI, bool SWZ_IN = false, bool SWZ_OUT = false>
 __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float* __restrict__ Wt,
                                            const float* __restrict__ bias, const float* __restrict__ in,
                                            float* __restrict__ out) {
@@ -80,7 +86,7 @@ __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       w[c] = *reinterpret_cast<const float4*>(Wt + k * CRL_H + tc.jb[c]);
-      a[c] = *reinterpret_cast<const float4*>(in + k * SP + tc.sb[c]);
+      a[c] = *reinterpret_cast<const float4*>(in + k * SP + (SWZ_IN ? (tc.sb[c] ^ act_swz(k)) : tc.sb[c]));
     }
 #pragma unroll
     for (int j = 0; j < TS; j++)
@@ -94,7 +100,7 @@ __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float
     if (EPI == EPI_BIAS_TANH) b = bias[row];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      float4* dst = reinterpret_cast<float4*>(out + row * SP + tc.sb[c]);
+      float4* dst = reinterpret_cast<float4*>(out + row * SP + (SWZ_OUT ? (tc.sb[c] ^ act_swz(row)) : tc.sb[c]));
       float4 o;
       if (EPI == EPI_BIAS_TANH) {
         o.x = tanh_fast(acc[j][4 * c + 0] + b);

@@ -345,9 +345,9 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     // ---- P1/P2 forward, both nets (logprob_actions ppo.jl:35 and critic ppo.jl:214)
     {
       const float* np = sp + net_base<ENV>(tc.net);
-      tile_layer<G, D, EPI_BIAS_TANH>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
+      tile_layer<G, D, EPI_BIAS_TANH, false, true>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
       __syncthreads();
-      tile_layer<G, CRL_H, EPI_BIAS_TANH>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
+      tile_layer<G, CRL_H, EPI_BIAS_TANH, true, true>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
       __syncthreads();
     }
     // ---- P3 heads
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         for (int o = 0; o < A; o++) acc[o] = 0.0f;
 #pragma unroll 8
         for (int k = 0; k < CRL_H; k++) {
-          const float h = h2[k * SP + s];
+          const float h = h2[k * SP + (s ^ act_swz(k))];
 #pragma unroll
           for (int o = 0; o < A; o++) acc[o] = fmaf(ap[NA::W3 + k * A + o], h, acc[o]);
         }
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         const float* cp = sp + SmemParams<ENV>::CRITIC;
         float acc = 0.0f;
 #pragma unroll 8
-        for (int k = 0; k < CRL_H; k++) acc = fmaf(cp[NO::W3 + k], h2[(CRL_H + k) * SP + s], acc);
+        for (int k = 0; k < CRL_H; k++) acc = fmaf(cp[NO::W3 + k], h2[(CRL_H + k) * SP + (s ^ act_swz(k))], acc);
         zo[A * S + s] = acc + cp[NO::B3];
       }
     }
@@ -474,10 +474,11 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
       const int o = tid / CRL_H, k = tid % CRL_H;
       const float* hrow = h2 + ((o < A ? 0 : CRL_H) + k) * SP;
       const float* drow = dout + o * S;
+      const int hsw = act_swz(k);
       float acc = 0.0f, bacc = 0.0f;
 #pragma unroll 4
       for (int s = 0; s < S; s += 4) {
-        const float4 h = *reinterpret_cast<const float4*>(hrow + s);
+        const float4 h = *reinterpret_cast<const float4*>(hrow + (s ^ hsw));
         const float4 d = *reinterpret_cast<const float4*>(drow + s);
         acc = fmaf(h.x, d.x, acc); acc = fmaf(h.y, d.y, acc); acc = fmaf(h.z, d.z, acc); acc = fmaf(h.w, d.w, acc);
         bacc += (d.x + d.y) + (d.z + d.w);
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         }
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-          float4* hp = reinterpret_cast<float4*>(hb + row * SP + tc.sb[cc]);
+          float4* hp = reinterpret_cast<float4*>(hb + row * SP + (tc.sb[cc] ^ act_swz(row)));
           const float4 h = *hp;
           float4 dh;
           if (tc.net == 0) {
@@ -538,9 +539,9 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
       for (int s = 0; s < S; s += 4) {
         float4 hk[4], dj[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) hk[i] = *reinterpret_cast<const float4*>(h1b + (w_kq + 16 * i) * SP + s);
+        for (int i = 0; i < 4; i++) hk[i] = *reinterpret_cast<const float4*>(h1b + (w_kq + 16 * i) * SP + (s ^ act_swz(w_kq + 16 * i)));
 #pragma unroll
-        for (int j = 0; j < 8; j++) dj[j] = *reinterpret_cast<const float4*>(d2b + (w_jq + 8 * j) * SP + s);
+        for (int j = 0; j < 8; j++) dj[j] = *reinterpret_cast<const float4*>(d2b + (w_jq + 8 * j) * SP + (s ^ act_swz(w_jq + 8 * j)));
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -558,19 +559,20 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     }
     __syncthreads();
     // ---- P8 dz1 = (W2^T dz2) .* (1 - h1^2), in place over h1
-    tile_layer<G, CRL_H, EPI_DTANH>(tc, w2t + tc.net * CRL_H * CRL_H, nullptr, h2 + tc.net * CRL_H * SP,
-                                    h1 + tc.net * CRL_H * SP);
+    tile_layer<G, CRL_H, EPI_DTANH, true, true>(tc, w2t + tc.net * CRL_H * CRL_H, nullptr, h2 + tc.net * CRL_H * SP,
+                                                h1 + tc.net * CRL_H * SP);
     __syncthreads();
     // ---- P9 row sums: tid<128: db1[row], dW1[k][row]; tid>=128: db2[row]
     {
       const int row = tid & 127;
       const float* src = (tid < 128 ? h1 : h2) + row * SP;
+      const int rsw = act_swz(row);
       float bacc = 0.0f, wacc[D];
 #pragma unroll
       for (int k = 0; k < D; k++) wacc[k] = 0.0f;
 #pragma unroll 4
       for (int s = 0; s < S; s += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(src + s);
+        const float4 d = *reinterpret_cast<const float4*>(src + (s ^ rsw));
         bacc += (d.x + d.y) + (d.z + d.w);
         if (tid < 128) {
 #pragma unroll

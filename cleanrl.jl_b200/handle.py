@@ -138,10 +138,11 @@ class PPOHandle:
         """enqueue rollout + GAE + all epochs (asynchronous)"""
         L.check(self.lib.crl_train_update(self.h, float(lr)))
 
-    def fetch_update(self):
+    def fetch_update(self, lag=0):
+        """results of the latest update (lag=0) or of the one before it (lag=1, does not wait for the latest)"""
         st = (_abi.crl_loss_stats * max(self.n_mb, 1))()
         agg = _abi.crl_episode_agg()
-        L.check(self.lib.crl_fetch_update(self.h, st, C.byref(agg)))
+        L.check(self.lib.crl_fetch_update_at(self.h, int(lag), st, C.byref(agg)))
         return _stats_array(st[:self.n_mb]), agg
 
     # ---- data

@@ -100,10 +100,32 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
         start_time = time.time()  # ppo.jl:111
         h.env_reset()             # ppo.jl:112-115
         rng = np.random.default_rng(config.seed + 7919 * rank)
-        last_stats = None
-        episodes = 0
-        ret_sum = 0.0
 
+        state = {"last_log_step": last_log_step, "episodes": 0, "ret_sum": 0.0, "d2h": 0, "last_stats": None}
+
+        def log_update(stats, agg, gs):
+            """records of one finished update (rank 0): aggregated episodes + one record per minibatch"""
+            state["d2h"] += stats.nbytes + 40
+            state["last_stats"] = stats
+            if rank != 0:
+                return
+            if agg is not None and agg.count > 0:
+                # throughput mode: one aggregated "Episode Statistics" record per rollout
+                steps_per_sec = np.trunc(gs / max(time.time() - start_time, 1e-9))   # ppo.jl:148
+                inc = 0 if state["last_log_step"] == 0 else gs - state["last_log_step"]  # ppo.jl:156
+                logger.info("Episode Statistics", episode_return=agg.sum_return / agg.count,
+                            episode_length=agg.sum_length / agg.count, global_step=gs,
+                            steps_per_sec=steps_per_sec, log_step_increment=inc)
+                state["last_log_step"] = gs
+                state["episodes"] += agg.count
+                state["ret_sum"] += agg.sum_return
+            for row in stats:  # ppo.jl:246-248, one record per minibatch
+                inc = 0 if state["last_log_step"] == 0 else gs - state["last_log_step"]
+                logger.info("Training Statistics", loss=row[0], pg_loss=row[1], v_loss=row[2],
+                            entropy_loss=row[3], log_step_increment=inc)
+                state["last_log_step"] = gs
+
+        pending = None  # (update, global_step) of the update whose results have not been logged yet
         for update in range(1, num_updates_run + 1):  # ppo.jl:117
             lr_now = annealed_lr(config, update, num_updates)
             step_base = global_step
@@ -111,17 +133,17 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
                 # stage-by-stage path: same call sequence as the reference's loop body
                 h.rollout()                                  # ppo.jl:123-166
                 if config.log_episodes and rank == 0:
-                    recs, agg = h.pop_episodes()
-                    d2h_bytes += 24 * len(recs)
+                    recs, _ = h.pop_episodes()
+                    state["d2h"] += 24 * len(recs)
                     for (step, env, length, ep_ret) in recs:  # (step, env) order = ppo.jl:149
                         gs = step_base + (step + 1) * nt      # ppo.jl:124
                         steps_per_sec = np.trunc(gs / max(time.time() - start_time, 1e-9))  # ppo.jl:148
-                        inc = 0 if last_log_step == 0 else gs - last_log_step  # ppo.jl:156
+                        inc = 0 if state["last_log_step"] == 0 else gs - state["last_log_step"]  # ppo.jl:156
                         logger.info("Episode Statistics", episode_return=ep_ret, episode_length=float(length),
                                     global_step=gs, steps_per_sec=steps_per_sec, log_step_increment=inc)  # ppo.jl:157
-                        last_log_step = gs  # ppo.jl:161
-                        episodes += 1
-                        ret_sum += ep_ret
+                        state["last_log_step"] = gs  # ppo.jl:161
+                        state["episodes"] += 1
+                        state["ret_sum"] += ep_ret
                 global_step += config.num_steps * nt
                 h.gae()                                      # ppo.jl:169-181
                 perms = None
@@ -129,32 +151,27 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
                     perms = np.stack([rng.permutation(h.B) for _ in range(config.update_epochs)]).astype(np.int32)
                     h2d_bytes += perms.nbytes
                 stats = h.update_epochs(perms, lr_now)       # ppo.jl:191-252
-                agg = None
+                log_update(stats, None, global_step)
+                if on_update is not None:
+                    on_update(update, h, stats, None)
             else:
+                # throughput path: the whole update is one asynchronous CUDA-graph launch; the host logs
+                # update u-1 (double-buffered results) while the GPU runs update u
                 h.train_update(lr_now)
                 global_step += config.num_steps * nt
-                stats, agg = h.fetch_update()
                 h2d_bytes += 8
-            d2h_bytes += stats.nbytes + 40
-            if rank == 0:
-                if agg is not None and agg.count > 0:
-                    # throughput mode: one aggregated "Episode Statistics" record per rollout
-                    steps_per_sec = np.trunc(global_step / max(time.time() - start_time, 1e-9))
-                    inc = 0 if last_log_step == 0 else global_step - last_log_step
-                    logger.info("Episode Statistics", episode_return=agg.sum_return / agg.count,
-                                episode_length=agg.sum_length / agg.count, global_step=global_step,
-                                steps_per_sec=steps_per_sec, log_step_increment=inc)
-                    last_log_step = global_step
-                    episodes += agg.count
-                    ret_sum += agg.sum_return
-                for row in stats:  # ppo.jl:246-248, one record per minibatch
-                    inc = 0 if last_log_step == 0 else global_step - last_log_step
-                    logger.info("Training Statistics", loss=row[0], pg_loss=row[1], v_loss=row[2],
-                                entropy_loss=row[3], log_step_increment=inc)
-                    last_log_step = global_step
-            last_stats = stats
+                if pending is not None:
+                    stats, agg = h.fetch_update(lag=1)
+                    log_update(stats, agg, pending[1])
+                    if on_update is not None:
+                        on_update(pending[0], h, stats, agg)
+                pending = (update, global_step)
+        if pending is not None:
+            stats, agg = h.fetch_update(lag=0)
+            log_update(stats, agg, pending[1])
             if on_update is not None:
-                on_update(update, h, stats, agg)
+                on_update(pending[0], h, stats, agg)
+        last_stats, episodes, ret_sum, d2h_bytes = state["last_stats"], state["episodes"], state["ret_sum"], state["d2h"]
         h.sync()
         elapsed = time.time() - start_time
         return {

@@ -218,6 +218,9 @@ CRL_API int crl_device_permutation(crl_ctx* ctx, int64_t update_index, int32_t e
 CRL_API int crl_train_update(crl_ctx* ctx, double lr);
 CRL_API int crl_fetch_update(crl_ctx* ctx, crl_loss_stats* stats /* epochs*minibatches, may be NULL */,
                      crl_episode_agg* agg /* may be NULL */);
+/* same, for the update enqueued `lag` calls before the latest (0 or 1). With lag = 1 the host can log
+ * update u-1 (waits only for that update) while update u is running: the results are double-buffered. */
+CRL_API int crl_fetch_update_at(crl_ctx* ctx, int32_t lag, crl_loss_stats* stats, crl_episode_agg* agg);
 
 /* ---- data access ----------------------------------------------------------------- */
 CRL_API int crl_read_field(crl_ctx* ctx, int32_t field, void* host, size_t bytes);
