@@ -84,7 +84,7 @@ struct crl_ctx {
   int sm_count;
   cudaStream_t stream;
   // parameters / optimiser
-  float *params, *grads, *adam_m, *adam_v;
+  float *params, *grads, *adam_m, *adam_v, *image;
   double* beta_pow;
   DevState* ds;
   // envs
@@ -244,6 +244,7 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
   if (se != cudaSuccess) { delete c; return fail(CRL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
   A_(dalloc(&c->params, L.P)); A_(dalloc(&c->grads, L.P)); A_(dalloc(&c->adam_m, L.P)); A_(dalloc(&c->adam_v, L.P));
   A_(dalloc(&c->beta_pow, 2 * CRL_MAX_ARRAYS)); A_(dalloc(&c->ds, 1));
+  A_(dalloc(&c->image, param_image_floats(cfg->env_kind)));
   A_(dalloc(&c->env_state, N * L.S)); A_(dalloc(&c->env_t, N)); A_(dalloc(&c->ep_return, N)); A_(dalloc(&c->ep_length, N));
   A_(dalloc(&c->reset_count, N)); A_(dalloc(&c->next_obs, N * L.D)); A_(dalloc(&c->next_done, N)); A_(dalloc(&c->next_value, N));
   A_(dalloc(&c->state, B * L.D));
@@ -290,7 +291,7 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& p : c->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
-  void* ptrs[] = {c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
+  void* ptrs[] = {c->image, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
                   c->ep_length, c->reset_count, c->next_obs, c->next_done, c->next_value, c->state, c->action, c->logprob,
                   c->reward, c->value, c->advantage, c->ret, c->terminal, c->eb, c->records, c->vnew, c->parts,
                   c->parts_send, c->parts_recv, c->fin, c->gpart, c->mpart, c->advparts, c->spart, c->gsum, c->stats_dev, c->idx_dev,
@@ -340,7 +341,14 @@ static int copy_vec(crl_ctx* c, void* dst, const void* src, size_t bytes, cudaMe
 }
 extern "C" CRL_API int crl_set_params(crl_ctx* c, const float* host, int32_t n) {
   if (!c || !host || n != c->L.P) return fail(CRL_ERR_INVALID, "crl_set_params: expected %d floats", c ? c->L.P : -1);
-  return copy_vec(c, c->params, host, 4 * (size_t)n, cudaMemcpyHostToDevice);
+  CKRC(use_device(c));
+  CK(cudaMemcpyAsync(c->params, host, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  {
+    KernelScope ks(c, CRL_K_OTHER);
+    CK(launch_param_image(c->cfg.env_kind, c->params, c->image, c->stream));  // keep the staging image in sync
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return CRL_OK;
 }
 extern "C" CRL_API int crl_get_params(crl_ctx* c, float* host, int32_t n) {
   if (!c || !host || n != c->L.P) return fail(CRL_ERR_INVALID, "crl_get_params: expected %d floats", c ? c->L.P : -1);
@@ -491,7 +499,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   const bool local_stats = (c->cfg.flags & CRL_FLAG_LOCAL_STATS) != 0;
   if (multi && !c->comm) return fail(CRL_ERR_STATE, "world_size > 1 but crl_comm_init was not called");
   UpdateArgs ua;
-  ua.env_kind = c->cfg.env_kind; ua.params = c->params; ua.idx = ix; ua.M = M;
+  ua.env_kind = c->cfg.env_kind; ua.params = c->params; ua.image = c->image; ua.idx = ix; ua.M = M;
   ua.states = c->state; ua.actions = c->action; ua.logprobs = c->logprob; ua.advantages = c->advantage;
   ua.returns = c->ret; ua.values = c->value;
   ua.clip_coef = c->cfg.clip_coef; ua.ent_coeff = c->cfg.ent_coeff; ua.v_coef = c->cfg.v_coef;
@@ -547,7 +555,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   }
   }  // multi
   AdamArgs aa;
-  aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.gsum = c->gsum; aa.gf = nullptr;
+  aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
   aa.grad_scale = (multi && local_stats) ? 1.0 / c->cfg.world_size : 1.0;
   aa.stat_ranks = (multi && local_stats) ? (double)c->cfg.world_size : 1.0;
   aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v; aa.beta_pow = c->beta_pow; aa.ds = c->ds;
@@ -909,7 +917,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
     g_raw.device = dev; g_raw.M = M;
   }
   UpdateArgs ua;
-  ua.env_kind = env_kind; ua.params = params; ua.M = M;
+  ua.env_kind = env_kind; ua.params = params; ua.image = nullptr; ua.M = M;
   ua.idx.arr = idx; ua.idx.start = 0; ua.idx.B = (uint32_t)M; ua.idx.half_bits = 1; ua.idx.epoch = 0; ua.idx.rank = 0;
   ua.idx.seed = 0; ua.idx.ds = g_raw.ds;
   ua.states = states; ua.actions = actions; ua.logprobs = logprobs; ua.advantages = advantages; ua.returns = returns;
@@ -944,7 +952,7 @@ extern "C" CRL_API int crl_clip_adam_raw(int32_t env_kind, float* params, const 
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(need_sm100());
   AdamArgs aa;
-  aa.env_kind = env_kind; aa.params = params; aa.gsum = nullptr; aa.gf = grads; aa.grad_scale = 1.0; aa.stat_ranks = 1.0;
+  aa.env_kind = env_kind; aa.params = params; aa.image = nullptr; aa.gsum = nullptr; aa.gf = grads; aa.grad_scale = 1.0; aa.stat_ranks = 1.0;
   aa.grads_out = nullptr; aa.m = m; aa.v = v; aa.beta_pow = beta_pow; aa.ds = nullptr; aa.lr_host = lr;
   aa.clip_norm = clip_norm; aa.ent_coeff = 0.f; aa.v_coef = 0.f; aa.M_global = 1.0; aa.A = L.A; aa.stats_out = nullptr;
   CK(launch_clip_adam(aa, (cudaStream_t)stream));

@@ -70,6 +70,7 @@ struct AdvStatsArgs {
 struct UpdateArgs {
   int env_kind;
   const float* params;
+  const float* image;  // shared-memory image of the parameters (see param_image_floats) or nullptr
   IdxSrc idx;
   int M;  // local minibatch size
   // flattened rollout data (ppo.jl:184-189)
@@ -105,6 +106,7 @@ struct AdamArgs {
   const float* gf;     // [P] Float32 gradient (raw entry point)
   double grad_scale;   // 1, or 1/world with CRL_FLAG_LOCAL_STATS
   double stat_ranks;   // ranks whose loss sums were added into gsum[P..] when M_global is local
+  float* image;        // parameter image kept in sync with params (may be nullptr)
   float* grads_out;    // [P] un-clipped Float32 gradient (may be nullptr)
   float* m;
   float* v;
@@ -133,6 +135,10 @@ cudaError_t launch_gae(const float* values, const float* rewards, const uint8_t*
 
 int mb_stats_grid(int M, int sm_count);
 int loss_grad_grid(int M, int sm_count);
+// The parameter image is the exact shared-memory layout loss_grad wants (each net at a 16-byte aligned base,
+// then both W2 matrices transposed), kept in global memory so a CTA can stage it with one bulk async copy.
+int param_image_floats(int env_kind);
+cudaError_t launch_param_image(int env_kind, const float* params, float* image, cudaStream_t s);
 cudaError_t launch_adv_stats(const AdvStatsArgs& a, cudaStream_t s);
 cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);

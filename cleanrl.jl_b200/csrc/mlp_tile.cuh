@@ -75,11 +75,13 @@ __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float
                                            const float* __restrict__ bias, const float* __restrict__ in,
                                            float* __restrict__ out) {
   constexpr int TS = G::TS, NC = G::NC, SP = G::S_PAD;
-  float acc[TS][TS];
+  // accumulators are packed pairs along the sample axis so the inner product runs on Blackwell's packed
+  // FP32 pipe (fma.rn.f32x2 / FFMA2: two FMAs per lane per issued instruction)
+  float2 acc2[TS][TS / 2];
 #pragma unroll
   for (int j = 0; j < TS; j++)
 #pragma unroll
-    for (int s = 0; s < TS; s++) acc[j][s] = 0.0f;
+    for (int s = 0; s < TS / 2; s++) acc2[j][s] = make_float2(0.0f, 0.0f);
 #pragma unroll 4
   for (int k = 0; k < K; k++) {
     float4 w[NC], a[NC];
@@ -89,10 +91,21 @@ __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float
       a[c] = *reinterpret_cast<const float4*>(in + k * SP + (SWZ_IN ? (tc.sb[c] ^ act_swz(k)) : tc.sb[c]));
     }
 #pragma unroll
-    for (int j = 0; j < TS; j++)
+    for (int j = 0; j < TS; j++) {
+      const float wj = f4_get(w[j / 4], j % 4);
+      const float2 ww = make_float2(wj, wj);
 #pragma unroll
-      for (int s = 0; s < TS; s++) acc[j][s] = fmaf(f4_get(w[j / 4], j % 4), f4_get(a[s / 4], s % 4), acc[j][s]);
+      for (int c = 0; c < NC; c++) {
+        acc2[j][2 * c + 0] = __ffma2_rn(ww, make_float2(a[c].x, a[c].y), acc2[j][2 * c + 0]);
+        acc2[j][2 * c + 1] = __ffma2_rn(ww, make_float2(a[c].z, a[c].w), acc2[j][2 * c + 1]);
+      }
+    }
   }
+  float acc[TS][TS];
+#pragma unroll
+  for (int j = 0; j < TS; j++)
+#pragma unroll
+    for (int s = 0; s < TS / 2; s++) { acc[j][2 * s] = acc2[j][s].x; acc[j][2 * s + 1] = acc2[j][s].y; }
 #pragma unroll
   for (int j = 0; j < TS; j++) {
     const int row = tc.jb[j / 4] + (j % 4);

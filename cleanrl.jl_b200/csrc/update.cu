@@ -226,10 +226,75 @@ template <int ENV> struct LossSmem {
   static constexpr int DOUT = ZO + 3 * S;       // dz[A][S] then dv[S]
   static constexpr int KEYS = DOUT + 3 * S;
   static constexpr int RED = KEYS + 8;
-  static constexpr int FLOATS = RED + 32;
+  static constexpr int XIN = RED + 32;           // [2][S][4] raw states of the current / next tile (cp.async target)
+  static constexpr int SCAL = XIN + 2 * S * 4;   // [2][6][S] adv, old logprob, return, value, action (A <= 2 words)
+  static constexpr int FLOATS = SCAL + 2 * 6 * S;
   static constexpr size_t BYTES = FLOATS * sizeof(float);
   static_assert(BYTES <= 227 * 1024, "loss_grad shared memory exceeds 227 KB");
 };
+
+// flat parameter index -> position(s) in the parameter image
+template <int ENV> __device__ __forceinline__ void image_scatter(float* image, int flat, float v) {
+  using E = EnvTraits<ENV>;
+  using SPm = SmemParams<ENV>;
+  using NO = NetOff<E::D, 1>;
+  int net, within;
+  if (flat < E::NET_A) { net = 0; within = flat; image[SPm::ACTOR + within] = v; }
+  else if (flat < E::NET_A + E::NET_C) { net = 1; within = flat - E::NET_A; image[SPm::CRITIC + within] = v; }
+  else { image[SPm::LOGSTD + (flat - E::NET_A - E::NET_C)] = v; return; }
+  if (within >= NO::W2 && within < NO::W2 + CRL_H * CRL_H) {
+    const int e = within - NO::W2, j = e % CRL_H, k = e / CRL_H;  // Flux W2 is (out=j, in=k) at j + 64 k
+    image[SPm::SIZE + net * CRL_H * CRL_H + j * CRL_H + k] = v;
+  }
+}
+template <int ENV> __global__ void param_image_kernel(const float* params, float* image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < EnvTraits<ENV>::P) image_scatter<ENV>(image, i, params[i]);
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Asynchronous gather of one tile (128 samples by permuted index) into shared memory: the loads of tile i+1
+// are in flight while tile i runs its backward pass, so the random-access latency never stalls a barrier.
+template <int ENV>
+__device__ __forceinline__ void prefetch_tile(const UpdateArgs& a, const uint32_t* keys, int m0, float* xin, float* scal) {
+  using E = EnvTraits<ENV>;
+  constexpr int S = 128, D = E::D, A = E::A;
+  const int tid = threadIdx.x;
+  if (tid < S) {
+    const int m = m0 + tid;
+    float* x = xin + tid * 4;
+    if (m < a.M) {
+      const int b = sample_index(a.idx, keys, m);
+      if (D == 4) {
+        cp_async16(x, a.states + (long long)b * 4);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) cp_async4(x + k, a.states + (long long)b * D + k);
+        x[3] = 0.0f;
+      }
+      cp_async4(scal + 0 * S + tid, a.advantages + b);
+      cp_async4(scal + 1 * S + tid, a.logprobs + b);
+      cp_async4(scal + 2 * S + tid, a.returns + b);
+      cp_async4(scal + 3 * S + tid, a.values + b);
+#pragma unroll
+      for (int k = 0; k < A; k++)
+        cp_async4(scal + (4 + k) * S + tid, reinterpret_cast<const float*>(a.actions) + (E::CONT ? (long long)b * A + k : (long long)b));
+    } else {
+      *reinterpret_cast<float4*>(x) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 6; k++) scal[k * S + tid] = 0.0f;
+    }
+  }
+  cp_async_commit();
+}
 
 template <int ENV>
 __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a) {
@@ -252,14 +317,43 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   const ThreadCoord<G> tc;
   const int tid = threadIdx.x;
   if (a.fixup && !a.fin->need_fixup) return;  // speculation held: nothing to redo
+  float* xin = smem + SM::XIN;
+  float* scal = smem + SM::SCAL;
 
-  load_params<ENV>(a.params, sp);
   if (tid == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
   __syncthreads();
-  // W2T[net][j][k] = W2(j,k): the k-major operand of the dh1 = W2^T dz2 contraction
-  for (int i = tid; i < 2 * CRL_H * CRL_H; i += blockDim.x) {
-    const int net = i / (CRL_H * CRL_H), r = i % (CRL_H * CRL_H), j = r / CRL_H, k = r % CRL_H;
-    w2t[i] = sp[net_base<ENV>(net) + NO::W2 + k * CRL_H + j];
+  prefetch_tile<ENV>(a, keys, blockIdx.x * S, xin, scal);  // overlaps the parameter staging below
+  if (a.image) {
+    // one elected thread stages parameters + W2^T with bulk asynchronous copies (TMA engine, no registers);
+    // completion is signalled on an mbarrier by transaction bytes
+    constexpr uint32_t IMG_BYTES = (SmemParams<ENV>::SIZE + 2 * CRL_H * CRL_H) * 4;
+    constexpr uint32_t CHUNK = 16384;
+    __shared__ __align__(8) unsigned long long pbar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&pbar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(IMG_BYTES) : "memory");
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sp);
+      for (uint32_t off = 0; off < IMG_BYTES; off += CHUNK) {
+        const uint32_t n = IMG_BYTES - off < CHUNK ? IMG_BYTES - off : CHUNK;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(reinterpret_cast<const char*>(a.image) + off), "r"(n), "r"(bar) : "memory");
+      }
+    }
+    __syncthreads();  // the barrier object is initialised before anyone polls it
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(bar), "r"(0) : "memory");
+  } else {
+    load_params<ENV>(a.params, sp);
+    __syncthreads();
+    // W2T[net][j][k] = W2(j,k): the k-major operand of the dh1 = W2^T dz2 contraction
+    for (int i = tid; i < 2 * CRL_H * CRL_H; i += blockDim.x) {
+      const int net = i / (CRL_H * CRL_H), r = i % (CRL_H * CRL_H), j = r / CRL_H, k = r % CRL_H;
+      w2t[i] = sp[net_base<ENV>(net) + NO::W2 + k * CRL_H + j];
+    }
   }
   const bool spec = a.mode == LG_SPEC;
   float mean_f, std_f, s_f;
@@ -305,43 +399,39 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   const int w_jq = tid & 7;            // j rows jq + 8*i2
   const int w_kq = (tid & 127) >> 3;   // k rows kq + 16*i
 
+  int tile_no = 0;
   for (int m0 = blockIdx.x * S; m0 < a.M; m0 += gridDim.x * S) {
-    // ---- P0 gather (threads 0..127 own one sample each for the scalar phases)
+    // ---- P0: this tile's inputs were gathered asynchronously (prefetch_tile); unpack them
+    const int buf = tile_no & 1;
+    cp_async_wait_all();
+    __syncthreads();
     float s_adv = 0.0f, s_oldlp = 0.0f, s_R = 0.0f, s_V = 0.0f, s_actf[A];
     int s_act = 0;
     bool valid = false;
 #pragma unroll
     for (int k = 0; k < A; k++) s_actf[k] = 0.0f;
     if (tid < S) {
-      const int m = m0 + tid;
-      valid = m < a.M;
-      float x[D];
+      valid = m0 + tid < a.M;
+      const float4 x4 = *reinterpret_cast<const float4*>(xin + buf * S * 4 + tid * 4);
+      const float xk[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-      for (int k = 0; k < D; k++) x[k] = 0.0f;
-      if (valid) {
-        const int b = sample_index(a.idx, keys, m);
-        if (D == 4) {
-          const float4 v4 = reinterpret_cast<const float4*>(a.states)[b];
-          x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[D - 1] = v4.w;
-        } else {
+      for (int k = 0; k < D; k++) xs[k * SP + tid] = xk[k];
+      const float* sc = scal + buf * 6 * S;
+      s_adv = sc[0 * S + tid];
+      s_oldlp = sc[1 * S + tid];
+      s_R = sc[2 * S + tid];
+      s_V = sc[3 * S + tid];
+      if (E::CONT) {
 #pragma unroll
-          for (int k = 0; k < D; k++) x[k] = a.states[(long long)b * D + k];
-        }
-        s_adv = a.advantages[b];
-        s_oldlp = a.logprobs[b];
-        s_R = a.returns[b];
-        s_V = a.values[b];
-        if (E::CONT) {
-#pragma unroll
-          for (int k = 0; k < A; k++) s_actf[k] = reinterpret_cast<const float*>(a.actions)[(long long)b * A + k];
-        } else {
-          s_act = reinterpret_cast<const int32_t*>(a.actions)[b];
-        }
+        for (int k = 0; k < A; k++) s_actf[k] = sc[(4 + k) * S + tid];
+      } else {
+        s_act = __float_as_int(sc[4 * S + tid]);
       }
-#pragma unroll
-      for (int k = 0; k < D; k++) xs[k * SP + tid] = x[k];
     }
     __syncthreads();
+    // next tile's gather goes out now and lands while this tile computes
+    if (m0 + gridDim.x * S < a.M) prefetch_tile<ENV>(a, keys, m0 + gridDim.x * S, xin + (buf ^ 1) * S * 4, scal + (buf ^ 1) * 6 * S);
+    tile_no++;
     // ---- P1/P2 forward, both nets (logprob_actions ppo.jl:35 and critic ppo.jl:214)
     {
       const float* np = sp + net_base<ENV>(tc.net);
@@ -530,11 +620,12 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     {
       const float* h1b = h1 + w_net * CRL_H * SP;
       const float* d2b = h2 + w_net * CRL_H * SP;
-      float acc[4][8];
+      // packed FP32 (FFMA2): each accumulator pair holds the partial sums over the even / odd samples
+      float2 acc[4][8];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; j++) acc[i][j] = make_float2(0.0f, 0.0f);
 #pragma unroll 2
       for (int s = 0; s < S; s += 4) {
         float4 hk[4], dj[8];
@@ -546,16 +637,14 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         for (int i = 0; i < 4; i++)
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            acc[i][j] = fmaf(hk[i].x, dj[j].x, acc[i][j]);
-            acc[i][j] = fmaf(hk[i].y, dj[j].y, acc[i][j]);
-            acc[i][j] = fmaf(hk[i].z, dj[j].z, acc[i][j]);
-            acc[i][j] = fmaf(hk[i].w, dj[j].w, acc[i][j]);
+            acc[i][j] = __ffma2_rn(make_float2(hk[i].x, hk[i].y), make_float2(dj[j].x, dj[j].y), acc[i][j]);
+            acc[i][j] = __ffma2_rn(make_float2(hk[i].z, hk[i].w), make_float2(dj[j].z, dj[j].w), acc[i][j]);
           }
       }
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) gW2[i][j] += acc[i][j];
+        for (int j = 0; j < 8; j++) gW2[i][j] += acc[i][j].x + acc[i][j].y;
     }
     __syncthreads();
     // ---- P8 dz1 = (W2^T dz2) .* (1 - h1^2), in place over h1
@@ -804,7 +893,12 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
     a.v[o + k] = vt;
     const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - bp2)), eps);
     const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - bp1), den), lr);
-    a.params[o + k] = __fsub_rn(a.params[o + k], step);
+    const float pnew = __fsub_rn(a.params[o + k], step);
+    a.params[o + k] = pnew;
+    if (a.image) {
+      if (a.env_kind == CRL_ENV_CARTPOLE) image_scatter<CRL_ENV_CARTPOLE>(a.image, o + k, pnew);
+      else image_scatter<CRL_ENV_PENDULUM>(a.image, o + k, pnew);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -881,6 +975,17 @@ cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s) {
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s) {
   const int grid = (P + 4 + 63) / 64 + 1;  // + the verification block
   grad_reduce_kernel<<<grid, 256, 0, s>>>(a, P);
+  return cudaGetLastError();
+}
+
+int param_image_floats(int env_kind) {
+  return (env_kind == CRL_ENV_CARTPOLE ? SmemParams<CRL_ENV_CARTPOLE>::SIZE : SmemParams<CRL_ENV_PENDULUM>::SIZE) + 2 * CRL_H * CRL_H;
+}
+cudaError_t launch_param_image(int env_kind, const float* params, float* image, cudaStream_t s) {
+  if (env_kind == CRL_ENV_CARTPOLE)
+    param_image_kernel<CRL_ENV_CARTPOLE><<<(EnvTraits<CRL_ENV_CARTPOLE>::P + 255) / 256, 256, 0, s>>>(params, image);
+  else
+    param_image_kernel<CRL_ENV_PENDULUM><<<(EnvTraits<CRL_ENV_PENDULUM>::P + 255) / 256, 256, 0, s>>>(params, image);
   return cudaGetLastError();
 }
 
