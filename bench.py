@@ -308,7 +308,7 @@ def run_ours(args):
     h.close()
 
     # ---- e2e: the public ppo(config) call, wall clock as the reference defines it (ppo.jl:111,148)
-    e2e_updates = max(10, min(args.steps, 200))
+    e2e_updates = max(300, args.steps)  # long enough to amortise graph capture / NCCL warm-up inside the wall clock
     tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
     logger = Logger.make_logger("bench", to_terminal=False, to_tensorboard=True, log_dir=tmp) if rank == 0 else None
     pcfg2 = PPOConfig(total_timesteps=e2e_updates * B_local * world, num_steps=NUM_STEPS, num_envs=n_local * world,
@@ -319,7 +319,7 @@ def run_ours(args):
     e2e_s = parallel.max_over_ranks(res["elapsed_s"])
     e2e = {"value": res["global_step"] / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": res["h2d_bytes"] / res["num_updates"], "d2h_bytes_per_step": res["d2h_bytes"] / res["num_updates"],
-           "updates": res["num_updates"], "wall_s": e2e_s,
+           "updates": res["num_updates"], "wall_s": e2e_s, "host_s_rank0": res["host_s"],
            "note": "ppo(config) public API: parameter upload, per-update lr upload, per-update loss/episode statistics "
                    "read-back and logging inside the timed region; envs live on the device so there is no per-step input copy"}
     if logger:

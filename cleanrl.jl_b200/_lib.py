@@ -54,6 +54,7 @@ SIGNATURES = {
     "crl_comm_unique_id": (C.c_int, [V]),
     "crl_comm_init": (C.c_int, [V, V]),
     "crl_kernel_launches": (C.c_int, [V, V]),
+    "crl_spec_replays": (C.c_int, [V, V]),
     "crl_profile": (C.c_int, [V, I32]),
     "crl_profile_read": (C.c_int, [V, V, I32]),
     "crl_stream": (C.c_int, [V, V]),

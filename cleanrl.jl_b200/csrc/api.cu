@@ -122,6 +122,13 @@ struct crl_ctx {
   cudaEvent_t fetch_ev[2];
   uint64_t update_seq;            // number of crl_train_update calls so far
   double* lr_host;
+  // multi-GPU speculative updates: state snapshots for the (rare) exact replay
+  unsigned char* snap[2];
+  size_t snap_bytes;
+  int* flag_host[2];              // pinned copy of DevState.spec_failed per result slot
+  double lr_hist[2];
+  uint64_t validated_seq;         // updates [0, validated_seq) are known to be exact
+  uint64_t replays;               // speculative updates that had to be replayed exactly
   // graph
   cudaGraphExec_t graph_exec;
   uint64_t graph_kernels;
@@ -209,6 +216,7 @@ static int check_cfg(const crl_config* c) {
     return fail(CRL_ERR_INVALID, "num_envs*num_steps = %lld is not divisible by num_minibatches = %d", B, c->num_minibatches);
   if (B / c->num_minibatches < 2) return fail(CRL_ERR_INVALID, "minibatch size must be >= 2 (corrected std, ppo.jl:221)");
   if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) return fail(CRL_ERR_INVALID, "bad world_size/rank");
+  if (c->world_size > CRL_MAX_WORLD) return fail(CRL_ERR_INVALID, "world_size > %d is not supported", CRL_MAX_WORLD);
   if (c->gae_mode != CRL_GAE_REF_COMPAT && c->gae_mode != CRL_GAE_FIXED) return fail(CRL_ERR_INVALID, "bad gae_mode");
   return CRL_OK;
 }
@@ -258,7 +266,7 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
   A_(dalloc(&c->vnew, c->M)); A_(dalloc(&c->parts, c->sm_count)); A_(dalloc(&c->parts_send, 1));
   A_(dalloc(&c->parts_recv, cfg->world_size)); A_(dalloc(&c->fin, 1));
   A_(dalloc(&c->gpart, (size_t)c->sm_count * L.P)); A_(dalloc(&c->spart, (size_t)c->sm_count * 4));
-  A_(dalloc(&c->gsum, L.P + 4)); A_(dalloc(&c->mpart, c->sm_count));
+  A_(dalloc(&c->gsum, L.P + 4 + CRL_MAX_WORLD)); A_(dalloc(&c->mpart, c->sm_count));
   const size_t nmb = (size_t)std::max(1, cfg->update_epochs) * cfg->num_minibatches;
   A_(dalloc(&c->advparts, nmb * ADV_CHUNKS * 2));
   A_(dalloc(&c->stats_dev, nmb * 4)); A_(dalloc(&c->idx_dev, B)); A_(dalloc(&c->perm_dev, (size_t)std::max(1, cfg->update_epochs) * B));
@@ -271,8 +279,13 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
       ok = ok && cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming) == cudaSuccess;
       if (ok) { memset(c->stats_host[i], 0, nmb * sizeof(crl_loss_stats)); memset(c->eb_host[i], 0, sizeof(EpisodeBuf)); }
     }
+    for (int i = 0; i < 2 && ok; i++) {
+      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&c->flag_host[i]), sizeof(int)) == cudaSuccess;
+      if (ok) *c->flag_host[i] = 0;
+    }
     if (!ok) { crl_destroy(c); return fail(CRL_ERR_CUDA, "pinned host allocation failed"); }
     c->update_seq = 0;
+    c->validated_seq = 0;
   }
 #undef A_
   // Flux keeps (β1, β2) as the initial power state of every array
@@ -301,6 +314,8 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
     if (c->stats_host[i]) cudaFreeHost(c->stats_host[i]);
     if (c->eb_host[i]) cudaFreeHost(c->eb_host[i]);
     if (c->fetch_ev[i]) cudaEventDestroy(c->fetch_ev[i]);
+    if (c->flag_host[i]) cudaFreeHost(c->flag_host[i]);
+    if (c->snap[i]) cudaFree(c->snap[i]);
   }
   if (c->lr_host) cudaFreeHost(c->lr_host);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -478,6 +493,33 @@ static IdxSrc idx_array(crl_ctx* c, const int32_t* arr) {
 
 // one minibatch: mb_stats -> [all-gather] -> mb_count -> [allreduce cnt] -> loss_grad -> grad_reduce
 // -> [allreduce grads] -> clip_adam. lr_host < 0 reads lr from DevState.
+// ---- snapshots (multi-GPU speculative path) ---------------------------------------------------------------
+struct SnapItem { void* ptr; size_t bytes; };
+static std::vector<SnapItem> snap_items(crl_ctx* c) {
+  const size_t P = c->L.P, N = c->N;
+  return {{c->params, 4 * P}, {c->image, 4 * (size_t)param_image_floats(c->cfg.env_kind)}, {c->adam_m, 4 * P},
+          {c->adam_v, 4 * P}, {c->beta_pow, 16 * (size_t)CRL_MAX_ARRAYS}, {c->env_state, 4 * N * c->L.S}, {c->env_t, 4 * N},
+          {c->ep_return, 8 * N}, {c->ep_length, 4 * N}, {c->reset_count, 4 * N}, {c->ds, sizeof(DevState)}};
+}
+static int snapshot_copy(crl_ctx* c, int slot, bool restore) {
+  size_t off = 0;
+  for (auto& it : snap_items(c)) {
+    const size_t b = (it.bytes + 15) & ~size_t(15);
+    if (restore) CK(cudaMemcpyAsync(it.ptr, c->snap[slot] + off, it.bytes, cudaMemcpyDeviceToDevice, c->stream));
+    else CK(cudaMemcpyAsync(c->snap[slot] + off, it.ptr, it.bytes, cudaMemcpyDeviceToDevice, c->stream));
+    off += b;
+  }
+  return CRL_OK;
+}
+static int snapshot_alloc(crl_ctx* c) {
+  if (c->snap[0]) return CRL_OK;
+  size_t tot = 0;
+  for (auto& it : snap_items(c)) tot += (it.bytes + 15) & ~size_t(15);
+  c->snap_bytes = tot;
+  for (int i = 0; i < 2; i++) CK(cudaMalloc(reinterpret_cast<void**>(&c->snap[i]), tot));
+  return CRL_OK;
+}
+
 static int enqueue_adv_stats(crl_ctx* c, const int32_t* arr_base, int M, int nmb, int n_sets) {
   AdvStatsArgs aa;
   aa.idx.arr = nullptr; aa.idx.start = 0; aa.idx.B = (uint32_t)c->B; aa.idx.half_bits = perm_half_bits((uint32_t)c->B);
@@ -494,7 +536,8 @@ static int enqueue_adv_stats(crl_ctx* c, const int32_t* arr_base, int M, int nmb
 //   speculation failed] -> clip_adam.   `set` indexes the advantage sums written by enqueue_adv_stats.
 // Multi GPU (exact global statistics): mb_stats -> all-gather -> mb_count -> allreduce(cnt) -> loss_grad(EXACT) ->
 //   grad_reduce -> allreduce(grads) -> clip_adam.          lr_host < 0 reads lr from DevState.
-static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host, double* stats_slot, int set) {
+static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host, double* stats_slot, int set,
+                             bool spec_multi = false) {
   const bool multi = c->cfg.world_size > 1;
   const bool local_stats = (c->cfg.flags & CRL_FLAG_LOCAL_STATS) != 0;
   if (multi && !c->comm) return fail(CRL_ERR_STATE, "world_size > 1 but crl_comm_init was not called");
@@ -509,6 +552,29 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.parts_in = c->parts; ua.n_parts_in = gs; ua.fin = c->fin; ua.world = 1;
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
   ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
+  ua.defer_verify = 0; ua.rank = c->cfg.rank;
+  if (spec_multi) {
+    // multi-GPU throughput path: speculative loss_grad with GLOBAL advantage statistics, then ONE sum-allreduce that
+    // carries gradient + loss sums + sum s + every rank's min; verify_kernel reaches the same verdict on all ranks
+    const int W = c->cfg.world_size;
+    ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
+    { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
+    { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
+    {
+      KernelScope ks(c, CRL_K_ALLREDUCE, false);
+      CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4 + W, ncclFloat64, ncclSum, c->comm, c->stream));
+    }
+    { KernelScope ks(c, CRL_K_OTHER); CK(launch_verify(ua, c->L.P, c->ds, c->stream)); }
+    AdamArgs aa;
+    aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
+    aa.grad_scale = 1.0; aa.stat_ranks = 1.0; aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v;
+    aa.beta_pow = c->beta_pow; aa.ds = c->ds; aa.lr_host = lr_host; aa.clip_norm = c->cfg.clip_norm;
+    aa.ent_coeff = c->cfg.ent_coeff; aa.v_coef = c->cfg.v_coef; aa.M_global = (double)M * W; aa.A = c->L.A;
+    aa.stats_out = stats_slot;
+    KernelScope ks(c, CRL_K_CLIP_ADAM);
+    CK(launch_clip_adam(aa, c->stream));
+    return CRL_OK;
+  }
   const bool exchange = multi && !local_stats;
   if (exchange) { ua.parts_in = c->parts_recv; ua.n_parts_in = c->cfg.world_size; ua.world = c->cfg.world_size; }
   if (!multi) {
@@ -590,14 +656,18 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
   return CRL_OK;
 }
 
-static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host) {
+static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, bool spec_multi = false) {
   int k = 0;
-  if (c->cfg.world_size == 1)
-    CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, c->cfg.update_epochs * c->cfg.num_minibatches));
+  const int n_sets = c->cfg.update_epochs * c->cfg.num_minibatches;
+  if (c->cfg.world_size == 1 || spec_multi) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
+  if (spec_multi) {  // global advantage sums for all minibatches of the update: one collective per update
+    KernelScope ks(c, CRL_K_ALLREDUCE, false);
+    CKN(g_nccl.AllReduce(c->advparts, c->advparts, (size_t)n_sets * ADV_CHUNKS * 2, ncclFloat64, ncclSum, c->comm, c->stream));
+  }
   for (int e = 0; e < c->cfg.update_epochs; e++) {  // ppo.jl:193
     for (int start = 0; start < c->B; start += c->M) {  // ppo.jl:197
       IdxSrc ix = perm_dev ? idx_array(c, perm_dev + (size_t)e * c->B + start) : idx_perm(c, e, start);
-      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k, k));
+      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k, k, spec_multi));
       k++;
     }
   }
@@ -637,10 +707,10 @@ extern "C" CRL_API int crl_device_permutation(crl_ctx* c, int64_t update_index, 
 }
 
 // the body of one PPO update with device RNG (what the CUDA graph captures)
-static int enqueue_train_update(crl_ctx* c) {
+static int enqueue_train_update(crl_ctx* c, bool spec_multi) {
   CKRC(enqueue_rollout(c, nullptr, nullptr));
   CKRC(enqueue_gae(c));
-  CKRC(enqueue_epochs(c, nullptr, -1.0));
+  CKRC(enqueue_epochs(c, nullptr, -1.0, spec_multi));
   {
     KernelScope ks(c, CRL_K_OTHER);
     CK(launch_advance(c->ds, (unsigned long long)c->T, 1ull, c->stream));
@@ -648,22 +718,29 @@ static int enqueue_train_update(crl_ctx* c) {
   return CRL_OK;
 }
 
-extern "C" CRL_API int crl_train_update(crl_ctx* c, double lr) {
-  if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
-  if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
-  CKRC(use_device(c));
-  *c->lr_host = lr;
-  CK(cudaMemcpyAsync(&c->ds->lr, c->lr_host, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  const bool use_graph = !c->profiling && getenv("CRL_NO_GRAPH") == nullptr;
+static bool multi_speculative(const crl_ctx* c) {
+  return c->cfg.world_size > 1 && !(c->cfg.flags & CRL_FLAG_LOCAL_STATS) && getenv("CRL_MULTI_EXACT") == nullptr;
+}
+
+// enqueue one update into result slot `slot`. exact = true forces the non-speculative multi-GPU sequence (replay).
+static int run_update(crl_ctx* c, double lr, int slot, bool exact) {
+  const bool spec_multi = multi_speculative(c) && !exact;
+  if (spec_multi) {
+    CKRC(snapshot_alloc(c));
+    CKRC(snapshot_copy(c, slot, false));  // state BEFORE the update, for the (rare) exact replay
+  }
+  c->lr_hist[slot] = lr;
+  c->lr_host[slot] = lr;
+  CK(cudaMemcpyAsync(&c->ds->lr, c->lr_host + slot, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const bool use_graph = !exact && !c->profiling && getenv("CRL_NO_GRAPH") == nullptr;
   if (!use_graph) {
-    CKRC(enqueue_train_update(c));
+    CKRC(enqueue_train_update(c, spec_multi));
   } else {
     if (!c->graph_exec) {
-      // warm the lazily-initialised function attributes outside capture
       const uint64_t before = c->launches;
       cudaGraph_t graph = nullptr;
       CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_train_update(c);
+      int rc = enqueue_train_update(c, spec_multi);
       cudaError_t ee = cudaStreamEndCapture(c->stream, &graph);
       if (rc != CRL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
       if (ee != cudaSuccess) return fail(CRL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
@@ -676,17 +753,48 @@ extern "C" CRL_API int crl_train_update(crl_ctx* c, double lr) {
     CK(cudaGraphLaunch(c->graph_exec, c->stream));
     c->launches += c->graph_kernels;
   }
-  {
-    // results of this update -> pinned slot (update_seq & 1); the event lets the host fetch update u-1
-    // while update u is still running (crl_fetch_update_at with lag = 1)
-    const int slot = (int)(c->update_seq & 1);
-    const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
-    static_assert(sizeof(crl_loss_stats) == 4 * sizeof(double), "crl_loss_stats must be 4 doubles");
-    if (nmb) CK(cudaMemcpyAsync(c->stats_host[slot], c->stats_dev, nmb * sizeof(crl_loss_stats), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->eb_host[slot], c->eb, sizeof(EpisodeBuf), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(c->fetch_ev[slot], c->stream));
-    c->update_seq += 1;
+  // results of this update -> pinned slot; the event lets the host fetch update u-1 while update u is still
+  // running (crl_fetch_update_at with lag = 1)
+  const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
+  static_assert(sizeof(crl_loss_stats) == 4 * sizeof(double), "crl_loss_stats must be 4 doubles");
+  if (nmb) CK(cudaMemcpyAsync(c->stats_host[slot], c->stats_dev, nmb * sizeof(crl_loss_stats), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->eb_host[slot], c->eb, sizeof(EpisodeBuf), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->flag_host[slot], &c->ds->spec_failed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemsetAsync(&c->ds->spec_failed, 0, sizeof(int), c->stream));
+  CK(cudaEventRecord(c->fetch_ev[slot], c->stream));
+  return CRL_OK;
+}
+
+// Make sure every update with index <= upto is exact. A speculative multi-GPU update whose verification failed
+// (identically on every rank) is repaired here: wait for the stream, restore the snapshot taken before that update
+// and replay it -- and anything enqueued after it -- with the exact statistics-exchange sequence.
+static int validate_updates(crl_ctx* c, uint64_t upto) {
+  while (c->validated_seq <= upto && c->validated_seq < c->update_seq) {
+    const uint64_t u = c->validated_seq;
+    const int slot = (int)(u & 1);
+    CK(cudaEventSynchronize(c->fetch_ev[slot]));
+    if (multi_speculative(c) && *c->flag_host[slot]) {
+      CK(cudaStreamSynchronize(c->stream));
+      c->replays += 1;
+      CKRC(snapshot_copy(c, slot, true));
+      for (uint64_t r = u; r < c->update_seq; r++) CKRC(run_update(c, c->lr_hist[r & 1], (int)(r & 1), true));
+      CK(cudaStreamSynchronize(c->stream));
+      c->validated_seq = c->update_seq;
+      return CRL_OK;
+    }
+    c->validated_seq = u + 1;
   }
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_train_update(crl_ctx* c, double lr) {
+  if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
+  if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
+  CKRC(use_device(c));
+  // the result slot (and snapshot) about to be reused belongs to update seq-2: it must be validated first
+  if (c->update_seq >= 2) CKRC(validate_updates(c, c->update_seq - 2));
+  CKRC(run_update(c, lr, (int)(c->update_seq & 1), false));
+  c->update_seq += 1;
   c->rolled = true;
   c->gae_done = true;
   c->have_update = true;
@@ -698,7 +806,9 @@ extern "C" CRL_API int crl_fetch_update_at(crl_ctx* c, int32_t lag, crl_loss_sta
   if (lag < 0 || lag > 1) return fail(CRL_ERR_INVALID, "lag must be 0 (latest update) or 1 (the one before)");
   if (!c->have_update || c->update_seq < (uint64_t)lag + 1) return fail(CRL_ERR_STATE, "no such update has been enqueued yet");
   CKRC(use_device(c));
-  const int slot = (int)((c->update_seq - 1 - (uint64_t)lag) & 1);
+  const uint64_t target = c->update_seq - 1 - (uint64_t)lag;
+  CKRC(validate_updates(c, target));
+  const int slot = (int)(target & 1);
   CK(cudaEventSynchronize(c->fetch_ev[slot]));
   const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
   if (stats && nmb) memcpy(stats, c->stats_host[slot], nmb * sizeof(crl_loss_stats));
@@ -801,6 +911,11 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   CKN(g_nccl.CommInitRank(&c->comm, c->cfg.world_size, id, c->cfg.rank));
+  // NCCL connects its channels lazily on the first collective: do that here (set-up time), not inside the first update
+  CK(cudaMemsetAsync(c->gsum, 0, sizeof(double) * 8, c->stream));
+  CKN(g_nccl.AllReduce(c->gsum, c->gsum, 8, ncclFloat64, ncclSum, c->comm, c->stream));
+  CKN(g_nccl.AllGather(c->parts_send, c->parts_recv, sizeof(MbScalars), ncclChar, c->comm, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return CRL_OK;
 }
 
@@ -808,6 +923,11 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
 extern "C" CRL_API int crl_kernel_launches(const crl_ctx* c, uint64_t* count) {
   if (!c || !count) return fail(CRL_ERR_INVALID, "NULL argument");
   *count = c->launches;
+  return CRL_OK;
+}
+extern "C" CRL_API int crl_spec_replays(const crl_ctx* c, uint64_t* count) {
+  if (!c || !count) return fail(CRL_ERR_INVALID, "NULL argument");
+  *count = c->replays;
   return CRL_OK;
 }
 extern "C" CRL_API int crl_profile(crl_ctx* c, int32_t enable) {

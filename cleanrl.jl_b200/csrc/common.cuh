@@ -64,6 +64,8 @@ struct DevState {
   unsigned long long policy_step;   // global policy step (Philox action stream counter)
   unsigned long long update_index;  // PPO update counter (Philox permutation stream)
   double lr;                        // opt.eta for the current update (ppo.jl:120)
+  int spec_failed;                  // multi-GPU: a speculative minibatch failed verification during this update
+  int _pad;
 };
 
 // per-rollout episode bookkeeping (device)

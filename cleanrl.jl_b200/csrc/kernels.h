@@ -97,7 +97,10 @@ struct UpdateArgs {
   int fixup;             // 1: this launch is the verification re-run; exits at once unless fin->need_fixup
   const double* advparts;  // [ADV_CHUNKS][2] of this minibatch (LG_SPEC)
   float* mpart;          // [grid] per-CTA min (clip_i - R_i)^2 (LG_SPEC)
+  int defer_verify;      // multi-GPU: grad_reduce only packs (sum s, per-rank min) behind the gradient; verify_kernel
+  int rank;              //            checks the speculation after the allreduce
 };
+#define CRL_MAX_WORLD 16
 
 struct AdamArgs {
   int env_kind;
@@ -145,6 +148,7 @@ cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);
+cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, cudaStream_t s);
 cudaError_t launch_loss_finalize(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
                                  float v_coef, double* stats_out, cudaStream_t s);
 cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cudaStream_t s);

@@ -756,6 +756,14 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
     mn = warp_min(mn);
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; mred[threadIdx.x >> 5] = mn; }
     __syncthreads();
+    if (threadIdx.x == 0 && a.defer_verify) {
+      // multi-GPU: this rank's min rides behind the gradient in its own slot (the other ranks add 0 there),
+      // so ONE sum-allreduce delivers gradient, loss sums, sum s and every rank's min
+      float m8 = mred[0];
+      for (int w = 0; w < 8; w++) m8 = fminf(m8, mred[w]);
+      for (int r = 0; r < a.world; r++) a.gsum[P + 4 + r] = (r == a.rank) ? (double)m8 : 0.0;
+      return;
+    }
     if (threadIdx.x == 0) {
       double tot = 0.0;
       float m8 = mred[0];
@@ -784,6 +792,19 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   sh[g][el] = s;
   __syncthreads();
   if (g == 0 && e < P + 4) a.gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+}
+
+// multi-GPU: after the allreduce every rank holds the global sum s and all per-rank minima and reaches the same
+// verdict; a failed speculation is recorded in DevState and repaired by the host (snapshot + exact replay)
+__global__ void verify_kernel(UpdateArgs a, int P, DevState* ds) {
+  if (threadIdx.x != 0) return;
+  float m = INFINITY;
+  for (int r = 0; r < a.world; r++) m = fminf(m, (float)a.gsum[P + 4 + r]);
+  const double Mg = (double)a.M * (double)a.world;
+  const float s_f = (float)(a.gsum[P + 3] / Mg);
+  a.fin->s_unclipped = s_f; a.fin->min_vlc = m; a.fin->M_global = Mg; a.fin->cnt = 0ull;
+  a.fin->need_fixup = (s_f > m) ? 1 : 0;
+  if (s_f > m) ds->spec_failed = 1;
 }
 
 // advantage sums of every minibatch of an update in one launch: grid (ADV_CHUNKS, n_sets)
@@ -986,6 +1007,11 @@ cudaError_t launch_param_image(int env_kind, const float* params, float* image, 
     param_image_kernel<CRL_ENV_CARTPOLE><<<(EnvTraits<CRL_ENV_CARTPOLE>::P + 255) / 256, 256, 0, s>>>(params, image);
   else
     param_image_kernel<CRL_ENV_PENDULUM><<<(EnvTraits<CRL_ENV_PENDULUM>::P + 255) / 256, 256, 0, s>>>(params, image);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, cudaStream_t s) {
+  verify_kernel<<<1, 32, 0, s>>>(a, P, ds);
   return cudaGetLastError();
 }
 

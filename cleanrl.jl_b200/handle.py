@@ -190,6 +190,11 @@ class PPOHandle:
         L.check(self.lib.crl_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def spec_replays(self):
+        n = C.c_uint64()
+        L.check(self.lib.crl_spec_replays(self.h, C.byref(n)))
+        return n.value
+
     def profile(self, enable):
         L.check(self.lib.crl_profile(self.h, 1 if enable else 0))
 

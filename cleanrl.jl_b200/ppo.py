@@ -102,6 +102,7 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
         rng = np.random.default_rng(config.seed + 7919 * rank)
 
         state = {"last_log_step": last_log_step, "episodes": 0, "ret_sum": 0.0, "d2h": 0, "last_stats": None}
+        host = {"enqueue_s": 0.0, "fetch_s": 0.0, "log_s": 0.0}  # where the host thread spends its time
 
         def log_update(stats, agg, gs):
             """records of one finished update (rank 0): aggregated episodes + one record per minibatch"""
@@ -109,6 +110,7 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
             state["last_stats"] = stats
             if rank != 0:
                 return
+            t_log = time.perf_counter()
             if agg is not None and agg.count > 0:
                 # throughput mode: one aggregated "Episode Statistics" record per rollout
                 steps_per_sec = np.trunc(gs / max(time.time() - start_time, 1e-9))   # ppo.jl:148
@@ -124,6 +126,7 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
                 logger.info("Training Statistics", loss=row[0], pg_loss=row[1], v_loss=row[2],
                             entropy_loss=row[3], log_step_increment=inc)
                 state["last_log_step"] = gs
+            host["log_s"] += time.perf_counter() - t_log
 
         pending = None  # (update, global_step) of the update whose results have not been logged yet
         for update in range(1, num_updates_run + 1):  # ppo.jl:117
@@ -157,11 +160,15 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
             else:
                 # throughput path: the whole update is one asynchronous CUDA-graph launch; the host logs
                 # update u-1 (double-buffered results) while the GPU runs update u
+                t0 = time.perf_counter()
                 h.train_update(lr_now)
+                t1 = time.perf_counter()
+                host["enqueue_s"] += t1 - t0
                 global_step += config.num_steps * nt
                 h2d_bytes += 8
                 if pending is not None:
                     stats, agg = h.fetch_update(lag=1)
+                    host["fetch_s"] += time.perf_counter() - t1
                     log_update(stats, agg, pending[1])
                     if on_update is not None:
                         on_update(pending[0], h, stats, agg)
@@ -179,7 +186,7 @@ def ppo(config=PPOConfig(), *, logger=None, initial_params=None, on_update=None,
             "steps_per_sec": global_step / max(elapsed, 1e-9), "last_stats": last_stats,
             "episodes": int(episodes), "mean_episode_return": (ret_sum / episodes) if episodes else float("nan"),
             "params": h.get_params(), "kernel_launches": h.kernel_launches(),
-            "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes,
+            "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes, "host_s": host,
         }
     finally:
         h.close()

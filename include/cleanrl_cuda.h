@@ -235,6 +235,9 @@ CRL_API int crl_comm_init(crl_ctx* ctx, const void* id128);   /* all ranks, coll
 
 /* ---- instrumentation -------------------------------------------------------------- */
 CRL_API int crl_kernel_launches(const crl_ctx* ctx, uint64_t* count); /* kernels launched so far */
+/* multi-GPU: number of speculative updates whose on-device verification failed and that were replayed with the
+ * exact statistics-exchange sequence (results are exact either way; this is a performance counter) */
+CRL_API int crl_spec_replays(const crl_ctx* ctx, uint64_t* count);
 CRL_API int crl_profile(crl_ctx* ctx, int32_t enable);  /* per-kernel CUDA-event timing on/off (disables graphs) */
 CRL_API int crl_profile_read(crl_ctx* ctx, crl_kernel_times* out, int32_t reset);
 CRL_API int crl_stream(const crl_ctx* ctx, void** cuda_stream);

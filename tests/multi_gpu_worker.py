@@ -88,17 +88,46 @@ def main():
                 "param_maxerr": float(np.max(np.abs(gathered[0]["params"] - p_o) / (np.abs(p_o) + 1e-2))),
                 "stats_maxerr": float(np.max(np.abs(np.array(st_o) - gathered[0]["stats"]) / (np.abs(np.array(st_o)) + 1e-3))),
             }
-        # graph path with collectives inside, twice
-        h.train_update(lr)
-        h.train_update(lr)
-        st, agg = h.fetch_update()
-        pa = h.get_params()
-        g2 = [None] * world
-        dist.all_gather_object(g2, pa)
-        if rank == 0:
-            res["kind%d" % kind]["graph_ranks_agree"] = bool(all(np.array_equal(x, g2[0]) for x in g2))
-            res["kind%d" % kind]["graph_finite"] = bool(np.all(np.isfinite(st)))
         h.close()
+        # throughput path (CUDA graph, speculative loss_grad + ONE allreduce per minibatch) against the exact
+        # statistics-exchange path, from identical starting states. scenario "fail": gamma = lambda = 0 and a critic
+        # bias of 1.5 make s = mean(v - R^2) win the max (Q5), so the on-device verification fails and the host
+        # replays the update exactly: the results must then be BIT-identical to the exact path.
+        for scenario in ("normal", "fail"):
+            kw = dict(gamma=0.0, gae_lambda=0.0) if scenario == "fail" else {}
+            p2 = p.copy()
+            if scenario == "fail":
+                p2[olib.param_layout(kind)[0][11]] = 1.5
+            outs = {}
+            for mode in ("spec", "exact"):
+                cfg2 = _abi.make_config(env_kind=kind, num_envs=n_local, num_steps=T, num_minibatches=mb, update_epochs=epochs,
+                                        seed=seed, device=local_rank, world_size=world, rank=rank, env_id_base=base, **kw)
+                h2 = PPOHandle(cfg2)
+                h2.comm_init(parallel.exchange_unique_id(comm_unique_id))
+                h2.set_params(p2)
+                h2.env_reset()
+                if mode == "exact":
+                    os.environ["CRL_MULTI_EXACT"] = "1"
+                for u in range(3):
+                    h2.train_update(lr)
+                    if u >= 1:
+                        h2.fetch_update(lag=1)
+                st2, agg2 = h2.fetch_update()
+                os.environ.pop("CRL_MULTI_EXACT", None)
+                outs[mode] = (h2.get_params(), st2, h2.spec_replays())
+                h2.close()
+            g2 = [None] * world
+            dist.all_gather_object(g2, outs["spec"][0])
+            if rank == 0:
+                ps, pe = outs["spec"][0], outs["exact"][0]
+                res["kind%d" % kind][scenario] = {
+                    "ranks_agree": bool(all(np.array_equal(x, g2[0]) for x in g2)),
+                    "finite": bool(np.all(np.isfinite(outs["spec"][1]))),
+                    "replays": int(outs["spec"][2]), "replays_exact_mode": int(outs["exact"][2]),
+                    "bit_identical": bool(np.array_equal(ps, pe)),
+                    "maxerr": float(np.max(np.abs(ps - pe) / (np.abs(pe) + 1e-2))),
+                    "stats_maxerr": float(np.max(np.abs(outs["spec"][1] - outs["exact"][1]) / (np.abs(outs["exact"][1]) + 1e-3))),
+                }
     if rank == 0:
         json.dump(res, open(out_path, "w"))
     dist.barrier()

@@ -26,4 +26,14 @@ def test_two_gpu_sharded_update_matches_single_process_oracle(tmp_path, torch_cu
         assert r["ranks_agree"], r            # replicated parameters stay bit-identical across ranks
         assert r["param_maxerr"] < 2e-5, r    # post-step parameters vs the oracle on the union minibatches
         assert r["stats_maxerr"] < 1e-4, r
-        assert r["graph_ranks_agree"] and r["graph_finite"], r
+        n, f = r["normal"], r["fail"]
+        assert n["ranks_agree"] and n["finite"] and n["replays"] == 0, n
+        assert n["maxerr"] < 2e-5 and n["stats_maxerr"] < 1e-4, n      # speculative == exact within fp32 tolerance
+        assert f["ranks_agree"] and f["finite"] and f["replays_exact_mode"] == 0, (kind, f)
+        if kind == "kind0":
+            # CartPole with gamma = 0: R in {0, 1, v} so s = mean(v - R^2) > min (clip - R)^2 = 0: verification fails
+            assert f["replays"] >= 1, (kind, f)
+        if f["replays"] >= 1:
+            assert f["bit_identical"], (kind, f)                        # a failed speculation is replayed exactly
+        else:
+            assert f["maxerr"] < 2e-5, (kind, f)
