@@ -134,6 +134,15 @@ struct crl_ctx {
   uint64_t graph_kernels;
   // nccl
   ncclComm_t comm;
+  // peer-memory (NVLink) exchange for the per-minibatch gradient allreduce
+  unsigned char* p2p_buf;          // own exchange buffer (cudaMalloc, exported with cudaIpc)
+  unsigned char* p2p_peer[CRL_MAX_WORLD];
+  unsigned char** p2p_peers_dev;
+  unsigned long long* p2p_seq;
+  int* p2p_err;
+  int p2p_stride;
+  size_t p2p_flags_off;
+  bool p2p_on;
   // instrumentation
   uint64_t launches;
   bool profiling;
@@ -280,8 +289,8 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
       if (ok) { memset(c->stats_host[i], 0, nmb * sizeof(crl_loss_stats)); memset(c->eb_host[i], 0, sizeof(EpisodeBuf)); }
     }
     for (int i = 0; i < 2 && ok; i++) {
-      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&c->flag_host[i]), sizeof(int)) == cudaSuccess;
-      if (ok) *c->flag_host[i] = 0;
+      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&c->flag_host[i]), 2 * sizeof(int)) == cudaSuccess;
+      if (ok) { c->flag_host[i][0] = 0; c->flag_host[i][1] = 0; }
     }
     if (!ok) { crl_destroy(c); return fail(CRL_ERR_CUDA, "pinned host allocation failed"); }
     c->update_seq = 0;
@@ -302,6 +311,9 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (int r = 0; r < CRL_MAX_WORLD; r++)
+    if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_buf) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+  { void* pp[] = {c->p2p_buf, c->p2p_peers_dev, c->p2p_seq, c->p2p_err}; for (void* q : pp) if (q) cudaFree(q); }
   for (auto& p : c->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {c->image, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
@@ -552,19 +564,26 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.parts_in = c->parts; ua.n_parts_in = gs; ua.fin = c->fin; ua.world = 1;
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
   ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
-  ua.defer_verify = 0; ua.rank = c->cfg.rank;
+  ua.defer_verify = 0; ua.rank = c->cfg.rank; ua.p2p_data = nullptr; ua.p2p_stride = 0; ua.p2p_seq = nullptr;
   if (spec_multi) {
     // multi-GPU throughput path: speculative loss_grad with GLOBAL advantage statistics, then ONE sum-allreduce that
     // carries gradient + loss sums + sum s + every rank's min; verify_kernel reaches the same verdict on all ranks
     const int W = c->cfg.world_size;
     ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
+    if (c->p2p_on) { ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq; }
     { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
     { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
-    {
+    if (c->p2p_on) {
+      P2PArgs pa;
+      pa.peers = c->p2p_peers_dev; pa.seq = c->p2p_seq; pa.error = c->p2p_err; pa.out = c->gsum;
+      pa.n = c->L.P + 4 + W; pa.stride = c->p2p_stride; pa.world = W; pa.rank = c->cfg.rank; pa.flags_offset = c->p2p_flags_off;
+      KernelScope ks(c, CRL_K_ALLREDUCE);
+      CK(launch_p2p_allreduce(pa, c->stream));
+    } else {
       KernelScope ks(c, CRL_K_ALLREDUCE, false);
       CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4 + W, ncclFloat64, ncclSum, c->comm, c->stream));
     }
-    { KernelScope ks(c, CRL_K_OTHER); CK(launch_verify(ua, c->L.P, c->ds, c->stream)); }
+    { KernelScope ks(c, CRL_K_OTHER); CK(launch_verify(ua, c->L.P, c->ds, c->p2p_on ? c->p2p_seq : nullptr, c->stream)); }
     AdamArgs aa;
     aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
     aa.grad_scale = 1.0; aa.stat_ranks = 1.0; aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v;
@@ -760,6 +779,7 @@ static int run_update(crl_ctx* c, double lr, int slot, bool exact) {
   if (nmb) CK(cudaMemcpyAsync(c->stats_host[slot], c->stats_dev, nmb * sizeof(crl_loss_stats), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(c->eb_host[slot], c->eb, sizeof(EpisodeBuf), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(c->flag_host[slot], &c->ds->spec_failed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->p2p_on) CK(cudaMemcpyAsync(c->flag_host[slot] + 1, c->p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemsetAsync(&c->ds->spec_failed, 0, sizeof(int), c->stream));
   CK(cudaEventRecord(c->fetch_ev[slot], c->stream));
   return CRL_OK;
@@ -773,7 +793,7 @@ static int validate_updates(crl_ctx* c, uint64_t upto) {
     const uint64_t u = c->validated_seq;
     const int slot = (int)(u & 1);
     CK(cudaEventSynchronize(c->fetch_ev[slot]));
-    if (multi_speculative(c) && *c->flag_host[slot]) {
+    if (multi_speculative(c) && c->flag_host[slot][0]) {
       CK(cudaStreamSynchronize(c->stream));
       c->replays += 1;
       CKRC(snapshot_copy(c, slot, true));
@@ -808,6 +828,8 @@ extern "C" CRL_API int crl_fetch_update_at(crl_ctx* c, int32_t lag, crl_loss_sta
   CKRC(use_device(c));
   const uint64_t target = c->update_seq - 1 - (uint64_t)lag;
   CKRC(validate_updates(c, target));
+  if (c->p2p_on && (c->flag_host[0][1] || c->flag_host[1][1]))
+    return fail(CRL_ERR_NCCL, "peer-memory allreduce timed out waiting for another rank");
   const int slot = (int)(target & 1);
   CK(cudaEventSynchronize(c->fetch_ev[slot]));
   const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
@@ -916,6 +938,45 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
   CKN(g_nccl.AllReduce(c->gsum, c->gsum, 8, ncclFloat64, ncclSum, c->comm, c->stream));
   CKN(g_nccl.AllGather(c->parts_send, c->parts_recv, sizeof(MbScalars), ncclChar, c->comm, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (getenv("CRL_NO_P2P") == nullptr) {
+    // peer-memory exchange buffers: every rank exports its buffer with cudaIpc, the handles travel through one
+    // NCCL all-gather, and each rank maps all peers (NVLink P2P). Any failure leaves the NCCL path in place.
+    const int W = c->cfg.world_size;
+    c->p2p_stride = (c->L.P + 4 + CRL_MAX_WORLD + 1) & ~1;
+    c->p2p_flags_off = (size_t)2 * c->p2p_stride * sizeof(double);
+    const size_t bytes = c->p2p_flags_off + CRL_MAX_WORLD * sizeof(unsigned long long);
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&c->p2p_buf), bytes) == cudaSuccess &&
+              cudaMemset(c->p2p_buf, 0, bytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    ok = ok && cudaIpcGetMemHandle(&mine, c->p2p_buf) == cudaSuccess;
+    unsigned char* stage = nullptr;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&stage), (size_t)(W + 1) * sizeof(mine)) == cudaSuccess;
+    std::vector<cudaIpcMemHandle_t> all(W);
+    if (ok) {
+      ok = cudaMemcpy(stage, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && g_nccl.AllGather(stage, stage + sizeof(mine), sizeof(mine), ncclChar, c->comm, c->stream) == ncclSuccess;
+      ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+      ok = ok && cudaMemcpy(all.data(), stage + sizeof(mine), (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (stage) cudaFree(stage);
+    for (int r = 0; r < W && ok; r++) {
+      if (r == c->cfg.rank) { c->p2p_peer[r] = c->p2p_buf; continue; }
+      void* ptr = nullptr;
+      ok = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      c->p2p_peer[r] = static_cast<unsigned char*>(ptr);
+    }
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&c->p2p_peers_dev), CRL_MAX_WORLD * sizeof(void*)) == cudaSuccess;
+    ok = ok && cudaMemcpy(c->p2p_peers_dev, c->p2p_peer, CRL_MAX_WORLD * sizeof(void*), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && dalloc(&c->p2p_seq, 1) == CRL_OK && dalloc(&c->p2p_err, 1) == CRL_OK;
+    // all ranks must agree on using the peer path: one more collective carries the verdict
+    double verdict = ok ? 1.0 : 0.0;
+    CK(cudaMemcpy(c->gsum, &verdict, sizeof(double), cudaMemcpyHostToDevice));
+    CKN(g_nccl.AllReduce(c->gsum, c->gsum, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&verdict, c->gsum, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaGetLastError();  // clear any sticky-free error from a failed IPC attempt
+    c->p2p_on = verdict > W - 0.5;
+  }
   return CRL_OK;
 }
 
@@ -1051,6 +1112,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
   as.idx = ua.idx; as.arr_base = idx; as.B = M; as.M = M; as.nmb = 1; as.n_sets = 1; as.advantages = advantages;
   as.advparts = g_raw.advparts;
   ua.advparts = g_raw.advparts; ua.mpart = g_raw.mpart;
+  ua.defer_verify = 0; ua.rank = 0; ua.p2p_data = nullptr; ua.p2p_stride = 0; ua.p2p_seq = nullptr;
   CK(launch_adv_stats(as, s));
   ua.mode = LG_SPEC; ua.fixup = 0;
   CK(launch_loss_grad(ua, s));

@@ -99,6 +99,19 @@ struct UpdateArgs {
   float* mpart;          // [grid] per-CTA min (clip_i - R_i)^2 (LG_SPEC)
   int defer_verify;      // multi-GPU: grad_reduce only packs (sum s, per-rank min) behind the gradient; verify_kernel
   int rank;              //            checks the speculation after the allreduce
+  // peer-memory allreduce (NVLink/NVSwitch): grad_reduce writes into this rank's exchange slot instead of gsum
+  double* p2p_data;                     // own exchange buffer: [2 slots][p2p_stride doubles]
+  int p2p_stride;
+  const unsigned long long* p2p_seq;    // device counter of completed exchanges (slot = (seq + 1) & 1)
+};
+
+struct P2PArgs {
+  unsigned char* const* peers;          // device array [world] of every rank's exchange buffer (IPC-mapped)
+  unsigned long long* seq;              // this rank's exchange counter (advanced by verify_kernel)
+  int* error;                           // set if a peer did not arrive in time
+  double* out;                          // local result buffer (gsum)
+  int n, stride, world, rank;
+  size_t flags_offset;                  // byte offset of the arrival flags inside an exchange buffer
 };
 #define CRL_MAX_WORLD 16
 
@@ -148,7 +161,8 @@ cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);
-cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, cudaStream_t s);
+cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, unsigned long long* p2p_seq, cudaStream_t s);
+cudaError_t launch_p2p_allreduce(const P2PArgs& a, cudaStream_t s);
 cudaError_t launch_loss_finalize(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
                                  float v_coef, double* stats_out, cudaStream_t s);
 cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cudaStream_t s);

@@ -745,6 +745,8 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   __shared__ double sh[4][64];
   if (a.fixup && !a.fin->need_fixup) return;
   const int grid = a.grid_loss;
+  // with the peer-memory allreduce the sums go straight into this rank's exchange slot
+  double* gsum = a.p2p_data ? a.p2p_data + (size_t)((*a.p2p_seq + 1ull) & 1ull) * a.p2p_stride : a.gsum;
   if (blockIdx.x == gridDim.x - 1) {
     if (a.mode != LG_SPEC || a.fixup) return;
     __shared__ double red[8];
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
       // so ONE sum-allreduce delivers gradient, loss sums, sum s and every rank's min
       float m8 = mred[0];
       for (int w = 0; w < 8; w++) m8 = fminf(m8, mred[w]);
-      for (int r = 0; r < a.world; r++) a.gsum[P + 4 + r] = (r == a.rank) ? (double)m8 : 0.0;
+      for (int r = 0; r < a.world; r++) gsum[P + 4 + r] = (r == a.rank) ? (double)m8 : 0.0;
       return;
     }
     if (threadIdx.x == 0) {
@@ -791,13 +793,14 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   }
   sh[g][el] = s;
   __syncthreads();
-  if (g == 0 && e < P + 4) a.gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+  if (g == 0 && e < P + 4) gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
 }
 
 // multi-GPU: after the allreduce every rank holds the global sum s and all per-rank minima and reaches the same
 // verdict; a failed speculation is recorded in DevState and repaired by the host (snapshot + exact replay)
-__global__ void verify_kernel(UpdateArgs a, int P, DevState* ds) {
+__global__ void verify_kernel(UpdateArgs a, int P, DevState* ds, unsigned long long* p2p_seq) {
   if (threadIdx.x != 0) return;
+  if (p2p_seq) *p2p_seq += 1ull;  // the exchange that just completed
   float m = INFINITY;
   for (int r = 0; r < a.world; r++) m = fminf(m, (float)a.gsum[P + 4 + r]);
   const double Mg = (double)a.M * (double)a.world;
@@ -805,6 +808,43 @@ __global__ void verify_kernel(UpdateArgs a, int P, DevState* ds) {
   a.fin->s_unclipped = s_f; a.fin->min_vlc = m; a.fin->M_global = Mg; a.fin->cnt = 0ull;
   a.fin->need_fixup = (s_f > m) ? 1 : 0;
   if (s_f > m) ds->spec_failed = 1;
+}
+
+// One-shot allreduce over NVLink / NVSwitch peer memory (replaces the latency-bound NCCL call for the ~73 KB
+// gradient message). Every rank's partial vector already sits in its own exchange slot (written by grad_reduce).
+//   1. each rank pushes its arrival sequence number into every peer's flag array (system-scope store),
+//   2. every block spins on its LOCAL flags until all peers have arrived (no polling traffic on the links),
+//   3. each thread loads its element from all peers (L1-bypassing loads straight over NVLink) and adds them in
+//      rank order, so all ranks compute bit-identical sums.
+// Two slots alternate; a slot is rewritten only after a full exchange has completed in between, which implies every
+// peer finished reading the older contents. A peer that never arrives trips a timeout flag.
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PArgs a) {
+  const unsigned long long q = *a.seq + 1ull;
+  const int slot = (int)(q & 1ull);
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(a.peers[threadIdx.x] + a.flags_offset) + a.rank;
+    *flag = q;
+  }
+  if (threadIdx.x < a.world) {
+    const volatile unsigned long long* mine =
+        reinterpret_cast<const volatile unsigned long long*>(a.peers[a.rank] + a.flags_offset) + threadIdx.x;
+    const long long t0 = clock64();
+    while (*mine < q) {
+      if (clock64() - t0 > 4000000000ll) { *a.error = 1; break; }  // ~2 s: a peer is gone; fail instead of hanging
+    }
+  }
+  __syncthreads();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.n) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; r++) {
+      const double* src = reinterpret_cast<const double*>(a.peers[r]) + (size_t)slot * a.stride + e;
+      s += __ldcv(src);
+    }
+    a.out[e] = s;
+  }
 }
 
 // advantage sums of every minibatch of an update in one launch: grid (ADV_CHUNKS, n_sets)
@@ -1010,8 +1050,13 @@ cudaError_t launch_param_image(int env_kind, const float* params, float* image, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, cudaStream_t s) {
-  verify_kernel<<<1, 32, 0, s>>>(a, P, ds);
+cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, unsigned long long* p2p_seq, cudaStream_t s) {
+  verify_kernel<<<1, 32, 0, s>>>(a, P, ds, p2p_seq);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_p2p_allreduce(const P2PArgs& a, cudaStream_t s) {
+  p2p_allreduce_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 
