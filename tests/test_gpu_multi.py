@@ -11,11 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_sharded_update_matches_single_process_oracle(tmp_path, torch_cuda):
-    if torch_cuda.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+def test_multi_gpu_sharded_update_matches_single_process_oracle(tmp_path, torch_cuda):
+    ngpu = torch_cuda.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2|4|8)")
+    nproc = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)  # one rank per GPU
     out = tmp_path / "res.json"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
            "--master-port", "29544", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(out)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
