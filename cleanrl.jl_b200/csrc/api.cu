@@ -543,17 +543,34 @@ static int enqueue_adv_stats(crl_ctx* c, const int32_t* arr_base, int M, int nmb
   return CRL_OK;
 }
 
-// one minibatch. Single GPU (speculative, no critic pre-pass):
-//   loss_grad(SPEC) -> grad_reduce(+verify) -> [mb_count -> loss_grad(EXACT) -> grad_reduce: exit at once unless the
-//   speculation failed] -> clip_adam.   `set` indexes the advantage sums written by enqueue_adv_stats.
-// Multi GPU (exact global statistics): mb_stats -> all-gather -> mb_count -> allreduce(cnt) -> loss_grad(EXACT) ->
-//   grad_reduce -> allreduce(grads) -> clip_adam.          lr_host < 0 reads lr from DevState.
+static AdamArgs adam_args(crl_ctx* c, int M, double lr_host, double* stats_slot) {
+  AdamArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
+  aa.grad_scale = 1.0; aa.stat_ranks = 1.0; aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v;
+  aa.beta_pow = c->beta_pow; aa.ds = c->ds; aa.lr_host = lr_host; aa.clip_norm = c->cfg.clip_norm;
+  aa.ent_coeff = c->cfg.ent_coeff; aa.v_coef = c->cfg.v_coef; aa.M_global = (double)M; aa.A = c->L.A;
+  aa.stats_out = stats_slot; aa.world = 1; aa.rank = c->cfg.rank; aa.M = M; aa.P = c->L.P; aa.ds_rw = c->ds; aa.fin = c->fin;
+  return aa;
+}
+
+// One minibatch (ppo.jl:197-251).
+//  spec = true (throughput path, any number of GPUs): loss_grad speculates that the scalar s of the value loss never
+//    wins the max (Q5) and uses advantage statistics precomputed for the whole update; grad_reduce packs
+//    gradient + loss sums + sum s + this rank's min behind each other; the finishing kernel exchanges them with the
+//    peers (NVLink peer memory, or one NCCL allreduce), verifies the speculation and applies clip + Adam.
+//    3 launches per minibatch, 1 exchange. A failed verification is repaired by validate_updates().
+//  spec = false (stage-by-stage API, replay): exact statistics first: mb_stats -> [all-gather] -> mb_count ->
+//    [allreduce count] -> loss_grad(EXACT) -> grad_reduce -> [allreduce] -> clip_adam.
+// lr_host < 0 reads lr from DevState. `set` indexes the advantage sums written by enqueue_adv_stats.
 static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host, double* stats_slot, int set,
-                             bool spec_multi = false) {
-  const bool multi = c->cfg.world_size > 1;
+                             bool spec = false) {
+  const int W = c->cfg.world_size;
+  const bool multi = W > 1;
   const bool local_stats = (c->cfg.flags & CRL_FLAG_LOCAL_STATS) != 0;
   if (multi && !c->comm) return fail(CRL_ERR_STATE, "world_size > 1 but crl_comm_init was not called");
   UpdateArgs ua;
+  memset(&ua, 0, sizeof(ua));
   ua.env_kind = c->cfg.env_kind; ua.params = c->params; ua.image = c->image; ua.idx = ix; ua.M = M;
   ua.states = c->state; ua.actions = c->action; ua.logprobs = c->logprob; ua.advantages = c->advantage;
   ua.returns = c->ret; ua.values = c->value;
@@ -564,93 +581,50 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.parts_in = c->parts; ua.n_parts_in = gs; ua.fin = c->fin; ua.world = 1;
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
   ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
-  ua.defer_verify = 0; ua.rank = c->cfg.rank; ua.p2p_data = nullptr; ua.p2p_stride = 0; ua.p2p_seq = nullptr;
-  if (spec_multi) {
-    // multi-GPU throughput path: speculative loss_grad with GLOBAL advantage statistics, then ONE sum-allreduce that
-    // carries gradient + loss sums + sum s + every rank's min; verify_kernel reaches the same verdict on all ranks
-    const int W = c->cfg.world_size;
+  ua.rank = c->cfg.rank;
+  AdamArgs aa = adam_args(c, M, lr_host, stats_slot);
+  if (spec) {
+    const bool p2p = multi && c->p2p_on;
     ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
-    if (c->p2p_on) { ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq; }
+    if (p2p) { ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq; }
     { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
     { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
-    if (c->p2p_on) {
-      P2PArgs pa;
-      pa.peers = c->p2p_peers_dev; pa.seq = c->p2p_seq; pa.error = c->p2p_err; pa.out = c->gsum;
-      pa.n = c->L.P + 4 + W; pa.stride = c->p2p_stride; pa.world = W; pa.rank = c->cfg.rank; pa.flags_offset = c->p2p_flags_off;
-      KernelScope ks(c, CRL_K_ALLREDUCE);
-      CK(launch_p2p_allreduce(pa, c->stream));
-    } else {
+    if (multi && !p2p) {
       KernelScope ks(c, CRL_K_ALLREDUCE, false);
       CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4 + W, ncclFloat64, ncclSum, c->comm, c->stream));
     }
-    { KernelScope ks(c, CRL_K_OTHER); CK(launch_verify(ua, c->L.P, c->ds, c->p2p_on ? c->p2p_seq : nullptr, c->stream)); }
-    AdamArgs aa;
-    aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
-    aa.grad_scale = 1.0; aa.stat_ranks = 1.0; aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v;
-    aa.beta_pow = c->beta_pow; aa.ds = c->ds; aa.lr_host = lr_host; aa.clip_norm = c->cfg.clip_norm;
-    aa.ent_coeff = c->cfg.ent_coeff; aa.v_coef = c->cfg.v_coef; aa.M_global = (double)M * W; aa.A = c->L.A;
-    aa.stats_out = stats_slot;
+    aa.M_global = (double)M * W; aa.world = W; aa.verify = 1;
+    if (p2p) {
+      aa.peers = c->p2p_peers_dev; aa.p2p_seq = c->p2p_seq; aa.p2p_err = c->p2p_err; aa.p2p_stride = c->p2p_stride;
+      aa.p2p_flags_off = c->p2p_flags_off;
+    }
     KernelScope ks(c, CRL_K_CLIP_ADAM);
     CK(launch_clip_adam(aa, c->stream));
     return CRL_OK;
   }
   const bool exchange = multi && !local_stats;
-  if (exchange) { ua.parts_in = c->parts_recv; ua.n_parts_in = c->cfg.world_size; ua.world = c->cfg.world_size; }
-  if (!multi) {
-    ua.mode = LG_SPEC;
-    { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
-    { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
-    ua.fixup = 1;
-    { KernelScope ks(c, CRL_K_MB_COUNT); CK(launch_mb_count(ua, c->stream)); }
-    ua.mode = LG_EXACT;
-    { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
-    { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
-  } else {
-  {
-    KernelScope ks(c, CRL_K_MB_STATS);
-    CK(launch_mb_stats(ua, gs, c->stream));
-  }
+  if (exchange) { ua.parts_in = c->parts_recv; ua.n_parts_in = W; ua.world = W; }
+  { KernelScope ks(c, CRL_K_MB_STATS); CK(launch_mb_stats(ua, gs, c->stream)); }
   if (exchange) {
-    {
-      KernelScope ks(c, CRL_K_OTHER);
-      CK(launch_stats_pack(c->parts, gs, c->parts_send, c->stream));
-    }
+    { KernelScope ks(c, CRL_K_OTHER); CK(launch_stats_pack(c->parts, gs, c->parts_send, c->stream)); }
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllGather(c->parts_send, c->parts_recv, sizeof(MbScalars), ncclChar, c->comm, c->stream));
   }
-  {
-    KernelScope ks(c, CRL_K_MB_COUNT);
-    CK(launch_mb_count(ua, c->stream));
-  }
+  { KernelScope ks(c, CRL_K_MB_COUNT); CK(launch_mb_count(ua, c->stream)); }
   if (exchange) {
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(&c->fin->cnt, &c->fin->cnt, 1, ncclUint64, ncclSum, c->comm, c->stream));
   }
-  {
-    KernelScope ks(c, CRL_K_LOSS_GRAD);
-    CK(launch_loss_grad(ua, c->stream));
-  }
-  {
-    KernelScope ks(c, CRL_K_GRAD_REDUCE);
-    CK(launch_grad_reduce(ua, c->L.P, c->stream));
-  }
-  {
+  { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
+  { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
+  if (multi) {
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4, ncclFloat64, ncclSum, c->comm, c->stream));
   }
-  }  // multi
-  AdamArgs aa;
-  aa.env_kind = c->cfg.env_kind; aa.params = c->params; aa.image = c->image; aa.gsum = c->gsum; aa.gf = nullptr;
-  aa.grad_scale = (multi && local_stats) ? 1.0 / c->cfg.world_size : 1.0;
-  aa.stat_ranks = (multi && local_stats) ? (double)c->cfg.world_size : 1.0;
-  aa.grads_out = c->grads; aa.m = c->adam_m; aa.v = c->adam_v; aa.beta_pow = c->beta_pow; aa.ds = c->ds;
-  aa.lr_host = lr_host; aa.clip_norm = c->cfg.clip_norm; aa.ent_coeff = c->cfg.ent_coeff; aa.v_coef = c->cfg.v_coef;
-  aa.M_global = (double)M * (exchange ? c->cfg.world_size : 1);
-  aa.A = c->L.A; aa.stats_out = stats_slot;
-  {
-    KernelScope ks(c, CRL_K_CLIP_ADAM);
-    CK(launch_clip_adam(aa, c->stream));
-  }
+  aa.grad_scale = (multi && local_stats) ? 1.0 / W : 1.0;
+  aa.stat_ranks = (multi && local_stats) ? (double)W : 1.0;
+  aa.M_global = (double)M * (exchange ? W : 1);
+  { KernelScope ks(c, CRL_K_CLIP_ADAM); CK(launch_clip_adam(aa, c->stream)); }
   return CRL_OK;
 }
 
@@ -666,7 +640,6 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(use_device(c));
   CK(cudaMemcpyAsync(c->idx_dev, idx, 4 * (size_t)M, cudaMemcpyHostToDevice, c->stream));
-  if (c->cfg.world_size == 1) CKRC(enqueue_adv_stats(c, c->idx_dev, M, 1, 1));
   CKRC(enqueue_minibatch(c, idx_array(c, c->idx_dev), M, lr, c->stats_dev, 0));
   double s4[4];
   CK(cudaMemcpyAsync(s4, c->stats_dev, sizeof(s4), cudaMemcpyDeviceToHost, c->stream));
@@ -675,18 +648,18 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
   return CRL_OK;
 }
 
-static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, bool spec_multi = false) {
+static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, bool spec = false) {
   int k = 0;
   const int n_sets = c->cfg.update_epochs * c->cfg.num_minibatches;
-  if (c->cfg.world_size == 1 || spec_multi) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
-  if (spec_multi) {  // global advantage sums for all minibatches of the update: one collective per update
+  if (spec) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
+  if (spec && c->cfg.world_size > 1) {  // global advantage sums for all minibatches of the update: one collective per update
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(c->advparts, c->advparts, (size_t)n_sets * ADV_CHUNKS * 2, ncclFloat64, ncclSum, c->comm, c->stream));
   }
   for (int e = 0; e < c->cfg.update_epochs; e++) {  // ppo.jl:193
     for (int start = 0; start < c->B; start += c->M) {  // ppo.jl:197
       IdxSrc ix = perm_dev ? idx_array(c, perm_dev + (size_t)e * c->B + start) : idx_perm(c, e, start);
-      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k, k, spec_multi));
+      CKRC(enqueue_minibatch(c, ix, c->M, lr_host, c->stats_dev + 4 * (size_t)k, k, spec));
       k++;
     }
   }
@@ -726,10 +699,10 @@ extern "C" CRL_API int crl_device_permutation(crl_ctx* c, int64_t update_index, 
 }
 
 // the body of one PPO update with device RNG (what the CUDA graph captures)
-static int enqueue_train_update(crl_ctx* c, bool spec_multi) {
+static int enqueue_train_update(crl_ctx* c, bool spec) {
   CKRC(enqueue_rollout(c, nullptr, nullptr));
   CKRC(enqueue_gae(c));
-  CKRC(enqueue_epochs(c, nullptr, -1.0, spec_multi));
+  CKRC(enqueue_epochs(c, nullptr, -1.0, spec));
   {
     KernelScope ks(c, CRL_K_OTHER);
     CK(launch_advance(c->ds, (unsigned long long)c->T, 1ull, c->stream));
@@ -737,13 +710,14 @@ static int enqueue_train_update(crl_ctx* c, bool spec_multi) {
   return CRL_OK;
 }
 
-static bool multi_speculative(const crl_ctx* c) {
-  return c->cfg.world_size > 1 && !(c->cfg.flags & CRL_FLAG_LOCAL_STATS) && getenv("CRL_MULTI_EXACT") == nullptr;
+// crl_train_update speculates (see enqueue_minibatch) unless per-shard statistics were requested or CRL_EXACT is set
+static bool speculative(const crl_ctx* c) {
+  return !(c->cfg.flags & CRL_FLAG_LOCAL_STATS) && getenv("CRL_EXACT") == nullptr && getenv("CRL_MULTI_EXACT") == nullptr;
 }
 
 // enqueue one update into result slot `slot`. exact = true forces the non-speculative multi-GPU sequence (replay).
 static int run_update(crl_ctx* c, double lr, int slot, bool exact) {
-  const bool spec_multi = multi_speculative(c) && !exact;
+  const bool spec_multi = speculative(c) && !exact;
   if (spec_multi) {
     CKRC(snapshot_alloc(c));
     CKRC(snapshot_copy(c, slot, false));  // state BEFORE the update, for the (rare) exact replay
@@ -793,7 +767,7 @@ static int validate_updates(crl_ctx* c, uint64_t upto) {
     const uint64_t u = c->validated_seq;
     const int slot = (int)(u & 1);
     CK(cudaEventSynchronize(c->fetch_ev[slot]));
-    if (multi_speculative(c) && c->flag_host[slot][0]) {
+    if (speculative(c) && c->flag_host[slot][0]) {
       CK(cudaStreamSynchronize(c->stream));
       c->replays += 1;
       CKRC(snapshot_copy(c, slot, true));
@@ -1107,19 +1081,11 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
   const int gs = mb_stats_grid(M, g_raw.sm);
   ua.parts_in = g_raw.parts; ua.n_parts_in = gs; ua.fin = g_raw.fin; ua.world = 1;
   ua.gpart = g_raw.gpart; ua.spart = g_raw.spart; ua.grid_loss = loss_grad_grid(M, g_raw.sm); ua.gsum = g_raw.gsum;
-  (void)gs;
-  AdvStatsArgs as;
-  as.idx = ua.idx; as.arr_base = idx; as.B = M; as.M = M; as.nmb = 1; as.n_sets = 1; as.advantages = advantages;
-  as.advparts = g_raw.advparts;
   ua.advparts = g_raw.advparts; ua.mpart = g_raw.mpart;
   ua.defer_verify = 0; ua.rank = 0; ua.p2p_data = nullptr; ua.p2p_stride = 0; ua.p2p_seq = nullptr;
-  CK(launch_adv_stats(as, s));
-  ua.mode = LG_SPEC; ua.fixup = 0;
-  CK(launch_loss_grad(ua, s));
-  CK(launch_grad_reduce(ua, L.P, s));
-  ua.fixup = 1;
+  ua.mode = LG_EXACT; ua.fixup = 0;
+  CK(launch_mb_stats(ua, gs, s));
   CK(launch_mb_count(ua, s));
-  ua.mode = LG_EXACT;
   CK(launch_loss_grad(ua, s));
   CK(launch_grad_reduce(ua, L.P, s));
   CK(launch_loss_finalize(g_raw.gsum, L.P, grads_out, (double)M, L.A, ent_coeff, v_coef, stats_out, s));
@@ -1134,6 +1100,8 @@ extern "C" CRL_API int crl_clip_adam_raw(int32_t env_kind, float* params, const 
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(need_sm100());
   AdamArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.world = 1;
   aa.env_kind = env_kind; aa.params = params; aa.image = nullptr; aa.gsum = nullptr; aa.gf = grads; aa.grad_scale = 1.0; aa.stat_ranks = 1.0;
   aa.grads_out = nullptr; aa.m = m; aa.v = v; aa.beta_pow = beta_pow; aa.ds = nullptr; aa.lr_host = lr;
   aa.clip_norm = clip_norm; aa.ent_coeff = 0.f; aa.v_coef = 0.f; aa.M_global = 1.0; aa.A = L.A; aa.stats_out = nullptr;

@@ -102,17 +102,9 @@ struct UpdateArgs {
   // peer-memory allreduce (NVLink/NVSwitch): grad_reduce writes into this rank's exchange slot instead of gsum
   double* p2p_data;                     // own exchange buffer: [2 slots][p2p_stride doubles]
   int p2p_stride;
-  const unsigned long long* p2p_seq;    // device counter of completed exchanges (slot = (seq + 1) & 1)
+  unsigned long long* p2p_seq;          // exchange sequence number: loss_grad advances it, slot = seq & 1
 };
 
-struct P2PArgs {
-  unsigned char* const* peers;          // device array [world] of every rank's exchange buffer (IPC-mapped)
-  unsigned long long* seq;              // this rank's exchange counter (advanced by verify_kernel)
-  int* error;                           // set if a peer did not arrive in time
-  double* out;                          // local result buffer (gsum)
-  int n, stride, world, rank;
-  size_t flags_offset;                  // byte offset of the arrival flags inside an exchange buffer
-};
 #define CRL_MAX_WORLD 16
 
 struct AdamArgs {
@@ -134,6 +126,18 @@ struct AdamArgs {
   double M_global;
   int A;
   double* stats_out;   // 4 doubles: loss, pg_loss, v_loss, entropy_loss (may be nullptr)
+  // ---- speculative throughput path: the finishing kernel also exchanges the reduced sums with the peers
+  //      (NVLink peer memory), verifies the speculation and records a failure for the host
+  unsigned char* const* peers;          // device array [world] of exchange buffers, or nullptr (single GPU / NCCL)
+  const unsigned long long* p2p_seq;    // exchange sequence number (advanced by loss_grad)
+  int* p2p_err;
+  int p2p_stride;
+  size_t p2p_flags_off;
+  int world, rank;
+  int verify;                           // 1: check s <= min (clip-R)^2 and set ds_rw->spec_failed otherwise
+  int M, P;
+  DevState* ds_rw;
+  MbFinal* fin;
 };
 
 // per-device opt-in to large dynamic shared memory; call once per device outside stream capture
@@ -161,8 +165,7 @@ cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);
-cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, unsigned long long* p2p_seq, cudaStream_t s);
-cudaError_t launch_p2p_allreduce(const P2PArgs& a, cudaStream_t s);
+
 cudaError_t launch_loss_finalize(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
                                  float v_coef, double* stats_out, cudaStream_t s);
 cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cudaStream_t s);

@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   const ThreadCoord<G> tc;
   const int tid = threadIdx.x;
   if (a.fixup && !a.fin->need_fixup) return;  // speculation held: nothing to redo
+  // a new peer exchange begins with this minibatch: grad_reduce and the finishing kernel only READ the counter
+  if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
   float* xin = smem + SM::XIN;
   float* scal = smem + SM::SCAL;
 
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   if (a.fixup && !a.fin->need_fixup) return;
   const int grid = a.grid_loss;
   // with the peer-memory allreduce the sums go straight into this rank's exchange slot
-  double* gsum = a.p2p_data ? a.p2p_data + (size_t)((*a.p2p_seq + 1ull) & 1ull) * a.p2p_stride : a.gsum;
+  double* gsum = a.p2p_data ? a.p2p_data + (size_t)(*a.p2p_seq & 1ull) * a.p2p_stride : a.gsum;
   if (blockIdx.x == gridDim.x - 1) {
     if (a.mode != LG_SPEC || a.fixup) return;
     __shared__ double red[8];
@@ -796,57 +798,6 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   if (g == 0 && e < P + 4) gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
 }
 
-// multi-GPU: after the allreduce every rank holds the global sum s and all per-rank minima and reaches the same
-// verdict; a failed speculation is recorded in DevState and repaired by the host (snapshot + exact replay)
-__global__ void verify_kernel(UpdateArgs a, int P, DevState* ds, unsigned long long* p2p_seq) {
-  if (threadIdx.x != 0) return;
-  if (p2p_seq) *p2p_seq += 1ull;  // the exchange that just completed
-  float m = INFINITY;
-  for (int r = 0; r < a.world; r++) m = fminf(m, (float)a.gsum[P + 4 + r]);
-  const double Mg = (double)a.M * (double)a.world;
-  const float s_f = (float)(a.gsum[P + 3] / Mg);
-  a.fin->s_unclipped = s_f; a.fin->min_vlc = m; a.fin->M_global = Mg; a.fin->cnt = 0ull;
-  a.fin->need_fixup = (s_f > m) ? 1 : 0;
-  if (s_f > m) ds->spec_failed = 1;
-}
-
-// One-shot allreduce over NVLink / NVSwitch peer memory (replaces the latency-bound NCCL call for the ~73 KB
-// gradient message). Every rank's partial vector already sits in its own exchange slot (written by grad_reduce).
-//   1. each rank pushes its arrival sequence number into every peer's flag array (system-scope store),
-//   2. every block spins on its LOCAL flags until all peers have arrived (no polling traffic on the links),
-//   3. each thread loads its element from all peers (L1-bypassing loads straight over NVLink) and adds them in
-//      rank order, so all ranks compute bit-identical sums.
-// Two slots alternate; a slot is rewritten only after a full exchange has completed in between, which implies every
-// peer finished reading the older contents. A peer that never arrives trips a timeout flag.
-__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PArgs a) {
-  const unsigned long long q = *a.seq + 1ull;
-  const int slot = (int)(q & 1ull);
-  if (blockIdx.x == 0 && threadIdx.x < a.world) {
-    __threadfence_system();
-    volatile unsigned long long* flag =
-        reinterpret_cast<volatile unsigned long long*>(a.peers[threadIdx.x] + a.flags_offset) + a.rank;
-    *flag = q;
-  }
-  if (threadIdx.x < a.world) {
-    const volatile unsigned long long* mine =
-        reinterpret_cast<const volatile unsigned long long*>(a.peers[a.rank] + a.flags_offset) + threadIdx.x;
-    const long long t0 = clock64();
-    while (*mine < q) {
-      if (clock64() - t0 > 4000000000ll) { *a.error = 1; break; }  // ~2 s: a peer is gone; fail instead of hanging
-    }
-  }
-  __syncthreads();
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < a.n) {
-    double s = 0.0;
-    for (int r = 0; r < a.world; r++) {
-      const double* src = reinterpret_cast<const double*>(a.peers[r]) + (size_t)slot * a.stride + e;
-      s += __ldcv(src);
-    }
-    a.out[e] = s;
-  }
-}
-
 // advantage sums of every minibatch of an update in one launch: grid (ADV_CHUNKS, n_sets)
 __global__ void __launch_bounds__(256) adv_stats_kernel(AdvStatsArgs a) {
   __shared__ double red[8];
@@ -887,9 +838,6 @@ __device__ __forceinline__ void finalize_stats(const double* sums, double Mg, in
   out[2] = vl;
   out[3] = en;
 }
-__device__ __forceinline__ float load_grad(const AdamArgs& a, int e) {
-  return a.gsum ? (float)(a.gsum[e] * a.grad_scale) : a.gf[e];
-}
 
 // raw path: Float32 gradient + loss scalars out of the double sums
 __global__ void loss_finalize_kernel(const double* gsum, int P, float* grads_out, double Mg, int A, float ent_coeff,
@@ -925,16 +873,61 @@ __global__ void stats_pack_kernel(const MbScalars* parts, int n, MbScalars* out)
 
 // ------------------------------------------------------------------ clip + Adam
 // Flux.Optimiser(ClipNorm(thresh), Adam(η)) [Flux 0.13.4], one CTA per parameter array.
+// Finishing kernel of a minibatch, one CTA per parameter array (ppo.jl:250):
+//   [multi-GPU] one-shot exchange of the reduced sums over NVLink / NVSwitch peer memory: every rank's vector sits in
+//   its own exchange slot (written by grad_reduce); block 0 pushes this rank's sequence number into every peer's flag
+//   array, each block spins on its LOCAL flags, then loads its elements straight from all peers (L1-bypassing loads)
+//   and adds them in rank order, so all ranks hold bit-identical sums. Two slots alternate; a slot is rewritten only
+//   after a complete exchange in between, which implies every peer finished reading the older contents.
+//   [speculative path] block 0 verifies s = mean(v_new - R^2) <= min_i (clip_i - R_i)^2 with the exchanged values.
+//   Then Flux.Optimiser(ClipNorm, Adam): Float32 norm per array, clip, Adam with Float64 scalars, parameter image.
+__device__ __forceinline__ double finish_load(const AdamArgs& a, int slot, int e) {
+  if (a.peers) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; r++)
+      s += __ldcv(reinterpret_cast<const double*>(a.peers[r]) + (size_t)slot * a.p2p_stride + e);
+    return s;
+  }
+  return a.gsum[e];
+}
+
 __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
   __shared__ double red[32];
   Layout L;
   make_layout(a.env_kind, &L);
   const int i = blockIdx.x;
   const int o = L.off[i], n = L.size[i];
+  int slot = 0;
+  if (a.peers) {
+    const unsigned long long q = *a.p2p_seq;
+    slot = (int)(q & 1ull);
+    if (i == 0 && threadIdx.x < a.world) {
+      __threadfence_system();
+      volatile unsigned long long* flag =
+          reinterpret_cast<volatile unsigned long long*>(a.peers[threadIdx.x] + a.p2p_flags_off) + a.rank;
+      *flag = q;
+    }
+    if (threadIdx.x < a.world) {
+      const volatile unsigned long long* mine =
+          reinterpret_cast<const volatile unsigned long long*>(a.peers[a.rank] + a.p2p_flags_off) + threadIdx.x;
+      const long long t0 = clock64();
+      while (*mine < q) {
+        if (clock64() - t0 > 4000000000ll) { *a.p2p_err = 1; break; }  // ~2 s: a peer is gone; fail instead of hanging
+      }
+    }
+    __syncthreads();
+  }
+  // this array's gradient: at most 4 elements per thread (arrays have <= 4096 elements)
+  float g[4];
   double ss = 0.0;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-    const double g = (double)load_grad(a, o + k);  // the Float32 gradient array Zygote returns
-    ss += g * g;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int k = threadIdx.x + c * 1024;
+    g[c] = 0.0f;
+    if (k < n) {
+      g[c] = a.gf ? a.gf[o + k] : (float)(finish_load(a, slot, o + k) * a.grad_scale);  // the Float32 gradient Zygote returns
+      ss += (double)g[c] * (double)g[c];
+    }
   }
   ss = block_sum<32>(ss, red);
   const float nrm = (float)sqrt(ss);  // norm(Δ::Array{Float32})::Float32
@@ -943,10 +936,12 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
   const double lr = a.lr_host >= 0.0 ? a.lr_host : a.ds->lr;
   const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
   const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-    const float g = load_grad(a, o + k);
-    if (a.grads_out) a.grads_out[o + k] = g;
-    float d = g;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int k = threadIdx.x + c * 1024;
+    if (k >= n) continue;
+    if (a.grads_out) a.grads_out[o + k] = g[c];
+    float d = g[c];
     if (clip) d = (float)__dmul_rn((double)d, scale);  // rmul!(Δ, thresh/nrm)
     const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[o + k]), __dmul_rn(1.0 - b1, (double)d));
     const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[o + k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
@@ -965,8 +960,20 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
   if (threadIdx.x == 0) {
     a.beta_pow[2 * i] = bp1 * b1;
     a.beta_pow[2 * i + 1] = bp2 * b2;
-    if (i == 0 && a.stats_out && a.gsum)
-      finalize_stats(a.gsum + L.P, a.M_global * a.stat_ranks, a.A, a.ent_coeff, a.v_coef, a.stats_out);
+    if (i == 0 && !a.gf) {
+      double tail[4 + CRL_MAX_WORLD];
+      const int nt = 4 + (a.verify ? a.world : 0);
+      for (int k = 0; k < nt; k++) tail[k] = finish_load(a, slot, L.P + k);
+      if (a.stats_out) finalize_stats(tail, a.M_global * a.stat_ranks, a.A, a.ent_coeff, a.v_coef, a.stats_out);
+      if (a.verify) {
+        float m = INFINITY;
+        for (int r = 0; r < a.world; r++) m = fminf(m, (float)tail[4 + r]);
+        const float s_f = (float)(tail[3] / a.M_global);
+        a.fin->s_unclipped = s_f; a.fin->min_vlc = m; a.fin->M_global = a.M_global; a.fin->cnt = 0ull;
+        a.fin->need_fixup = (s_f > m) ? 1 : 0;
+        if (s_f > m) a.ds_rw->spec_failed = 1;  // the host replays this update exactly
+      }
+    }
   }
 }
 
@@ -1047,16 +1054,6 @@ cudaError_t launch_param_image(int env_kind, const float* params, float* image, 
     param_image_kernel<CRL_ENV_CARTPOLE><<<(EnvTraits<CRL_ENV_CARTPOLE>::P + 255) / 256, 256, 0, s>>>(params, image);
   else
     param_image_kernel<CRL_ENV_PENDULUM><<<(EnvTraits<CRL_ENV_PENDULUM>::P + 255) / 256, 256, 0, s>>>(params, image);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_verify(const UpdateArgs& a, int P, DevState* ds, unsigned long long* p2p_seq, cudaStream_t s) {
-  verify_kernel<<<1, 32, 0, s>>>(a, P, ds, p2p_seq);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_p2p_allreduce(const P2PArgs& a, cudaStream_t s) {
-  p2p_allreduce_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -407,7 +407,35 @@ def test_train_update_graph_matches_oracle(crl, olib, abi, torch_cuda, kind):
         np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=1e-4, atol=2e-6)
         _, ao = o.pop_episodes()
         assert agg.count == ao.count
-    assert h.kernel_launches() > 3 * (2 + 8 * 5)
+    assert h.kernel_launches() >= 3 * (4 + 8 * 3)  # per update: init, rollout, gae, adv_stats + 3 kernels per minibatch
+    assert h.spec_replays() == 0
+    h.close()
+
+
+def test_failed_speculation_is_replayed_exactly(crl, olib, abi, torch_cuda):
+    """gamma = lambda = 0 with a critic bias of 1.5: returns are in {0, 1, v}, so the scalar s = mean(v - R^2) of the
+    value loss (Q5) exceeds min (clip - R)^2 = 0 and the speculative update fails its on-device verification. The
+    library must notice, restore its snapshot and replay the update with the exact kernels: results still match the
+    oracle, and the replay counter shows the slow path really ran."""
+    N, T = 64, 16
+    h, o = make_pair(crl, olib, abi, 0, N=N, T=T, mb=4, epochs=2, seed=29, gamma=0.0, gae_lambda=0.0)
+    p = h.get_params()
+    p[olib.param_layout(0)[0][11]] = 1.5
+    h.set_params(p); o.set_params(p)
+    h.env_reset(); o.env_reset()
+    lr = float(F(2.5e-4))
+    outs = []
+    for u in range(3):
+        h.train_update(lr)
+        if u >= 1:
+            outs.append(h.fetch_update(lag=1)[0])   # pipelined fetch: validates update u-1 while u is in flight
+    outs.append(h.fetch_update(lag=0)[0])
+    for u in range(3):
+        so = o.train_update(lr)
+        np.testing.assert_allclose(outs[u], so, rtol=5e-4, atol=1e-5, err_msg="update %d" % u)
+    assert h.spec_replays() >= 1
+    np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_array_equal(h.read_field(abi.CRL_F_TERMINAL), o.read_field(abi.CRL_F_TERMINAL))
     h.close()
 
 
