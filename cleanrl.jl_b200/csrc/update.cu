@@ -891,17 +891,27 @@ __device__ __forceinline__ double finish_load(const AdamArgs& a, int slot, int e
   return a.gsum[e];
 }
 
-__global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
-  __shared__ double red[32];
+constexpr int ADAM_CL = 8;     // CTAs per parameter array = one thread-block cluster
+constexpr int ADAM_NT = 256;   // threads per CTA; 8 x 256 x 2 elements covers the largest array (4096)
+
+__global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_adam_kernel(AdamArgs a) {
+  // The Float64 Adam arithmetic of a 4096-element array would keep ONE SM's FP64 pipe busy for ~8 us, so each array is
+  // spread over a cluster of 8 CTAs; the per-array L2 norm (ClipNorm is per array, ppo.jl:93) is combined through
+  // distributed shared memory: every CTA stores its partial sum of squares into all 8 CTAs' shared memory, one
+  // cluster barrier, then everybody adds the 8 partials in the same order.
+  __shared__ double red[8];
+  __shared__ double part[ADAM_CL];
   Layout L;
   make_layout(a.env_kind, &L);
-  const int i = blockIdx.x;
+  const int i = blockIdx.x / ADAM_CL;         // parameter array
+  unsigned int crank;                          // rank of this CTA inside its cluster
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int o = L.off[i], n = L.size[i];
   int slot = 0;
   if (a.peers) {
     const unsigned long long q = *a.p2p_seq;
     slot = (int)(q & 1ull);
-    if (i == 0 && threadIdx.x < a.world) {
+    if (blockIdx.x == 0 && threadIdx.x < a.world) {
       __threadfence_system();
       volatile unsigned long long* flag =
           reinterpret_cast<volatile unsigned long long*>(a.peers[threadIdx.x] + a.p2p_flags_off) + a.rank;
@@ -917,28 +927,38 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
     }
     __syncthreads();
   }
-  // this array's gradient: at most 4 elements per thread (arrays have <= 4096 elements)
-  float g[4];
+  // this CTA's slice of the array: elements crank*512 + tid + c*256, c < 2
+  float g[2];
   double ss = 0.0;
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const int k = threadIdx.x + c * 1024;
+  for (int c = 0; c < 2; c++) {
+    const int k = (int)crank * (2 * ADAM_NT) + threadIdx.x + c * ADAM_NT;
     g[c] = 0.0f;
     if (k < n) {
       g[c] = a.gf ? a.gf[o + k] : (float)(finish_load(a, slot, o + k) * a.grad_scale);  // the Float32 gradient Zygote returns
       ss += (double)g[c] * (double)g[c];
     }
   }
-  ss = block_sum<32>(ss, red);
-  const float nrm = (float)sqrt(ss);  // norm(Δ::Array{Float32})::Float32
+  ss = block_sum<8>(ss, red);
+  const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];  // read BEFORE the cluster barrier (rank 0 rewrites them after)
+  if (threadIdx.x < ADAM_CL) {
+    // distributed shared memory: part[crank] of CTA `threadIdx.x` of this cluster
+    unsigned int local = (unsigned int)__cvta_generic_to_shared(&part[crank]), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(threadIdx.x));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(ss) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  double tot = 0.0;
+#pragma unroll
+  for (int r = 0; r < ADAM_CL; r++) tot += part[r];
+  const float nrm = (float)sqrt(tot);  // norm(Δ::Array{Float32})::Float32
   const bool clip = (double)nrm > (double)a.clip_norm;
   const double scale = clip ? (double)a.clip_norm / (double)nrm : 1.0;
   const double lr = a.lr_host >= 0.0 ? a.lr_host : a.ds->lr;
   const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-  const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const int k = threadIdx.x + c * 1024;
+  for (int c = 0; c < 2; c++) {
+    const int k = (int)crank * (2 * ADAM_NT) + threadIdx.x + c * ADAM_NT;
     if (k >= n) continue;
     if (a.grads_out) a.grads_out[o + k] = g[c];
     float d = g[c];
@@ -956,8 +976,7 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
       else image_scatter<CRL_ENV_PENDULUM>(a.image, o + k, pnew);
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     a.beta_pow[2 * i] = bp1 * b1;
     a.beta_pow[2 * i + 1] = bp2 * b2;
     if (i == 0 && !a.gf) {
@@ -1066,7 +1085,7 @@ cudaError_t launch_adv_stats(const AdvStatsArgs& a, cudaStream_t s) {
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s) {
   Layout L;
   if (!make_layout(a.env_kind, &L)) return cudaErrorInvalidValue;
-  clip_adam_kernel<<<L.n_arrays, 1024, 0, s>>>(a);
+  clip_adam_kernel<<<L.n_arrays * ADAM_CL, ADAM_NT, 0, s>>>(a);  // __cluster_dims__(8): one cluster per parameter array
   return cudaGetLastError();
 }
 
