@@ -296,6 +296,10 @@ __device__ __forceinline__ void prefetch_tile(const UpdateArgs& a, const uint32_
   cp_async_commit();
 }
 
+// barrier over the 4 warps that own one net (actor: warps 0-3, critic: warps 4-7); the two nets only meet at the
+// CTA-wide barriers around the per-sample loss
+__device__ __forceinline__ void net_sync(int net) { asm volatile("bar.sync %0, %1;" ::"r"(net + 1), "r"(128) : "memory"); }
+
 template <int ENV>
 __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a) {
   using G = TileGeom<8, 2>;
@@ -400,6 +404,14 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   const int w_net = tid >> 7;          // dW2 phase: warps 0-3 actor, 4-7 critic
   const int w_jq = tid & 7;            // j rows jq + 8*i2
   const int w_kq = (tid & 127) >> 3;   // k rows kq + 16*i
+  // head-backward phase: threads of a net own (output o, row k) pairs of that net's head
+  const int p5_tl = tid & 127, p5_nout = w_net == 0 ? A : 1;
+  const bool p5_active = p5_tl < CRL_H * p5_nout;
+  const int p5_k = p5_tl % CRL_H;
+  const int p5_o = w_net == 0 ? p5_tl / CRL_H : A;   // index into dout: actor outputs 0..A-1, critic = A
+  // row-sum phase: each net's threads own that net's rows
+  const int p9_kind = (tid & 127) >> 6;              // 0: dz1 row (db1, dW1), 1: dz2 row (db2)
+  const int p9_row = w_net * CRL_H + (tid & 63);
 
   int tile_no = 0;
   for (int m0 = blockIdx.x * S; m0 < a.M; m0 += gridDim.x * S) {
@@ -438,9 +450,9 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     {
       const float* np = sp + net_base<ENV>(tc.net);
       tile_layer<G, D, EPI_BIAS_TANH, false, true>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
-      __syncthreads();
+      net_sync(tc.net);
       tile_layer<G, CRL_H, EPI_BIAS_TANH, true, true>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
-      __syncthreads();
+      net_sync(tc.net);
     }
     // ---- P3 heads
     {
@@ -562,10 +574,10 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
     }
     __syncthreads();
     // ---- P5 head backward: dW3 += h2 * dout^T, db3 += sum dout
-    if (tid < CRL_H * (A + 1)) {
-      const int o = tid / CRL_H, k = tid % CRL_H;
-      const float* hrow = h2 + ((o < A ? 0 : CRL_H) + k) * SP;
-      const float* drow = dout + o * S;
+    if (p5_active) {
+      const int k = p5_k;
+      const float* hrow = h2 + (w_net * CRL_H + k) * SP;
+      const float* drow = dout + p5_o * S;
       const int hsw = act_swz(k);
       float acc = 0.0f, bacc = 0.0f;
 #pragma unroll 4
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
       gW3 += acc;
       gb3 += bacc;
     }
-    __syncthreads();
+    net_sync(w_net);
     // ---- P6 dz2 = (W3^T dout) .* (1 - h2^2), in place over this thread's own h2 tile
     {
       float* hb = h2 + tc.net * CRL_H * SP;
@@ -617,7 +629,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         }
       }
     }
-    __syncthreads();
+    net_sync(w_net);
     // ---- P7 dW2 += dz2 * h1^T (per net): 4 k-rows x 8 j-rows per thread, reduce over samples
     {
       const float* h1b = h1 + w_net * CRL_H * SP;
@@ -648,15 +660,15 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
 #pragma unroll
         for (int j = 0; j < 8; j++) gW2[i][j] += acc[i][j].x + acc[i][j].y;
     }
-    __syncthreads();
+    net_sync(w_net);
     // ---- P8 dz1 = (W2^T dz2) .* (1 - h1^2), in place over h1
     tile_layer<G, CRL_H, EPI_DTANH, true, true>(tc, w2t + tc.net * CRL_H * CRL_H, nullptr, h2 + tc.net * CRL_H * SP,
                                                 h1 + tc.net * CRL_H * SP);
-    __syncthreads();
-    // ---- P9 row sums: tid<128: db1[row], dW1[k][row]; tid>=128: db2[row]
+    net_sync(w_net);
+    // ---- P9 row sums of this net's rows: first 64 threads of the net: db1[row], dW1[k][row]; other 64: db2[row]
     {
-      const int row = tid & 127;
-      const float* src = (tid < 128 ? h1 : h2) + row * SP;
+      const int row = p9_row;
+      const float* src = (p9_kind == 0 ? h1 : h2) + row * SP;
       const int rsw = act_swz(row);
       float bacc = 0.0f, wacc[D];
 #pragma unroll
@@ -665,7 +677,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
       for (int s = 0; s < S; s += 4) {
         const float4 d = *reinterpret_cast<const float4*>(src + (s ^ rsw));
         bacc += (d.x + d.y) + (d.z + d.w);
-        if (tid < 128) {
+        if (p9_kind == 0) {
 #pragma unroll
           for (int k = 0; k < D; k++) {
             const float4 x4 = *reinterpret_cast<const float4*>(xs + k * SP + s);
@@ -678,7 +690,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
 #pragma unroll
       for (int k = 0; k < D; k++) gW1[k] += wacc[k];
     }
-    __syncthreads();
+    // no barrier here: the next tile starts with a CTA-wide barrier (or the kernel epilogue follows)
   }
 
   // ---- write this CTA's partial gradient (every element of [0,P) exactly once)
@@ -690,20 +702,20 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
 #pragma unroll
       for (int j = 0; j < 8; j++) gp[nb + NO::W2 + (w_jq + 8 * j) + CRL_H * (w_kq + 16 * i)] = gW2[i][j];
   }
-  if (tid < CRL_H * (A + 1)) {
-    const int o = tid / CRL_H, k = tid % CRL_H;
-    if (o < A) {
-      gp[NA::W3 + o + A * k] = gW3;
-      if (k == 0) gp[NA::B3 + o] = gb3;
+  if (p5_active) {
+    const int k = p5_k;
+    if (w_net == 0) {
+      gp[NA::W3 + p5_o + A * k] = gW3;
+      if (k == 0) gp[NA::B3 + p5_o] = gb3;
     } else {
       gp[E::NET_A + NO::W3 + k] = gW3;
       if (k == 0) gp[E::NET_A + NO::B3] = gb3;
     }
   }
   {
-    const int row = tid & 127, net = row >> 6, j = row & 63;
-    const int nb = net == 0 ? 0 : E::NET_A;
-    if (tid < 128) {
+    const int j = tid & 63;
+    const int nb = w_net == 0 ? 0 : E::NET_A;
+    if (p9_kind == 0) {
       gp[nb + NO::B1 + j] = gb12;
 #pragma unroll
       for (int k = 0; k < D; k++) gp[nb + NO::W1 + j + CRL_H * k] = gW1[k];
