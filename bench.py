@@ -30,6 +30,7 @@ NUM_MINIBATCHES = 4
 UPDATE_EPOCHS = 4
 FWD_FLOP = 17_792          # actor 8,960 + critic 8,832 FLOP per sample
 UPDATE_FLOP = 53_376       # forward + backward per sample per epoch
+A2C_ENVS, A2C_STEPS = 16384, 32
 METRIC = "ppo_env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -45,10 +46,17 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gae-n", type=int, default=1 << 20, help="envs in the GAE HBM measurement (T=128)")
     ap.add_argument("--local-stats", action="store_true")
+    ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c"],
+                    help="a2c = BASELINE.json configs[2]: A2C CartPole, 16384 envs, n-step returns + fused update (1 GPU)")
     return ap.parse_args()
 
 
 def workload_config(args, world):
+    if args.algo == "a2c":
+        return {"workload": "A2C %s, %d vectorized envs x %d steps, 64-64 MLP, n-step returns + one fused update per rollout "
+                            "(BASELINE.json configs[2])" % (args.env, A2C_ENVS, A2C_STEPS), "env": args.env,
+                "num_envs_per_gpu": A2C_ENVS, "num_steps": A2C_STEPS, "batch_per_gpu": A2C_ENVS * A2C_STEPS,
+                "parallelism": "single GPU"}
     return {"workload": "PPO %s, %d vectorized envs x %d steps per GPU, 64-64 MLP, %d epochs x %d minibatches "
                         "(BASELINE.json configs[1] per GPU)" % (args.env, args.envs_per_gpu, NUM_STEPS, UPDATE_EPOCHS,
                                                                 NUM_MINIBATCHES),
@@ -229,13 +237,24 @@ def run_ours(args):
                      num_minibatches=NUM_MINIBATCHES, update_epochs=UPDATE_EPOCHS, env_id=args.env, seed=1,
                      local_stats=args.local_stats)
     cfg = make_crl_config(pcfg, n_local, local_rank, world, rank, rank * n_local)
+    n_steps, n_mb, n_ep = NUM_STEPS, NUM_MINIBATCHES, UPDATE_EPOCHS
+    if args.algo == "a2c":
+        if world != 1:
+            raise SystemExit("bench.py --algo a2c is a single-GPU configuration")
+        from cleanrl_jl_b200 import a2c as a2c_mod
+        acfg = a2c_mod.A2CConfig(num_envs=A2C_ENVS, num_steps=A2C_STEPS, env_id=args.env, total_timesteps=10 ** 12)
+        cfg = a2c_mod.make_crl_config(acfg, local_rank)
+        n_local, n_steps, n_mb, n_ep = A2C_ENVS, A2C_STEPS, 1, 1
+        lr = acfg.lr
     h = PPOHandle(cfg)
     if world > 1:
         h.comm_init(parallel.exchange_unique_id(comm_unique_id))
     h.set_params(networks.init_params(kind == 1, h.d["D"], h.d["A"], seed=1))
+    h_params = h.d["P"]
     h.env_reset()
-    lr = float(np.float32(2.5e-4))
-    B_local = n_local * NUM_STEPS
+    if args.algo != "a2c":
+        lr = float(np.float32(2.5e-4))
+    B_local = n_local * n_steps
 
     def barrier():
         if dist is not None:
@@ -275,10 +294,8 @@ def run_ours(args):
     kernels = {k: {"ms_per_update": v["ms"] / prof_updates, "launches_per_update": v["launches"] / prof_updates,
                    "share": v["ms"] / total_k} for k, v in kt.items() if v["launches"]}
     lg = kt["loss_grad"]
-    M_local = B_local // NUM_MINIBATCHES
-    # the speculative path launches loss_grad twice per minibatch; the second (verification) launch exits at
-    # once unless the speculation failed, so the time is attributed to the epochs*minibatches real launches
-    real_launches = prof_updates * UPDATE_EPOCHS * NUM_MINIBATCHES
+    M_local = B_local // n_mb
+    real_launches = prof_updates * n_ep * n_mb
     lg_ms = lg["ms"] / real_launches
     flops = UPDATE_FLOP * M_local
     peaks = measured_peaks()
@@ -315,7 +332,12 @@ def run_ours(args):
                       num_minibatches=NUM_MINIBATCHES, update_epochs=UPDATE_EPOCHS, env_id=args.env, seed=1,
                       local_stats=args.local_stats)
     barrier()
-    res = ppo(pcfg2, logger=logger, device=local_rank)
+    if args.algo == "a2c":
+        acfg2 = a2c_mod.A2CConfig(num_envs=A2C_ENVS, num_steps=A2C_STEPS, env_id=args.env, total_timesteps=e2e_updates * B_local)
+        res = a2c_mod.a2c(acfg2, logger=logger, device=local_rank)
+        res.update(h2d_bytes=4 * h_params + 8 * res["num_updates"], d2h_bytes=72 * res["num_updates"], host_s={})
+    else:
+        res = ppo(pcfg2, logger=logger, device=local_rank)
     e2e_s = parallel.max_over_ranks(res["elapsed_s"])
     e2e = {"value": res["global_step"] / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": res["h2d_bytes"] / res["num_updates"], "d2h_bytes_per_step": res["d2h_bytes"] / res["num_updates"],
@@ -326,7 +348,7 @@ def run_ours(args):
         logger.close()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.algo == "ppo":
         cores = os.cpu_count() or 1
         rate, _, build = cpu_ppo_throughput(kind, 256, 1, 1, cores)
         n_s = int(min(n_local, max(64, (rate * 15.0) // NUM_STEPS)))
@@ -340,7 +362,7 @@ def run_ours(args):
         dist.barrier()
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC if args.algo == "ppo" else "a2c_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world),
                                                                 l2="not flushed: every step regenerates its 16.5 MB rollout buffer on the device "

@@ -9,7 +9,7 @@ nothing — the library is dlopen'ed on first use and there is no CPU fallback.
 from . import _abi  # noqa: F401
 from .config import PPOConfig, argparse_struct  # noqa: F401
 
-__all__ = ["PPOConfig", "argparse_struct", "ppo", "PPOHandle", "Networks", "Logger", "ConfigParser"]
+__all__ = ["PPOConfig", "A2CConfig", "argparse_struct", "ppo", "a2c", "PPOHandle", "Networks", "Logger", "ConfigParser"]
 
 
 def __getattr__(name):
@@ -17,6 +17,12 @@ def __getattr__(name):
     if name == "ppo":
         from .ppo import ppo
         return ppo
+    if name == "a2c":
+        from .a2c import a2c
+        return a2c
+    if name == "A2CConfig":
+        from .a2c import A2CConfig
+        return A2CConfig
     if name == "PPOHandle":
         from .handle import PPOHandle
         return PPOHandle

@@ -226,7 +226,8 @@ static int check_cfg(const crl_config* c) {
   if (B / c->num_minibatches < 2) return fail(CRL_ERR_INVALID, "minibatch size must be >= 2 (corrected std, ppo.jl:221)");
   if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) return fail(CRL_ERR_INVALID, "bad world_size/rank");
   if (c->world_size > CRL_MAX_WORLD) return fail(CRL_ERR_INVALID, "world_size > %d is not supported", CRL_MAX_WORLD);
-  if (c->gae_mode != CRL_GAE_REF_COMPAT && c->gae_mode != CRL_GAE_FIXED) return fail(CRL_ERR_INVALID, "bad gae_mode");
+  if (c->gae_mode != CRL_GAE_REF_COMPAT && c->gae_mode != CRL_GAE_FIXED && c->gae_mode != CRL_GAE_A2C_RETURNS)
+    return fail(CRL_ERR_INVALID, "bad gae_mode");
   return CRL_OK;
 }
 
@@ -551,6 +552,7 @@ static AdamArgs adam_args(crl_ctx* c, int M, double lr_host, double* stats_slot)
   aa.beta_pow = c->beta_pow; aa.ds = c->ds; aa.lr_host = lr_host; aa.clip_norm = c->cfg.clip_norm;
   aa.ent_coeff = c->cfg.ent_coeff; aa.v_coef = c->cfg.v_coef; aa.M_global = (double)M; aa.A = c->L.A;
   aa.stats_out = stats_slot; aa.world = 1; aa.rank = c->cfg.rank; aa.M = M; aa.P = c->L.P; aa.ds_rw = c->ds; aa.fin = c->fin;
+  aa.algo = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
   return aa;
 }
 
@@ -582,8 +584,9 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
   ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
   ua.rank = c->cfg.rank;
+  ua.algo = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
   AdamArgs aa = adam_args(c, M, lr_host, stats_slot);
-  if (spec) {
+  if (spec || ua.algo == 1) {  // the A2C losses have no minibatch-global scalars: the 3-kernel chain is already exact
     const bool p2p = multi && c->p2p_on;
     ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
     if (p2p) { ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq; }
@@ -651,8 +654,9 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
 static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, bool spec = false) {
   int k = 0;
   const int n_sets = c->cfg.update_epochs * c->cfg.num_minibatches;
-  if (spec) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
-  if (spec && c->cfg.world_size > 1) {  // global advantage sums for all minibatches of the update: one collective per update
+  const bool a2c = (c->cfg.flags & CRL_FLAG_A2C) != 0;  // the A2C losses use no advantage normalisation
+  if (spec && !a2c) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
+  if (spec && !a2c && c->cfg.world_size > 1) {  // global advantage sums for all minibatches of the update: one collective per update
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(c->advparts, c->advparts, (size_t)n_sets * ADV_CHUNKS * 2, ncclFloat64, ncclSum, c->comm, c->stream));
   }
@@ -1008,8 +1012,8 @@ extern "C" CRL_API int crl_gae_raw(const float* values, const float* rewards, co
                            float lambda, int32_t mode, void* stream) {
   if (!values || !rewards || !dones || !adv || !ret) return fail(CRL_ERR_INVALID, "NULL argument");
   if (T < 1 || N < 0) return fail(CRL_ERR_INVALID, "T must be >= 1 and N >= 0");
-  if (mode != CRL_GAE_REF_COMPAT && mode != CRL_GAE_FIXED) return fail(CRL_ERR_INVALID, "bad gae mode");
-  if (mode == CRL_GAE_FIXED && (!next_value || !next_done)) return fail(CRL_ERR_INVALID, "FIXED mode needs the bootstrap arrays");
+  if (mode != CRL_GAE_REF_COMPAT && mode != CRL_GAE_FIXED && mode != CRL_GAE_A2C_RETURNS) return fail(CRL_ERR_INVALID, "bad gae mode");
+  if (mode != CRL_GAE_REF_COMPAT && (!next_value || !next_done)) return fail(CRL_ERR_INVALID, "FIXED / A2C modes need the bootstrap arrays");
   CK(launch_gae(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, lambda, mode, (cudaStream_t)stream));
   return CRL_OK;
 }
@@ -1072,7 +1076,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
     g_raw.device = dev; g_raw.M = M;
   }
   UpdateArgs ua;
-  ua.env_kind = env_kind; ua.params = params; ua.image = nullptr; ua.M = M;
+  ua.env_kind = env_kind; ua.algo = 0; ua.params = params; ua.image = nullptr; ua.M = M;
   ua.idx.arr = idx; ua.idx.start = 0; ua.idx.B = (uint32_t)M; ua.idx.half_bits = 1; ua.idx.epoch = 0; ua.idx.rank = 0;
   ua.idx.seed = 0; ua.idx.ds = g_raw.ds;
   ua.states = states; ua.actions = actions; ua.logprobs = logprobs; ua.advantages = advantages; ua.returns = returns;

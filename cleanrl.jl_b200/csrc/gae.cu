@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ valu
     unpack(reinterpret_cast<const VF*>(next_value)[i], vnext);
     unpack(reinterpret_cast<const VB*>(next_done)[i], dnext);
     t_hi = T - 1;
+    if (MODE == CRL_GAE_A2C_RETURNS) {
+      // discounted_future_rewards (a2c.jl:13-24): the carried quantity is the return itself, seeded with final_value
+#pragma unroll
+      for (int k = 0; k < VEC; k++) gae[k] = (double)vnext[k];
+    }
   }
 
   for (int t0 = t_hi; t0 >= 0; t0 -= U) {
@@ -102,6 +107,14 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ valu
         unpack(d[u], df);
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
+          if (MODE == CRL_GAE_A2C_RETURNS) {
+            // future[t] = terminals[t] ? 0 : r[t] + γ future[t+1]; advantage = future - value (a2c.jl:20,83)
+            gae[k] = dnext[k] ? 0.0 : __dadd_rn((double)rf[k], __dmul_rn(g, gae[k]));
+            rt[k] = (float)gae[k];
+            af[k] = (float)__dsub_rn(gae[k], (double)vf[k]);
+            dnext[k] = df[k];
+            continue;
+          }
           const double nonterm = dnext[k] ? 0.0 : 1.0;  // 1.0 - terminals[t+1]
           const double delta =
               __dsub_rn(__dadd_rn((double)rf[k], __dmul_rn(__dmul_rn(g, nonterm), (double)vnext[k])), (double)vf[k]);
@@ -157,5 +170,7 @@ cudaError_t launch_gae(const float* values, const float* rewards, const uint8_t*
   const float gl = gamma * lambda;  // Float32 product first (γ * λ * ..., ppo.jl:68)
   if (mode == CRL_GAE_REF_COMPAT)
     return launch_mode<CRL_GAE_REF_COMPAT>(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, gl, s);
+  if (mode == CRL_GAE_A2C_RETURNS)
+    return launch_mode<CRL_GAE_A2C_RETURNS>(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, gl, s);
   return launch_mode<CRL_GAE_FIXED>(values, rewards, dones, next_value, next_done, adv, ret, T, N, gamma, gl, s);
 }

@@ -69,6 +69,7 @@ struct AdvStatsArgs {
 
 struct UpdateArgs {
   int env_kind;
+  int algo;            // 0 = PPO clipped surrogate (ppo.jl:213-243), 1 = A2C losses (a2c.jl:78-97)
   const float* params;
   const float* image;  // shared-memory image of the parameters (see param_image_floats) or nullptr
   IdxSrc idx;
@@ -134,6 +135,7 @@ struct AdamArgs {
   int p2p_stride;
   size_t p2p_flags_off;
   int world, rank;
+  int algo;                             // 0 = PPO loss scalars, 1 = A2C (actor_loss, critic_loss)
   int verify;                           // 1: check s <= min (clip-R)^2 and set ds_rw->spec_failed otherwise
   int M, P;
   DevState* ds_rw;

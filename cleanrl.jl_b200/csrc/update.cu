@@ -524,6 +524,29 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
           }
           newlp = acc;
         }
+        if (a.algo == 1) {
+          // A2C (a2c.jl:78-97): critic_loss = mean((R - v)^2), gradient through v; actor_loss = -mean(logp .* (R - v))
+          // with the advantage held constant. One combined step == the reference's two update! calls (disjoint
+          // parameter sets, per-array ClipNorm/Adam).
+          const double advd = (double)s_R - (double)v;
+          st_vmax += advd * advd;
+          st_pg += -(double)newlp * advd;
+          dv = (float)(-2.0 * advd / Mg);
+          const double g_a = -advd / Mg;
+          if (!E::CONT) {
+#pragma unroll
+            for (int k = 0; k < A; k++) dz[k] = (float)(g_a * ((k == s_act ? 1.0 : 0.0) - (double)p[k]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < A; k++) {
+              const float sd = expf(sp[SmemParams<ENV>::LOGSTD + k]);
+              const double diff = (double)__fsub_rn(s_actf[k], z[k]);
+              const double var = (double)sd * (double)sd;
+              dz[k] = (float)(g_a * diff / var);
+              g_logstd[k] += g_a * (diff * diff / var - 1.0);
+            }
+          }
+        } else {
         const float logratio = __fsub_rn(newlp, s_oldlp);  // ppo.jl:224
         const float ratio = expf(logratio);                // ppo.jl:225
         const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
@@ -567,6 +590,7 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
             g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
           }
         }
+        }  // PPO
       }
 #pragma unroll
       for (int k = 0; k < A; k++) dout[k * S + s] = dz[k];
@@ -841,7 +865,14 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(AdvStatsArgs a) {
 
 // loss scalars from the reduced sums (ppo.jl:228,237,242,243)
 __device__ __forceinline__ void finalize_stats(const double* sums, double Mg, int A, float ent_coeff, float v_coef,
-                                               double* out) {
+                                               double* out, int algo = 0) {
+  if (algo == 1) {  // A2C: @info "Training Statistics" actor_loss critic_loss (a2c.jl:100)
+    out[1] = sums[0] / Mg;
+    out[2] = sums[1] / Mg;
+    out[3] = 0.0;
+    out[0] = out[1] + out[2];
+    return;
+  }
   const double pg = sums[0] / Mg;                                   // ppo.jl:228
   const double vl = 0.5 * (double)(float)(sums[1] / Mg);            // ppo.jl:237
   const double en = (double)(float)(sums[2] / ((double)A * Mg));    // ppo.jl:242
@@ -995,7 +1026,7 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
       double tail[4 + CRL_MAX_WORLD];
       const int nt = 4 + (a.verify ? a.world : 0);
       for (int k = 0; k < nt; k++) tail[k] = finish_load(a, slot, L.P + k);
-      if (a.stats_out) finalize_stats(tail, a.M_global * a.stat_ranks, a.A, a.ent_coeff, a.v_coef, a.stats_out);
+      if (a.stats_out) finalize_stats(tail, a.M_global * a.stat_ranks, a.A, a.ent_coeff, a.v_coef, a.stats_out, a.algo);
       if (a.verify) {
         float m = INFINITY;
         for (int r = 0; r < a.world; r++) m = fminf(m, (float)tail[4 + r]);

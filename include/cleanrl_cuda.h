@@ -62,9 +62,13 @@ extern "C" {
 /* GAE scan variants */
 #define CRL_GAE_REF_COMPAT 0 /* ppo.jl:66 as written: scan starts at T-1 with zero carry; adv[T] := 0 */
 #define CRL_GAE_FIXED 1      /* scan starts at T and uses the bootstrap value/flag */
+#define CRL_GAE_A2C_RETURNS 2 /* discounted_future_rewards of a2c.jl:13-24: ret[t] = term[t] ? 0 : r[t] + γ ret[t+1], bootstrap
+                                 final_value; adv = ret - value (a2c.jl:83). term[t] = is_terminated AFTER step t. */
 
 /* crl_config.flags */
 #define CRL_FLAG_LOCAL_STATS 1u /* multi-GPU: per-shard minibatch statistics (no pre-backward exchange) */
+#define CRL_FLAG_A2C 2u         /* A2C losses (a2c.jl:78-97) instead of the PPO clipped surrogate: critic mean((ret-v)^2),
+                                   actor -mean(logp * (ret - v)); use with CRL_GAE_A2C_RETURNS, 1 epoch x 1 minibatch */
 
 /* buffer fields for crl_read_field / crl_write_field */
 #define CRL_F_STATE 0       /* float  [T][N][D]                                    */

@@ -59,6 +59,7 @@ class OracleLib:
             [C.c_float] * 3 + [C.c_void_p] * 3
         L.orc_ppo_loss_phase.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + \
             [C.c_float] * 3 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_a2c_loss_raw.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 5
         L.orc_clip_adam_raw.argtypes = [C.c_int32] + [C.c_void_p] * 5 + [C.c_double, C.c_float]
         L.orc_create.argtypes = [C.POINTER(_abi.crl_config), C.POINTER(C.c_void_p)]
         for f in ("orc_destroy", "orc_env_reset", "orc_gae"):
@@ -185,6 +186,20 @@ class OracleLib:
                                        clip_coef, ent_coeff, v_coef, _ptr(grads), _ptr(stats), _ptr(vnew))
         assert rc == 0, rc
         return grads, stats, vnew
+
+    def a2c_loss_raw(self, env_kind, params, idx, states, actions, returns):
+        d = self.dims(env_kind)
+        params = np.ascontiguousarray(params, np.float32)
+        idx = np.ascontiguousarray(idx, np.int32)
+        states = np.ascontiguousarray(states, np.float32)
+        actions = np.ascontiguousarray(actions, np.int32 if env_kind == _abi.CRL_ENV_CARTPOLE else np.float32)
+        returns = np.ascontiguousarray(returns, np.float32)
+        grads = np.zeros(d["P"], np.float32)
+        stats = np.zeros(4, np.float64)
+        rc = self.lib.orc_a2c_loss_raw(env_kind, _ptr(params), _ptr(idx), idx.shape[0], _ptr(states), _ptr(actions),
+                                       _ptr(returns), _ptr(grads), _ptr(stats))
+        assert rc == 0, rc
+        return grads, stats
 
     def ppo_loss_phase(self, env_kind, params, idx, states, actions, logprobs, advantages, returns, values,
                        clip_coef, ent_coeff, v_coef, phase, io, vnew):

@@ -392,6 +392,19 @@ static void gae_range(int64_t lo, int64_t hi, int tid, void* argp) {
   const int64_t N = a->N;
   const float gl = a->gamma * a->lambda; /* Float32 product */
   for (int64_t n = lo; n < hi; n++) {
+    if (a->mode == CRL_GAE_A2C_RETURNS) {
+      /* discounted_future_rewards, a2c.jl:13-24 (Float64 there): future[t] = terminals[t] ? 0 : r[t] + γ future[t+1],
+       * seeded with final_value; terminals[t] is is_terminated AFTER step t = the flag stored one row later here.
+       * advantage = discounted_rewards - values (a2c.jl:83). */
+      double fut = (double)a->next_value[n];
+      for (int t = T - 1; t >= 0; t--) {
+        const int term = t == T - 1 ? a->next_done[n] : a->dones[(int64_t)(t + 1) * N + n];
+        fut = term ? 0.0 : (double)a->rewards[(int64_t)t * N + n] + (double)a->gamma * fut;
+        a->ret[(int64_t)t * N + n] = (float)fut;
+        a->adv[(int64_t)t * N + n] = (float)(fut - (double)a->values[(int64_t)t * N + n]);
+      }
+      continue;
+    }
     double gae = 0.0;
     int tstart;
     if (a->mode == CRL_GAE_REF_COMPAT) {
@@ -910,6 +923,57 @@ int orc_ppo_loss_phase(int32_t env_kind, const float* params, const int32_t* idx
   return 0;
 }
 
+/* A2C losses and their gradient for one batch (a2c.jl:78-97): critic_loss = mean((R - v)^2) with the gradient flowing
+ * through v; actor_loss = -mean(logp(a) .* advantage) with advantage = R - v held constant. The reference applies two
+ * update! calls (critic, then actor) with one optimiser; the parameter sets are disjoint and ClipNorm/Adam are per array,
+ * so one combined step is identical. stats_out = {actor+critic, actor_loss, critic_loss, 0}. */
+int orc_a2c_loss_raw(int32_t env_kind, const float* params, const int32_t* idx, int32_t M, const float* states,
+                     const void* actions, const float* returns, float* grads_out, double* stats_out) {
+  layout_t L;
+  if (make_layout(env_kind, &L) || M < 1) return CRL_ERR_INVALID;
+  double* g = (double*)calloc(L.P, 8);
+  double actor = 0.0, critic = 0.0;
+  for (int i = 0; i < M; i++) {
+    const int b = idx[i];
+    const float* x = states + (int64_t)b * L.D;
+    float h1a[H], h2a[H], h1c[H], h2c[H], z[MAXA], v, p[MAXA], lp[MAXA], dz[MAXA];
+    mlp_forward(params + L.actor, L.D, L.A, x, h1a, h2a, z);
+    mlp_forward(params + L.critic, L.D, 1, x, h1c, h2c, &v);
+    const double adv = (double)returns[b] - (double)v; /* a2c.jl:83 */
+    critic += adv * adv;                               /* a2c.jl:84 */
+    const float dv = (float)(-2.0 * adv / (double)M);
+    const double g_lp = -adv / (double)M;              /* d(-mean(logp .* adv))/dlogp, a2c.jl:95 */
+    double newlp;
+    if (!L.continuous) {
+      softmax_logsoftmax(z, L.A, p, lp);
+      const int act = ((const int32_t*)actions)[b];
+      newlp = (double)lp[act];
+      for (int k = 0; k < L.A; k++) dz[k] = (float)(g_lp * ((k == act ? 1.0 : 0.0) - (double)p[k]));
+    } else {
+      float s = 0.0f;
+      for (int k = 0; k < L.A; k++) {
+        const float logstd = params[L.logstd + k], sd = expf(logstd);
+        const float diff = ((const float*)actions)[(int64_t)b * L.A + k] - z[k];
+        s += -(diff * diff) / (2.0f * sd * sd) - logstd - 0.9189385332046727f;
+        const double var = (double)sd * (double)sd;
+        dz[k] = (float)(g_lp * (double)diff / var);
+        g[L.logstd + k] += g_lp * ((double)diff * (double)diff / var - 1.0);
+      }
+      newlp = (double)s;
+    }
+    actor += -newlp * adv;
+    mlp_backward(params + L.actor, g + L.actor, L.D, L.A, x, h1a, h2a, dz);
+    mlp_backward(params + L.critic, g + L.critic, L.D, 1, x, h1c, h2c, &dv);
+  }
+  for (int k = 0; k < L.P; k++) grads_out[k] = (float)g[k];
+  stats_out[1] = actor / M;
+  stats_out[2] = critic / M;
+  stats_out[3] = 0.0;
+  stats_out[0] = stats_out[1] + stats_out[2];
+  free(g);
+  return 0;
+}
+
 /* Flux.Optimise.update!(Optimiser(ClipNorm(thresh), Adam(η)), params, gs), ppo.jl:93,250
  * [Flux 0.13.4]: per ARRAY: if norm(Δ) > thresh: Δ *= thresh/norm(Δ); then Adam with
  * Float64 scalars (β=(0.9,0.999), ε=1e-8) on Float32 state, per-array β powers. */
@@ -946,8 +1010,12 @@ int orc_clip_adam_raw(int32_t env_kind, float* params, const float* grads, float
 int orc_update_minibatch(orc_ctx* c, const int32_t* idx, int32_t M, double lr, crl_loss_stats* stats) {
   if (!c->gae_done) return CRL_ERR_STATE;
   double st[4];
-  int rc = orc_ppo_loss_raw(c->cfg.env_kind, c->params, idx, M, c->state, c->action, c->logprob, c->advantage,
-                            c->ret, c->value, c->cfg.clip_coef, c->cfg.ent_coeff, c->cfg.v_coef, c->grads, st, c->vnew);
+  int rc;
+  if (c->cfg.flags & CRL_FLAG_A2C)
+    rc = orc_a2c_loss_raw(c->cfg.env_kind, c->params, idx, M, c->state, c->action, c->ret, c->grads, st);
+  else
+    rc = orc_ppo_loss_raw(c->cfg.env_kind, c->params, idx, M, c->state, c->action, c->logprob, c->advantage,
+                          c->ret, c->value, c->cfg.clip_coef, c->cfg.ent_coeff, c->cfg.v_coef, c->grads, st, c->vnew);
   if (rc) return rc;
   if (stats) { stats->loss = st[0]; stats->pg_loss = st[1]; stats->v_loss = st[2]; stats->entropy_loss = st[3]; }
   return orc_clip_adam_raw(c->cfg.env_kind, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, lr, c->cfg.clip_norm);
