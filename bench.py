@@ -220,7 +220,7 @@ def run_ours(args):
     from cleanrl_jl_b200 import _abi, _lib, networks, parallel
     from cleanrl_jl_b200.config import PPOConfig
     from cleanrl_jl_b200.handle import PPOHandle, comm_unique_id
-    from cleanrl_jl_b200.ppo import ppo, make_crl_config
+    from cleanrl_jl_b200.ppo_algo import ppo, make_crl_config
     from cleanrl_jl_b200 import logger as Logger
 
     rank, local_rank, world = parallel.dist_info()
@@ -241,7 +241,7 @@ def run_ours(args):
     if args.algo == "a2c":
         if world != 1:
             raise SystemExit("bench.py --algo a2c is a single-GPU configuration")
-        from cleanrl_jl_b200 import a2c as a2c_mod
+        from cleanrl_jl_b200 import a2c_algo as a2c_mod
         acfg = a2c_mod.A2CConfig(num_envs=A2C_ENVS, num_steps=A2C_STEPS, env_id=args.env, total_timesteps=10 ** 12)
         cfg = a2c_mod.make_crl_config(acfg, local_rank)
         n_local, n_steps, n_mb, n_ep = A2C_ENVS, A2C_STEPS, 1, 1

@@ -12,16 +12,22 @@ from .config import PPOConfig, argparse_struct  # noqa: F401
 __all__ = ["PPOConfig", "A2CConfig", "argparse_struct", "ppo", "a2c", "PPOHandle", "Networks", "Logger", "ConfigParser"]
 
 
+def ppo(*args, **kwargs):
+    """Drop-in for CleanRL.ppo(config) (ppo.jl:75); see ppo_algo.py."""
+    from .ppo_algo import ppo as _ppo
+    return _ppo(*args, **kwargs)
+
+
+def a2c(*args, **kwargs):
+    """Vectorised A2C on the same kernels (a2c.jl:30); see a2c_algo.py."""
+    from .a2c_algo import a2c as _a2c
+    return _a2c(*args, **kwargs)
+
+
 def __getattr__(name):
     # lazy: keep `import cleanrl_jl_b200` free of ctypes/torch side effects
-    if name == "ppo":
-        from .ppo import ppo
-        return ppo
-    if name == "a2c":
-        from .a2c import a2c
-        return a2c
     if name == "A2CConfig":
-        from .a2c import A2CConfig
+        from .a2c_algo import A2CConfig
         return A2CConfig
     if name == "PPOHandle":
         from .handle import PPOHandle

@@ -87,7 +87,7 @@ def test_a2c_loss_gradient_matches_float64_autograd(olib, kind):
 
 
 def test_a2c_config_defaults_match_a2c_jl():
-    from cleanrl_jl_b200.a2c import A2CConfig, make_crl_config
+    from cleanrl_jl_b200.a2c_algo import A2CConfig, make_crl_config
     c = A2CConfig()
     assert (c.lr, c.total_timesteps, c.min_replay_size, c.gamma) == (0.0001, 1_000_000, 512, 0.99)  # a2c.jl:4-9
     cfg = make_crl_config(c)

@@ -45,7 +45,7 @@ def test_argparse_struct_round_trip():
 
 
 def test_annealed_lr_matches_ppo_jl_118_121():
-    from cleanrl_jl_b200.ppo import annealed_lr
+    from cleanrl_jl_b200.ppo_algo import annealed_lr
     c = PPOConfig()
     n = 3906
     assert annealed_lr(c, 1, n) == float(F(2.5e-4))
@@ -54,7 +54,7 @@ def test_annealed_lr_matches_ppo_jl_118_121():
 
 
 def test_make_crl_config_and_error_behaviour(abi):
-    from cleanrl_jl_b200.ppo import make_crl_config
+    from cleanrl_jl_b200.ppo_algo import make_crl_config
     cfg = make_crl_config(PPOConfig())
     assert (cfg.env_kind, cfg.num_envs, cfg.num_steps, cfg.max_episode_steps, cfg.gae_mode) == (0, 4, 32, 500, 0)
     assert cfg.clip_norm == 0.5 and F(cfg.gamma) == F(0.99)
