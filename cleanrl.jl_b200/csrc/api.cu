@@ -585,6 +585,8 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
   ua.rank = c->cfg.rank;
   ua.algo = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
+  ua.tc_net_a = c->L.critic - c->L.actor; ua.tc_net_c = (c->L.continuous ? c->L.logstd : c->L.P) - c->L.critic;
+  loss_grad_tc_plan(&ua, c->sm_count);  // tensor-core kernel when it applies: sets grid_loss / tc_actor_ctas
   AdamArgs aa = adam_args(c, M, lr_host, stats_slot);
   if (spec || ua.algo == 1) {  // the A2C losses have no minibatch-global scalars: the 3-kernel chain is already exact
     const bool p2p = multi && c->p2p_on;

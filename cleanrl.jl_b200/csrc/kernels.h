@@ -104,6 +104,10 @@ struct UpdateArgs {
   double* p2p_data;                     // own exchange buffer: [2 slots][p2p_stride doubles]
   int p2p_stride;
   unsigned long long* p2p_seq;          // exchange sequence number: loss_grad advances it, slot = seq & 1
+  // tcgen05 kernel (update_tc.cu): CTAs [0, tc_actor_ctas) own the actor, the rest the critic, and each CTA writes
+  // only its own net's slice of gpart; 0 = the FFMA kernel (every CTA writes all P elements)
+  int tc_actor_ctas;
+  int tc_net_a, tc_net_c;               // sizes of the actor / critic slices of the flat parameter vector
 };
 
 #define CRL_MAX_WORLD 16
@@ -165,6 +169,10 @@ cudaError_t launch_adv_stats(const AdvStatsArgs& a, cudaStream_t s);
 cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
+// tensor-core variant: loss_grad_tc_plan decides whether it applies and sets grid_loss / tc_actor_ctas
+cudaError_t kernels_init_update_tc();
+int loss_grad_tc_plan(UpdateArgs* a, int sm_count);
+cudaError_t launch_loss_grad_tc(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);
 

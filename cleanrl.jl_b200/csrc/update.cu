@@ -15,36 +15,11 @@
 // FP32 FFMA throughout (no TF32): results are within fp32 rounding of the oracle.
 #include "kernels.h"
 #include "mlp_tile.cuh"
+#include "update_common.cuh"
 
 namespace {
 
-// ------------------------------------------------------------------ helpers
-__device__ __forceinline__ int sample_index(const IdxSrc& ix, const uint32_t* keys, int m) {
-  if (ix.arr) return ix.arr[m];
-  return (int)perm_index(ix.start + (uint32_t)m, ix.B, ix.half_bits, keys);
-}
-
-// value-loss pieces of ppo.jl:234-235, evaluated identically in all three kernels
-__device__ __forceinline__ void value_clip(float v, float V, float R, float c, float& vc_minus_R, float& vlc,
-                                           bool& inside) {
-  const float dv = __fsub_rn(v, V);
-  const float cl = dv < -c ? -c : (dv > c ? c : dv);
-  const float vc = __fadd_rn(V, cl);
-  vc_minus_R = __fsub_rn(vc, R);
-  vlc = __fmul_rn(vc_minus_R, vc_minus_R);
-  inside = dv >= -c && dv <= c;
-}
-
-template <int NW> __device__ __forceinline__ double block_sum(double v, double* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double s = 0.0;
-#pragma unroll
-  for (int w = 0; w < NW; w++) s += red[w];
-  return s;
-}
+using namespace crl_upd;
 
 // ------------------------------------------------------------------ mb_stats
 template <int ENV> struct StatsSmem {
@@ -245,6 +220,7 @@ template <int ENV> __device__ __forceinline__ void image_scatter(float* image, i
   if (within >= NO::W2 && within < NO::W2 + CRL_H * CRL_H) {
     const int e = within - NO::W2, j = e % CRL_H, k = e / CRL_H;  // Flux W2 is (out=j, in=k) at j + 64 k
     image[SPm::SIZE + net * CRL_H * CRL_H + j * CRL_H + k] = v;
+    tc_image_scatter<ENV>(image, net, j, k, v);  // hi/lo tensor-core operand images (update_tc.cu)
   }
 }
 template <int ENV> __global__ void param_image_kernel(const float* params, float* image) {
@@ -824,8 +800,13 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   const int e = blockIdx.x * 64 + el;
   double s = 0.0;
   if (e < P) {
+    int c_lo = 0, c_hi = grid;
+    if (a.tc_actor_ctas) {  // one net per CTA: only that net's CTAs hold element e
+      const bool critic = e >= a.tc_net_a && e < a.tc_net_a + a.tc_net_c;
+      if (critic) c_lo = a.tc_actor_ctas; else c_hi = a.tc_actor_ctas;
+    }
 #pragma unroll 8
-    for (int c = g; c < grid; c += 4) s += (double)a.gpart[(long long)c * P + e];
+    for (int c = c_lo + g; c < c_hi; c += 4) s += (double)a.gpart[(long long)c * P + e];
   } else if (e < P + 4) {
     for (int c = g; c < grid; c += 4) s += a.spart[(long long)c * 4 + (e - P)];
   }
@@ -1075,7 +1056,9 @@ cudaError_t kernels_init_update() {
   if (e != cudaSuccess) return e;
   e = set_smem(loss_grad_kernel<CRL_ENV_CARTPOLE>, LossSmem<CRL_ENV_CARTPOLE>::BYTES);
   if (e != cudaSuccess) return e;
-  return set_smem(loss_grad_kernel<CRL_ENV_PENDULUM>, LossSmem<CRL_ENV_PENDULUM>::BYTES);
+  e = set_smem(loss_grad_kernel<CRL_ENV_PENDULUM>, LossSmem<CRL_ENV_PENDULUM>::BYTES);
+  if (e != cudaSuccess) return e;
+  return kernels_init_update_tc();
 }
 
 cudaError_t launch_mb_stats(const UpdateArgs& a, int grid, cudaStream_t s) {
@@ -1095,6 +1078,7 @@ cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s) {
+  if (a.tc_actor_ctas) return launch_loss_grad_tc(a, s);
   if (a.env_kind == CRL_ENV_CARTPOLE)
     loss_grad_kernel<CRL_ENV_CARTPOLE><<<a.grid_loss, CRL_THREADS, LossSmem<CRL_ENV_CARTPOLE>::BYTES, s>>>(a);
   else
@@ -1109,7 +1093,7 @@ cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s) {
 }
 
 int param_image_floats(int env_kind) {
-  return (env_kind == CRL_ENV_CARTPOLE ? SmemParams<CRL_ENV_CARTPOLE>::SIZE : SmemParams<CRL_ENV_PENDULUM>::SIZE) + 2 * CRL_H * CRL_H;
+  return env_kind == CRL_ENV_CARTPOLE ? TcImage<CRL_ENV_CARTPOLE>::FLOATS : TcImage<CRL_ENV_PENDULUM>::FLOATS;
 }
 cudaError_t launch_param_image(int env_kind, const float* params, float* image, cudaStream_t s) {
   if (env_kind == CRL_ENV_CARTPOLE)

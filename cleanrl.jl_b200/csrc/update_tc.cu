@@ -1,0 +1,715 @@
+// update_tc.cu — the PPO minibatch forward + loss + backward (ppo.jl:197-246) with every 64-wide contraction on
+// the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM), as 3xTF32 so the results stay
+// within fp32 tolerance of the oracle (operands are split x = hi + lo with hi = TF32(x); hi*hi + lo*hi + hi*lo).
+//
+// Work decomposition. Actor and critic gradients are independent given the rollout data, so a CTA owns ONE net and a
+// persistent stride of 128-sample tiles; the first `tc_actor_ctas` CTAs take the actor, the rest the critic. Inside
+// a CTA sample s of the tile IS TMEM lane s: warp w works on lanes 32*(w%4).. (the only lanes tcgen05.ld/st lets
+// it touch) and on the feature half (w/4)*32.. of every 64-wide row, so each thread owns (1 sample, 32 features).
+//
+// Per tile (the four contractions are the only cross-thread data flow besides one 2-float head exchange):
+//   L1   h1 = tanh(W1 x + b1) on the CUDA cores (K = 4); hi/lo go to TMEM (A operand of G1, tcgen05.st) and,
+//        feature-major, to shared memory (B operand of G2)
+//   G1   z2[s][j] = sum_k h1[s][k] W2(j,k)            A = TMEM, B = weight image (rows j)          M128 N64 K64 x3
+//   E1   h2 = tanh(z2 + b2); head; per-sample loss and d(loss)/d(head) in Float64 where Julia promotes (same code
+//        as the FFMA kernel); dz2 = (W3^T dl) .* (1 - h2^2): hi/lo to TMEM (A of G3) and feature-major, hi rows
+//        stacked over lo rows, to shared memory (A of G2); dW3/db2 by warp reduce-scatter shuffles
+//   G3   dh1[s][k] = sum_j dz2[s][j] W2(j,k)          A = TMEM, B = weight image (rows k)          M128 N64 K64 x3
+//   G2   dW2(j,k) += sum_s dz2[s][j] h1[s][k]         A = [dz2_hi ; dz2_lo] (M = 128), B = h1_hi then h1_lo: rows j
+//        and 64+j of the accumulator add up to the full 4-term product; accumulates in TMEM over ALL tiles of the CTA
+//   E3   dz1 = dh1 .* (1 - h1^2), hi/lo written in place over h1's feature-major copy
+//   G4   dW1(k,d), db1(k) += sum_s x~[d][s] dz1[s][k]  A = x~^T (rows x_0..x_D-1, ones; 8 rows aliased with SBO = 0),
+//        B = [dz1_hi ; dz1_lo] (N = 128); accumulates in TMEM over all tiles
+// The weight-gradient accumulators are read out of TMEM once per launch.
+//
+// Shared memory (bytes): weight images 65,536 | dz2^T stacked 73,728 | h1^T/dz1^T hi,lo 73,728 | x~^T 8,192 |
+// small parameters + scratch ~6 KB = ~222 KB: one CTA per SM. The feature-major operands use a 144-byte chunk
+// stride (LBO) so that the 32 lanes of a warp (32 consecutive samples) store one feature conflict-free.
+// Layouts and descriptor conventions were validated on a B200 by tools/tc_probe.cu and tools/tc_probe3.cu.
+#include "kernels.h"
+#include "mlp_tile.cuh"
+#include "update_common.cuh"
+
+#include <stdlib.h>
+
+namespace {
+using namespace crl_upd;
+
+constexpr int TC_S = 128;        // samples per tile = TMEM lanes
+constexpr int TC_THREADS = 256;  // 4 lane quadrants x 2 feature halves
+constexpr int TC_FG = 32;        // features per thread
+constexpr int F_LBO = 144, F_SBO = 32 * F_LBO;  // bytes; feature-major operand: rows r, K = 128 samples
+constexpr int X_LBO = 128;                      // x~^T: 8 rows, K = 128 samples
+__device__ __forceinline__ int f_off(int r, int s) { return (r & 7) * 4 + (r >> 3) * (F_SBO / 4) + (s >> 2) * (F_LBO / 4) + (s & 3); }
+__device__ __forceinline__ int xt_off(int d, int s) { return d * 4 + (s >> 2) * (X_LBO / 4) + (s & 3); }
+
+// TMEM columns (fp32): z2/dh1 accumulator | A operand hi | A operand lo | dW2 accumulator | dW1,db1 accumulator
+constexpr uint32_t COL_D = 0, COL_AH = 64, COL_AL = 128, COL_D2 = 192, COL_D4 = 256, TMEM_COLS = 512;
+
+template <int ENV> struct TcSmem {
+  static constexpr int WB = 0;                      // [4][4096] weight images of this CTA's net
+  static constexpr int FZ = WB + 4 * TC_W_FLOATS;   // dz2^T, rows 0-63 hi, 64-127 lo
+  static constexpr int FH = FZ + 16 * F_SBO / 4;    // h1^T (later dz1^T), rows 0-63 hi, 64-127 lo
+  static constexpr int XT = FH + 16 * F_SBO / 4;    // [hi | lo][8 rows][128 samples]
+  static constexpr int W1P = XT + 2 * 1024;         // [64][4]: W1(f, d)
+  static constexpr int B1 = W1P + 4 * CRL_H;
+  static constexpr int B2 = B1 + CRL_H;
+  static constexpr int W3P = B2 + CRL_H;            // [2][64]: W3(o, f)
+  static constexpr int B3 = W3P + 2 * CRL_H;        // b3[2], logstd[2]
+  static constexpr int EXCH = B3 + 8;               // [2 feature halves][2 outputs][128 samples]
+  static constexpr int RED = EXCH + 4 * TC_S;       // 16 doubles
+  static constexpr int KEYS = RED + 32;
+  static constexpr int FLOATS = KEYS + 8;
+  static constexpr size_t BYTES = FLOATS * sizeof(float);
+  static_assert(BYTES + 256 <= 227 * 1024, "loss_grad_tc shared memory exceeds 227 KB");
+};
+
+// ---------------------------------------------------------------- tcgen05 / mbarrier wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout type 0 = no swizzle
+  return d;
+}
+// kind::tf32, fp32 accumulate, both operands K-major
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+               "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+               "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  __syncwarp();  // the lanes may arrive from a divergent mbarrier poll; the load is .sync.aligned
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr + 16));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Warp reduce-scatter: on return v[r] (r < V/32) holds the sum over the 32 lanes of the original element
+// r + (V/32) * lane. V/2 + V/4 + ... shuffles instead of 5 V for V separate butterfly reductions.
+template <int N, int OFF, int V> __device__ __forceinline__ void rs_step(float (&v)[V], int lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const float keep = up ? v[i + N] : v[i];
+    const float send = up ? v[i] : v[i + N];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+template <int V> __device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane) {
+  rs_step<V / 2, 16>(v, lane);
+  rs_step<V / 4, 8>(v, lane);
+  rs_step<V / 8, 4>(v, lane);
+  rs_step<V / 16, 2>(v, lane);
+  rs_step<V / 32, 1>(v, lane);
+}
+// element index held in v[r] after warp_reduce_scatter<V>: bit b of the lane selects the upper half at step b
+template <int V> __device__ __forceinline__ int rs_index(int lane, int r) {
+  return r + (V / 32) * ((lane & 1) | (lane & 2) | (lane & 4) | (lane & 8) | (lane & 16));
+}
+
+template <int ENV> struct Sample {
+  float x[4];
+  float adv, oldlp, R, V;
+  float actf[EnvTraits<ENV>::A];
+  int act;
+  bool valid;
+};
+template <int ENV, int NET>
+__device__ __forceinline__ void load_sample(const UpdateArgs& a, const uint32_t* keys, int m, Sample<ENV>& in) {
+  using E = EnvTraits<ENV>;
+  in.valid = m < a.M;
+  in.x[0] = in.x[1] = in.x[2] = in.x[3] = 0.0f;
+  in.adv = in.oldlp = in.R = in.V = 0.0f;
+  in.act = 0;
+#pragma unroll
+  for (int k = 0; k < E::A; k++) in.actf[k] = 0.0f;
+  if (!in.valid) return;
+  const int b = sample_index(a.idx, keys, m);
+  if (E::D == 4) {
+    const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.states) + b);
+    in.x[0] = x4.x; in.x[1] = x4.y; in.x[2] = x4.z; in.x[3] = x4.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < E::D; k++) in.x[k] = __ldg(a.states + (long long)b * E::D + k);
+  }
+  if (NET == 0) {
+    in.adv = __ldg(a.advantages + b);
+    in.oldlp = __ldg(a.logprobs + b);
+    if (E::CONT) {
+#pragma unroll
+      for (int k = 0; k < E::A; k++) in.actf[k] = __ldg(reinterpret_cast<const float*>(a.actions) + (long long)b * E::A + k);
+    } else {
+      in.act = __ldg(reinterpret_cast<const int*>(a.actions) + b);
+    }
+  } else {
+    in.R = __ldg(a.returns + b);
+    in.V = __ldg(a.values + b);
+  }
+}
+
+struct TcBars { unsigned long long pbar, g1, g2, g3, g4; };
+
+template <int ENV, int NET>
+__device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars* bars, const uint32_t tmem) {
+  using E = EnvTraits<ENV>;
+  using SM = TcSmem<ENV>;
+  using NO = NetOff<E::D, 1>;
+  using NA = NetOff<E::D, E::A>;
+  constexpr int D = E::D, A = E::A;
+  constexpr int NOUT = NET == 0 ? A : 1;
+  float* wb = smem + SM::WB;
+  float* fz = smem + SM::FZ;
+  float* fh = smem + SM::FH;
+  float* xt = smem + SM::XT;
+  const float4* w1p = reinterpret_cast<const float4*>(smem + SM::W1P);
+  const float* b1s = smem + SM::B1;
+  const float* b2s = smem + SM::B2;
+  const float* w3p = smem + SM::W3P;
+  const float* b3s = smem + SM::B3;
+  float* exch = smem + SM::EXCH;
+  double* red = reinterpret_cast<double*>(smem + SM::RED);
+  const uint32_t* keys = reinterpret_cast<const uint32_t*>(smem + SM::KEYS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, g = warp >> 2;
+  const int s = q * 32 + lane;   // sample of the tile = TMEM lane
+  const int f0 = g * TC_FG;      // this thread's feature half
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t bar1 = smem_u32(&bars->g1), bar2 = smem_u32(&bars->g2), bar3 = smem_u32(&bars->g3), bar4 = smem_u32(&bars->g4);
+
+  const int n_cta = NET == 0 ? a.tc_actor_ctas : (int)gridDim.x - a.tc_actor_ctas;
+  const int cta = NET == 0 ? (int)blockIdx.x : (int)blockIdx.x - a.tc_actor_ctas;
+  const int n_tiles = (a.M + TC_S - 1) / TC_S;
+
+  // minibatch scalars (same derivation as loss_grad_kernel)
+  const bool spec = a.mode == LG_SPEC;
+  float mean_f, std_f, s_f;
+  double Mg, cnt_over_M;
+  if (spec) {
+    double sa = 0.0, sa2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < ADV_CHUNKS; i++) { sa += a.advparts[2 * i]; sa2 += a.advparts[2 * i + 1]; }
+    Mg = (double)a.M * (double)a.world;
+    const double mean = sa / Mg;
+    double var = (sa2 - Mg * mean * mean) / (Mg - 1.0);
+    if (var < 0.0) var = 0.0;
+    mean_f = (float)mean; std_f = (float)sqrt(var); s_f = 0.0f; cnt_over_M = 0.0;
+  } else {
+    mean_f = a.fin->adv_mean; std_f = a.fin->adv_std; s_f = a.fin->s_unclipped;
+    Mg = a.fin->M_global;
+    cnt_over_M = (double)a.fin->cnt / Mg;
+  }
+  const float c = a.clip_coef;
+  const float lo_c = 1.0f - c, hi_c = 1.0f + c;
+
+  // accumulators that live for the whole kernel
+  double st_pg = 0.0, st_vmax = 0.0, st_ent = 0.0, st_s = 0.0, g_logstd[A];
+  float st_min = INFINITY;
+  float gw3[NOUT], gb2 = 0.0f, gb3[NOUT];
+#pragma unroll
+  for (int k = 0; k < A; k++) g_logstd[k] = 0.0;
+#pragma unroll
+  for (int o = 0; o < NOUT; o++) { gw3[o] = 0.0f; gb3[o] = 0.0f; }
+
+  const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
+  const uint32_t wb_a = smem_u32(wb), fz_a = smem_u32(fz), fh_a = smem_u32(fh), xt_a = smem_u32(xt);
+
+  Sample<ENV> cur, nxt;
+  if (cta < n_tiles) load_sample<ENV, NET>(a, keys, cta * TC_S + s, cur);
+  int it = 0;
+  for (int t = cta; t < n_tiles; t += n_cta, it++) {
+    const uint32_t ph = it & 1;
+    const int m0 = t * TC_S;
+    // next tile's inputs: the loads are in flight during this whole tile
+    if (t + n_cta < n_tiles) load_sample<ENV, NET>(a, keys, (t + n_cta) * TC_S + s, nxt);
+
+    // ---- L1: h1 = tanh(W1 x + b1) for this thread's 32 features
+    float h1[TC_FG];
+#pragma unroll
+    for (int i = 0; i < TC_FG; i++) {
+      const float4 w = w1p[f0 + i];
+      float acc = 0.0f;
+      acc = fmaf(w.x, cur.x[0], acc);
+      acc = fmaf(w.y, cur.x[1], acc);
+      acc = fmaf(w.z, cur.x[2], acc);
+      if (D == 4) acc = fmaf(w.w, cur.x[3], acc);
+      h1[i] = tanh_fast(acc + b1s[f0 + i]);
+    }
+    // the previous tile's G4 still reads h1^T/dz1^T and x~^T
+    if (it > 0) mbar_wait(bar4, ph ^ 1);
+    {
+      float vh[TC_FG], vl[TC_FG];
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) {
+        vh[i] = tf32_hi(h1[i]);
+        vl[i] = h1[i] - vh[i];
+        fh[f_off(f0 + i, s)] = vh[i];
+        fh[f_off(CRL_H + f0 + i, s)] = vl[i];
+      }
+      tmem_st16(lane_addr + COL_AH + f0, vh);
+      tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
+      tmem_st16(lane_addr + COL_AL + f0, vl);
+      tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+      if (g == 0) {
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+          const float xh = tf32_hi(cur.x[d]);
+          xt[xt_off(d, s)] = xh;
+          xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
+        }
+      }
+    }
+    tmem_st_wait();
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G1: z2 = h1 W2^T
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int grp = 0; grp < 3; grp++) {
+        const uint32_t acol = tmem + (grp == 1 ? COL_AL : COL_AH);
+        const uint32_t wsel = wb_a + (grp == 2 ? 1 : 0) * TC_W_FLOATS * 4;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+          mma_ts(tmem + COL_D, acol + ks * 8, make_desc(wsel + ks * 2 * TC_W_LBO, TC_W_LBO, TC_W_SBO), idesc64, (grp | ks) ? 1u : 0u);
+      }
+      mma_commit(bar1);
+    }
+    mbar_wait(bar1, ph);
+    tc_fence_after();
+    // ---- E1: h2, head, loss, dz2
+    float h2[TC_FG];
+    tmem_ld32(lane_addr + COL_D + f0, h2);
+    {
+      float part[NOUT];
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) part[o] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) {
+        h2[i] = tanh_fast(h2[i] + b2s[f0 + i]);
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) part[o] = fmaf(w3p[o * CRL_H + f0 + i], h2[i], part[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o];
+    }
+    __syncthreads();
+    float dl[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) dl[o] = 0.0f;
+    if (cur.valid) {
+      float z[NOUT];
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) z[o] = (exch[(0 * 2 + o) * TC_S + s] + exch[(1 * 2 + o) * TC_S + s]) + b3s[o];
+      const bool own = g == 0;  // both feature halves evaluate the loss; only one of them accumulates its statistics
+      if (NET == 0) {
+        // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
+        const double adv_n = (double)__fsub_rn(cur.adv, mean_f) / ((double)std_f + 1e-8);
+        float newlp, p[A], lp[A];
+        double ent_sum = 0.0;
+        if (!E::CONT) {
+          float m = z[0];
+#pragma unroll
+          for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+          float ex[A], sum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
+          const float ls = logf(sum);
+          newlp = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            p[k] = __fdiv_rn(ex[k], sum);
+            lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+            ent_sum += (double)(-__fmul_rn(p[k], lp[k]));  // ppo.jl:42 (Q4: A x M matrix)
+            if (k == cur.act) newlp = lp[k];
+          }
+        } else {
+          float acc = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            const float logstd = b3s[2 + k];
+            const float sd = expf(logstd);
+            const float diff = __fsub_rn(cur.actf[k], z[k]);
+            const float qq = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+            acc = __fadd_rn(acc, __fsub_rn(__fsub_rn(qq, logstd), 0.9189385332046727f));
+            ent_sum += (double)__fadd_rn(__fadd_rn(0.5f, 0.9189385332046727f), logstd);
+            p[k] = 0.0f; lp[k] = 0.0f;
+          }
+          newlp = acc;
+        }
+        const float logratio = __fsub_rn(newlp, cur.oldlp);  // ppo.jl:224
+        const float ratio = expf(logratio);                  // ppo.jl:225
+        const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
+        const double pg1 = -adv_n * (double)ratio;  // ppo.jl:226
+        const double pg2 = -adv_n * (double)rc;     // ppo.jl:227
+        double pgm, dratio;
+        if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
+        else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
+        const double g_lp = dratio * (double)ratio / Mg;
+        const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);
+        if (own) { st_pg += pgm; st_ent += ent_sum; }
+        if (!E::CONT) {
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            double dd = g_lp * ((k == cur.act ? 1.0 : 0.0) - (double)p[k]);
+            dd += ent_scale * (double)p[k] * ((double)lp[k] + ent_sum);
+            dl[k] = (float)dd;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            const float sd = expf(b3s[2 + k]);
+            const double diff = (double)__fsub_rn(cur.actf[k], z[k]);
+            const double var = (double)sd * (double)sd;
+            dl[k] = (float)(g_lp * diff / var);
+            if (own) g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
+          }
+        }
+      } else {
+        // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
+        const float v = z[0];
+        float d_vcR, vlc;
+        bool inside;
+        value_clip(v, cur.V, cur.R, c, d_vcR, vlc, inside);
+        const bool s_wins = !spec && s_f > vlc;
+        if (own) {
+          st_vmax += (double)(s_wins ? s_f : vlc);
+          if (spec) {
+            st_s += (double)__fsub_rn(v, __fmul_rn(cur.R, cur.R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
+            st_min = fminf(st_min, vlc);
+            a.vnew[m0 + s] = v;
+          }
+        }
+        double dv_d = cnt_over_M;
+        if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
+        dl[0] = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
+      }
+    }
+    // dz2 = (W3^T dl) .* (1 - h2^2)
+    float dz2[TC_FG];
+    {
+      float vh[TC_FG], vl[TC_FG];
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) {
+        float dh = 0.0f;
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) dh = fmaf(w3p[o * CRL_H + f0 + i], dl[o], dh);
+        dz2[i] = dh * (1.0f - h2[i] * h2[i]);
+        vh[i] = tf32_hi(dz2[i]);
+        vl[i] = dz2[i] - vh[i];
+        fz[f_off(f0 + i, s)] = vh[i];
+        fz[f_off(CRL_H + f0 + i, s)] = vl[i];
+      }
+      tmem_st16(lane_addr + COL_AH + f0, vh);
+      tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
+      tmem_st16(lane_addr + COL_AL + f0, vl);
+      tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+    }
+    tmem_st_wait();
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G3: dh1 = dz2 W2 ; G2: dW2 += dz2^T h1
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int grp = 0; grp < 3; grp++) {
+        const uint32_t acol = tmem + (grp == 1 ? COL_AL : COL_AH);
+        const uint32_t wsel = wb_a + (2 + (grp == 2 ? 1 : 0)) * TC_W_FLOATS * 4;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+          mma_ts(tmem + COL_D, acol + ks * 8, make_desc(wsel + ks * 2 * TC_W_LBO, TC_W_LBO, TC_W_SBO), idesc64, (grp | ks) ? 1u : 0u);
+      }
+      mma_commit(bar3);
+#pragma unroll
+      for (int grp = 0; grp < 2; grp++)
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++)
+          mma_ss(tmem + COL_D2, make_desc(fz_a + ks * 2 * F_LBO, F_LBO, F_SBO),
+                 make_desc(fh_a + grp * 8 * F_SBO + ks * 2 * F_LBO, F_LBO, F_SBO), idesc64, (it | grp | ks) ? 1u : 0u);
+      mma_commit(bar2);
+    }
+    // ---- head gradients while the tensor core works: dW3(o,f) += dl[o] h2[f], db3 += dl, db2 += dz2
+    {
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) {
+        float v[TC_FG];
+#pragma unroll
+        for (int i = 0; i < TC_FG; i++) v[i] = dl[o] * h2[i];
+        warp_reduce_scatter<TC_FG>(v, lane);
+        gw3[o] += v[0];   // feature f0 + lane
+        if (g == 0) gb3[o] += dl[o];
+      }
+      warp_reduce_scatter<TC_FG>(dz2, lane);
+      gb2 += dz2[0];      // feature f0 + lane
+    }
+    // ---- E3: dz1 = dh1 .* (1 - h1^2), in place over h1^T
+    mbar_wait(bar3, ph);
+    tc_fence_after();
+    float dh1[TC_FG];
+    tmem_ld32(lane_addr + COL_D + f0, dh1);
+    mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
+#pragma unroll
+    for (int i = 0; i < TC_FG; i++) {
+      const float dz1 = dh1[i] * (1.0f - h1[i] * h1[i]);
+      const float vh = tf32_hi(dz1);
+      fh[f_off(f0 + i, s)] = vh;
+      fh[f_off(CRL_H + f0 + i, s)] = dz1 - vh;
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G4: dW1, db1 += x~^T dz1
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int grp = 0; grp < 2; grp++)
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++)
+          mma_ss(tmem + COL_D4, make_desc(xt_a + grp * 4096 + ks * 2 * X_LBO, X_LBO, 0),
+                 make_desc(fh_a + ks * 2 * F_LBO, F_LBO, F_SBO), idesc128, (it | grp | ks) ? 1u : 0u);
+      mma_commit(bar4);
+    }
+    cur = nxt;
+  }
+
+  // ---------------------------------------------------------------- epilogue: this CTA's partial gradient
+  float* gp = a.gpart + (long long)blockIdx.x * E::P;
+  const int nb = NET == 0 ? 0 : E::NET_A;
+  using NN = NetOff<D, NOUT>;
+  if (it > 0) {
+    mbar_wait(bar4, (it - 1) & 1);  // the last commit covers every MMA issued before it
+    tc_fence_after();
+    // dW2(j,k) = D2[j][k] + D2[64+j][k]: lanes 64.. hand their half over through shared memory (fz is free now)
+    float d2[TC_FG];
+    tmem_ld32(lane_addr + COL_D2 + f0, d2);
+    if (q >= 2) {
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) fz[(f0 + i) * CRL_H + (s - 64)] = d2[i];
+    }
+    __syncthreads();
+    if (q < 2) {
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) gp[nb + NO::W2 + s + CRL_H * (f0 + i)] = d2[i] + fz[(f0 + i) * CRL_H + s];
+    }
+    // dW1(k,d) = D4[d][k] + D4[d][64+k], db1(k) = row D
+    if (q == 0) {
+      float hi4[TC_FG], lo4[TC_FG];
+      tmem_ld32(lane_addr + COL_D4 + f0, hi4);
+      tmem_ld32(lane_addr + COL_D4 + CRL_H + f0, lo4);
+      if (lane <= D) {
+#pragma unroll
+        for (int i = 0; i < TC_FG; i++) {
+          const float v = hi4[i] + lo4[i];
+          if (lane < D) gp[nb + NO::W1 + (f0 + i) + CRL_H * lane] = v;
+          else gp[nb + NO::B1 + f0 + i] = v;
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < CRL_H * CRL_H; i += TC_THREADS) gp[nb + NO::W2 + i] = 0.0f;
+    for (int i = tid; i < CRL_H * (D + 1); i += TC_THREADS) gp[nb + NO::W1 + i] = 0.0f;  // W1 and b1 are adjacent
+  }
+  __syncthreads();
+  // head and bias partials: one value per (warp, lane) -> sum the four lane quadrants of each feature half
+  {
+    float* scr = fz + CRL_H * CRL_H;  // [NOUT + 1][8 warps][32]
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) scr[(o * 8 + warp) * 32 + lane] = gw3[o];
+    scr[(NOUT * 8 + warp) * 32 + lane] = gb2;
+    __syncthreads();
+    if (tid < CRL_H) {
+      const int gg = tid >> 5, ll = tid & 31;  // feature tid = gg*32 + ll lives in warps gg*4 .. gg*4+3, lane ll
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) sum += scr[(o * 8 + gg * 4 + qq) * 32 + ll];
+        gp[nb + NN::W3 + o + NOUT * tid] = sum;  // Flux W3 is (out=o, in=f) at o + NOUT f
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int qq = 0; qq < 4; qq++) sum += scr[(NOUT * 8 + gg * 4 + qq) * 32 + ll];
+      gp[nb + NO::B2 + tid] = sum;
+    }
+  }
+  double t_b3[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; o++) t_b3[o] = block_sum<8>((double)gb3[o], red);
+  const double t_pg = block_sum<8>(st_pg, red);
+  const double t_vm = block_sum<8>(st_vmax, red);
+  const double t_en = block_sum<8>(st_ent, red);
+  const double t_ss = block_sum<8>(st_s, red);
+  double t_ls[A];
+#pragma unroll
+  for (int k = 0; k < A; k++) t_ls[k] = block_sum<8>(g_logstd[k], red);
+  float* mred = reinterpret_cast<float*>(red + 8);
+  st_min = warp_min(st_min);
+  __syncthreads();
+  if (lane == 0) mred[warp] = st_min;
+  __syncthreads();
+  if (tid == 0) {
+    float mn = mred[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mn = fminf(mn, mred[w]);
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) gp[nb + NN::B3 + o] = (float)t_b3[o];
+    double* spp = a.spart + (long long)blockIdx.x * 4;
+    spp[0] = t_pg; spp[1] = t_vm; spp[2] = t_en; spp[3] = t_ss;
+    if (spec) a.mpart[blockIdx.x] = mn;
+    if (E::CONT && NET == 0) {
+#pragma unroll
+      for (int k = 0; k < A; k++) gp[E::NET_A + E::NET_C + k] = (float)t_ls[k];
+    }
+  }
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs a) {
+  using E = EnvTraits<ENV>;
+  using SM = TcSmem<ENV>;
+  using NO = NetOff<E::D, 1>;
+  using NA = NetOff<E::D, E::A>;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ TcBars bars;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (a.fixup && !a.fin->need_fixup) return;
+  if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
+  const int net = (int)blockIdx.x < a.tc_actor_ctas ? 0 : 1;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SM::KEYS);
+  if (tid == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    const uint32_t b[5] = {smem_u32(&bars.pbar), smem_u32(&bars.g1), smem_u32(&bars.g2), smem_u32(&bars.g3), smem_u32(&bars.g4)};
+#pragma unroll
+    for (int i = 0; i < 5; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b[i]));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  // small parameters of this net, x~^T constant rows
+  {
+    const float* np = a.params + (net == 0 ? 0 : E::NET_A);
+    const int nout = net == 0 ? E::A : 1;
+    float* w1p = smem + SM::W1P;
+    for (int i = tid; i < 4 * CRL_H; i += TC_THREADS) {
+      const int f = i >> 2, d = i & 3;
+      w1p[i] = d < E::D ? np[NO::W1 + f + CRL_H * d] : 0.0f;
+    }
+    for (int i = tid; i < CRL_H; i += TC_THREADS) { smem[SM::B1 + i] = np[NO::B1 + i]; smem[SM::B2 + i] = np[NO::B2 + i]; }
+    for (int i = tid; i < 2 * CRL_H; i += TC_THREADS) {
+      const int o = i / CRL_H, f = i % CRL_H;
+      smem[SM::W3P + i] = o < nout ? np[NO::W3 + o + nout * f] : 0.0f;   // W3 offset is the same for both head widths
+    }
+    if (tid < 2) smem[SM::B3 + tid] = tid < nout ? np[(net == 0 ? NA::B3 : NO::B3) + tid] : 0.0f;
+    if (tid >= 2 && tid < 4) smem[SM::B3 + tid] = (E::CONT && tid - 2 < E::A) ? a.params[E::NET_A + E::NET_C + (tid - 2)] : 0.0f;
+    float* xt = smem + SM::XT;
+    for (int i = tid; i < 2 * 1024; i += TC_THREADS) {
+      const int half = i >> 10, r = (i & 1023), d = (r >> 2) & 7;  // xt_off: d*4 + chunk*32 + (s&3)
+      xt[i] = (half == 0 && d == E::D) ? 1.0f : 0.0f;
+    }
+  }
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  // this net's four weight images: one elected thread, bulk asynchronous copies completed on an mbarrier
+  const uint32_t pbar = smem_u32(&bars.pbar);
+  if (tid == 0) {
+    constexpr uint32_t BYTES = 4 * TC_W_FLOATS * 4, CHUNK = 16384;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbar), "r"(BYTES) : "memory");
+    const char* src = reinterpret_cast<const char*>(a.image + TcImage<ENV>::BASE + net * TcImage<ENV>::NET_FLOATS);
+    const uint32_t dst = smem_u32(smem + SM::WB);
+    for (uint32_t off = 0; off < BYTES; off += CHUNK)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + off), "l"(src + off), "r"(CHUNK), "r"(pbar) : "memory");
+  }
+  mbar_wait(pbar, 0);
+  if (net == 0) tc_body<ENV, 0>(a, smem, &bars, tmem);
+  else tc_body<ENV, 1>(a, smem, &bars, tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+}  // namespace
+
+cudaError_t kernels_init_update_tc() {
+  cudaError_t e = cudaFuncSetAttribute(loss_grad_tc_kernel<CRL_ENV_CARTPOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)TcSmem<CRL_ENV_CARTPOLE>::BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(loss_grad_tc_kernel<CRL_ENV_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)TcSmem<CRL_ENV_PENDULUM>::BYTES);
+}
+
+// Chooses the tensor-core kernel for this minibatch when it applies (PPO losses, parameter image present) and fills
+// in the launch geometry; CRL_NO_TC=1 keeps the FFMA kernel.
+int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
+  static int disabled = -1, actor_share = -1;
+  if (disabled < 0) {
+    const char* e = getenv("CRL_NO_TC");
+    disabled = (e && atoi(e) != 0) ? 1 : 0;
+    const char* s = getenv("CRL_TC_ACTOR_CTAS");
+    actor_share = s ? atoi(s) : 0;
+  }
+  a->tc_actor_ctas = 0;
+  if (disabled || !a->image || a->algo != 0) return 0;
+  const int n_tiles = (a->M + TC_S - 1) / TC_S;
+  int grid = 2 * n_tiles < sm_count ? 2 * n_tiles : sm_count;
+  grid &= ~1;
+  if (grid < 2) grid = 2;
+  int na = grid / 2;
+  if (actor_share > 0 && actor_share < grid && grid == (sm_count & ~1)) na = actor_share;
+  a->grid_loss = grid;
+  a->tc_actor_ctas = na;
+  return 1;
+}
+
+cudaError_t launch_loss_grad_tc(const UpdateArgs& a, cudaStream_t s) {
+  if (a.env_kind == CRL_ENV_CARTPOLE)
+    loss_grad_tc_kernel<CRL_ENV_CARTPOLE><<<a.grid_loss, TC_THREADS, TcSmem<CRL_ENV_CARTPOLE>::BYTES, s>>>(a);
+  else
+    loss_grad_tc_kernel<CRL_ENV_PENDULUM><<<a.grid_loss, TC_THREADS, TcSmem<CRL_ENV_PENDULUM>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
