@@ -7,6 +7,11 @@
 // a CTA sample s of the tile IS TMEM lane s: warp w works on lanes 32*(w%4).. (the only lanes tcgen05.ld/st lets
 // it touch) and on the feature half (w/4)*32.. of every 64-wide row, so each thread owns (1 sample, 32 features).
 //
+// Warp 0 also issues the MMAs: the other warps hand each operand set over with a NON-blocking named-barrier arrive
+// (only warp 0 syncs on it) and everybody picks the results up on the mbarrier the issue is committed to, so the
+// warps never wait for each other and the next tile's first layer is computed in the shadow of the current tile's
+// first contraction. (A dedicated ninth issuer warp would cap the kernel at 168 registers per thread.)
+//
 // Per tile (the four contractions are the only cross-thread data flow besides one 2-float head exchange):
 //   L1   h1 = tanh(W1 x + b1) on the CUDA cores (K = 4); hi/lo go to TMEM (A operand of G1, tcgen05.st) and,
 //        feature-major, to shared memory (B operand of G2)
@@ -18,8 +23,8 @@
 //   G2   dW2(j,k) += sum_s dz2[s][j] h1[s][k]         A = [dz2_hi ; dz2_lo] (M = 128), B = h1_hi then h1_lo: rows j
 //        and 64+j of the accumulator add up to the full 4-term product; accumulates in TMEM over ALL tiles of the CTA
 //   E3   dz1 = dh1 .* (1 - h1^2), hi/lo written in place over h1's feature-major copy
-//   G4   dW1(k,d), db1(k) += sum_s x~[d][s] dz1[s][k]  A = x~^T (rows x_0..x_D-1, ones; 8 rows aliased with SBO = 0),
-//        B = [dz1_hi ; dz1_lo] (N = 128); accumulates in TMEM over all tiles
+//   G4   dW1(k,d), db1(k) += sum_s dz1[s][k] x~[d][s]  A = [dz1_hi ; dz1_lo] (M = 128), B = x~^T hi then lo (rows
+//        x_0..x_D-1, ones; N = 16 with the two 8-row groups aliased by SBO = 0); accumulates in TMEM over all tiles
 // The weight-gradient accumulators are read out of TMEM once per launch.
 //
 // Shared memory (bytes): weight images 65,536 | dz2^T stacked 73,728 | h1^T/dz1^T hi,lo 73,728 | x~^T 8,192 |
@@ -37,6 +42,7 @@ using namespace crl_upd;
 
 constexpr int TC_S = 128;        // samples per tile = TMEM lanes
 constexpr int TC_THREADS = 256;  // 4 lane quadrants x 2 feature halves
+constexpr int TC_COMPUTE = TC_THREADS;
 constexpr int TC_FG = 32;        // features per thread
 constexpr int F_LBO = 144, F_SBO = 32 * F_LBO;  // bytes; feature-major operand: rows r, K = 128 samples
 constexpr int X_LBO = 128;                      // x~^T: 8 rows, K = 128 samples
@@ -45,6 +51,8 @@ __device__ __forceinline__ int xt_off(int d, int s) { return d * 4 + (s >> 2) * 
 
 // TMEM columns (fp32): z2/dh1 accumulator | A operand hi | A operand lo | dW2 accumulator | dW1,db1 accumulator
 constexpr uint32_t COL_D = 0, COL_AH = 64, COL_AL = 128, COL_D2 = 192, COL_D4 = 256, TMEM_COLS = 512;
+// named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4 = head exchange
+constexpr int BAR_G1 = 1, BAR_G3 = 2, BAR_G4 = 3, BAR_X = 4;
 
 template <int ENV> struct TcSmem {
   static constexpr int WB = 0;                      // [4][4096] weight images of this CTA's net
@@ -86,6 +94,16 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// descriptors as (lo, hi) words: only the start-address field in lo changes between the K steps of one operand
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -119,6 +137,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  __syncwarp();
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
 // Warp reduce-scatter: on return v[r] (r < V/32) holds the sum over the 32 lanes of the original element
@@ -248,299 +277,327 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
 #pragma unroll
   for (int o = 0; o < NOUT; o++) { gw3[o] = 0.0f; gb3[o] = 0.0f; }
 
-  const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
   const uint32_t wb_a = smem_u32(wb), fz_a = smem_u32(fz), fh_a = smem_u32(fh), xt_a = smem_u32(xt);
 
-  Sample<ENV> cur, nxt;
-  if (cta < n_tiles) load_sample<ENV, NET>(a, keys, cta * TC_S + s, cur);
-  int it = 0;
-  for (int t = cta; t < n_tiles; t += n_cta, it++) {
-    const uint32_t ph = it & 1;
-    const int m0 = t * TC_S;
-    // next tile's inputs: the loads are in flight during this whole tile
-    if (t + n_cta < n_tiles) load_sample<ENV, NET>(a, keys, (t + n_cta) * TC_S + s, nxt);
+  // ---- MMA issue (warp 0, one lane). Descriptor words are loop constants + an immediate per K step.
+  const uint32_t idesc64 = make_idesc(128, 64), idesc16 = make_idesc(128, 16);
+  const uint32_t w_hi = desc_hi(TC_W_SBO), f_hi = desc_hi(F_SBO), x_hi = desc_hi(0);
+  const uint32_t w1h = desc_lo(wb_a, TC_W_LBO), w1l = desc_lo(wb_a + 1 * TC_W_FLOATS * 4, TC_W_LBO);
+  const uint32_t w3h = desc_lo(wb_a + 2 * TC_W_FLOATS * 4, TC_W_LBO), w3l = desc_lo(wb_a + 3 * TC_W_FLOATS * 4, TC_W_LBO);
+  const uint32_t fzd = desc_lo(fz_a, F_LBO), fhh = desc_lo(fh_a, F_LBO), fhl = desc_lo(fh_a + 8 * F_SBO, F_LBO);
+  const uint32_t xth = desc_lo(xt_a, X_LBO), xtl = desc_lo(xt_a + 4096, X_LBO);
+  constexpr uint32_t WK = 2 * TC_W_LBO / 16, FK = 2 * F_LBO / 16, XK = 2 * X_LBO / 16;  // descriptor step per K = 8
+  // hand-over point: the other warps only arrive, warp 0 waits for them and issues
+  auto handover = [&](int bar_id, auto&& issue) {
+    if (warp == 0) {
+      bar_sync(bar_id, TC_THREADS);
+      if (lane == 0) { tc_fence_after(); issue(); }
+      __syncwarp();
+    } else {
+      bar_arrive(bar_id, TC_THREADS);
+    }
+  };
+  auto issue_g1 = [&]() {   // z2 = h1 W2^T
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w1h + ks * WK, w_hi), idesc64, ks ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AL + ks * 8, pack64(w1h + ks * WK, w_hi), idesc64, 1u);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w1l + ks * WK, w_hi), idesc64, 1u);
+    mma_commit(bar1);
+  };
+  auto issue_g3_g2 = [&](int it) {   // dh1 = dz2 W2 ; dW2 += dz2^T h1
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w3h + ks * WK, w_hi), idesc64, ks ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AL + ks * 8, pack64(w3h + ks * WK, w_hi), idesc64, 1u);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w3l + ks * WK, w_hi), idesc64, 1u);
+    mma_commit(bar3);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++)
+      mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhh + ks * FK, f_hi), idesc64, (it | ks) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhl + ks * FK, f_hi), idesc64, 1u);
+    mma_commit(bar2);
+  };
+  auto issue_g4 = [&](int it) {   // dW1, db1 += dz1^T x~
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++)
+      mma_ss(tmem + COL_D4, pack64(fhh + ks * FK, f_hi), pack64(xth + ks * XK, x_hi), idesc16, (it | ks) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) mma_ss(tmem + COL_D4, pack64(fhh + ks * FK, f_hi), pack64(xtl + ks * XK, x_hi), idesc16, 1u);
+    mma_commit(bar4);
+  };
 
-    // ---- L1: h1 = tanh(W1 x + b1) for this thread's 32 features
-    float h1[TC_FG];
+  // L1 for one tile: h1 = tanh(W1 x + b1) for this thread's 32 features
+  auto layer1 = [&](const Sample<ENV>& in, float (&h)[TC_FG]) {
 #pragma unroll
     for (int i = 0; i < TC_FG; i++) {
       const float4 w = w1p[f0 + i];
       float acc = 0.0f;
-      acc = fmaf(w.x, cur.x[0], acc);
-      acc = fmaf(w.y, cur.x[1], acc);
-      acc = fmaf(w.z, cur.x[2], acc);
-      if (D == 4) acc = fmaf(w.w, cur.x[3], acc);
-      h1[i] = tanh_fast(acc + b1s[f0 + i]);
+      acc = fmaf(w.x, in.x[0], acc);
+      acc = fmaf(w.y, in.x[1], acc);
+      acc = fmaf(w.z, in.x[2], acc);
+      if (D == 4) acc = fmaf(w.w, in.x[3], acc);
+      h[i] = tanh_fast(acc + b1s[f0 + i]);
     }
-    // the previous tile's G4 still reads h1^T/dz1^T and x~^T
-    if (it > 0) mbar_wait(bar4, ph ^ 1);
-    {
-      float vh[TC_FG], vl[TC_FG];
+  };
+
+  int it = 0;
+  {
+    Sample<ENV> cur, nxt;
+    float h1[TC_FG];
+    if (cta < n_tiles) {
+      load_sample<ENV, NET>(a, keys, cta * TC_S + s, cur);
+      layer1(cur, h1);
+    }
+    for (int t = cta; t < n_tiles; t += n_cta, it++) {
+      const uint32_t ph = it & 1;
+      const int m0 = t * TC_S;
+      const bool more = t + n_cta < n_tiles;
+      // next tile's inputs: consumed in the shadow of G1 below
+      if (more) load_sample<ENV, NET>(a, keys, (t + n_cta) * TC_S + s, nxt);
+
+      // ---- L1 hand-over: h1 hi/lo -> TMEM (A of G1) and feature-major shared memory (B of G2); x~^T
+      if (it > 0) mbar_wait(bar4, ph ^ 1);  // the previous tile's G4 still reads dz1^T (same buffer) and x~^T
+      {
+        float vh[TC_FG], vl[TC_FG];
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) {
-        vh[i] = tf32_hi(h1[i]);
-        vl[i] = h1[i] - vh[i];
-        fh[f_off(f0 + i, s)] = vh[i];
-        fh[f_off(CRL_H + f0 + i, s)] = vl[i];
-      }
-      tmem_st16(lane_addr + COL_AH + f0, vh);
-      tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
-      tmem_st16(lane_addr + COL_AL + f0, vl);
-      tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
-      if (g == 0) {
+        for (int i = 0; i < TC_FG; i++) {
+          vh[i] = tf32_hi(h1[i]);
+          vl[i] = h1[i] - vh[i];
+          fh[f_off(f0 + i, s)] = vh[i];
+          fh[f_off(CRL_H + f0 + i, s)] = vl[i];
+        }
+        tmem_st16(lane_addr + COL_AH + f0, vh);
+        tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
+        tmem_st16(lane_addr + COL_AL + f0, vl);
+        tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+        if (g == 0) {
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-          const float xh = tf32_hi(cur.x[d]);
-          xt[xt_off(d, s)] = xh;
-          xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
+          for (int d = 0; d < D; d++) {
+            const float xh = tf32_hi(cur.x[d]);
+            xt[xt_off(d, s)] = xh;
+            xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
+          }
         }
       }
-    }
-    tmem_st_wait();
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- G1: z2 = h1 W2^T
-    if (tid == 0) {
+      tmem_st_wait();
+      proxy_fence();
+      tc_fence_before();
+      handover(BAR_G1, issue_g1);
+
+      // ---- in the shadow of G1: the next tile's first layer
+      if (more) layer1(nxt, h1);
+
+      // ---- E1: h2, head, loss, dz2
+      mbar_wait(bar1, ph);
       tc_fence_after();
+      float h2[TC_FG];
+      tmem_ld32(lane_addr + COL_D + f0, h2);
+      {
+        float part[NOUT];
 #pragma unroll
-      for (int grp = 0; grp < 3; grp++) {
-        const uint32_t acol = tmem + (grp == 1 ? COL_AL : COL_AH);
-        const uint32_t wsel = wb_a + (grp == 2 ? 1 : 0) * TC_W_FLOATS * 4;
+        for (int o = 0; o < NOUT; o++) part[o] = 0.0f;
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++)
-          mma_ts(tmem + COL_D, acol + ks * 8, make_desc(wsel + ks * 2 * TC_W_LBO, TC_W_LBO, TC_W_SBO), idesc64, (grp | ks) ? 1u : 0u);
+        for (int i = 0; i < TC_FG; i++) {
+          h2[i] = tanh_fast(h2[i] + b2s[f0 + i]);
+#pragma unroll
+          for (int o = 0; o < NOUT; o++) part[o] = fmaf(w3p[o * CRL_H + f0 + i], h2[i], part[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o];
       }
-      mma_commit(bar1);
-    }
-    mbar_wait(bar1, ph);
-    tc_fence_after();
-    // ---- E1: h2, head, loss, dz2
-    float h2[TC_FG];
-    tmem_ld32(lane_addr + COL_D + f0, h2);
-    {
-      float part[NOUT];
+      bar_sync(BAR_X, TC_COMPUTE);
+      float dl[NOUT];
 #pragma unroll
-      for (int o = 0; o < NOUT; o++) part[o] = 0.0f;
+      for (int o = 0; o < NOUT; o++) dl[o] = 0.0f;
+      if (cur.valid) {
+        float z[NOUT];
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) {
-        h2[i] = tanh_fast(h2[i] + b2s[f0 + i]);
+        for (int o = 0; o < NOUT; o++) z[o] = (exch[(0 * 2 + o) * TC_S + s] + exch[(1 * 2 + o) * TC_S + s]) + b3s[o];
+        const bool own = g == 0;  // both feature halves evaluate the loss; only one of them accumulates its statistics
+        if (NET == 0) {
+          // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
+          const double adv_n = (double)__fsub_rn(cur.adv, mean_f) / ((double)std_f + 1e-8);
+          float newlp, p[A], lp[A];
+          double ent_sum = 0.0;
+          if (!E::CONT) {
+            float m = z[0];
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) part[o] = fmaf(w3p[o * CRL_H + f0 + i], h2[i], part[o]);
-      }
+            for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+            float ex[A], sum = 0.0f;
 #pragma unroll
-      for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o];
-    }
-    __syncthreads();
-    float dl[NOUT];
+            for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
+            const float ls = logf(sum);
+            newlp = 0.0f;
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) dl[o] = 0.0f;
-    if (cur.valid) {
-      float z[NOUT];
+            for (int k = 0; k < A; k++) {
+              p[k] = __fdiv_rn(ex[k], sum);
+              lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+              ent_sum += (double)(-__fmul_rn(p[k], lp[k]));  // ppo.jl:42 (Q4: A x M matrix)
+              if (k == cur.act) newlp = lp[k];
+            }
+          } else {
+            float acc = 0.0f;
 #pragma unroll
-      for (int o = 0; o < NOUT; o++) z[o] = (exch[(0 * 2 + o) * TC_S + s] + exch[(1 * 2 + o) * TC_S + s]) + b3s[o];
-      const bool own = g == 0;  // both feature halves evaluate the loss; only one of them accumulates its statistics
-      if (NET == 0) {
-        // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
-        const double adv_n = (double)__fsub_rn(cur.adv, mean_f) / ((double)std_f + 1e-8);
-        float newlp, p[A], lp[A];
-        double ent_sum = 0.0;
-        if (!E::CONT) {
-          float m = z[0];
+            for (int k = 0; k < A; k++) {
+              const float logstd = b3s[2 + k];
+              const float sd = expf(logstd);
+              const float diff = __fsub_rn(cur.actf[k], z[k]);
+              const float qq = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+              acc = __fadd_rn(acc, __fsub_rn(__fsub_rn(qq, logstd), 0.9189385332046727f));
+              ent_sum += (double)__fadd_rn(__fadd_rn(0.5f, 0.9189385332046727f), logstd);
+              p[k] = 0.0f; lp[k] = 0.0f;
+            }
+            newlp = acc;
+          }
+          const float logratio = __fsub_rn(newlp, cur.oldlp);  // ppo.jl:224
+          const float ratio = expf(logratio);                  // ppo.jl:225
+          const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
+          const double pg1 = -adv_n * (double)ratio;  // ppo.jl:226
+          const double pg2 = -adv_n * (double)rc;     // ppo.jl:227
+          double pgm, dratio;
+          if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
+          else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
+          const double g_lp = dratio * (double)ratio / Mg;
+          const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);
+          if (own) { st_pg += pgm; st_ent += ent_sum; }
+          if (!E::CONT) {
 #pragma unroll
-          for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
-          float ex[A], sum = 0.0f;
+            for (int k = 0; k < A; k++) {
+              double dd = g_lp * ((k == cur.act ? 1.0 : 0.0) - (double)p[k]);
+              dd += ent_scale * (double)p[k] * ((double)lp[k] + ent_sum);
+              dl[k] = (float)dd;
+            }
+          } else {
 #pragma unroll
-          for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
-          const float ls = logf(sum);
-          newlp = 0.0f;
-#pragma unroll
-          for (int k = 0; k < A; k++) {
-            p[k] = __fdiv_rn(ex[k], sum);
-            lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
-            ent_sum += (double)(-__fmul_rn(p[k], lp[k]));  // ppo.jl:42 (Q4: A x M matrix)
-            if (k == cur.act) newlp = lp[k];
+            for (int k = 0; k < A; k++) {
+              const float sd = expf(b3s[2 + k]);
+              const double diff = (double)__fsub_rn(cur.actf[k], z[k]);
+              const double var = (double)sd * (double)sd;
+              dl[k] = (float)(g_lp * diff / var);
+              if (own) g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
+            }
           }
         } else {
-          float acc = 0.0f;
-#pragma unroll
-          for (int k = 0; k < A; k++) {
-            const float logstd = b3s[2 + k];
-            const float sd = expf(logstd);
-            const float diff = __fsub_rn(cur.actf[k], z[k]);
-            const float qq = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
-            acc = __fadd_rn(acc, __fsub_rn(__fsub_rn(qq, logstd), 0.9189385332046727f));
-            ent_sum += (double)__fadd_rn(__fadd_rn(0.5f, 0.9189385332046727f), logstd);
-            p[k] = 0.0f; lp[k] = 0.0f;
+          // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
+          const float v = z[0];
+          float d_vcR, vlc;
+          bool inside;
+          value_clip(v, cur.V, cur.R, c, d_vcR, vlc, inside);
+          const bool s_wins = !spec && s_f > vlc;
+          if (own) {
+            st_vmax += (double)(s_wins ? s_f : vlc);
+            if (spec) {
+              st_s += (double)__fsub_rn(v, __fmul_rn(cur.R, cur.R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
+              st_min = fminf(st_min, vlc);
+              a.vnew[m0 + s] = v;
+            }
           }
-          newlp = acc;
+          double dv_d = cnt_over_M;
+          if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
+          dl[0] = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
         }
-        const float logratio = __fsub_rn(newlp, cur.oldlp);  // ppo.jl:224
-        const float ratio = expf(logratio);                  // ppo.jl:225
-        const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
-        const double pg1 = -adv_n * (double)ratio;  // ppo.jl:226
-        const double pg2 = -adv_n * (double)rc;     // ppo.jl:227
-        double pgm, dratio;
-        if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
-        else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
-        const double g_lp = dratio * (double)ratio / Mg;
-        const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);
-        if (own) { st_pg += pgm; st_ent += ent_sum; }
-        if (!E::CONT) {
-#pragma unroll
-          for (int k = 0; k < A; k++) {
-            double dd = g_lp * ((k == cur.act ? 1.0 : 0.0) - (double)p[k]);
-            dd += ent_scale * (double)p[k] * ((double)lp[k] + ent_sum);
-            dl[k] = (float)dd;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < A; k++) {
-            const float sd = expf(b3s[2 + k]);
-            const double diff = (double)__fsub_rn(cur.actf[k], z[k]);
-            const double var = (double)sd * (double)sd;
-            dl[k] = (float)(g_lp * diff / var);
-            if (own) g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
-          }
-        }
-      } else {
-        // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
-        const float v = z[0];
-        float d_vcR, vlc;
-        bool inside;
-        value_clip(v, cur.V, cur.R, c, d_vcR, vlc, inside);
-        const bool s_wins = !spec && s_f > vlc;
-        if (own) {
-          st_vmax += (double)(s_wins ? s_f : vlc);
-          if (spec) {
-            st_s += (double)__fsub_rn(v, __fmul_rn(cur.R, cur.R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
-            st_min = fminf(st_min, vlc);
-            a.vnew[m0 + s] = v;
-          }
-        }
-        double dv_d = cnt_over_M;
-        if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
-        dl[0] = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
       }
-    }
-    // dz2 = (W3^T dl) .* (1 - h2^2)
-    float dz2[TC_FG];
-    {
-      float vh[TC_FG], vl[TC_FG];
+      // dz2 = (W3^T dl) .* (1 - h2^2)
+      float dz2[TC_FG];
+      {
+        float vh[TC_FG], vl[TC_FG];
+#pragma unroll
+        for (int i = 0; i < TC_FG; i++) {
+          float dh = 0.0f;
+#pragma unroll
+          for (int o = 0; o < NOUT; o++) dh = fmaf(w3p[o * CRL_H + f0 + i], dl[o], dh);
+          dz2[i] = dh * (1.0f - h2[i] * h2[i]);
+          vh[i] = tf32_hi(dz2[i]);
+          vl[i] = dz2[i] - vh[i];
+          fz[f_off(f0 + i, s)] = vh[i];            // the previous tile's G2 was waited for in its E3
+          fz[f_off(CRL_H + f0 + i, s)] = vl[i];
+        }
+        tmem_st16(lane_addr + COL_AH + f0, vh);
+        tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
+        tmem_st16(lane_addr + COL_AL + f0, vl);
+        tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+      }
+      tmem_st_wait();
+      proxy_fence();
+      tc_fence_before();
+      handover(BAR_G3, [&]() { issue_g3_g2(it); });
+
+      // ---- in the shadow of G3/G2: dW3(o,f) += dl[o] h2[f], db3 += dl, db2 += dz2
+      {
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) {
+          float v[TC_FG];
+#pragma unroll
+          for (int i = 0; i < TC_FG; i++) v[i] = dl[o] * h2[i];
+          warp_reduce_scatter<TC_FG>(v, lane);
+          gw3[o] += v[0];   // feature f0 + lane
+          if (g == 0) gb3[o] += dl[o];
+        }
+        warp_reduce_scatter<TC_FG>(dz2, lane);
+        gb2 += dz2[0];      // feature f0 + lane
+      }
+      // ---- E3: dz1 = dh1 .* (1 - h1^2), in place over h1^T (whose hi + lo is this tile's h1 exactly)
+      mbar_wait(bar3, ph);
+      tc_fence_after();
+      float dz1[TC_FG];
+      tmem_ld32(lane_addr + COL_D + f0, dz1);
 #pragma unroll
       for (int i = 0; i < TC_FG; i++) {
-        float dh = 0.0f;
-#pragma unroll
-        for (int o = 0; o < NOUT; o++) dh = fmaf(w3p[o * CRL_H + f0 + i], dl[o], dh);
-        dz2[i] = dh * (1.0f - h2[i] * h2[i]);
-        vh[i] = tf32_hi(dz2[i]);
-        vl[i] = dz2[i] - vh[i];
-        fz[f_off(f0 + i, s)] = vh[i];
-        fz[f_off(CRL_H + f0 + i, s)] = vl[i];
+        const float h = fh[f_off(f0 + i, s)] + fh[f_off(CRL_H + f0 + i, s)];
+        dz1[i] *= 1.0f - h * h;
       }
-      tmem_st16(lane_addr + COL_AH + f0, vh);
-      tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
-      tmem_st16(lane_addr + COL_AL + f0, vl);
-      tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
-    }
-    tmem_st_wait();
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- G3: dh1 = dz2 W2 ; G2: dW2 += dz2^T h1
-    if (tid == 0) {
-      tc_fence_after();
+      mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
 #pragma unroll
-      for (int grp = 0; grp < 3; grp++) {
-        const uint32_t acol = tmem + (grp == 1 ? COL_AL : COL_AH);
-        const uint32_t wsel = wb_a + (2 + (grp == 2 ? 1 : 0)) * TC_W_FLOATS * 4;
-#pragma unroll
-        for (int ks = 0; ks < 8; ks++)
-          mma_ts(tmem + COL_D, acol + ks * 8, make_desc(wsel + ks * 2 * TC_W_LBO, TC_W_LBO, TC_W_SBO), idesc64, (grp | ks) ? 1u : 0u);
+      for (int i = 0; i < TC_FG; i++) {
+        const float vh = tf32_hi(dz1[i]);
+        fh[f_off(f0 + i, s)] = vh;
+        fh[f_off(CRL_H + f0 + i, s)] = dz1[i] - vh;
       }
-      mma_commit(bar3);
-#pragma unroll
-      for (int grp = 0; grp < 2; grp++)
-#pragma unroll
-        for (int ks = 0; ks < 16; ks++)
-          mma_ss(tmem + COL_D2, make_desc(fz_a + ks * 2 * F_LBO, F_LBO, F_SBO),
-                 make_desc(fh_a + grp * 8 * F_SBO + ks * 2 * F_LBO, F_LBO, F_SBO), idesc64, (it | grp | ks) ? 1u : 0u);
-      mma_commit(bar2);
+      proxy_fence();
+      tc_fence_before();
+      handover(BAR_G4, [&]() { issue_g4(it); });
+      cur = nxt;
     }
-    // ---- head gradients while the tensor core works: dW3(o,f) += dl[o] h2[f], db3 += dl, db2 += dz2
-    {
-#pragma unroll
-      for (int o = 0; o < NOUT; o++) {
-        float v[TC_FG];
-#pragma unroll
-        for (int i = 0; i < TC_FG; i++) v[i] = dl[o] * h2[i];
-        warp_reduce_scatter<TC_FG>(v, lane);
-        gw3[o] += v[0];   // feature f0 + lane
-        if (g == 0) gb3[o] += dl[o];
-      }
-      warp_reduce_scatter<TC_FG>(dz2, lane);
-      gb2 += dz2[0];      // feature f0 + lane
-    }
-    // ---- E3: dz1 = dh1 .* (1 - h1^2), in place over h1^T
-    mbar_wait(bar3, ph);
-    tc_fence_after();
-    float dh1[TC_FG];
-    tmem_ld32(lane_addr + COL_D + f0, dh1);
-    mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
-#pragma unroll
-    for (int i = 0; i < TC_FG; i++) {
-      const float dz1 = dh1[i] * (1.0f - h1[i] * h1[i]);
-      const float vh = tf32_hi(dz1);
-      fh[f_off(f0 + i, s)] = vh;
-      fh[f_off(CRL_H + f0 + i, s)] = dz1 - vh;
-    }
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- G4: dW1, db1 += x~^T dz1
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int grp = 0; grp < 2; grp++)
-#pragma unroll
-        for (int ks = 0; ks < 16; ks++)
-          mma_ss(tmem + COL_D4, make_desc(xt_a + grp * 4096 + ks * 2 * X_LBO, X_LBO, 0),
-                 make_desc(fh_a + ks * 2 * F_LBO, F_LBO, F_SBO), idesc128, (it | grp | ks) ? 1u : 0u);
-      mma_commit(bar4);
-    }
-    cur = nxt;
   }
 
   // ---------------------------------------------------------------- epilogue: this CTA's partial gradient
   float* gp = a.gpart + (long long)blockIdx.x * E::P;
   const int nb = NET == 0 ? 0 : E::NET_A;
   using NN = NetOff<D, NOUT>;
-  if (it > 0) {
+  const bool has_tiles = cta < n_tiles;
+  float* scr = fz;  // the operand buffers are free once the last G4 has completed
+  if (has_tiles) {
     mbar_wait(bar4, (it - 1) & 1);  // the last commit covers every MMA issued before it
     tc_fence_after();
-    // dW2(j,k) = D2[j][k] + D2[64+j][k]: lanes 64.. hand their half over through shared memory (fz is free now)
-    float d2[TC_FG];
-    tmem_ld32(lane_addr + COL_D2 + f0, d2);
-    if (q >= 2) {
+    // dW2(j,k) = D2[j][k] + D2[64+j][k]; dW1(k,d), db1(k) = D4[k][d] + D4[64+k][d]: lanes 64.. hand their (lo)
+    // halves over through shared memory
+    float d2[TC_FG], d4[16];
+    {
+      tmem_ld32(lane_addr + COL_D2 + f0, d2);
+      if (g == 0) tmem_ld16(lane_addr + COL_D4, d4);
+      if (q >= 2) {
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) fz[(f0 + i) * CRL_H + (s - 64)] = d2[i];
+        for (int i = 0; i < TC_FG; i++) scr[(f0 + i) * CRL_H + (s - 64)] = d2[i];
+        if (g == 0) {
+#pragma unroll
+          for (int d = 0; d <= D; d++) scr[CRL_H * CRL_H + d * CRL_H + (s - 64)] = d4[d];
+        }
+      }
     }
     __syncthreads();
     if (q < 2) {
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) gp[nb + NO::W2 + s + CRL_H * (f0 + i)] = d2[i] + fz[(f0 + i) * CRL_H + s];
-    }
-    // dW1(k,d) = D4[d][k] + D4[d][64+k], db1(k) = row D
-    if (q == 0) {
-      float hi4[TC_FG], lo4[TC_FG];
-      tmem_ld32(lane_addr + COL_D4 + f0, hi4);
-      tmem_ld32(lane_addr + COL_D4 + CRL_H + f0, lo4);
-      if (lane <= D) {
+      for (int i = 0; i < TC_FG; i++) gp[nb + NO::W2 + s + CRL_H * (f0 + i)] = d2[i] + scr[(f0 + i) * CRL_H + s];
+      if (g == 0) {
 #pragma unroll
-        for (int i = 0; i < TC_FG; i++) {
-          const float v = hi4[i] + lo4[i];
-          if (lane < D) gp[nb + NO::W1 + (f0 + i) + CRL_H * lane] = v;
-          else gp[nb + NO::B1 + f0 + i] = v;
+        for (int d = 0; d <= D; d++) {
+          const float v = d4[d] + scr[CRL_H * CRL_H + d * CRL_H + s];
+          if (d < D) gp[nb + NO::W1 + s + CRL_H * d] = v;
+          else gp[nb + NO::B1 + s] = v;
         }
       }
     }
@@ -551,10 +608,10 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   __syncthreads();
   // head and bias partials: one value per (warp, lane) -> sum the four lane quadrants of each feature half
   {
-    float* scr = fz + CRL_H * CRL_H;  // [NOUT + 1][8 warps][32]
+    float* hs = scr + CRL_H * CRL_H + 8 * CRL_H;  // [NOUT + 1][8 warps][32]
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) scr[(o * 8 + warp) * 32 + lane] = gw3[o];
-    scr[(NOUT * 8 + warp) * 32 + lane] = gb2;
+    for (int o = 0; o < NOUT; o++) hs[(o * 8 + warp) * 32 + lane] = gw3[o];
+    hs[(NOUT * 8 + warp) * 32 + lane] = gb2;
     __syncthreads();
     if (tid < CRL_H) {
       const int gg = tid >> 5, ll = tid & 31;  // feature tid = gg*32 + ll lives in warps gg*4 .. gg*4+3, lane ll
@@ -562,12 +619,12 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       for (int o = 0; o < NOUT; o++) {
         float sum = 0.0f;
 #pragma unroll
-        for (int qq = 0; qq < 4; qq++) sum += scr[(o * 8 + gg * 4 + qq) * 32 + ll];
+        for (int qq = 0; qq < 4; qq++) sum += hs[(o * 8 + gg * 4 + qq) * 32 + ll];
         gp[nb + NN::W3 + o + NOUT * tid] = sum;  // Flux W3 is (out=o, in=f) at o + NOUT f
       }
       float sum = 0.0f;
 #pragma unroll
-      for (int qq = 0; qq < 4; qq++) sum += scr[(NOUT * 8 + gg * 4 + qq) * 32 + ll];
+      for (int qq = 0; qq < 4; qq++) sum += hs[(NOUT * 8 + gg * 4 + qq) * 32 + ll];
       gp[nb + NO::B2 + tid] = sum;
     }
   }
@@ -581,7 +638,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   double t_ls[A];
 #pragma unroll
   for (int k = 0; k < A; k++) t_ls[k] = block_sum<8>(g_logstd[k], red);
-  float* mred = reinterpret_cast<float*>(red + 8);
+  float* mred = reinterpret_cast<float*>(red + 10);
   st_min = warp_min(st_min);
   __syncthreads();
   if (lane == 0) mred[warp] = st_min;
