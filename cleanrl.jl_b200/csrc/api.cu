@@ -657,6 +657,13 @@ static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, b
   int k = 0;
   const int n_sets = c->cfg.update_epochs * c->cfg.num_minibatches;
   const bool a2c = (c->cfg.flags & CRL_FLAG_A2C) != 0;  // the A2C losses use no advantage normalisation
+  if (spec && !perm_dev) {
+    // throughput path: materialise this update's epoch permutations once (8 MB, L2-resident) instead of
+    // re-evaluating the Feistel network per sample in adv_stats and in every loss_grad tile
+    KernelScope ks(c, CRL_K_OTHER);
+    CK(launch_fill_perms_dev(c->perm_dev, (uint32_t)c->B, c->cfg.seed, c->ds, c->cfg.update_epochs, (uint32_t)c->cfg.rank, c->stream));
+    perm_dev = c->perm_dev;
+  }
   if (spec && !a2c) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
   if (spec && !a2c && c->cfg.world_size > 1) {  // global advantage sums for all minibatches of the update: one collective per update
     KernelScope ks(c, CRL_K_ALLREDUCE, false);

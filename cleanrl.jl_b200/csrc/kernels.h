@@ -185,5 +185,8 @@ cudaError_t launch_env_reset(int env_kind, int N, unsigned long long seed, int e
 cudaError_t launch_env_refresh(int env_kind, int N, const float* env_state, float* next_obs, uint8_t* next_done,
                                cudaStream_t s);
 cudaError_t launch_advance(DevState* ds, unsigned long long d_policy_step, unsigned long long d_update, cudaStream_t s);
+// all epoch permutations of the current update (update_index from DevState): out[n_epochs][B]
+cudaError_t launch_fill_perms_dev(int32_t* out, uint32_t B, unsigned long long seed, const DevState* ds, int n_epochs,
+                                  uint32_t rank, cudaStream_t s);
 cudaError_t launch_fill_perm(int32_t* out, uint32_t B, unsigned long long seed, unsigned long long update_index,
                              uint32_t epoch, uint32_t rank, cudaStream_t s);

@@ -1025,6 +1025,18 @@ __global__ void advance_kernel(DevState* ds, unsigned long long dstep, unsigned 
   ds->update_index += dupd;
 }
 
+// all epoch permutations of one update, update_index read from the device (graph-capturable): out[epoch][B]
+__global__ void fill_perms_dev_kernel(int32_t* out, uint32_t B, int half_bits, unsigned long long seed,
+                                      const DevState* ds, uint32_t rank) {
+  __shared__ uint32_t keys[8];
+  const uint32_t epoch = blockIdx.y;
+  if (threadIdx.x == 0) perm_keys(seed, ds->update_index, epoch, rank, keys);
+  __syncthreads();
+  int32_t* o = out + (size_t)epoch * B;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+    o[i] = (int32_t)perm_index(i, B, half_bits, keys);
+}
+
 __global__ void fill_perm_kernel(int32_t* out, uint32_t B, int half_bits, unsigned long long seed,
                                  unsigned long long update_index, uint32_t epoch, uint32_t rank) {
   __shared__ uint32_t keys[8];
@@ -1129,6 +1141,15 @@ cudaError_t launch_stats_pack(const MbScalars* parts, int n, MbScalars* out, cud
 
 cudaError_t launch_advance(DevState* ds, unsigned long long d_policy_step, unsigned long long d_update, cudaStream_t s) {
   advance_kernel<<<1, 1, 0, s>>>(ds, d_policy_step, d_update);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_perms_dev(int32_t* out, uint32_t B, unsigned long long seed, const DevState* ds, int n_epochs,
+                                  uint32_t rank, cudaStream_t s) {
+  unsigned bx = (B + 1023) / 1024;
+  if (bx > 148) bx = 148;
+  if (bx < 1) bx = 1;
+  fill_perms_dev_kernel<<<dim3(bx, (unsigned)n_epochs), 256, 0, s>>>(out, B, perm_half_bits(B), seed, ds, rank);
   return cudaGetLastError();
 }
 

@@ -49,8 +49,8 @@ constexpr int X_LBO = 128;                      // x~^T: 8 rows, K = 128 samples
 __device__ __forceinline__ int f_off(int r, int s) { return (r & 7) * 4 + (r >> 3) * (F_SBO / 4) + (s >> 2) * (F_LBO / 4) + (s & 3); }
 __device__ __forceinline__ int xt_off(int d, int s) { return d * 4 + (s >> 2) * (X_LBO / 4) + (s & 3); }
 
-// TMEM columns (fp32): z2/dh1 accumulator | A operand hi | A operand lo | dW2 accumulator | dW1,db1 accumulator
-constexpr uint32_t COL_D = 0, COL_AH = 64, COL_AL = 128, COL_D2 = 192, COL_D4 = 256, TMEM_COLS = 512;
+// TMEM columns (fp32): z2/dh1 accumulator | A operand hi | A operand lo | dW2 acc. | dW1,db1 acc. (16) | db2 acc. (16)
+constexpr uint32_t COL_D = 0, COL_AH = 64, COL_AL = 128, COL_D2 = 192, COL_D4 = 256, COL_D5 = 272, TMEM_COLS = 512;
 // named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4 = head exchange
 constexpr int BAR_G1 = 1, BAR_G3 = 2, BAR_G4 = 3, BAR_X = 4;
 
@@ -59,7 +59,7 @@ template <int ENV> struct TcSmem {
   static constexpr int FZ = WB + 4 * TC_W_FLOATS;   // dz2^T, rows 0-63 hi, 64-127 lo
   static constexpr int FH = FZ + 16 * F_SBO / 4;    // h1^T (later dz1^T), rows 0-63 hi, 64-127 lo
   static constexpr int XT = FH + 16 * F_SBO / 4;    // [hi | lo][8 rows][128 samples]
-  static constexpr int W1P = XT + 2 * 1024;         // [64][4]: W1(f, d)
+  static constexpr int W1P = XT + 2 * 1024;         // [32 pairs][4][2]: W1(2p + e, d)
   static constexpr int B1 = W1P + 4 * CRL_H;
   static constexpr int B2 = B1 + CRL_H;
   static constexpr int W3P = B2 + CRL_H;            // [2][64]: W3(o, f)
@@ -150,6 +150,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- packed FP32 (fma.rn.f32x2) helpers
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+// tanh_fast (device_math.cuh) on two values at once: same operations, same roundings per lane. The numerator is
+// evaluated with negated coefficients and the reciprocal taken of -d, so both Newton FMAs and the final products
+// are plain packed instructions (the two sign flips cancel exactly).
+__device__ __forceinline__ float2 tanh_fast2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 n = __ffma2_rn(x2, f2s(-1.587199e-8f), f2s(-2.2332108e-5f));
+  n = __ffma2_rn(x2, n, f2s(-0.0035974074f));
+  n = __ffma2_rn(x2, n, f2s(-0.1346604f));
+  n = __ffma2_rn(x2, n, f2s(-1.0f));
+  float2 d = __ffma2_rn(x2, f2s(8.7767893e-7f), f2s(0.0003453992f));
+  d = __ffma2_rn(x2, d, f2s(0.026262015f));
+  d = __ffma2_rn(x2, d, f2s(0.4679937f));
+  d = __ffma2_rn(x2, d, f2s(1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(-d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(-d.y));
+  r = __ffma2_rn(__ffma2_rn(d, r, f2s(1.0f)), r, r);  // Newton step on -1/d
+  float2 y = __fmul2_rn(x, __fmul2_rn(n, r));
+  y.x = x2.x < 66.0f ? y.x : copysignf(1.0f, x.x);
+  y.y = x2.y < 66.0f ? y.y : copysignf(1.0f, x.y);
+  return y;
+}
+// x = hi + lo with hi = TF32(x) (see tf32_hi), two values at once
+__device__ __forceinline__ void split2(float2 v, float2& hi, float2& lo) {
+  hi = f2(tf32_hi(v.x), tf32_hi(v.y));
+  lo = __ffma2_rn(hi, f2s(-1.0f), v);
+}
+
 // Warp reduce-scatter: on return v[r] (r < V/32) holds the sum over the 32 lanes of the original element
 // r + (V/32) * lane. V/2 + V/4 + ... shuffles instead of 5 V for V separate butterfly reductions.
 template <int N, int OFF, int V> __device__ __forceinline__ void rs_step(float (&v)[V], int lane) {
@@ -227,10 +258,10 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   float* fz = smem + SM::FZ;
   float* fh = smem + SM::FH;
   float* xt = smem + SM::XT;
-  const float4* w1p = reinterpret_cast<const float4*>(smem + SM::W1P);
-  const float* b1s = smem + SM::B1;
-  const float* b2s = smem + SM::B2;
-  const float* w3p = smem + SM::W3P;
+  const float4* w1v = reinterpret_cast<const float4*>(smem + SM::W1P);   // [pair][d][2] as two float4 per pair
+  const float2* b1q = reinterpret_cast<const float2*>(smem + SM::B1);
+  const float2* b2q = reinterpret_cast<const float2*>(smem + SM::B2);
+  const float2* w3q = reinterpret_cast<const float2*>(smem + SM::W3P);   // [o][32 pairs]
   const float* b3s = smem + SM::B3;
   float* exch = smem + SM::EXCH;
   double* red = reinterpret_cast<double*>(smem + SM::RED);
@@ -271,11 +302,16 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   // accumulators that live for the whole kernel
   double st_pg = 0.0, st_vmax = 0.0, st_ent = 0.0, st_s = 0.0, g_logstd[A];
   float st_min = INFINITY;
-  float gw3[NOUT], gb2 = 0.0f, gb3[NOUT];
+  float2 gw3[NOUT][TC_FG / 2];  // dW3(o, f) summed over this thread's samples; reduced over the lanes at the end
+  float gb3[NOUT];
 #pragma unroll
   for (int k = 0; k < A; k++) g_logstd[k] = 0.0;
 #pragma unroll
-  for (int o = 0; o < NOUT; o++) { gw3[o] = 0.0f; gb3[o] = 0.0f; }
+  for (int o = 0; o < NOUT; o++) {
+    gb3[o] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < TC_FG / 2; i++) gw3[o][i] = f2s(0.0f);
+  }
 
   const uint32_t wb_a = smem_u32(wb), fz_a = smem_u32(fz), fh_a = smem_u32(fh), xt_a = smem_u32(xt);
 
@@ -306,7 +342,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w1l + ks * WK, w_hi), idesc64, 1u);
     mma_commit(bar1);
   };
-  auto issue_g3_g2 = [&](int it) {   // dh1 = dz2 W2 ; dW2 += dz2^T h1
+  auto issue_g3_g2 = [&](int it) {   // -dh1 = (-dz2) W2 ; -dW2 += (-dz2)^T h1 ; -db2 += (-dz2)^T 1
 #pragma unroll
     for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w3h + ks * WK, w_hi), idesc64, ks ? 1u : 0u);
 #pragma unroll
@@ -319,6 +355,9 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhh + ks * FK, f_hi), idesc64, (it | ks) ? 1u : 0u);
 #pragma unroll
     for (int ks = 0; ks < 16; ks++) mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhl + ks * FK, f_hi), idesc64, 1u);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++)   // the ones row of x~^T (exact in TF32) picks out the row sums
+      mma_ss(tmem + COL_D5, pack64(fzd + ks * FK, f_hi), pack64(xth + ks * XK, x_hi), idesc16, (it | ks) ? 1u : 0u);
     mma_commit(bar2);
   };
   auto issue_g4 = [&](int it) {   // dW1, db1 += dz1^T x~
@@ -330,24 +369,44 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     mma_commit(bar4);
   };
 
-  // L1 for one tile: h1 = tanh(W1 x + b1) for this thread's 32 features
-  auto layer1 = [&](const Sample<ENV>& in, float (&h)[TC_FG]) {
+  // L1 for one tile: h1 = tanh(W1 x + b1) for this thread's 16 feature pairs
+  const int p0 = f0 / 2;
+  auto layer1 = [&](const Sample<ENV>& in, float2 (&h)[TC_FG / 2]) {
+    const float2 xb[4] = {f2s(in.x[0]), f2s(in.x[1]), f2s(in.x[2]), f2s(in.x[3])};
 #pragma unroll
-    for (int i = 0; i < TC_FG; i++) {
-      const float4 w = w1p[f0 + i];
-      float acc = 0.0f;
-      acc = fmaf(w.x, in.x[0], acc);
-      acc = fmaf(w.y, in.x[1], acc);
-      acc = fmaf(w.z, in.x[2], acc);
-      if (D == 4) acc = fmaf(w.w, in.x[3], acc);
-      h[i] = tanh_fast(acc + b1s[f0 + i]);
+    for (int i = 0; i < TC_FG / 2; i++) {
+      const float4 wa = w1v[(p0 + i) * 2], wc = w1v[(p0 + i) * 2 + 1];
+      float2 acc = f2s(0.0f);
+      acc = __ffma2_rn(f2(wa.x, wa.y), xb[0], acc);
+      acc = __ffma2_rn(f2(wa.z, wa.w), xb[1], acc);
+      acc = __ffma2_rn(f2(wc.x, wc.y), xb[2], acc);
+      if (D == 4) acc = __ffma2_rn(f2(wc.z, wc.w), xb[3], acc);
+      h[i] = tanh_fast2(__fadd2_rn(acc, b1q[p0 + i]));
     }
+  };
+  // hi/lo of 32 values: TMEM columns col.. (A operand) and rows f0.. / 64+f0.. of a feature-major operand buffer
+  auto store_split = [&](const float2 (&v)[TC_FG / 2], float* buf) {
+    float vh[TC_FG], vl[TC_FG];
+#pragma unroll
+    for (int i = 0; i < TC_FG / 2; i++) {
+      float2 hi, lo;
+      split2(v[i], hi, lo);
+      vh[2 * i] = hi.x; vh[2 * i + 1] = hi.y; vl[2 * i] = lo.x; vl[2 * i + 1] = lo.y;
+      buf[f_off(f0 + 2 * i, s)] = hi.x;
+      buf[f_off(f0 + 2 * i + 1, s)] = hi.y;
+      buf[f_off(CRL_H + f0 + 2 * i, s)] = lo.x;
+      buf[f_off(CRL_H + f0 + 2 * i + 1, s)] = lo.y;
+    }
+    tmem_st16(lane_addr + COL_AH + f0, vh);
+    tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
+    tmem_st16(lane_addr + COL_AL + f0, vl);
+    tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
   };
 
   int it = 0;
   {
     Sample<ENV> cur, nxt;
-    float h1[TC_FG];
+    float2 h1[TC_FG / 2];
     if (cta < n_tiles) {
       load_sample<ENV, NET>(a, keys, cta * TC_S + s, cur);
       layer1(cur, h1);
@@ -361,26 +420,13 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
 
       // ---- L1 hand-over: h1 hi/lo -> TMEM (A of G1) and feature-major shared memory (B of G2); x~^T
       if (it > 0) mbar_wait(bar4, ph ^ 1);  // the previous tile's G4 still reads dz1^T (same buffer) and x~^T
-      {
-        float vh[TC_FG], vl[TC_FG];
+      store_split(h1, fh);
+      if (g == 0) {
 #pragma unroll
-        for (int i = 0; i < TC_FG; i++) {
-          vh[i] = tf32_hi(h1[i]);
-          vl[i] = h1[i] - vh[i];
-          fh[f_off(f0 + i, s)] = vh[i];
-          fh[f_off(CRL_H + f0 + i, s)] = vl[i];
-        }
-        tmem_st16(lane_addr + COL_AH + f0, vh);
-        tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
-        tmem_st16(lane_addr + COL_AL + f0, vl);
-        tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
-        if (g == 0) {
-#pragma unroll
-          for (int d = 0; d < D; d++) {
-            const float xh = tf32_hi(cur.x[d]);
-            xt[xt_off(d, s)] = xh;
-            xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
-          }
+        for (int d = 0; d < D; d++) {
+          const float xh = tf32_hi(cur.x[d]);
+          xt[xt_off(d, s)] = xh;
+          xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
         }
       }
       tmem_st_wait();
@@ -394,20 +440,21 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       // ---- E1: h2, head, loss, dz2
       mbar_wait(bar1, ph);
       tc_fence_after();
-      float h2[TC_FG];
-      tmem_ld32(lane_addr + COL_D + f0, h2);
+      float2 h2[TC_FG / 2];
       {
-        float part[NOUT];
+        float z2[TC_FG];
+        tmem_ld32(lane_addr + COL_D + f0, z2);
+        float2 part[NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) part[o] = 0.0f;
+        for (int o = 0; o < NOUT; o++) part[o] = f2s(0.0f);
 #pragma unroll
-        for (int i = 0; i < TC_FG; i++) {
-          h2[i] = tanh_fast(h2[i] + b2s[f0 + i]);
+        for (int i = 0; i < TC_FG / 2; i++) {
+          h2[i] = tanh_fast2(__fadd2_rn(f2(z2[2 * i], z2[2 * i + 1]), b2q[p0 + i]));
 #pragma unroll
-          for (int o = 0; o < NOUT; o++) part[o] = fmaf(w3p[o * CRL_H + f0 + i], h2[i], part[o]);
+          for (int o = 0; o < NOUT; o++) part[o] = __ffma2_rn(w3q[o * (CRL_H / 2) + p0 + i], h2[i], part[o]);
         }
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o];
+        for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o].x + part[o].y;
       }
       bar_sync(BAR_X, TC_COMPUTE);
       float dl[NOUT];
@@ -501,61 +548,49 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           dl[0] = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
         }
       }
-      // dz2 = (W3^T dl) .* (1 - h2^2)
-      float dz2[TC_FG];
+      // -dz2 = (W3^T dl) .* (h2^2 - 1): the sign is carried through G3/G2 and removed again by E3 / at the read-out,
+      // which saves negating a packed operand here. dW3(o,f) += dl[o] h2[f] stays in registers.
       {
-        float vh[TC_FG], vl[TC_FG];
+        float2 ndz2[TC_FG / 2];
 #pragma unroll
-        for (int i = 0; i < TC_FG; i++) {
-          float dh = 0.0f;
+        for (int i = 0; i < TC_FG / 2; i++) {
+          float2 dh = __fmul2_rn(w3q[p0 + i], f2s(dl[0]));
 #pragma unroll
-          for (int o = 0; o < NOUT; o++) dh = fmaf(w3p[o * CRL_H + f0 + i], dl[o], dh);
-          dz2[i] = dh * (1.0f - h2[i] * h2[i]);
-          vh[i] = tf32_hi(dz2[i]);
-          vl[i] = dz2[i] - vh[i];
-          fz[f_off(f0 + i, s)] = vh[i];            // the previous tile's G2 was waited for in its E3
-          fz[f_off(CRL_H + f0 + i, s)] = vl[i];
+          for (int o = 1; o < NOUT; o++) dh = __ffma2_rn(w3q[o * (CRL_H / 2) + p0 + i], f2s(dl[o]), dh);
+          ndz2[i] = __fmul2_rn(dh, __ffma2_rn(h2[i], h2[i], f2s(-1.0f)));
+#pragma unroll
+          for (int o = 0; o < NOUT; o++) gw3[o][i] = __ffma2_rn(f2s(dl[o]), h2[i], gw3[o][i]);
         }
-        tmem_st16(lane_addr + COL_AH + f0, vh);
-        tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
-        tmem_st16(lane_addr + COL_AL + f0, vl);
-        tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) if (g == 0) gb3[o] += dl[o];
+        store_split(ndz2, fz);   // the previous tile's G2 was waited for in its E3
       }
       tmem_st_wait();
       proxy_fence();
       tc_fence_before();
       handover(BAR_G3, [&]() { issue_g3_g2(it); });
 
-      // ---- in the shadow of G3/G2: dW3(o,f) += dl[o] h2[f], db3 += dl, db2 += dz2
-      {
-#pragma unroll
-        for (int o = 0; o < NOUT; o++) {
-          float v[TC_FG];
-#pragma unroll
-          for (int i = 0; i < TC_FG; i++) v[i] = dl[o] * h2[i];
-          warp_reduce_scatter<TC_FG>(v, lane);
-          gw3[o] += v[0];   // feature f0 + lane
-          if (g == 0) gb3[o] += dl[o];
-        }
-        warp_reduce_scatter<TC_FG>(dz2, lane);
-        gb2 += dz2[0];      // feature f0 + lane
-      }
-      // ---- E3: dz1 = dh1 .* (1 - h1^2), in place over h1^T (whose hi + lo is this tile's h1 exactly)
+      // ---- E3: dz1 = (-dh1) .* (h1^2 - 1), in place over h1^T (whose hi + lo is this tile's h1 exactly)
       mbar_wait(bar3, ph);
       tc_fence_after();
-      float dz1[TC_FG];
-      tmem_ld32(lane_addr + COL_D + f0, dz1);
+      float ndh1[TC_FG];
+      tmem_ld32(lane_addr + COL_D + f0, ndh1);
+      float2 dz1[TC_FG / 2];
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) {
-        const float h = fh[f_off(f0 + i, s)] + fh[f_off(CRL_H + f0 + i, s)];
-        dz1[i] *= 1.0f - h * h;
+      for (int i = 0; i < TC_FG / 2; i++) {
+        const float2 h = __fadd2_rn(f2(fh[f_off(f0 + 2 * i, s)], fh[f_off(f0 + 2 * i + 1, s)]),
+                                    f2(fh[f_off(CRL_H + f0 + 2 * i, s)], fh[f_off(CRL_H + f0 + 2 * i + 1, s)]));
+        dz1[i] = __fmul2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), __ffma2_rn(h, h, f2s(-1.0f)));
       }
       mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) {
-        const float vh = tf32_hi(dz1[i]);
-        fh[f_off(f0 + i, s)] = vh;
-        fh[f_off(CRL_H + f0 + i, s)] = dz1[i] - vh;
+      for (int i = 0; i < TC_FG / 2; i++) {
+        float2 hi, lo;
+        split2(dz1[i], hi, lo);
+        fh[f_off(f0 + 2 * i, s)] = hi.x;
+        fh[f_off(f0 + 2 * i + 1, s)] = hi.y;
+        fh[f_off(CRL_H + f0 + 2 * i, s)] = lo.x;
+        fh[f_off(CRL_H + f0 + 2 * i + 1, s)] = lo.y;
       }
       proxy_fence();
       tc_fence_before();
@@ -573,25 +608,24 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   if (has_tiles) {
     mbar_wait(bar4, (it - 1) & 1);  // the last commit covers every MMA issued before it
     tc_fence_after();
-    // dW2(j,k) = D2[j][k] + D2[64+j][k]; dW1(k,d), db1(k) = D4[k][d] + D4[64+k][d]: lanes 64.. hand their (lo)
-    // halves over through shared memory
-    float d2[TC_FG], d4[16];
-    {
-      tmem_ld32(lane_addr + COL_D2 + f0, d2);
-      if (g == 0) tmem_ld16(lane_addr + COL_D4, d4);
-      if (q >= 2) {
+    // dW2(j,k) = -(D2[j][k] + D2[64+j][k]); dW1(k,d), db1(k) = D4[k][d] + D4[64+k][d]; db2(j) = -(D5[j][D] + D5[64+j][D]):
+    // lanes 64.. hand their (lo) halves over through shared memory
+    float d2[TC_FG], d4[16], d5[16];
+    tmem_ld32(lane_addr + COL_D2 + f0, d2);
+    if (g == 0) { tmem_ld16(lane_addr + COL_D4, d4); tmem_ld16(lane_addr + COL_D5, d5); }
+    if (q >= 2) {
 #pragma unroll
-        for (int i = 0; i < TC_FG; i++) scr[(f0 + i) * CRL_H + (s - 64)] = d2[i];
-        if (g == 0) {
+      for (int i = 0; i < TC_FG; i++) scr[(f0 + i) * CRL_H + (s - 64)] = d2[i];
+      if (g == 0) {
 #pragma unroll
-          for (int d = 0; d <= D; d++) scr[CRL_H * CRL_H + d * CRL_H + (s - 64)] = d4[d];
-        }
+        for (int d = 0; d <= D; d++) scr[CRL_H * CRL_H + d * CRL_H + (s - 64)] = d4[d];
+        scr[CRL_H * CRL_H + 7 * CRL_H + (s - 64)] = d5[D];
       }
     }
     __syncthreads();
     if (q < 2) {
 #pragma unroll
-      for (int i = 0; i < TC_FG; i++) gp[nb + NO::W2 + s + CRL_H * (f0 + i)] = d2[i] + scr[(f0 + i) * CRL_H + s];
+      for (int i = 0; i < TC_FG; i++) gp[nb + NO::W2 + s + CRL_H * (f0 + i)] = -(d2[i] + scr[(f0 + i) * CRL_H + s]);
       if (g == 0) {
 #pragma unroll
         for (int d = 0; d <= D; d++) {
@@ -599,19 +633,26 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           if (d < D) gp[nb + NO::W1 + s + CRL_H * d] = v;
           else gp[nb + NO::B1 + s] = v;
         }
+        gp[nb + NO::B2 + s] = -(d5[D] + scr[CRL_H * CRL_H + 7 * CRL_H + s]);
       }
     }
   } else {
     for (int i = tid; i < CRL_H * CRL_H; i += TC_THREADS) gp[nb + NO::W2 + i] = 0.0f;
     for (int i = tid; i < CRL_H * (D + 1); i += TC_THREADS) gp[nb + NO::W1 + i] = 0.0f;  // W1 and b1 are adjacent
+    for (int i = tid; i < CRL_H; i += TC_THREADS) gp[nb + NO::B2 + i] = 0.0f;
   }
   __syncthreads();
-  // head and bias partials: one value per (warp, lane) -> sum the four lane quadrants of each feature half
+  // head partials: reduce-scatter over the 32 lanes (samples) of each warp, then sum the four lane quadrants
   {
-    float* hs = scr + CRL_H * CRL_H + 8 * CRL_H;  // [NOUT + 1][8 warps][32]
+    float* hs = scr + CRL_H * CRL_H + 8 * CRL_H;  // [NOUT][8 warps][32]
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) hs[(o * 8 + warp) * 32 + lane] = gw3[o];
-    hs[(NOUT * 8 + warp) * 32 + lane] = gb2;
+    for (int o = 0; o < NOUT; o++) {
+      float v[TC_FG];
+#pragma unroll
+      for (int i = 0; i < TC_FG / 2; i++) { v[2 * i] = gw3[o][i].x; v[2 * i + 1] = gw3[o][i].y; }
+      warp_reduce_scatter<TC_FG>(v, lane);
+      hs[(o * 8 + warp) * 32 + lane] = v[0];  // feature f0 + lane
+    }
     __syncthreads();
     if (tid < CRL_H) {
       const int gg = tid >> 5, ll = tid & 31;  // feature tid = gg*32 + ll lives in warps gg*4 .. gg*4+3, lane ll
@@ -622,10 +663,6 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
         for (int qq = 0; qq < 4; qq++) sum += hs[(o * 8 + gg * 4 + qq) * 32 + ll];
         gp[nb + NN::W3 + o + NOUT * tid] = sum;  // Flux W3 is (out=o, in=f) at o + NOUT f
       }
-      float sum = 0.0f;
-#pragma unroll
-      for (int qq = 0; qq < 4; qq++) sum += hs[(NOUT * 8 + gg * 4 + qq) * 32 + ll];
-      gp[nb + NO::B2 + tid] = sum;
     }
   }
   double t_b3[NOUT];
@@ -690,7 +727,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
     const int nout = net == 0 ? E::A : 1;
     float* w1p = smem + SM::W1P;
     for (int i = tid; i < 4 * CRL_H; i += TC_THREADS) {
-      const int f = i >> 2, d = i & 3;
+      const int f = 2 * (i >> 3) + (i & 1), d = (i >> 1) & 3;
       w1p[i] = d < E::D ? np[NO::W1 + f + CRL_H * d] : 0.0f;
     }
     for (int i = tid; i < CRL_H; i += TC_THREADS) { smem[SM::B1 + i] = np[NO::B1 + i]; smem[SM::B2 + i] = np[NO::B2 + i]; }
