@@ -37,20 +37,32 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace {
 using namespace crl_upd;
+
+// -DTC_TRACE: per-phase clock stamps of tile 3 of CTA 0 (warps 0 and 5), printed from the kernel (development aid)
+#ifdef TC_TRACE
+#define TR(i) do { if (trace_on) tr[i] = clock64(); } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
 
 constexpr int TC_S = 128;        // samples per tile = TMEM lanes
 constexpr int TC_THREADS = 256;  // 4 lane quadrants x 2 feature halves
 constexpr int TC_COMPUTE = TC_THREADS;
 constexpr int TC_FG = 32;        // features per thread
 constexpr int F_LBO = 144, F_SBO = 32 * F_LBO;  // bytes; feature-major operand: rows r, K = 128 samples
-constexpr int X_LBO = 128;                      // x~^T: 8 rows, K = 128 samples
 __device__ __forceinline__ int f_off(int r, int s) { return (r & 7) * 4 + (r >> 3) * (F_SBO / 4) + (s >> 2) * (F_LBO / 4) + (s & 3); }
-__device__ __forceinline__ int xt_off(int d, int s) { return d * 4 + (s >> 2) * (X_LBO / 4) + (s & 3); }
+// x~^T (rows x_0..x_D-1, ones, zeros): two more 8-row groups (hi, lo) right behind h1^T, same strides, so that
+// [h1_hi ; h1_lo ; x~_hi ; x~_lo] is ONE 144-row B operand
+__device__ __forceinline__ int xt_off(int d, int s) { return d * 4 + (s >> 2) * (F_LBO / 4) + (s & 3); }
+constexpr int XT_GROUP = F_SBO / 4;  // floats per 8-row group
 
-// TMEM columns (fp32): z2/dh1 accumulator | A operand hi | A operand lo | dW2 acc. | dW1,db1 acc. (16) | db2 acc. (16)
-constexpr uint32_t COL_D = 0, COL_AH = 64, COL_AL = 128, COL_D2 = 192, COL_D4 = 256, COL_D5 = 272, TMEM_COLS = 512;
+// TMEM columns (fp32): z2/dh1 accumulator (A W_hi^T | A_hi W_lo^T: 128) | A operand hi (64) | A operand lo (64) |
+// dW2 accumulator (x h1_hi | x h1_lo | x x~: 144) | dW1,db1 accumulator (x x~_hi | x x~_lo: 16)
+constexpr uint32_t COL_D = 0, COL_AH = 128, COL_AL = 192, COL_D2 = 256, COL_D4 = 400, TMEM_COLS = 512;
 // named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4 = head exchange
 constexpr int BAR_G1 = 1, BAR_G3 = 2, BAR_G4 = 3, BAR_X = 4;
 
@@ -58,8 +70,8 @@ template <int ENV> struct TcSmem {
   static constexpr int WB = 0;                      // [4][4096] weight images of this CTA's net
   static constexpr int FZ = WB + 4 * TC_W_FLOATS;   // dz2^T, rows 0-63 hi, 64-127 lo
   static constexpr int FH = FZ + 16 * F_SBO / 4;    // h1^T (later dz1^T), rows 0-63 hi, 64-127 lo
-  static constexpr int XT = FH + 16 * F_SBO / 4;    // [hi | lo][8 rows][128 samples]
-  static constexpr int W1P = XT + 2 * 1024;         // [32 pairs][4][2]: W1(2p + e, d)
+  static constexpr int XT = FH + 16 * F_SBO / 4;    // [hi | lo] 8-row groups, directly behind FH
+  static constexpr int W1P = XT + 2 * XT_GROUP;     // [32 pairs][4][2]: W1(2p + e, d)
   static constexpr int B1 = W1P + 4 * CRL_H;
   static constexpr int B2 = B1 + CRL_H;
   static constexpr int W3P = B2 + CRL_H;            // [2][64]: W3(o, f)
@@ -74,14 +86,6 @@ template <int ENV> struct TcSmem {
 
 // ---------------------------------------------------------------- tcgen05 / mbarrier wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout type 0 = no swizzle
-  return d;
-}
 // kind::tf32, fp32 accumulate, both operands K-major
 __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -204,6 +208,8 @@ template <int V> __device__ __forceinline__ int rs_index(int lane, int r) {
   return r + (V / 32) * ((lane & 1) | (lane & 2) | (lane & 4) | (lane & 8) | (lane & 16));
 }
 
+template <int I> using IC = std::integral_constant<int, I>;
+
 template <int ENV> struct Sample {
   float x[4];
   float adv, oldlp, R, V;
@@ -211,17 +217,20 @@ template <int ENV> struct Sample {
   int act;
   bool valid;
 };
+// buffer index of minibatch position m (-1 past the end); loaded one tile ahead of the fields that depend on it
+__device__ __forceinline__ int load_index(const UpdateArgs& a, const uint32_t* keys, int m) {
+  return m < a.M ? sample_index(a.idx, keys, m) : -1;
+}
 template <int ENV, int NET>
-__device__ __forceinline__ void load_sample(const UpdateArgs& a, const uint32_t* keys, int m, Sample<ENV>& in) {
+__device__ __forceinline__ void load_sample(const UpdateArgs& a, int b, Sample<ENV>& in) {
   using E = EnvTraits<ENV>;
-  in.valid = m < a.M;
+  in.valid = b >= 0;
   in.x[0] = in.x[1] = in.x[2] = in.x[3] = 0.0f;
   in.adv = in.oldlp = in.R = in.V = 0.0f;
   in.act = 0;
 #pragma unroll
   for (int k = 0; k < E::A; k++) in.actf[k] = 0.0f;
   if (!in.valid) return;
-  const int b = sample_index(a.idx, keys, m);
   if (E::D == 4) {
     const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.states) + b);
     in.x[0] = x4.x; in.x[1] = x4.y; in.x[2] = x4.z; in.x[3] = x4.w;
@@ -298,6 +307,10 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   }
   const float c = a.clip_coef;
   const float lo_c = 1.0f - c, hi_c = 1.0f + c;
+  // loop-invariant Float64 factors, hoisted as reciprocals (one rounding in the 53rd bit instead of a division per
+  // sample; invisible after the cast to Float32)
+  const double inv_std = 1.0 / ((double)std_f + 1e-8), inv_Mg = 1.0 / Mg;
+  const double ent_scale = (double)a.ent_coeff / ((double)A * Mg), v_scale = (double)a.v_coef * 0.5 / Mg;
 
   // accumulators that live for the whole kernel
   double st_pg = 0.0, st_vmax = 0.0, st_ent = 0.0, st_s = 0.0, g_logstd[A];
@@ -316,13 +329,14 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   const uint32_t wb_a = smem_u32(wb), fz_a = smem_u32(fz), fh_a = smem_u32(fh), xt_a = smem_u32(xt);
 
   // ---- MMA issue (warp 0, one lane). Descriptor words are loop constants + an immediate per K step.
-  const uint32_t idesc64 = make_idesc(128, 64), idesc16 = make_idesc(128, 16);
-  const uint32_t w_hi = desc_hi(TC_W_SBO), f_hi = desc_hi(F_SBO), x_hi = desc_hi(0);
-  const uint32_t w1h = desc_lo(wb_a, TC_W_LBO), w1l = desc_lo(wb_a + 1 * TC_W_FLOATS * 4, TC_W_LBO);
-  const uint32_t w3h = desc_lo(wb_a + 2 * TC_W_FLOATS * 4, TC_W_LBO), w3l = desc_lo(wb_a + 3 * TC_W_FLOATS * 4, TC_W_LBO);
-  const uint32_t fzd = desc_lo(fz_a, F_LBO), fhh = desc_lo(fh_a, F_LBO), fhl = desc_lo(fh_a + 8 * F_SBO, F_LBO);
-  const uint32_t xth = desc_lo(xt_a, X_LBO), xtl = desc_lo(xt_a + 4096, X_LBO);
-  constexpr uint32_t WK = 2 * TC_W_LBO / 16, FK = 2 * F_LBO / 16, XK = 2 * X_LBO / 16;  // descriptor step per K = 8
+  // An MMA instruction costs ~50 cycles of operand fetch whatever its N, so the hi/lo products are stacked along N:
+  // every operand is read once per K step.
+  const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128), idesc144 = make_idesc(128, 144),
+                 idesc16 = make_idesc(128, 16);
+  const uint32_t w_hi = desc_hi(TC_W_SBO), f_hi = desc_hi(F_SBO);
+  const uint32_t w1d = desc_lo(wb_a, TC_W_LBO), w3d = desc_lo(wb_a + 2 * TC_W_FLOATS * 4, TC_W_LBO);  // [W_hi ; W_lo], 128 rows
+  const uint32_t fzd = desc_lo(fz_a, F_LBO), fhd = desc_lo(fh_a, F_LBO), xtd = desc_lo(xt_a, F_LBO);
+  constexpr uint32_t WK = 2 * TC_W_LBO / 16, FK = 2 * F_LBO / 16;  // descriptor step per K = 8
   // hand-over point: the other warps only arrive, warp 0 waits for them and issues
   auto handover = [&](int bar_id, auto&& issue) {
     if (warp == 0) {
@@ -333,48 +347,37 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       bar_arrive(bar_id, TC_THREADS);
     }
   };
-  auto issue_g1 = [&]() {   // z2 = h1 W2^T
+  // D[:, 0:64] = A_hi W_hi^T + A_lo W_hi^T, D[:, 64:128] = A_hi W_lo^T (added by the reader)
+  auto issue_ts = [&](uint32_t wd, uint32_t bar) {
 #pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w1h + ks * WK, w_hi), idesc64, ks ? 1u : 0u);
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(wd + ks * WK, w_hi), idesc128, ks ? 1u : 0u);
 #pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AL + ks * 8, pack64(w1h + ks * WK, w_hi), idesc64, 1u);
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w1l + ks * WK, w_hi), idesc64, 1u);
-    mma_commit(bar1);
+    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AL + ks * 8, pack64(wd + ks * WK, w_hi), idesc64, 1u);
+    mma_commit(bar);
   };
-  auto issue_g3_g2 = [&](int it) {   // -dh1 = (-dz2) W2 ; -dW2 += (-dz2)^T h1 ; -db2 += (-dz2)^T 1
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w3h + ks * WK, w_hi), idesc64, ks ? 1u : 0u);
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AL + ks * 8, pack64(w3h + ks * WK, w_hi), idesc64, 1u);
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) mma_ts(tmem + COL_D, tmem + COL_AH + ks * 8, pack64(w3l + ks * WK, w_hi), idesc64, 1u);
-    mma_commit(bar3);
+  auto issue_g1 = [&]() { issue_ts(w1d, bar1); };   // z2 = h1 W2^T
+  auto issue_g3_g2 = [&](int it) {
+    issue_ts(w3d, bar3);                              // -dh1 = (-dz2) W2
+    // [-dz2_hi ; -dz2_lo]^T x [h1_hi ; h1_lo ; x~_hi ; x~_lo]: -dW2 (4 terms) and, through the ones row, -db2
 #pragma unroll
     for (int ks = 0; ks < 16; ks++)
-      mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhh + ks * FK, f_hi), idesc64, (it | ks) ? 1u : 0u);
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhl + ks * FK, f_hi), idesc64, 1u);
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++)   // the ones row of x~^T (exact in TF32) picks out the row sums
-      mma_ss(tmem + COL_D5, pack64(fzd + ks * FK, f_hi), pack64(xth + ks * XK, x_hi), idesc16, (it | ks) ? 1u : 0u);
+      mma_ss(tmem + COL_D2, pack64(fzd + ks * FK, f_hi), pack64(fhd + ks * FK, f_hi), idesc144, (it | ks) ? 1u : 0u);
     mma_commit(bar2);
   };
-  auto issue_g4 = [&](int it) {   // dW1, db1 += dz1^T x~
+  auto issue_g4 = [&](int it) {   // [dz1_hi ; dz1_lo]^T x [x~_hi ; x~_lo]: dW1, db1
 #pragma unroll
     for (int ks = 0; ks < 16; ks++)
-      mma_ss(tmem + COL_D4, pack64(fhh + ks * FK, f_hi), pack64(xth + ks * XK, x_hi), idesc16, (it | ks) ? 1u : 0u);
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) mma_ss(tmem + COL_D4, pack64(fhh + ks * FK, f_hi), pack64(xtl + ks * XK, x_hi), idesc16, 1u);
+      mma_ss(tmem + COL_D4, pack64(fhd + ks * FK, f_hi), pack64(xtd + ks * FK, f_hi), idesc16, (it | ks) ? 1u : 0u);
     mma_commit(bar4);
   };
 
   // L1 for one tile: h1 = tanh(W1 x + b1) for this thread's 16 feature pairs
   const int p0 = f0 / 2;
-  auto layer1 = [&](const Sample<ENV>& in, float2 (&h)[TC_FG / 2]) {
+  auto layer1 = [&](const Sample<ENV>& in, float2 (&h)[TC_FG / 2], auto i0c, auto i1c) {
+    constexpr int I0 = decltype(i0c)::value, I1 = decltype(i1c)::value;
     const float2 xb[4] = {f2s(in.x[0]), f2s(in.x[1]), f2s(in.x[2]), f2s(in.x[3])};
 #pragma unroll
-    for (int i = 0; i < TC_FG / 2; i++) {
+    for (int i = I0; i < I1; i++) {
       const float4 wa = w1v[(p0 + i) * 2], wc = w1v[(p0 + i) * 2 + 1];
       float2 acc = f2s(0.0f);
       acc = __ffma2_rn(f2(wa.x, wa.y), xb[0], acc);
@@ -384,79 +387,106 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       h[i] = tanh_fast2(__fadd2_rn(acc, b1q[p0 + i]));
     }
   };
-  // hi/lo of 32 values: TMEM columns col.. (A operand) and rows f0.. / 64+f0.. of a feature-major operand buffer
-  auto store_split = [&](const float2 (&v)[TC_FG / 2], float* buf) {
-    float vh[TC_FG], vl[TC_FG];
+  // hi/lo of 32 values: TMEM columns (A operand of G1/G3) and rows f0.. / 64+f0.. of a feature-major operand buffer
+  auto split_to_tmem = [&](const float2 (&v)[TC_FG / 2], float (&vh)[TC_FG], float (&vl)[TC_FG]) {
 #pragma unroll
     for (int i = 0; i < TC_FG / 2; i++) {
       float2 hi, lo;
       split2(v[i], hi, lo);
       vh[2 * i] = hi.x; vh[2 * i + 1] = hi.y; vl[2 * i] = lo.x; vl[2 * i + 1] = lo.y;
-      buf[f_off(f0 + 2 * i, s)] = hi.x;
-      buf[f_off(f0 + 2 * i + 1, s)] = hi.y;
-      buf[f_off(CRL_H + f0 + 2 * i, s)] = lo.x;
-      buf[f_off(CRL_H + f0 + 2 * i + 1, s)] = lo.y;
     }
     tmem_st16(lane_addr + COL_AH + f0, vh);
     tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
     tmem_st16(lane_addr + COL_AL + f0, vl);
     tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
   };
+  auto split_to_smem = [&](const float (&vh)[TC_FG], const float (&vl)[TC_FG], float* buf) {
+#pragma unroll
+    for (int i = 0; i < TC_FG; i++) {
+      buf[f_off(f0 + i, s)] = vh[i];
+      buf[f_off(CRL_H + f0 + i, s)] = vl[i];
+    }
+  };
 
   int it = 0;
   {
     Sample<ENV> cur, nxt;
     float2 h1[TC_FG / 2];
+    int b_next = -1;  // buffer index of this thread's sample in the NEXT tile
     if (cta < n_tiles) {
-      load_sample<ENV, NET>(a, keys, cta * TC_S + s, cur);
-      layer1(cur, h1);
+      load_sample<ENV, NET>(a, load_index(a, keys, cta * TC_S + s), cur);
+      if (cta + n_cta < n_tiles) b_next = load_index(a, keys, (cta + n_cta) * TC_S + s);
+      layer1(cur, h1, IC<0>(), IC<TC_FG / 2>());
     }
+#ifdef TC_TRACE
+    long long tr[16];
+    for (int i = 0; i < 16; i++) tr[i] = 0;
+#endif
     for (int t = cta; t < n_tiles; t += n_cta, it++) {
+#ifdef TC_TRACE
+      const bool trace_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && it == 3 && lane == 0 && (warp == 0 || warp == 5);
+#endif
+      TR(0);
       const uint32_t ph = it & 1;
       const int m0 = t * TC_S;
       const bool more = t + n_cta < n_tiles;
-      // next tile's inputs: consumed in the shadow of G1 below
-      if (more) load_sample<ENV, NET>(a, keys, (t + n_cta) * TC_S + s, nxt);
+      // next tile's inputs (consumed in the shadow of G1 below) and the index for the tile after it
+      if (more) {
+        load_sample<ENV, NET>(a, b_next, nxt);
+        if (t + 2 * n_cta < n_tiles) b_next = load_index(a, keys, (t + 2 * n_cta) * TC_S + s);
+      }
 
-      // ---- L1 hand-over: h1 hi/lo -> TMEM (A of G1) and feature-major shared memory (B of G2); x~^T
-      if (it > 0) mbar_wait(bar4, ph ^ 1);  // the previous tile's G4 still reads dz1^T (same buffer) and x~^T
-      store_split(h1, fh);
+      // ---- L1 hand-over, TMEM half: h1 hi/lo are the A operand of G1, which can start while the previous tile's
+      //      G4 is still reading the shared-memory buffers
+      float h1h[TC_FG], h1l[TC_FG];
+      TR(1);
+      split_to_tmem(h1, h1h, h1l);
+      tmem_st_wait();
+      tc_fence_before();
+      TR(2);
+      handover(BAR_G1, issue_g1);
+      TR(3);
+      // ---- in the shadow of G1: the shared-memory half (h1^T is the B operand of G2; x~^T), then part of the next
+      //      tile's first layer (the rest follows G3 and G4)
+      if (it > 0) mbar_wait(bar4, ph ^ 1);  // the previous tile's G4 has read dz1^T (same buffer as h1^T) and x~^T
+      split_to_smem(h1h, h1l, fh);
       if (g == 0) {
 #pragma unroll
         for (int d = 0; d < D; d++) {
           const float xh = tf32_hi(cur.x[d]);
           xt[xt_off(d, s)] = xh;
-          xt[1024 + xt_off(d, s)] = cur.x[d] - xh;
+          xt[XT_GROUP + xt_off(d, s)] = cur.x[d] - xh;
         }
       }
-      tmem_st_wait();
-      proxy_fence();
-      tc_fence_before();
-      handover(BAR_G1, issue_g1);
-
-      // ---- in the shadow of G1: the next tile's first layer
-      if (more) layer1(nxt, h1);
+      double adv_n = 0.0;  // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
+      if (NET == 0) adv_n = (double)__fsub_rn(cur.adv, mean_f) * inv_std;
+      if (more) layer1(nxt, h1, IC<0>(), IC<6>());
+      TR(4);
 
       // ---- E1: h2, head, loss, dz2
       mbar_wait(bar1, ph);
+      TR(5);
       tc_fence_after();
       float2 h2[TC_FG / 2];
       {
-        float z2[TC_FG];
+        float z2[TC_FG], z2b[TC_FG];
         tmem_ld32(lane_addr + COL_D + f0, z2);
+        tmem_ld32(lane_addr + COL_D + CRL_H + f0, z2b);
         float2 part[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; o++) part[o] = f2s(0.0f);
 #pragma unroll
         for (int i = 0; i < TC_FG / 2; i++) {
-          h2[i] = tanh_fast2(__fadd2_rn(f2(z2[2 * i], z2[2 * i + 1]), b2q[p0 + i]));
+          h2[i] = tanh_fast2(__fadd2_rn(__fadd2_rn(f2(z2[2 * i], z2[2 * i + 1]), f2(z2b[2 * i], z2b[2 * i + 1])), b2q[p0 + i]));
 #pragma unroll
           for (int o = 0; o < NOUT; o++) part[o] = __ffma2_rn(w3q[o * (CRL_H / 2) + p0 + i], h2[i], part[o]);
         }
 #pragma unroll
         for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o].x + part[o].y;
       }
+      TR(6);
       bar_sync(BAR_X, TC_COMPUTE);
+      TR(7);
       float dl[NOUT];
 #pragma unroll
       for (int o = 0; o < NOUT; o++) dl[o] = 0.0f;
@@ -466,8 +496,6 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
         for (int o = 0; o < NOUT; o++) z[o] = (exch[(0 * 2 + o) * TC_S + s] + exch[(1 * 2 + o) * TC_S + s]) + b3s[o];
         const bool own = g == 0;  // both feature halves evaluate the loss; only one of them accumulates its statistics
         if (NET == 0) {
-          // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
-          const double adv_n = (double)__fsub_rn(cur.adv, mean_f) / ((double)std_f + 1e-8);
           float newlp, p[A], lp[A];
           double ent_sum = 0.0;
           if (!E::CONT) {
@@ -508,8 +536,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           double pgm, dratio;
           if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
           else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
-          const double g_lp = dratio * (double)ratio / Mg;
-          const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);
+          const double g_lp = dratio * (double)ratio * inv_Mg;
           if (own) { st_pg += pgm; st_ent += ent_sum; }
           if (!E::CONT) {
 #pragma unroll
@@ -545,9 +572,10 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           }
           double dv_d = cnt_over_M;
           if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
-          dl[0] = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
+          dl[0] = (float)(v_scale * dv_d);
         }
       }
+      TR(8);
       // -dz2 = (W3^T dl) .* (h2^2 - 1): the sign is carried through G3/G2 and removed again by E3 / at the read-out,
       // which saves negating a packed operand here. dW3(o,f) += dl[o] h2[f] stays in registers.
       {
@@ -563,26 +591,35 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
         }
 #pragma unroll
         for (int o = 0; o < NOUT; o++) if (g == 0) gb3[o] += dl[o];
-        store_split(ndz2, fz);   // the previous tile's G2 was waited for in its E3
+        float zh[TC_FG], zl[TC_FG];
+        split_to_tmem(ndz2, zh, zl);
+        split_to_smem(zh, zl, fz);   // the previous tile's G2 was waited for in its E3
       }
       tmem_st_wait();
       proxy_fence();
       tc_fence_before();
+      TR(9);
       handover(BAR_G3, [&]() { issue_g3_g2(it); });
+      if (more) layer1(nxt, h1, IC<6>(), IC<12>());
+      TR(10);
 
       // ---- E3: dz1 = (-dh1) .* (h1^2 - 1), in place over h1^T (whose hi + lo is this tile's h1 exactly)
       mbar_wait(bar3, ph);
+      TR(11);
       tc_fence_after();
-      float ndh1[TC_FG];
+      float ndh1[TC_FG], ndh1b[TC_FG];
       tmem_ld32(lane_addr + COL_D + f0, ndh1);
+      tmem_ld32(lane_addr + COL_D + CRL_H + f0, ndh1b);
       float2 dz1[TC_FG / 2];
 #pragma unroll
       for (int i = 0; i < TC_FG / 2; i++) {
         const float2 h = __fadd2_rn(f2(fh[f_off(f0 + 2 * i, s)], fh[f_off(f0 + 2 * i + 1, s)]),
                                     f2(fh[f_off(CRL_H + f0 + 2 * i, s)], fh[f_off(CRL_H + f0 + 2 * i + 1, s)]));
-        dz1[i] = __fmul2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), __ffma2_rn(h, h, f2s(-1.0f)));
+        dz1[i] = __fmul2_rn(__fadd2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), f2(ndh1b[2 * i], ndh1b[2 * i + 1])), __ffma2_rn(h, h, f2s(-1.0f)));
       }
+      TR(12);
       mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
+      TR(13);
 #pragma unroll
       for (int i = 0; i < TC_FG / 2; i++) {
         float2 hi, lo;
@@ -594,7 +631,17 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       }
       proxy_fence();
       tc_fence_before();
+      TR(14);
       handover(BAR_G4, [&]() { issue_g4(it); });
+      if (more) layer1(nxt, h1, IC<12>(), IC<16>());
+      TR(15);
+#ifdef TC_TRACE
+      if (trace_on)
+        printf("net %d warp %d: wait4 %lld | st_h1 %lld | hand1 %lld | L1next %lld | waitG1 %lld | E1a %lld | barX %lld | loss %lld | dz2+st %lld | "
+               "hand3 %lld | waitG3 %lld | E3a %lld | waitG2 %lld | st_dz1 %lld | hand4 %lld | total %lld\n", NET, warp, tr[1] - tr[0],
+               tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8],
+               tr[10] - tr[9], tr[11] - tr[10], tr[12] - tr[11], tr[13] - tr[12], tr[14] - tr[13], tr[15] - tr[14], tr[15] - tr[0]);
+#endif
       cur = nxt;
     }
   }
@@ -611,14 +658,20 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     // dW2(j,k) = -(D2[j][k] + D2[64+j][k]); dW1(k,d), db1(k) = D4[k][d] + D4[64+k][d]; db2(j) = -(D5[j][D] + D5[64+j][D]):
     // lanes 64.. hand their (lo) halves over through shared memory
     float d2[TC_FG], d4[16], d5[16];
-    tmem_ld32(lane_addr + COL_D2 + f0, d2);
-    if (g == 0) { tmem_ld16(lane_addr + COL_D4, d4); tmem_ld16(lane_addr + COL_D5, d5); }
+    {
+      float d2b[TC_FG];
+      tmem_ld32(lane_addr + COL_D2 + f0, d2);
+      tmem_ld32(lane_addr + COL_D2 + CRL_H + f0, d2b);
+#pragma unroll
+      for (int i = 0; i < TC_FG; i++) d2[i] += d2b[i];
+    }
+    if (g == 0) { tmem_ld16(lane_addr + COL_D4, d4); tmem_ld16(lane_addr + COL_D2 + 2 * CRL_H, d5); }
     if (q >= 2) {
 #pragma unroll
       for (int i = 0; i < TC_FG; i++) scr[(f0 + i) * CRL_H + (s - 64)] = d2[i];
       if (g == 0) {
 #pragma unroll
-        for (int d = 0; d <= D; d++) scr[CRL_H * CRL_H + d * CRL_H + (s - 64)] = d4[d];
+        for (int d = 0; d <= D; d++) scr[CRL_H * CRL_H + d * CRL_H + (s - 64)] = d4[d] + d4[8 + d];
         scr[CRL_H * CRL_H + 7 * CRL_H + (s - 64)] = d5[D];
       }
     }
@@ -629,7 +682,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       if (g == 0) {
 #pragma unroll
         for (int d = 0; d <= D; d++) {
-          const float v = d4[d] + scr[CRL_H * CRL_H + d * CRL_H + s];
+          const float v = (d4[d] + d4[8 + d]) + scr[CRL_H * CRL_H + d * CRL_H + s];
           if (d < D) gp[nb + NO::W1 + s + CRL_H * d] = v;
           else gp[nb + NO::B1 + s] = v;
         }
@@ -738,8 +791,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
     if (tid < 2) smem[SM::B3 + tid] = tid < nout ? np[(net == 0 ? NA::B3 : NO::B3) + tid] : 0.0f;
     if (tid >= 2 && tid < 4) smem[SM::B3 + tid] = (E::CONT && tid - 2 < E::A) ? a.params[E::NET_A + E::NET_C + (tid - 2)] : 0.0f;
     float* xt = smem + SM::XT;
-    for (int i = tid; i < 2 * 1024; i += TC_THREADS) {
-      const int half = i >> 10, r = (i & 1023), d = (r >> 2) & 7;  // xt_off: d*4 + chunk*32 + (s&3)
+    for (int i = tid; i < 2 * XT_GROUP; i += TC_THREADS) {
+      const int half = i / XT_GROUP, r = (i % XT_GROUP) % (F_LBO / 4);  // xt_off: d*4 + chunk*36 + (s&3); floats 32..35 are padding
+      const int d = r >> 2;
       xt[i] = (half == 0 && d == E::D) ? 1.0f : 0.0f;
     }
   }
@@ -793,7 +847,17 @@ int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   int grid = 2 * n_tiles < sm_count ? 2 * n_tiles : sm_count;
   grid &= ~1;
   if (grid < 2) grid = 2;
+  // An actor tile (two heads, softmax, entropy) costs ~1.15x a critic tile, and every CTA runs a whole number of
+  // tiles: pick the split that minimises the slower side.
   int na = grid / 2;
+  {
+    double best = 1e30;
+    for (int cand = 1; cand < grid; cand++) {
+      const double ta = 1.15 * ((n_tiles + cand - 1) / cand), tc = (double)((n_tiles + (grid - cand) - 1) / (grid - cand));
+      const double cost = ta > tc ? ta : tc;
+      if (cost < best - 1e-9) { best = cost; na = cand; }
+    }
+  }
   if (actor_share > 0 && actor_share < grid && grid == (sm_count & ~1)) na = actor_share;
   a->grid_loss = grid;
   a->tc_actor_ctas = na;

@@ -370,8 +370,10 @@ def test_single_minibatch_first_step_parameters(crl, olib, abi, torch_cuda):
     idx = np.random.default_rng(0).permutation(128)[:32].astype(np.int32)
     lr = float(F(2.5e-4))
     s1, s2 = h.update_minibatch(idx, lr), o.update_minibatch(idx, lr)
+    # pg_loss is a mean of 32 terms -adv_n * ratio of magnitude ~1 that cancel to ~1e-7 on the first step; ratio =
+    # exp(~1e-8) is quantised to 1 or 1 + 2^-23, so the sum carries ~1e-7 of rounding noise: atol 5e-7 = 5e-7 of a summand
     np.testing.assert_allclose([s1.loss, s1.pg_loss, s1.v_loss, s1.entropy_loss],
-                               [s2.loss, s2.pg_loss, s2.v_loss, s2.entropy_loss], rtol=RTOL, atol=1e-7)
+                               [s2.loss, s2.pg_loss, s2.v_loss, s2.entropy_loss], rtol=RTOL, atol=5e-7)
     np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(h.read_field(abi.CRL_F_VNEW)[:32], o.read_field(abi.CRL_F_VNEW)[:32], rtol=RTOL, atol=2e-6)
     h.close()
