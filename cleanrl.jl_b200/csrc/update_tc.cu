@@ -647,6 +647,9 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   }
 
   // ---------------------------------------------------------------- epilogue: this CTA's partial gradient
+#ifdef TC_TRACE
+  const long long e_t0 = clock64();
+#endif
   float* gp = a.gpart + (long long)blockIdx.x * E::P;
   const int nb = NET == 0 ? 0 : E::NET_A;
   using NN = NetOff<D, NOUT>;
@@ -746,6 +749,9 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
 #pragma unroll
       for (int k = 0; k < A; k++) gp[E::NET_A + E::NET_C + k] = (float)t_ls[k];
     }
+#ifdef TC_TRACE
+    if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) printf("  net %d epilogue %lld tiles %d\n", NET, clock64() - e_t0, it);
+#endif
   }
 }
 
@@ -759,6 +765,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
   __shared__ TcBars bars;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef TC_TRACE
+  const long long k_t0 = clock64();
+#endif
   if (a.fixup && !a.fin->need_fixup) return;
   if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
   const int net = (int)blockIdx.x < a.tc_actor_ctas ? 0 : 1;
@@ -814,8 +823,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
                    ::"r"(dst + off), "l"(src + off), "r"(CHUNK), "r"(pbar) : "memory");
   }
   mbar_wait(pbar, 0);
+#ifdef TC_TRACE
+  const long long k_t1 = clock64();
+#endif
   if (net == 0) tc_body<ENV, 0>(a, smem, &bars, tmem);
   else tc_body<ENV, 1>(a, smem, &bars, tmem);
+#ifdef TC_TRACE
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("kernel net %d: prologue %lld  body+epilogue %lld\n", net, k_t1 - k_t0, clock64() - k_t1);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
