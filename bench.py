@@ -30,6 +30,9 @@ NUM_MINIBATCHES = 4
 UPDATE_EPOCHS = 4
 FWD_FLOP = 17_792          # actor 8,960 + critic 8,832 FLOP per sample
 UPDATE_FLOP = 53_376       # forward + backward per sample per epoch
+# tensor-pipe FLOP per sample of the tcgen05 kernel (both nets): per 128-sample tile and net, M=128 MMAs with
+# N x K = (128+64)x64 [z2, 3 terms] + (128+64)x64 [dh1] + 144x128 [dW2, db2, 4 terms] + 16x128 [dW1, db1]
+TC_EXEC_FLOP = 2 * 2 * 128 * ((128 + 64) * 64 * 2 + 144 * 128 + 16 * 128) // 128
 A2C_ENVS, A2C_STEPS = 16384, 32
 METRIC = "ppo_env_steps_per_sec"
 UNIT = "env-steps/s"
@@ -301,13 +304,34 @@ def run_ours(args):
     peaks = measured_peaks()
     sm_max = (clocks.get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-    roofline = {"kernel": "loss_grad_kernel", "bound": "fp32",
-                "achieved": flops / (lg_ms * 1e-3) / 1e12 if lg_ms else None, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": (flops / (lg_ms * 1e-3) / 1e12 / fp32_peak) if lg_ms else None, "traffic": None,
-                "avg_launch_ms": lg_ms, "share_of_step": kernels.get("loss_grad", {}).get("share"),
-                "algorithmic": "%d FLOP/sample x %d samples per launch" % (UPDATE_FLOP, M_local),
-                "peak_source": "derived FP32 FFMA peak: 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json has no fp32 "
-                               "figure); FFMA path, no tensor cores, so neither 'hbm' nor 'tensor' applies"}
+    ach = flops / (lg_ms * 1e-3) / 1e12 if lg_ms else None
+    use_tc = args.algo == "ppo" and not int(os.environ.get("CRL_NO_TC", "0") or 0)
+    if use_tc:
+        # tcgen05 kernel (csrc/update_tc.cu): kind::tf32 MMAs, 3xTF32 (hi/lo split) so the tensor cores execute
+        # TC_EXEC_FLOP per sample for UPDATE_FLOP algorithmic fp32 FLOP. MEASURED_PEAKS.json holds a bf16 figure only;
+        # the TF32 peak is that measurement scaled by the nominal TF32:bf16 ratio (1.1 : 2.25 PFLOP/s dense).
+        bf16 = (peaks or {}).get("bf16_tflops")
+        tf32_peak = (bf16 if bf16 else 2250.0) * 1.1 / 2.25
+        exec_tf = TC_EXEC_FLOP * M_local / (lg_ms * 1e-3) / 1e12 if lg_ms else None
+        roofline = {"kernel": "loss_grad_tc_kernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf32_peak if ach else None, "traffic": None,
+                    "avg_launch_ms": lg_ms, "share_of_step": kernels.get("loss_grad", {}).get("share"),
+                    "algorithmic": "%d FLOP/sample x %d samples per launch (fp32-equivalent work of the three 64-wide "
+                                   "contractions per net, forward + backward)" % (UPDATE_FLOP, M_local),
+                    "executed_tensor_tflops": exec_tf, "executed_frac": exec_tf / tf32_peak if exec_tf else None,
+                    "executed": "%d FLOP/sample on the tensor pipe: 3xTF32 = 3-4 TF32 products per fp32 product" % TC_EXEC_FLOP,
+                    "fp32_equiv_frac_of_ffma_peak": ach / fp32_peak if ach else None,
+                    "peak_source": ("TF32 dense peak = MEASURED_PEAKS.json bf16_tflops x 1.1/2.25 (nominal TF32:bf16 ratio; no "
+                                    "TF32 measurement exists)" if bf16 else "nominal 1.1 PFLOP/s TF32 dense (no MEASURED_PEAKS.json)"),
+                    "note": "the kernel is bound by its CUDA-core work (tanh_fast on 2x64 activations per sample and layer, "
+                            "hi/lo splitting, feature-major operand stores), not by the tensor pipe: see DESIGN.md section 5"}
+    else:
+        roofline = {"kernel": "loss_grad_kernel", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak if ach else None, "traffic": None,
+                    "avg_launch_ms": lg_ms, "share_of_step": kernels.get("loss_grad", {}).get("share"),
+                    "algorithmic": "%d FLOP/sample x %d samples per launch" % (UPDATE_FLOP, M_local),
+                    "peak_source": "derived FP32 FFMA peak: 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json has no "
+                                   "fp32 figure); FFMA kernel (A2C, CRL_NO_TC=1, exact replay)"}
 
     # ---- GAE HBM roofline (the metric's second half) on rank 0
     roofline_gae = None
@@ -366,7 +390,9 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world),
                                                                 l2="not flushed: every step regenerates its 16.5 MB rollout buffer on the device "
-                                                                   "(L2-resident in production too); the GAE roofline uses a 2.29 GB input"),
+                                                                   "(L2-resident in production too); the GAE roofline uses a 2.29 GB input",
+                                                                arithmetic="fp32 results; the 64-wide contractions of the update run as 3xTF32 on "
+                                                                           "tcgen05 (fp32-accurate to ~1e-6), everything else fp32/fp64 on the CUDA cores"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gae": roofline_gae,
             "cpu_baseline": cpu_baseline, "kernels": kernels,
             "last_loss": float(stats[-1, 0]), "episodes_last_update": int(agg.count),

@@ -86,7 +86,8 @@ def main():
                 "rollout_ok": bool(ok_rollout),
                 "ranks_agree": bool(all(np.array_equal(g["params"], gathered[0]["params"]) for g in gathered)),
                 "param_maxerr": float(np.max(np.abs(gathered[0]["params"] - p_o) / (np.abs(p_o) + 1e-2))),
-                "stats_maxerr": float(np.max(np.abs(np.array(st_o) - gathered[0]["stats"]) / (np.abs(np.array(st_o)) + 1e-3))),
+                # pg_loss is a mean of O(1) terms that cancels to ~1e-4 .. 1e-7: the floor is 1e-2 of a summand, not of the sum
+                "stats_maxerr": float(np.max(np.abs(np.array(st_o) - gathered[0]["stats"]) / (np.abs(np.array(st_o)) + 1e-2))),
             }
         h.close()
         # throughput path (CUDA graph, speculative loss_grad + ONE allreduce per minibatch) against the exact
@@ -126,7 +127,7 @@ def main():
                     "replays": int(outs["spec"][2]), "replays_exact_mode": int(outs["exact"][2]),
                     "bit_identical": bool(np.array_equal(ps, pe)),
                     "maxerr": float(np.max(np.abs(ps - pe) / (np.abs(pe) + 1e-2))),
-                    "stats_maxerr": float(np.max(np.abs(outs["spec"][1] - outs["exact"][1]) / (np.abs(outs["exact"][1]) + 1e-3))),
+                    "stats_maxerr": float(np.max(np.abs(outs["spec"][1] - outs["exact"][1]) / (np.abs(outs["exact"][1]) + 1e-2))),
                 }
     if rank == 0:
         json.dump(res, open(out_path, "w"))
