@@ -305,7 +305,7 @@ def run_ours(args):
     sm_max = (clocks.get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     ach = flops / (lg_ms * 1e-3) / 1e12 if lg_ms else None
-    use_tc = args.algo == "ppo" and not int(os.environ.get("CRL_NO_TC", "0") or 0)
+    use_tc = not int(os.environ.get("CRL_NO_TC", "0") or 0)
     if use_tc:
         # tcgen05 kernel (csrc/update_tc.cu): kind::tf32 MMAs, 3xTF32 (hi/lo split) so the tensor cores execute
         # TC_EXEC_FLOP per sample for UPDATE_FLOP algorithmic fp32 FLOP. MEASURED_PEAKS.json holds a bf16 figure only;

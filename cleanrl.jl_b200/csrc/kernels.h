@@ -108,6 +108,8 @@ struct UpdateArgs {
   // only its own net's slice of gpart; 0 = the FFMA kernel (every CTA writes all P elements)
   int tc_actor_ctas;
   int tc_net_a, tc_net_c;               // sizes of the actor / critic slices of the flat parameter vector
+  int values_fresh;                     // `values` holds the critic's output under the CURRENT parameters (rollout ->
+                                        // one update, crl_train_update): lets the A2C actor CTAs take R - v from it
 };
 
 #define CRL_MAX_WORLD 16

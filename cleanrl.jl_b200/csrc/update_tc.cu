@@ -239,6 +239,7 @@ __device__ __forceinline__ void load_sample(const UpdateArgs& a, int b, Sample<E
     for (int k = 0; k < E::D; k++) in.x[k] = __ldg(a.states + (long long)b * E::D + k);
   }
   if (NET == 0) {
+    if (a.algo == 1) { in.R = __ldg(a.returns + b); in.V = __ldg(a.values + b); }
     in.adv = __ldg(a.advantages + b);
     in.oldlp = __ldg(a.logprobs + b);
     if (E::CONT) {
@@ -289,6 +290,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
 
   // minibatch scalars (same derivation as loss_grad_kernel)
   const bool spec = a.mode == LG_SPEC;
+  const bool a2c = a.algo == 1;
   float mean_f, std_f, s_f;
   double Mg, cnt_over_M;
   if (spec) {
@@ -528,6 +530,16 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
             }
             newlp = acc;
           }
+          double g_lp, ent_w = ent_scale;
+          if (a2c) {
+            // A2C (a2c.jl:88-97): actor_loss = -mean(logp .* advantage), advantage = R - critic(state) held constant.
+            // The critic lives in other CTAs: its output for this sample is the value recorded by the rollout (same
+            // parameters, A2C steps once per rollout; differs from a recomputation by fp32 summation order only).
+            const double advd = (double)cur.R - (double)cur.V;
+            if (own) st_pg += -(double)newlp * advd;
+            g_lp = -advd * inv_Mg;
+            ent_w = 0.0;
+          } else {
           const float logratio = __fsub_rn(newlp, cur.oldlp);  // ppo.jl:224
           const float ratio = expf(logratio);                  // ppo.jl:225
           const float rc = ratio < lo_c ? lo_c : (ratio > hi_c ? hi_c : ratio);
@@ -536,13 +548,14 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           double pgm, dratio;
           if (pg1 > pg2) { pgm = pg1; dratio = -adv_n; }
           else { pgm = pg2; dratio = (ratio >= lo_c && ratio <= hi_c) ? -adv_n : 0.0; }
-          const double g_lp = dratio * (double)ratio * inv_Mg;
+          g_lp = dratio * (double)ratio * inv_Mg;
           if (own) { st_pg += pgm; st_ent += ent_sum; }
+          }
           if (!E::CONT) {
 #pragma unroll
             for (int k = 0; k < A; k++) {
               double dd = g_lp * ((k == cur.act ? 1.0 : 0.0) - (double)p[k]);
-              dd += ent_scale * (double)p[k] * ((double)lp[k] + ent_sum);
+              dd += ent_w * (double)p[k] * ((double)lp[k] + ent_sum);
               dl[k] = (float)dd;
             }
           } else {
@@ -552,9 +565,14 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
               const double diff = (double)__fsub_rn(cur.actf[k], z[k]);
               const double var = (double)sd * (double)sd;
               dl[k] = (float)(g_lp * diff / var);
-              if (own) g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_scale;
+              if (own) g_logstd[k] += g_lp * (diff * diff / var - 1.0) - ent_w;
             }
           }
+        } else if (a2c) {
+          // critic_loss = mean((R - v)^2) (a2c.jl:79-84)
+          const double advd = (double)cur.R - (double)z[0];
+          if (own) st_vmax += advd * advd;
+          dl[0] = (float)(-2.0 * advd * inv_Mg);
         } else {
           // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
           const float v = z[0];
@@ -847,7 +865,7 @@ cudaError_t kernels_init_update_tc() {
                               (int)TcSmem<CRL_ENV_PENDULUM>::BYTES);
 }
 
-// Chooses the tensor-core kernel for this minibatch when it applies (PPO losses, parameter image present) and fills
+// Chooses the tensor-core kernel for this minibatch when it applies (parameter image present) and fills
 // in the launch geometry; CRL_NO_TC=1 keeps the FFMA kernel.
 int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   static int disabled = -1, actor_share = -1;
@@ -858,7 +876,9 @@ int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
     actor_share = s ? atoi(s) : 0;
   }
   a->tc_actor_ctas = 0;
-  if (disabled || !a->image || a->algo != 0) return 0;
+  // A2C: the actor's advantage needs the critic's output, which lives in other CTAs; only when the recorded values
+  // are that output (values_fresh) can the one-net-per-CTA kernel be used
+  if (disabled || !a->image || (a->algo == 1 && !a->values_fresh)) return 0;
   const int n_tiles = (a->M + TC_S - 1) / TC_S;
   int grid = 2 * n_tiles < sm_count ? 2 * n_tiles : sm_count;
   grid &= ~1;
