@@ -188,6 +188,37 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU arm
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch (read + write) of a kernel from the committed `ncu --set full` summaries under profiles/
+    (tools/ncu_summary.py output; newest file that has the kernel). Returns (bytes, file) or (None, None)."""
+    import csv
+    import glob
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu*summary*.csv")) +
+                       glob.glob(os.path.join(ROOT, "profiles", "*ncu_gae*.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            cols = {}
+            for i, h in enumerate(hdr):
+                name, _, unit = h.partition("[")
+                cols[name] = (i, unit.rstrip("]"))
+            if "dram_read" not in cols or "dram_write" not in cols:
+                continue
+            vals = [r for r in rows[1:] if r and r[0].startswith(kernel_prefix)]
+            if not vals:
+                continue
+            tot = 0.0
+            for r in vals:
+                for c in ("dram_read", "dram_write"):
+                    i, unit = cols[c]
+                    tot += float(r[i]) * scale.get(unit, 1.0)
+            return tot / len(vals), os.path.relpath(path, ROOT)
+        except Exception:  # pragma: no cover
+            continue
+    return None, None
+
+
 def gae_roofline(torch, lib_mod, N, T=NUM_STEPS):
     """GAE at a working set far larger than L2 (2.29 GB at N=2^20): achieved HBM GB/s."""
     lib = lib_mod.load()
@@ -313,8 +344,12 @@ def run_ours(args):
         bf16 = (peaks or {}).get("bf16_tflops")
         tf32_peak = (bf16 if bf16 else 2250.0) * 1.1 / 2.25
         exec_tf = TC_EXEC_FLOP * M_local / (lg_ms * 1e-3) / 1e12 if lg_ms else None
+        tc_traffic, tc_tfile = ncu_traffic("loss_grad_tc_kernel")
         roofline = {"kernel": "loss_grad_tc_kernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf32_peak if ach else None, "traffic": None,
+                    "frac": ach / tf32_peak if ach else None, "traffic": tc_traffic,
+                    "traffic_source": ("%s: dram__bytes_read.sum + dram__bytes_write.sum per launch under ncu (cold L2: the 16.5 MB "
+                                       "rollout buffer is re-read from HBM once; it is L2-resident inside a training step)" % tc_tfile)
+                                      if tc_tfile else None,
                     "avg_launch_ms": lg_ms, "share_of_step": kernels.get("loss_grad", {}).get("share"),
                     "algorithmic": "%d FLOP/sample x %d samples per launch (fp32-equivalent work of the three 64-wide "
                                    "contractions per net, forward + backward)" % (UPDATE_FLOP, M_local),
@@ -338,10 +373,12 @@ def run_ours(args):
     if rank == 0:
         try:
             gbs, gms, nbytes = gae_roofline(torch, _lib, args.gae_n)
+            gae_traffic, gae_tfile = ncu_traffic("gae_kernel<0, 4, 4>")
             hbm = (peaks or {}).get("hbm_gbs")
             peak = hbm or 6650.0
             roofline_gae = {"kernel": "gae_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                            "frac": gbs / peak, "traffic": None, "avg_launch_ms": gms, "bytes_per_launch": nbytes,
+                            "frac": gbs / peak, "traffic": gae_traffic, "traffic_source": gae_tfile,
+                            "avg_launch_ms": gms, "bytes_per_launch": nbytes,
                             "workload": "T=128, N=%d envs, %.2f GB > 126 MB L2" % (args.gae_n, nbytes / 1e9),
                             "peak_source": "of measured (MEASURED_PEAKS.json hbm_gbs)" if hbm else "of fallback 6.65 TB/s"}
         except Exception as e:  # pragma: no cover

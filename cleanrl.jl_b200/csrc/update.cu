@@ -1146,8 +1146,8 @@ cudaError_t launch_advance(DevState* ds, unsigned long long d_policy_step, unsig
 
 cudaError_t launch_fill_perms_dev(int32_t* out, uint32_t B, unsigned long long seed, const DevState* ds, int n_epochs,
                                   uint32_t rank, cudaStream_t s) {
-  unsigned bx = (B + 1023) / 1024;
-  if (bx > 148) bx = 148;
+  unsigned bx = (B + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
   if (bx < 1) bx = 1;
   fill_perms_dev_kernel<<<dim3(bx, (unsigned)n_epochs), 256, 0, s>>>(out, B, perm_half_bits(B), seed, ds, rank);
   return cudaGetLastError();
