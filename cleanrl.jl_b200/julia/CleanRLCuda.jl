@@ -19,6 +19,9 @@ const CRL_ENV_CARTPOLE = Int32(0)
 const CRL_ENV_PENDULUM = Int32(1)
 const CRL_GAE_REF_COMPAT = Int32(0)
 const CRL_GAE_FIXED = Int32(1)
+const CRL_GAE_A2C_RETURNS = Int32(2)
+const CRL_FLAG_LOCAL_STATS = UInt32(1)
+const CRL_FLAG_A2C = UInt32(2)
 
 # field ids for crl_read_field / crl_write_field
 const F_STATE, F_ACTION, F_LOGPROB, F_REWARD, F_TERMINAL, F_VALUE, F_ADVANTAGE, F_RETURN = Int32.(0:7)
@@ -86,11 +89,15 @@ mutable struct Handle
   end
 end
 
+getfield_or(c, f::Symbol, default) = hasproperty(c, f) ? getproperty(c, f) : default
+
 function make_config(config; env_kind=CRL_ENV_CARTPOLE, num_envs=config.num_envs, device=0, world_size=1, rank=0,
-                     env_id_base=0, max_steps=500, gae_mode=CRL_GAE_REF_COMPAT, seed=UInt64(1))
-  CrlConfig(Int32(sizeof(CrlConfig)), env_kind, num_envs, config.num_steps, config.num_minibatches,
-            config.update_epochs, max_steps, gae_mode, device, world_size, rank, env_id_base, 0, UInt32(0),
-            config.gamma, config.gae_lambda, config.clip_coef, config.ent_coeff, config.v_coef, 0.5f0, seed)
+                     env_id_base=0, max_steps=500, gae_mode=CRL_GAE_REF_COMPAT, seed=UInt64(1), flags=UInt32(0),
+                     num_minibatches=getfield_or(config, :num_minibatches, 1), update_epochs=getfield_or(config, :update_epochs, 1))
+  CrlConfig(Int32(sizeof(CrlConfig)), env_kind, num_envs, config.num_steps, num_minibatches,
+            update_epochs, max_steps, gae_mode, device, world_size, rank, env_id_base, 0, flags,
+            config.gamma, getfield_or(config, :gae_lambda, 1.0f0), getfield_or(config, :clip_coef, 0.2f0),
+            getfield_or(config, :ent_coeff, 0.0f0), getfield_or(config, :v_coef, 0.5f0), 0.5f0, seed)
 end
 
 # Flux.params(actor, critic) order (ppo.jl:196); each W is already (out,in) column-major in Flux,
@@ -134,6 +141,24 @@ function fetch_update(h::Handle)
   agg = Ref(EpisodeAgg(0, 0.0, 0.0, 0.0, 0))
   GC.@preserve stats check(ccall((:crl_fetch_update, LIB), Cint, (Ptr{Cvoid}, Ptr{LossStats}, Ref{EpisodeAgg}), h.ptr, stats, agg))
   stats, agg[]
+end
+
+# results of the update enqueued `lag` calls before the latest (0 or 1): with lag = 1 the host logs update u-1 while
+# update u is running (crl_fetch_update_at; the Python host's pipelined loop in ppo_algo.py does exactly this)
+function fetch_update(h::Handle, lag::Integer)
+  n = h.cfg.update_epochs * h.cfg.num_minibatches
+  stats = Vector{LossStats}(undef, n)
+  agg = Ref(EpisodeAgg(0, 0.0, 0.0, 0.0, 0))
+  GC.@preserve stats check(ccall((:crl_fetch_update_at, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{LossStats}, Ref{EpisodeAgg}),
+                                 h.ptr, Int32(lag), stats, agg))
+  stats, agg[]
+end
+
+# speculative updates that failed their on-device check and were replayed exactly (performance counter)
+function spec_replays(h::Handle)
+  n = Ref{UInt64}(0)
+  check(ccall((:crl_spec_replays, LIB), Cint, (Ptr{Cvoid}, Ref{UInt64}), h.ptr, n))
+  n[]
 end
 
 function pop_episodes(h::Handle, max_records::Integer=1 << 20)
@@ -211,6 +236,36 @@ function ppo(config; actor, critic, log_episodes::Bool=false)
       log_step_inc = last_log_step == 0 ? 0 : global_step - last_log_step
       @info "Training Statistics" loss = s.loss pg_loss = s.pg_loss v_loss = s.v_loss entropy_loss = s.entropy_loss log_step_increment = log_step_inc
       last_log_step = global_step
+    end
+  end
+  get_params(h, length(p))
+end
+
+"""
+    a2c(config; actor, critic)
+
+Vectorised counterpart of `CleanRL.a2c` (a2c.jl:27-110) on the same handle: `CRL_FLAG_A2C` selects the A2C losses
+(a2c.jl:78-97), `CRL_GAE_A2C_RETURNS` the discounted-return scan (a2c.jl:13-24); one `crl_train_update` is one
+rollout of `num_envs x num_steps` transitions followed by the critic and actor steps. `config` needs the fields
+`num_envs, num_steps, total_timesteps, lr, gamma, seed` (a2c.jl:1-11 has no env vector; see a2c_algo.py).
+"""
+function a2c(config; actor, critic)
+  cfg = make_config(config; gae_mode=CRL_GAE_A2C_RETURNS, flags=CRL_FLAG_A2C, num_minibatches=1, update_epochs=1)
+  h = Handle(cfg)
+  p = flat_params(actor, critic)
+  set_params!(h, p)
+  env_reset!(h)
+  batch = config.num_envs * config.num_steps
+  global_step = 0
+  start_time = time()
+  for update in 1:(config.total_timesteps ÷ batch)
+    train_update!(h, Float64(config.lr))
+    global_step += batch
+    stats, agg = fetch_update(h)
+    @info "Training Statistics" actor_loss = stats[1].pg_loss critic_loss = stats[1].v_loss            # a2c.jl:100
+    if agg.count > 0
+      steps_per_sec = trunc(global_step / (time() - start_time))
+      @info "Episode Statistics" episode_return = agg.sum_return / agg.count episode_length = agg.sum_length / agg.count global_step steps_per_sec   # a2c.jl:106
     end
   end
   get_params(h, length(p))
