@@ -139,6 +139,7 @@ struct crl_ctx {
   unsigned char* p2p_peer[CRL_MAX_WORLD];
   unsigned char** p2p_peers_dev;
   unsigned long long* p2p_seq;
+  unsigned int* p2p_count;
   int* p2p_err;
   int p2p_stride;
   size_t p2p_flags_off;
@@ -314,7 +315,7 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int r = 0; r < CRL_MAX_WORLD; r++)
     if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_buf) cudaIpcCloseMemHandle(c->p2p_peer[r]);
-  { void* pp[] = {c->p2p_buf, c->p2p_peers_dev, c->p2p_seq, c->p2p_err}; for (void* q : pp) if (q) cudaFree(q); }
+  { void* pp[] = {c->p2p_buf, c->p2p_peers_dev, c->p2p_seq, c->p2p_err, c->p2p_count}; for (void* q : pp) if (q) cudaFree(q); }
   for (auto& p : c->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {c->image, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
@@ -592,7 +593,10 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   if (spec || ua.algo == 1) {  // the A2C losses have no minibatch-global scalars: the 3-kernel chain is already exact
     const bool p2p = multi && c->p2p_on;
     ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
-    if (p2p) { ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq; }
+    if (p2p) {
+      ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq;
+      ua.p2p_peers = c->p2p_peers_dev; ua.p2p_flags_off = c->p2p_flags_off; ua.p2p_count = c->p2p_count;
+    }
     { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
     { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
     if (multi && !p2p) {
@@ -601,7 +605,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
     }
     aa.M_global = (double)M * W; aa.world = W; aa.verify = 1;
     if (p2p) {
-      aa.peers = c->p2p_peers_dev; aa.p2p_seq = c->p2p_seq; aa.p2p_err = c->p2p_err; aa.p2p_stride = c->p2p_stride;
+      aa.p2p_local = reinterpret_cast<const double*>(c->p2p_buf); aa.p2p_seq = c->p2p_seq; aa.p2p_err = c->p2p_err; aa.p2p_stride = c->p2p_stride;
       aa.p2p_flags_off = c->p2p_flags_off;
     }
     KernelScope ks(c, CRL_K_CLIP_ADAM);
@@ -931,7 +935,7 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
     // NCCL all-gather, and each rank maps all peers (NVLink P2P). Any failure leaves the NCCL path in place.
     const int W = c->cfg.world_size;
     c->p2p_stride = (c->L.P + 4 + CRL_MAX_WORLD + 1) & ~1;
-    c->p2p_flags_off = (size_t)2 * c->p2p_stride * sizeof(double);
+    c->p2p_flags_off = (size_t)2 * W * c->p2p_stride * sizeof(double);   // [2 slots][W ranks][stride] doubles, then the flags
     const size_t bytes = c->p2p_flags_off + CRL_MAX_WORLD * sizeof(unsigned long long);
     bool ok = cudaMalloc(reinterpret_cast<void**>(&c->p2p_buf), bytes) == cudaSuccess &&
               cudaMemset(c->p2p_buf, 0, bytes) == cudaSuccess;
@@ -955,7 +959,7 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
     }
     ok = ok && cudaMalloc(reinterpret_cast<void**>(&c->p2p_peers_dev), CRL_MAX_WORLD * sizeof(void*)) == cudaSuccess;
     ok = ok && cudaMemcpy(c->p2p_peers_dev, c->p2p_peer, CRL_MAX_WORLD * sizeof(void*), cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && dalloc(&c->p2p_seq, 1) == CRL_OK && dalloc(&c->p2p_err, 1) == CRL_OK;
+    ok = ok && dalloc(&c->p2p_seq, 1) == CRL_OK && dalloc(&c->p2p_err, 1) == CRL_OK && dalloc(&c->p2p_count, 1) == CRL_OK;
     // all ranks must agree on using the peer path: one more collective carries the verdict
     double verdict = ok ? 1.0 : 0.0;
     CK(cudaMemcpy(c->gsum, &verdict, sizeof(double), cudaMemcpyHostToDevice));

@@ -100,10 +100,15 @@ struct UpdateArgs {
   float* mpart;          // [grid] per-CTA min (clip_i - R_i)^2 (LG_SPEC)
   int defer_verify;      // multi-GPU: grad_reduce only packs (sum s, per-rank min) behind the gradient; verify_kernel
   int rank;              //            checks the speculation after the allreduce
-  // peer-memory allreduce (NVLink/NVSwitch): grad_reduce writes into this rank's exchange slot instead of gsum
-  double* p2p_data;                     // own exchange buffer: [2 slots][p2p_stride doubles]
+  // peer-memory allreduce (NVLink/NVSwitch): grad_reduce PUSHES its sums into every rank's exchange buffer
+  // (layout [2 slots][world][p2p_stride] doubles, then [world] arrival flags); the last block to finish raises this
+  // rank's flag on every peer, and clip_adam only ever reads its own memory
+  double* p2p_data;                     // own exchange buffer (non-null = peer path active)
   int p2p_stride;
   unsigned long long* p2p_seq;          // exchange sequence number: loss_grad advances it, slot = seq & 1
+  unsigned char* const* p2p_peers;      // device array [world] of all ranks' exchange buffers (this rank's included)
+  size_t p2p_flags_off;                 // byte offset of the arrival flags inside an exchange buffer
+  unsigned int* p2p_count;              // local count of grad_reduce blocks that have pushed their part
   // tcgen05 kernel (update_tc.cu): CTAs [0, tc_actor_ctas) own the actor, the rest the critic, and each CTA writes
   // only its own net's slice of gpart; 0 = the FFMA kernel (every CTA writes all P elements)
   int tc_actor_ctas;
@@ -135,7 +140,7 @@ struct AdamArgs {
   double* stats_out;   // 4 doubles: loss, pg_loss, v_loss, entropy_loss (may be nullptr)
   // ---- speculative throughput path: the finishing kernel also exchanges the reduced sums with the peers
   //      (NVLink peer memory), verifies the speculation and records a failure for the host
-  unsigned char* const* peers;          // device array [world] of exchange buffers, or nullptr (single GPU / NCCL)
+  const double* p2p_local;              // this rank's exchange buffer (every rank pushes into it), or nullptr
   const unsigned long long* p2p_seq;    // exchange sequence number (advanced by loss_grad)
   int* p2p_err;
   int p2p_stride;

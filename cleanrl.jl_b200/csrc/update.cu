@@ -759,10 +759,34 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   __shared__ double sh[4][64];
   if (a.fixup && !a.fin->need_fixup) return;
   const int grid = a.grid_loss;
-  // with the peer-memory allreduce the sums go straight into this rank's exchange slot
-  double* gsum = a.p2p_data ? a.p2p_data + (size_t)(*a.p2p_seq & 1ull) * a.p2p_stride : a.gsum;
+  // with the peer-memory allreduce the sums are pushed straight into every rank's exchange buffer
+  const bool push = a.p2p_data != nullptr;
+  const unsigned long long seq = push ? *a.p2p_seq : 0ull;
+  const size_t push_off = push ? ((size_t)(seq & 1ull) * a.world + a.rank) * a.p2p_stride : 0;
+  double* gsum = a.gsum;
+  auto put = [&](int e, double v) {
+    if (push) {
+      for (int r = 0; r < a.world; r++) reinterpret_cast<double*>(a.p2p_peers[r])[push_off + e] = v;
+    } else {
+      gsum[e] = v;
+    }
+  };
+  // every block that has pushed its part counts itself in; the last one raises this rank's flag on all peers
+  auto arrive = [&]() {
+    if (!push) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();  // cumulative: orders the whole block's pushes (CTA barrier above) before the count
+      const unsigned int old = atomicAdd(a.p2p_count, 1u);
+      if ((old + 1u) % gridDim.x == 0u) {
+        __threadfence_system();
+        for (int r = 0; r < a.world; r++)
+          *(reinterpret_cast<volatile unsigned long long*>(a.p2p_peers[r] + a.p2p_flags_off) + a.rank) = seq;
+      }
+    }
+  };
   if (blockIdx.x == gridDim.x - 1) {
-    if (a.mode != LG_SPEC || a.fixup) return;
+    if (a.mode != LG_SPEC || a.fixup) { arrive(); return; }
     __shared__ double red[8];
     __shared__ float mred[8];
     double ss = 0.0;
@@ -772,12 +796,15 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
     mn = warp_min(mn);
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; mred[threadIdx.x >> 5] = mn; }
     __syncthreads();
-    if (threadIdx.x == 0 && a.defer_verify) {
+    if (a.defer_verify) {
       // multi-GPU: this rank's min rides behind the gradient in its own slot (the other ranks add 0 there),
       // so ONE sum-allreduce delivers gradient, loss sums, sum s and every rank's min
-      float m8 = mred[0];
-      for (int w = 0; w < 8; w++) m8 = fminf(m8, mred[w]);
-      for (int r = 0; r < a.world; r++) gsum[P + 4 + r] = (r == a.rank) ? (double)m8 : 0.0;
+      if (threadIdx.x == 0) {
+        float m8 = mred[0];
+        for (int w = 0; w < 8; w++) m8 = fminf(m8, mred[w]);
+        for (int r = 0; r < a.world; r++) put(P + 4 + r, (r == a.rank) ? (double)m8 : 0.0);
+      }
+      arrive();
       return;
     }
     if (threadIdx.x == 0) {
@@ -812,7 +839,8 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   }
   sh[g][el] = s;
   __syncthreads();
-  if (g == 0 && e < P + 4) gsum[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+  if (g == 0 && e < P + 4) put(e, (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]));
+  arrive();
 }
 
 // advantage sums of every minibatch of an update in one launch: grid (ADV_CHUNKS, n_sets)
@@ -898,18 +926,19 @@ __global__ void stats_pack_kernel(const MbScalars* parts, int n, MbScalars* out)
 // ------------------------------------------------------------------ clip + Adam
 // Flux.Optimiser(ClipNorm(thresh), Adam(η)) [Flux 0.13.4], one CTA per parameter array.
 // Finishing kernel of a minibatch, one CTA per parameter array (ppo.jl:250):
-//   [multi-GPU] one-shot exchange of the reduced sums over NVLink / NVSwitch peer memory: every rank's vector sits in
-//   its own exchange slot (written by grad_reduce); block 0 pushes this rank's sequence number into every peer's flag
-//   array, each block spins on its LOCAL flags, then loads its elements straight from all peers (L1-bypassing loads)
-//   and adds them in rank order, so all ranks hold bit-identical sums. Two slots alternate; a slot is rewritten only
-//   after a complete exchange in between, which implies every peer finished reading the older contents.
+//   [multi-GPU] one-shot exchange of the reduced sums over NVLink / NVSwitch peer memory: grad_reduce has PUSHED this
+//   rank's vector into every rank's exchange buffer (posted remote stores) and its last block raised this rank's
+//   sequence flag on every peer; here each block spins on its LOCAL flags and adds the world vectors out of LOCAL
+//   memory in rank order, so all ranks hold bit-identical sums and no remote load sits on the critical path. Two
+//   slots alternate; a slot is rewritten only after a complete exchange in between, which implies every peer
+//   finished reading the older contents.
 //   [speculative path] block 0 verifies s = mean(v_new - R^2) <= min_i (clip_i - R_i)^2 with the exchanged values.
 //   Then Flux.Optimiser(ClipNorm, Adam): Float32 norm per array, clip, Adam with Float64 scalars, parameter image.
 __device__ __forceinline__ double finish_load(const AdamArgs& a, int slot, int e) {
-  if (a.peers) {
+  if (a.p2p_local) {  // every rank's sums were pushed into this rank's buffer: add them in rank order
     double s = 0.0;
     for (int r = 0; r < a.world; r++)
-      s += __ldcv(reinterpret_cast<const double*>(a.peers[r]) + (size_t)slot * a.p2p_stride + e);
+      s += __ldcv(a.p2p_local + ((size_t)slot * a.world + r) * a.p2p_stride + e);
     return s;
   }
   return a.gsum[e];
@@ -932,22 +961,17 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int o = L.off[i], n = L.size[i];
   int slot = 0;
-  if (a.peers) {
+  if (a.p2p_local) {
     const unsigned long long q = *a.p2p_seq;
     slot = (int)(q & 1ull);
-    if (blockIdx.x == 0 && threadIdx.x < a.world) {
-      __threadfence_system();
-      volatile unsigned long long* flag =
-          reinterpret_cast<volatile unsigned long long*>(a.peers[threadIdx.x] + a.p2p_flags_off) + a.rank;
-      *flag = q;
-    }
-    if (threadIdx.x < a.world) {
+    if (threadIdx.x < a.world) {   // wait until every rank's grad_reduce has pushed this minibatch's sums here
       const volatile unsigned long long* mine =
-          reinterpret_cast<const volatile unsigned long long*>(a.peers[a.rank] + a.p2p_flags_off) + threadIdx.x;
+          reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const unsigned char*>(a.p2p_local) + a.p2p_flags_off) + threadIdx.x;
       const long long t0 = clock64();
       while (*mine < q) {
         if (clock64() - t0 > 4000000000ll) { *a.p2p_err = 1; break; }  // ~2 s: a peer is gone; fail instead of hanging
       }
+      __threadfence_system();
     }
     __syncthreads();
   }
