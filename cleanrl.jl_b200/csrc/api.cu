@@ -1090,6 +1090,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
     g_raw.device = dev; g_raw.M = M;
   }
   UpdateArgs ua;
+  memset(&ua, 0, sizeof(ua));  // every optional path (peer exchange, tcgen05 split) off unless set below
   ua.env_kind = env_kind; ua.algo = 0; ua.params = params; ua.image = nullptr; ua.M = M;
   ua.idx.arr = idx; ua.idx.start = 0; ua.idx.B = (uint32_t)M; ua.idx.half_bits = 1; ua.idx.epoch = 0; ua.idx.rank = 0;
   ua.idx.seed = 0; ua.idx.ds = g_raw.ds;

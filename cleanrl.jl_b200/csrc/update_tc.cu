@@ -50,9 +50,15 @@ using namespace crl_upd;
 #endif
 
 constexpr int TC_S = 128;        // samples per tile = TMEM lanes
-constexpr int TC_THREADS = 256;  // 4 lane quadrants x 2 feature halves
+#ifndef TC_NG
+#define TC_NG 2                  // feature groups per sample: 2 (8 warps, 32 features per thread); 4 (16 warps, 16 features,
+                                 // 128 registers) measured 7 % slower on B200 and is not validated
+#endif
+constexpr int TC_THREADS = 128 * TC_NG;  // 4 lane quadrants x TC_NG feature groups
 constexpr int TC_COMPUTE = TC_THREADS;
-constexpr int TC_FG = 32;        // features per thread
+constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_FG = CRL_H / TC_NG;     // features per thread
+static_assert(TC_NG == 2 || TC_NG == 4, "feature groups per sample");
 constexpr int F_LBO = 144, F_SBO = 32 * F_LBO;  // bytes; feature-major operand: rows r, K = 128 samples
 __device__ __forceinline__ int f_off(int r, int s) { return (r & 7) * 4 + (r >> 3) * (F_SBO / 4) + (s >> 2) * (F_LBO / 4) + (s & 3); }
 // x~^T (rows x_0..x_D-1, ones, zeros): two more 8-row groups (hi, lo) right behind h1^T, same strides, so that
@@ -76,9 +82,9 @@ template <int ENV> struct TcSmem {
   static constexpr int B2 = B1 + CRL_H;
   static constexpr int W3P = B2 + CRL_H;            // [2][64]: W3(o, f)
   static constexpr int B3 = W3P + 2 * CRL_H;        // b3[2], logstd[2]
-  static constexpr int EXCH = B3 + 8;               // [2 feature halves][2 outputs][128 samples]
-  static constexpr int RED = EXCH + 4 * TC_S;       // 16 doubles
-  static constexpr int KEYS = RED + 32;
+  static constexpr int EXCH = B3 + 8;               // [TC_NG feature groups][2 outputs][128 samples]
+  static constexpr int RED = EXCH + TC_NG * 2 * TC_S;   // 16 doubles (block sums) + 16 floats (block min)
+  static constexpr int KEYS = RED + 48;
   static constexpr int FLOATS = KEYS + 8;
   static constexpr size_t BYTES = FLOATS * sizeof(float);
   static_assert(BYTES + 256 <= 227 * 1024, "loss_grad_tc shared memory exceeds 227 KB");
@@ -152,6 +158,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float* v) {
+  static_assert(N == 16 || N == 32, "");
+  tmem_st16(taddr, v);
+  if (N == 32) tmem_st16(taddr + 16, v + 16);
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
+  static_assert(N == 16 || N == 32, "");
+  if (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 
 // ---------------------------------------------------------------- packed FP32 (fma.rn.f32x2) helpers
@@ -397,10 +413,8 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       split2(v[i], hi, lo);
       vh[2 * i] = hi.x; vh[2 * i + 1] = hi.y; vl[2 * i] = lo.x; vl[2 * i + 1] = lo.y;
     }
-    tmem_st16(lane_addr + COL_AH + f0, vh);
-    tmem_st16(lane_addr + COL_AH + f0 + 16, vh + 16);
-    tmem_st16(lane_addr + COL_AL + f0, vl);
-    tmem_st16(lane_addr + COL_AL + f0 + 16, vl + 16);
+    tmem_st_n<TC_FG>(lane_addr + COL_AH + f0, vh);
+    tmem_st_n<TC_FG>(lane_addr + COL_AL + f0, vl);
   };
   auto split_to_smem = [&](const float (&vh)[TC_FG], const float (&vl)[TC_FG], float* buf) {
 #pragma unroll
@@ -410,6 +424,8 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     }
   };
 
+  // the next tile's first layer is spread over the shadows of G1, G3/G2 and G4 (pairs [0,A), [A,B), [B,end))
+  constexpr int L1_A = TC_FG / 2 * 3 / 8, L1_B = TC_FG / 2 * 3 / 4;
   int it = 0;
   {
     Sample<ENV> cur, nxt;
@@ -462,7 +478,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       }
       double adv_n = 0.0;  // (adv .- mean) ./ (std .+ 1e-8): Float32 numerator, Float64 quotient (Q6)
       if (NET == 0) adv_n = (double)__fsub_rn(cur.adv, mean_f) * inv_std;
-      if (more) layer1(nxt, h1, IC<0>(), IC<6>());
+      if (more) layer1(nxt, h1, IC<0>(), IC<L1_A>());
       TR(4);
 
       // ---- E1: h2, head, loss, dz2
@@ -472,8 +488,8 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       float2 h2[TC_FG / 2];
       {
         float z2[TC_FG], z2b[TC_FG];
-        tmem_ld32(lane_addr + COL_D + f0, z2);
-        tmem_ld32(lane_addr + COL_D + CRL_H + f0, z2b);
+        tmem_ld_n<TC_FG>(lane_addr + COL_D + f0, z2);
+        tmem_ld_n<TC_FG>(lane_addr + COL_D + CRL_H + f0, z2b);
         float2 part[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; o++) part[o] = f2s(0.0f);
@@ -495,7 +511,12 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       if (cur.valid) {
         float z[NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) z[o] = (exch[(0 * 2 + o) * TC_S + s] + exch[(1 * 2 + o) * TC_S + s]) + b3s[o];
+        for (int o = 0; o < NOUT; o++) {
+          float acc = exch[(0 * 2 + o) * TC_S + s];
+#pragma unroll
+          for (int gg = 1; gg < TC_NG; gg++) acc += exch[(gg * 2 + o) * TC_S + s];
+          z[o] = acc + b3s[o];
+        }
         const bool own = g == 0;  // both feature halves evaluate the loss; only one of them accumulates its statistics
         if (NET == 0) {
           float newlp, p[A], lp[A];
@@ -618,7 +639,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       tc_fence_before();
       TR(9);
       handover(BAR_G3, [&]() { issue_g3_g2(it); });
-      if (more) layer1(nxt, h1, IC<6>(), IC<12>());
+      if (more) layer1(nxt, h1, IC<L1_A>(), IC<L1_B>());
       TR(10);
 
       // ---- E3: dz1 = (-dh1) .* (h1^2 - 1), in place over h1^T (whose hi + lo is this tile's h1 exactly)
@@ -626,8 +647,8 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       TR(11);
       tc_fence_after();
       float ndh1[TC_FG], ndh1b[TC_FG];
-      tmem_ld32(lane_addr + COL_D + f0, ndh1);
-      tmem_ld32(lane_addr + COL_D + CRL_H + f0, ndh1b);
+      tmem_ld_n<TC_FG>(lane_addr + COL_D + f0, ndh1);
+      tmem_ld_n<TC_FG>(lane_addr + COL_D + CRL_H + f0, ndh1b);
       float2 dz1[TC_FG / 2];
 #pragma unroll
       for (int i = 0; i < TC_FG / 2; i++) {
@@ -651,7 +672,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       tc_fence_before();
       TR(14);
       handover(BAR_G4, [&]() { issue_g4(it); });
-      if (more) layer1(nxt, h1, IC<12>(), IC<16>());
+      if (more) layer1(nxt, h1, IC<L1_B>(), IC<TC_FG / 2>());
       TR(15);
 #ifdef TC_TRACE
       if (trace_on)
@@ -681,8 +702,8 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     float d2[TC_FG], d4[16], d5[16];
     {
       float d2b[TC_FG];
-      tmem_ld32(lane_addr + COL_D2 + f0, d2);
-      tmem_ld32(lane_addr + COL_D2 + CRL_H + f0, d2b);
+      tmem_ld_n<TC_FG>(lane_addr + COL_D2 + f0, d2);
+      tmem_ld_n<TC_FG>(lane_addr + COL_D2 + CRL_H + f0, d2b);
 #pragma unroll
       for (int i = 0; i < TC_FG; i++) d2[i] += d2b[i];
     }
@@ -718,38 +739,55 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   __syncthreads();
   // head partials: reduce-scatter over the 32 lanes (samples) of each warp, then sum the four lane quadrants
   {
-    float* hs = scr + CRL_H * CRL_H + 8 * CRL_H;  // [NOUT][8 warps][32]
+    float* hs = scr + CRL_H * CRL_H + 8 * CRL_H;  // [NOUT][warps][32] (TC_FG = 32) or [warps][32] (TC_FG = 16)
+    if (TC_FG == 32) {
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) {
-      float v[TC_FG];
+      for (int o = 0; o < NOUT; o++) {
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < TC_FG / 2; i++) { v[2 * i] = gw3[o][i].x; v[2 * i + 1] = gw3[o][i].y; }
-      warp_reduce_scatter<TC_FG>(v, lane);
-      hs[(o * 8 + warp) * 32 + lane] = v[0];  // feature f0 + lane
+        for (int i = 0; i < TC_FG / 2; i++) { v[(2 * i) & 31] = gw3[o][i].x; v[(2 * i + 1) & 31] = gw3[o][i].y; }
+        warp_reduce_scatter<32>(v, lane);
+        hs[(o * TC_WARPS + warp) * 32 + lane] = v[0];  // feature f0 + lane
+      }
+    } else {
+      // 16 features per thread: both outputs share one 32-element reduce-scatter, element o * 16 + i
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; e++) v[e] = 0.0f;
+#pragma unroll
+      for (int o = 0; o < NOUT; o++)
+#pragma unroll
+        for (int i = 0; i < TC_FG / 2; i++) {
+          v[(o * 16 + 2 * i) & 31] = gw3[o][i].x;
+          v[(o * 16 + 2 * i + 1) & 31] = gw3[o][i].y;
+        }
+      warp_reduce_scatter<32>(v, lane);
+      hs[warp * 32 + lane] = v[0];  // output lane / 16, feature f0 + lane % 16
     }
     __syncthreads();
     if (tid < CRL_H) {
-      const int gg = tid >> 5, ll = tid & 31;  // feature tid = gg*32 + ll lives in warps gg*4 .. gg*4+3, lane ll
+      const int gg = tid / TC_FG, ll = tid % TC_FG;  // feature tid lives in warps gg*4 .. gg*4+3
 #pragma unroll
       for (int o = 0; o < NOUT; o++) {
         float sum = 0.0f;
 #pragma unroll
-        for (int qq = 0; qq < 4; qq++) sum += hs[(o * 8 + gg * 4 + qq) * 32 + ll];
+        for (int qq = 0; qq < 4; qq++)
+          sum += TC_FG == 32 ? hs[(o * TC_WARPS + gg * 4 + qq) * 32 + ll] : hs[(gg * 4 + qq) * 32 + o * 16 + ll];
         gp[nb + NN::W3 + o + NOUT * tid] = sum;  // Flux W3 is (out=o, in=f) at o + NOUT f
       }
     }
   }
   double t_b3[NOUT];
 #pragma unroll
-  for (int o = 0; o < NOUT; o++) t_b3[o] = block_sum<8>((double)gb3[o], red);
-  const double t_pg = block_sum<8>(st_pg, red);
-  const double t_vm = block_sum<8>(st_vmax, red);
-  const double t_en = block_sum<8>(st_ent, red);
-  const double t_ss = block_sum<8>(st_s, red);
+  for (int o = 0; o < NOUT; o++) t_b3[o] = block_sum<TC_WARPS>((double)gb3[o], red);
+  const double t_pg = block_sum<TC_WARPS>(st_pg, red);
+  const double t_vm = block_sum<TC_WARPS>(st_vmax, red);
+  const double t_en = block_sum<TC_WARPS>(st_ent, red);
+  const double t_ss = block_sum<TC_WARPS>(st_s, red);
   double t_ls[A];
 #pragma unroll
-  for (int k = 0; k < A; k++) t_ls[k] = block_sum<8>(g_logstd[k], red);
-  float* mred = reinterpret_cast<float*>(red + 10);
+  for (int k = 0; k < A; k++) t_ls[k] = block_sum<TC_WARPS>(g_logstd[k], red);
+  float* mred = reinterpret_cast<float*>(red + 16);
   st_min = warp_min(st_min);
   __syncthreads();
   if (lane == 0) mred[warp] = st_min;
@@ -757,7 +795,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   if (tid == 0) {
     float mn = mred[0];
 #pragma unroll
-    for (int w = 1; w < 8; w++) mn = fminf(mn, mred[w]);
+    for (int w = 1; w < TC_WARPS; w++) mn = fminf(mn, mred[w]);
 #pragma unroll
     for (int o = 0; o < NOUT; o++) gp[nb + NN::B3 + o] = (float)t_b3[o];
     double* spp = a.spart + (long long)blockIdx.x * 4;
