@@ -9,7 +9,8 @@ nothing — the library is dlopen'ed on first use and there is no CPU fallback.
 from . import _abi  # noqa: F401
 from .config import PPOConfig, argparse_struct  # noqa: F401
 
-__all__ = ["PPOConfig", "A2CConfig", "argparse_struct", "ppo", "a2c", "PPOHandle", "Networks", "Logger", "ConfigParser"]
+__all__ = ["PPOConfig", "A2CConfig", "DQNConfig", "argparse_struct", "ppo", "a2c", "dqn", "PPOHandle", "Networks", "Logger",
+           "ConfigParser"]
 
 
 def ppo(*args, **kwargs):
@@ -24,7 +25,16 @@ def a2c(*args, **kwargs):
     return _a2c(*args, **kwargs)
 
 
+def dqn(*args, **kwargs):
+    """CleanRL.dqn(config) (dqn.jl:34), vectorised on the GPU: see dqn_algo.py"""
+    from .dqn_algo import dqn as _dqn
+    return _dqn(*args, **kwargs)
+
+
 def __getattr__(name):
+    if name == "DQNConfig":
+        from .dqn_algo import DQNConfig
+        return DQNConfig
     # lazy: keep `import cleanrl_jl_b200` free of ctypes/torch side effects
     if name == "A2CConfig":
         from .a2c_algo import A2CConfig

@@ -60,3 +60,31 @@ def make_config(env_kind=CRL_ENV_CARTPOLE, num_envs=4, num_steps=32, num_minibat
     return crl_config(C.sizeof(crl_config), env_kind, num_envs, num_steps, num_minibatches, update_epochs,
                       max_episode_steps, gae_mode, device, world_size, rank, env_id_base, episode_capacity,
                       flags, gamma, gae_lambda, clip_coef, ent_coeff, v_coef, clip_norm, seed)
+
+
+# ---- DQN (include/cleanrl_cuda.h, "DQN" section) -------------------------------------------------------------
+CRL_DQN_PARAMS = 10934
+
+
+class crl_dqn_config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("num_envs", C.c_int32), ("buffer_size", C.c_int32), ("min_buff_size", C.c_int32),
+        ("batch_size", C.c_int32), ("train_freq", C.c_int32), ("target_net_freq", C.c_int32),
+        ("max_episode_steps", C.c_int32), ("device", C.c_int32), ("_pad", C.c_int32),
+        ("lr", C.c_double), ("gamma", C.c_double), ("epsilon_start", C.c_double), ("epsilon_end", C.c_double),
+        ("epsilon_duration", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class crl_dqn_stats(C.Structure):
+    _fields_ = [("last_loss", C.c_double), ("sum_return", C.c_double), ("sum_length", C.c_double), ("epsilon", C.c_double),
+                ("episodes", C.c_int64), ("learn_steps", C.c_int64), ("iterations", C.c_int64)]
+
+
+def make_dqn_config(num_envs=1, buffer_size=10_000, min_buff_size=200, batch_size=120, train_freq=10, target_net_freq=100,
+                    max_episode_steps=200, device=0, lr=1e-4, gamma=0.99, epsilon_start=1.0, epsilon_end=0.05,
+                    epsilon_duration=10_000.0, seed=1):
+    """crl_dqn_config with the reference defaults (dqn.jl:1-20; CartPoleEnv() max_steps = 200)."""
+    return crl_dqn_config(C.sizeof(crl_dqn_config), num_envs, buffer_size, min_buff_size, batch_size, train_freq,
+                          target_net_freq, max_episode_steps, device, 0, lr, gamma, epsilon_start, epsilon_end,
+                          epsilon_duration, seed)

@@ -63,6 +63,13 @@ SIGNATURES = {
     "crl_policy_forward_raw": (C.c_int, [I32, V, V, V, V, V, I64, V]),
     "crl_ppo_loss_raw": (C.c_int, [I32, V, V, I32] + [V] * 6 + [F32] * 3 + [V, V, V]),
     "crl_clip_adam_raw": (C.c_int, [I32, V, V, V, V, V, F64, F32, V]),
+    "crl_dqn_create": (C.c_int, [C.POINTER(_abi.crl_dqn_config), C.POINTER(V)]),
+    "crl_dqn_destroy": (C.c_int, [V]),
+    "crl_dqn_set_params": (C.c_int, [V, V, I32]),
+    "crl_dqn_get_params": (C.c_int, [V, V, V, I32]),
+    "crl_dqn_reset": (C.c_int, [V]),
+    "crl_dqn_run": (C.c_int, [V, I64, V]),
+    "crl_dqn_read_buffer": (C.c_int, [V] * 8),
 }
 
 

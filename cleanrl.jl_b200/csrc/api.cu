@@ -25,6 +25,8 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+// for the other translation units of the library (dqn.cu): same thread-local message crl_last_error returns
+int crl_internal_fail(int code, const char* msg) { g_err = msg; return code; }
 #define CK(call)                                                                                        \
   do {                                                                                                  \
     cudaError_t e__ = (call);                                                                           \

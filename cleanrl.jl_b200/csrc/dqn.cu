@@ -1,0 +1,460 @@
+// dqn.cu — vectorised DQN (src/algorithms/dqn.jl) behind the crl_dqn_* entry points of
+// include/cleanrl_cuda.h: N CartPole envs stepping in lockstep with an epsilon-greedy Q-network, an HBM-resident
+// ring replay buffer, and one learning step (sample without replacement -> TD target from the target net -> MSE on
+// the taken action -> backward -> Adam -> optional target copy) every train_freq iterations.
+//
+//   dqn_act_kernel    one thread per env, 64 envs per CTA. The 10,934 parameters sit in shared memory; a thread walks
+//                     the three Dense layers with its activations in shared memory ([neuron][env lane]: conflict-free,
+//                     weight reads are warp broadcasts), draws epsilon / the random action from Philox, steps CartPole,
+//                     appends the transition at (ptr + env) % capacity and resets a finished env on the spot.
+//   dqn_learn_kernel  ONE CTA of 128 threads (batch_size <= 128 samples, one per thread): both parameter sets and the
+//                     batch activations live in shared memory (~195 KB); forward target net and q net per sample,
+//                     gradient reductions over the batch by one thread per weight in ascending sample order
+//                     (deterministic, same order as the oracle), Adam and the target copy in the same launch.
+// Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?") is taken on
+// the host, so a run is a plain sequence of launches on one stream without any device-to-host read.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int DQ_D = 4, DQ_H1 = 120, DQ_H2 = 84, DQ_A = 2;
+constexpr int DQ_W1 = 0, DQ_B1 = DQ_W1 + DQ_H1 * DQ_D, DQ_W2 = DQ_B1 + DQ_H1, DQ_B2 = DQ_W2 + DQ_H2 * DQ_H1,
+              DQ_W3 = DQ_B2 + DQ_H2, DQ_B3 = DQ_W3 + DQ_A * DQ_H2, DQ_P = DQ_B3 + DQ_A;
+static_assert(DQ_P == CRL_DQN_PARAMS, "parameter count");
+constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
+constexpr int ACT_T = 64;     // envs (threads) per CTA in dqn_act_kernel
+constexpr int LEARN_T = 128;  // threads = max batch size in dqn_learn_kernel
+
+struct DqnDev {               // device-resident scalars
+  double bp1, bp2;            // beta1^t, beta2^t of Adam
+  double last_loss;
+  double sum_return, sum_length;
+  unsigned long long episodes;
+};
+
+struct ActArgs {
+  const float* q;
+  float* env_state; int* env_t; double* ep_ret; int* ep_len; uint32_t* resets;
+  float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
+  DqnDev* dev;
+  unsigned long long seed, it;
+  double eps;
+  int N, C, ptr, max_steps;
+};
+
+// Dense -> relu -> Dense -> relu -> Dense for the sample of lane `l`; h1/h2 are [neuron][T] tiles in shared memory
+template <int T>
+__device__ __forceinline__ void q_forward(const float* __restrict__ p, const float x[DQ_D], float* h1, float* h2, int l,
+                                          float q[DQ_A]) {
+  for (int j = 0; j < DQ_H1; j++) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DQ_D; k++) acc = fmaf(p[DQ_W1 + j + DQ_H1 * k], x[k], acc);
+    acc += p[DQ_B1 + j];
+    h1[j * T + l] = fmaxf(acc, 0.0f);
+  }
+  for (int j = 0; j < DQ_H2; j++) {
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < DQ_H1; k++) acc = fmaf(p[DQ_W2 + j + DQ_H2 * k], h1[k * T + l], acc);
+    acc += p[DQ_B2 + j];
+    h2[j * T + l] = fmaxf(acc, 0.0f);
+  }
+#pragma unroll
+  for (int o = 0; o < DQ_A; o++) {
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * T + l], acc);
+    q[o] = acc + p[DQ_B3 + o];
+  }
+}
+
+__global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* p = smem;                       // [DQ_P]
+  float* h1 = p + ((DQ_P + 3) & ~3);     // [120][64]
+  float* h2 = h1 + DQ_H1 * ACT_T;        // [84][64]
+  for (int i = threadIdx.x; i < DQ_P; i += ACT_T) p[i] = a.q[i];
+  __syncthreads();
+  const int n = blockIdx.x * ACT_T + threadIdx.x;
+  if (n >= a.N) return;
+  float st[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+  const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
+  uint32_t r[4];
+  philox_draw(a.seed, (uint32_t)n, a.it, STREAM_DQN_ACT, r);
+  const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+  int action;
+  if (u < a.eps) {
+    action = (int)(r[2] & 1u);           // rand(action_space(env)), dqn.jl:54
+  } else {
+    float q[DQ_A];
+    q_forward<ACT_T>(p, st, h1, h2, threadIdx.x, q);
+    action = q[1] > q[0] ? 1 : 0;        // argmax: first maximum, dqn.jl:56-57
+  }
+  int t = a.env_t[n];
+  float rew;
+  bool done;
+  cartpole_step(st, t, action, a.max_steps, rew, done);
+  const int slot = (a.ptr + n) % a.C;    // add!, replay_buffer.jl:23-37, envs in order
+  reinterpret_cast<float4*>(a.b_state)[slot] = obs;
+  reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
+  a.b_action[slot] = action;
+  a.b_reward[slot] = rew;
+  a.b_term[slot] = done ? 1 : 0;
+  double ret = a.ep_ret[n] + (double)rew;
+  int len = a.ep_len[n] + 1;
+  if (done) {                            // dqn.jl:80-86
+    atomicAdd(&a.dev->episodes, 1ull);
+    atomicAdd(&a.dev->sum_return, ret);
+    atomicAdd(&a.dev->sum_length, (double)len);
+    ret = 0.0;
+    len = 0;
+    float u4[4];
+    uint32_t rc = a.resets[n];
+    rng_reset_uniforms(a.seed, (uint32_t)n, rc, u4);
+    a.resets[n] = rc + 1;
+    cartpole_reset(st, t, u4);
+  }
+  a.ep_ret[n] = ret;
+  a.ep_len[n] = len;
+  a.env_t[n] = t;
+#pragma unroll
+  for (int k = 0; k < 4; k++) a.env_state[4 * n + k] = st[k];
+}
+
+struct LearnArgs {
+  float* q; float* tgt; float* m; float* v; float* g;
+  const float *b_state, *b_next, *b_reward; const int* b_action; const uint8_t* b_term;
+  DqnDev* dev;
+  unsigned long long seed, learn_step;
+  double gamma, lr;
+  int B, size, copy_target;
+};
+
+__global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PP = (DQ_P + 3) & ~3;
+  float* pq = smem;                       // q_net parameters
+  float* pt = pq + PP;                    // target_net parameters
+  float* h1 = pt + PP;                    // [120][128]  (later dz1 in place)
+  float* h2 = h1 + DQ_H1 * LEARN_T;       // [84][128]   (later dz2 in place)
+  float* xs = h2 + DQ_H2 * LEARN_T;       // [4][128] states of the batch
+  float* dq = xs + DQ_D * LEARN_T;        // [2][128]
+  __shared__ uint32_t keys[8];
+  __shared__ double red[LEARN_T / 32];
+  const int tid = threadIdx.x, B = a.B;
+  for (int i = tid; i < DQ_P; i += LEARN_T) { pq[i] = a.q[i]; pt[i] = a.tgt[i]; }
+  if (tid == 0) {
+    philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
+    philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
+  }
+  __syncthreads();
+  double sq = 0.0;
+  dq[0 * LEARN_T + tid] = 0.0f;
+  dq[1 * LEARN_T + tid] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < DQ_D; k++) xs[k * LEARN_T + tid] = 0.0f;
+  if (tid < B) {
+    // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
+    const uint32_t idx = perm_index((uint32_t)tid, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
+    const float4 s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
+    const float4 n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
+    const float s[4] = {s4.x, s4.y, s4.z, s4.w}, nx[4] = {n4.x, n4.y, n4.z, n4.w};
+    const int act = a.b_action[idx];
+    const float rew = a.b_reward[idx];
+    const int term = a.b_term[idx];
+    float qn[DQ_A], qv[DQ_A];
+    q_forward<LEARN_T>(pt, nx, h1, h2, tid, qn);                     // target_net(next_state), dqn.jl:99
+    const float next_q = fmaxf(qn[0], qn[1]);
+    const double td = (double)rew + a.gamma * (double)next_q * (1.0 - (double)term);   // dqn.jl:100
+    q_forward<LEARN_T>(pq, s, h1, h2, tid, qv);                      // q_net(state), dqn.jl:105
+    const double diff = td - (double)qv[act];
+    sq = diff * diff;                                                // Flux.mse, dqn.jl:107
+    dq[act * LEARN_T + tid] = (float)(-2.0 * diff / (double)B);
+#pragma unroll
+    for (int k = 0; k < DQ_D; k++) xs[k * LEARN_T + tid] = s[k];
+  }
+  // loss
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) a.dev->last_loss = ((red[0] + red[1]) + (red[2] + red[3])) / (double)B;
+  // ---- backward; every reduction over the batch runs in ascending sample order in one thread
+  float* g = a.g;
+  for (int w = tid; w < DQ_A * DQ_H2 + DQ_A; w += LEARN_T) {         // dW3(o,k), db3(o)
+    if (w < DQ_A * DQ_H2) {
+      const int o = w % DQ_A, k = w / DQ_A;
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc = fmaf(dq[o * LEARN_T + i], h2[k * LEARN_T + i], acc);
+      g[DQ_W3 + w] = acc;
+    } else {
+      const int o = w - DQ_A * DQ_H2;
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += dq[o * LEARN_T + i];
+      g[DQ_B3 + o] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < B) {                                                     // dz2 = (W3^T dq) .* (h2 > 0), in place
+    const float d0 = dq[0 * LEARN_T + tid], d1 = dq[1 * LEARN_T + tid];
+    for (int k = 0; k < DQ_H2; k++) {
+      const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
+      h2[k * LEARN_T + tid] = h2[k * LEARN_T + tid] > 0.0f ? dh : 0.0f;
+    }
+  }
+  __syncthreads();
+  for (int w = tid; w < DQ_H2 * DQ_H1 + DQ_H2; w += LEARN_T) {       // dW2(j,k), db2(j)
+    if (w < DQ_H2 * DQ_H1) {
+      const int j = w % DQ_H2, k = w / DQ_H2;
+      float acc = 0.0f;
+#pragma unroll 4
+      for (int i = 0; i < B; i++) acc = fmaf(h2[j * LEARN_T + i], h1[k * LEARN_T + i], acc);
+      g[DQ_W2 + w] = acc;
+    } else {
+      const int j = w - DQ_H2 * DQ_H1;
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += h2[j * LEARN_T + i];
+      g[DQ_B2 + j] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < B) {                                                     // dz1 = (W2^T dz2) .* (h1 > 0), in place
+    for (int k = 0; k < DQ_H1; k++) {
+      float dh = 0.0f;
+#pragma unroll 4
+      for (int j = 0; j < DQ_H2; j++) dh = fmaf(pq[DQ_W2 + j + DQ_H2 * k], h2[j * LEARN_T + tid], dh);
+      h1[k * LEARN_T + tid] = h1[k * LEARN_T + tid] > 0.0f ? dh : 0.0f;
+    }
+  }
+  __syncthreads();
+  for (int w = tid; w < DQ_H1 * DQ_D + DQ_H1; w += LEARN_T) {        // dW1(j,k), db1(j)
+    if (w < DQ_H1 * DQ_D) {
+      const int j = w % DQ_H1, k = w / DQ_H1;
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc = fmaf(h1[j * LEARN_T + i], xs[k * LEARN_T + i], acc);
+      g[DQ_W1 + w] = acc;
+    } else {
+      const int j = w - DQ_H1 * DQ_D;
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += h1[j * LEARN_T + i];
+      g[DQ_B1 + j] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- Flux.Adam(lr) (dqn.jl:41,109), Float64 scalars as in clip_adam_kernel; then the target copy (dqn.jl:111-113)
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  const double bp1 = a.dev->bp1, bp2 = a.dev->bp2;
+  __syncthreads();
+  for (int k = tid; k < DQ_P; k += LEARN_T) {
+    const float d = g[k];
+    const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[k]), __dmul_rn(1.0 - b1, (double)d));
+    const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
+    a.m[k] = mt;
+    a.v[k] = vt;
+    const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - bp2)), eps);
+    const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - bp1), den), a.lr);
+    const float pn = __fsub_rn(pq[k], step);
+    a.q[k] = pn;
+    if (a.copy_target) a.tgt[k] = pn;
+  }
+  if (tid == 0) { a.dev->bp1 = bp1 * b1; a.dev->bp2 = bp2 * b2; }
+}
+
+constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2) * ACT_T) * sizeof(float);
+constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + DQ_A) * LEARN_T) * sizeof(float);
+static_assert(LEARN_SMEM <= 227 * 1024, "dqn_learn shared memory");
+
+int dfail(int code, const std::string& msg) { return crl_internal_fail(code, msg.c_str()); }
+#define DCK(call)                                                                                          \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess)                                                                                \
+      return dfail(CRL_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (dqn.cu)"); \
+  } while (0)
+
+template <typename T> cudaError_t dzalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+}
+
+}  // namespace
+
+struct crl_dqn_ctx {
+  crl_dqn_config cfg;
+  cudaStream_t stream;
+  float *q, *tgt, *m, *v, *g;
+  float* env_state; int* env_t; double* ep_ret; int* ep_len; uint32_t* resets;
+  float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
+  DqnDev* dev;
+  int size, ptr;
+  long long it, learn_steps;
+  bool params_set, reset_done;
+};
+
+__global__ void dqn_reset_kernel(int N, unsigned long long seed, float* env_state, int* env_t, double* ep_ret, int* ep_len,
+                                 uint32_t* resets) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float u4[4], st[4];
+  int t;
+  rng_reset_uniforms(seed, (uint32_t)n, 0, u4);
+  cartpole_reset(st, t, u4);
+  for (int k = 0; k < 4; k++) env_state[4 * n + k] = st[k];
+  env_t[n] = t; ep_ret[n] = 0.0; ep_len[n] = 0; resets[n] = 1;
+}
+
+static double linear_schedule(double start_e, double end_e, double duration, double t) {  // dqn.jl:28-31
+  const double slope = (end_e - start_e) / duration;
+  const double e = slope * t + start_e;
+  return e > end_e ? e : end_e;
+}
+
+extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** out) {
+  if (!cfg || !out) return dfail(CRL_ERR_INVALID, "NULL argument");
+  if (cfg->struct_size != (int32_t)sizeof(crl_dqn_config)) return dfail(CRL_ERR_INVALID, "crl_dqn_config.struct_size mismatch");
+  if (cfg->num_envs < 1 || cfg->buffer_size < cfg->num_envs) return dfail(CRL_ERR_INVALID, "need 1 <= num_envs <= buffer_size");
+  if (cfg->batch_size < 1 || cfg->batch_size > LEARN_T) return dfail(CRL_ERR_INVALID, "batch_size must be in [1, 128]");
+  if (cfg->train_freq < 1 || cfg->target_net_freq < 1 || cfg->max_episode_steps < 1 || !(cfg->epsilon_duration > 0.0))
+    return dfail(CRL_ERR_INVALID, "train_freq, target_net_freq, max_episode_steps, epsilon_duration must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return dfail(CRL_ERR_CUDA, "no CUDA device: libcleanrl_cuda has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return dfail(CRL_ERR_INVALID, "device ordinal out of range");
+  DCK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  DCK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return dfail(CRL_ERR_CUDA, "libcleanrl_cuda is built for sm_100a only");
+  crl_dqn_ctx* c = new crl_dqn_ctx();
+  memset(c, 0, sizeof(*c));
+  c->cfg = *cfg;
+  const size_t N = cfg->num_envs, C = cfg->buffer_size;
+  DCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  DCK(dzalloc(&c->q, DQ_P)); DCK(dzalloc(&c->tgt, DQ_P)); DCK(dzalloc(&c->m, DQ_P)); DCK(dzalloc(&c->v, DQ_P)); DCK(dzalloc(&c->g, DQ_P));
+  DCK(dzalloc(&c->env_state, 4 * N)); DCK(dzalloc(&c->env_t, N)); DCK(dzalloc(&c->ep_ret, N)); DCK(dzalloc(&c->ep_len, N));
+  DCK(dzalloc(&c->resets, N));
+  DCK(dzalloc(&c->b_state, 4 * C)); DCK(dzalloc(&c->b_next, 4 * C)); DCK(dzalloc(&c->b_reward, C)); DCK(dzalloc(&c->b_action, C));
+  DCK(dzalloc(&c->b_term, C)); DCK(dzalloc(&c->dev, 1));
+  DCK(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
+  DCK(cudaFuncSetAttribute(dqn_learn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEARN_SMEM));
+  *out = c;
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
+  if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->g, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
+                  c->b_reward, c->b_action, c->b_term, c->dev};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_set_params(crl_dqn_ctx* c, const float* params, int32_t n) {
+  if (!c || !params) return dfail(CRL_ERR_INVALID, "NULL argument");
+  if (n != DQ_P) return dfail(CRL_ERR_INVALID, "DQN parameter vector must have 10934 floats");
+  DCK(cudaSetDevice(c->cfg.device));
+  DCK(cudaMemcpyAsync(c->q, params, sizeof(float) * DQ_P, cudaMemcpyHostToDevice, c->stream));
+  DCK(cudaMemcpyAsync(c->tgt, c->q, sizeof(float) * DQ_P, cudaMemcpyDeviceToDevice, c->stream));   // deepcopy, dqn.jl:40
+  DCK(cudaMemsetAsync(c->m, 0, sizeof(float) * DQ_P, c->stream));
+  DCK(cudaMemsetAsync(c->v, 0, sizeof(float) * DQ_P, c->stream));
+  DqnDev d;
+  memset(&d, 0, sizeof(d));
+  d.bp1 = 0.9; d.bp2 = 0.999;
+  DCK(cudaMemcpyAsync(c->dev, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream));
+  DCK(cudaStreamSynchronize(c->stream));
+  c->params_set = true;
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_get_params(crl_dqn_ctx* c, float* q_params, float* target_params, int32_t n) {
+  if (!c || !q_params) return dfail(CRL_ERR_INVALID, "NULL argument");
+  if (n != DQ_P) return dfail(CRL_ERR_INVALID, "DQN parameter vector must have 10934 floats");
+  DCK(cudaSetDevice(c->cfg.device));
+  DCK(cudaMemcpyAsync(q_params, c->q, sizeof(float) * DQ_P, cudaMemcpyDeviceToHost, c->stream));
+  if (target_params) DCK(cudaMemcpyAsync(target_params, c->tgt, sizeof(float) * DQ_P, cudaMemcpyDeviceToHost, c->stream));
+  DCK(cudaStreamSynchronize(c->stream));
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_reset(crl_dqn_ctx* c) {
+  if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
+  DCK(cudaSetDevice(c->cfg.device));
+  const int N = c->cfg.num_envs;
+  dqn_reset_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(N, c->cfg.seed, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets);
+  DCK(cudaGetLastError());
+  c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0;
+  c->reset_done = true;
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_stats* stats) {
+  if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
+  if (iterations < 0) return dfail(CRL_ERR_INVALID, "iterations must be >= 0");
+  if (!c->params_set) return dfail(CRL_ERR_STATE, "crl_dqn_run called before crl_dqn_set_params");
+  if (!c->reset_done) return dfail(CRL_ERR_STATE, "crl_dqn_run called before crl_dqn_reset");
+  DCK(cudaSetDevice(c->cfg.device));
+  const int N = c->cfg.num_envs, C = c->cfg.buffer_size;
+  // per-call episode aggregate: clear the three accumulators, keep Adam's powers and the last loss
+  DCK(cudaMemsetAsync(&c->dev->sum_return, 0, sizeof(double) * 2 + sizeof(unsigned long long), c->stream));
+  double eps = 0.0;
+  for (int64_t k = 0; k < iterations; k++) {
+    c->it += 1;
+    const double gs = (double)c->it * (double)N;
+    eps = linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);   // dqn.jl:52
+    ActArgs a;
+    a.q = c->q; a.env_state = c->env_state; a.env_t = c->env_t; a.ep_ret = c->ep_ret; a.ep_len = c->ep_len; a.resets = c->resets;
+    a.b_state = c->b_state; a.b_next = c->b_next; a.b_reward = c->b_reward; a.b_action = c->b_action; a.b_term = c->b_term;
+    a.dev = c->dev; a.seed = c->cfg.seed; a.it = (unsigned long long)c->it; a.eps = eps; a.N = N; a.C = C; a.ptr = c->ptr;
+    a.max_steps = c->cfg.max_episode_steps;
+    dqn_act_kernel<<<(N + ACT_T - 1) / ACT_T, ACT_T, ACT_SMEM, c->stream>>>(a);
+    DCK(cudaGetLastError());
+    c->ptr = (c->ptr + N) % C;
+    c->size = c->size + N > C ? C : c->size + N;
+    if (gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size) {   // dqn.jl:94
+      LearnArgs l;
+      l.q = c->q; l.tgt = c->tgt; l.m = c->m; l.v = c->v; l.g = c->g;
+      l.b_state = c->b_state; l.b_next = c->b_next; l.b_reward = c->b_reward; l.b_action = c->b_action; l.b_term = c->b_term;
+      l.dev = c->dev; l.seed = c->cfg.seed; l.learn_step = (unsigned long long)c->learn_steps; l.gamma = c->cfg.gamma;
+      l.lr = c->cfg.lr; l.B = c->cfg.batch_size; l.size = c->size;
+      l.copy_target = (c->it % c->cfg.target_net_freq == 0) ? 1 : 0;                                             // dqn.jl:111
+      dqn_learn_kernel<<<1, LEARN_T, LEARN_SMEM, c->stream>>>(l);
+      DCK(cudaGetLastError());
+      c->learn_steps += 1;
+    }
+  }
+  if (stats) {
+    DqnDev d;
+    DCK(cudaMemcpyAsync(&d, c->dev, sizeof(d), cudaMemcpyDeviceToHost, c->stream));
+    DCK(cudaStreamSynchronize(c->stream));
+    stats->last_loss = d.last_loss; stats->sum_return = d.sum_return; stats->sum_length = d.sum_length; stats->epsilon = eps;
+    stats->episodes = (int64_t)d.episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
+  }
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_read_buffer(crl_dqn_ctx* c, float* state, int32_t* action, float* reward, float* next_state,
+                                           uint8_t* terminal, int32_t* size, int32_t* ptr) {
+  if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
+  DCK(cudaSetDevice(c->cfg.device));
+  const size_t C = c->cfg.buffer_size;
+  if (state) DCK(cudaMemcpyAsync(state, c->b_state, C * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (next_state) DCK(cudaMemcpyAsync(next_state, c->b_next, C * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (action) DCK(cudaMemcpyAsync(action, c->b_action, C * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (reward) DCK(cudaMemcpyAsync(reward, c->b_reward, C * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (terminal) DCK(cudaMemcpyAsync(terminal, c->b_term, C, cudaMemcpyDeviceToHost, c->stream));
+  DCK(cudaStreamSynchronize(c->stream));
+  if (size) *size = c->size;
+  if (ptr) *ptr = c->ptr;
+  return CRL_OK;
+}

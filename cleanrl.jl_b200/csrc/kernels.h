@@ -3,6 +3,9 @@
 #pragma once
 #include "common.cuh"
 
+// sets the message crl_last_error() returns (api.cu) and hands the code back
+int crl_internal_fail(int code, const char* msg);
+
 struct RolloutArgs {
   const float* params;
   const DevState* ds;

@@ -273,6 +273,58 @@ CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, const int32_
 CRL_API int crl_clip_adam_raw(int32_t env_kind, float* params, const float* grads, float* m, float* v,
                       double* beta_pow, double lr, float clip_norm, void* stream);
 
+/* ---- DQN (src/algorithms/dqn.jl) ---------------------------------------
+ * The reference runs ONE CartPole env (dqn.jl:38) and counts everything in env steps. Here N envs step in
+ * lockstep; iteration it (1-based) = one vector step, global_step = it * N. With N = 1 every rule below is the
+ * reference's: epsilon = linear_schedule(global_step) (dqn.jl:28-31,52); greedy action = argmax q (first maximum,
+ * dqn.jl:56-57); the N transitions are added to the ring buffer in env order (replay_buffer.jl:23-37); a learning
+ * step runs when global_step > min_buff_size and it % train_freq == 0 (dqn.jl:94): batch_size indices WITHOUT
+ * replacement from [0, size) (replay_buffer.jl:40-45), TD target r + gamma * max_a Q_target(s') * (1 - terminal)
+ * in Float64 (dqn.jl:99-100), Flux.mse on the taken action's Q (dqn.jl:104-108), plain Adam (dqn.jl:41); the target
+ * net is copied when it % target_net_freq == 0, checked on learning iterations only (dqn.jl:111-113).
+ * Network: Dense(4,120,relu), Dense(120,84,relu), Dense(84,2) (dqn.jl:22-26); flat parameters in Flux.params order,
+ * each W (out,in) column-major: 10,934 floats. Random draws are Philox streams 3 (epsilon test + random action,
+ * counter = it, word = env) and 4 (batch permutation keys, counter = learning step index). Single GPU. */
+typedef struct crl_dqn_ctx crl_dqn_ctx;
+typedef struct crl_dqn_config {
+  int32_t struct_size;       /* = sizeof(crl_dqn_config) */
+  int32_t num_envs;          /* N */
+  int32_t buffer_size;       /* replay capacity in transitions, dqn.jl:8 (>= num_envs) */
+  int32_t min_buff_size;     /* dqn.jl:9 */
+  int32_t batch_size;        /* dqn.jl:14, <= 128 */
+  int32_t train_freq;        /* dqn.jl:12, in iterations */
+  int32_t target_net_freq;   /* dqn.jl:13, in iterations */
+  int32_t max_episode_steps; /* CartPoleEnv() default: 200 */
+  int32_t device;
+  int32_t _pad;
+  double lr;                 /* dqn.jl:11 */
+  double gamma;              /* dqn.jl:15 */
+  double epsilon_start, epsilon_end, epsilon_duration; /* dqn.jl:17-19 */
+  uint64_t seed;
+} crl_dqn_config;
+#define CRL_DQN_PARAMS 10934
+typedef struct crl_dqn_stats {
+  double last_loss;     /* Flux.mse of the most recent learning step (dqn.jl:116) */
+  double sum_return;    /* episodes finished during the call (dqn.jl:80-86) */
+  double sum_length;
+  double epsilon;       /* at the last iteration */
+  int64_t episodes;
+  int64_t learn_steps;  /* learning steps so far */
+  int64_t iterations;   /* iterations so far; global_step = iterations * num_envs */
+} crl_dqn_stats;
+CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** out);
+CRL_API int crl_dqn_destroy(crl_dqn_ctx* ctx);
+/* q_net parameters; target_net = deepcopy(q_net) (dqn.jl:40); Adam state reset */
+CRL_API int crl_dqn_set_params(crl_dqn_ctx* ctx, const float* params, int32_t n);
+CRL_API int crl_dqn_get_params(crl_dqn_ctx* ctx, float* q_params, float* target_params /* may be NULL */, int32_t n);
+CRL_API int crl_dqn_reset(crl_dqn_ctx* ctx);   /* reset!(env) for every env, empty buffer, iteration counter 0 */
+/* `iterations` vector steps with the learning steps that fall on them; stats may be NULL */
+CRL_API int crl_dqn_run(crl_dqn_ctx* ctx, int64_t iterations, crl_dqn_stats* stats);
+/* replay buffer contents (host pointers, each may be NULL): state/next_state float [capacity][4], action int32,
+ * reward float, terminal uint8; size/ptr as in replay_buffer.jl:11-12 (ptr 0-based) */
+CRL_API int crl_dqn_read_buffer(crl_dqn_ctx* ctx, float* state, int32_t* action, float* reward, float* next_state,
+                        uint8_t* terminal, int32_t* size, int32_t* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,3 +367,81 @@ class OracleCtx:
         agg = _abi.crl_episode_agg()
         self._ck(self.L.orc_pop_episodes(self.h, recs, max_records, C.byref(n), C.byref(agg)))
         return [(r.step, r.env, r.length, r.episode_return) for r in recs[:n.value]], agg
+
+
+class OracleDQN:
+    """Mirror of the crl_dqn_* API on the CPU oracle (TEST INFRASTRUCTURE, like everything in this module)."""
+
+    def __init__(self, olib, cfg):
+        self.L = olib.lib
+        self.cfg = cfg
+        self.L.orc_dqn_linear_schedule.restype = C.c_double
+        self.L.orc_dqn_linear_schedule.argtypes = [C.c_double] * 4
+        self.L.orc_dqn_run.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        self.L.orc_dqn_loss_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        for f in ("orc_dqn_destroy", "orc_dqn_reset"):
+            getattr(self.L, f).argtypes = [C.c_void_p]
+        self.L.orc_dqn_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        self.L.orc_dqn_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        self.L.orc_dqn_read_buffer.argtypes = [C.c_void_p] * 8
+        self.L.orc_dqn_forward_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        h = C.c_void_p()
+        if self.L.orc_dqn_create(C.byref(cfg), C.byref(h)) != 0:
+            raise ValueError("orc_dqn_create failed")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.orc_dqn_destroy(self.h)
+            self.h = None
+
+    def set_params(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        assert self.L.orc_dqn_set_params(self.h, _ptr(p), p.size) == 0
+
+    def get_params(self):
+        q = np.zeros(_abi.CRL_DQN_PARAMS, np.float32)
+        t = np.zeros(_abi.CRL_DQN_PARAMS, np.float32)
+        assert self.L.orc_dqn_get_params(self.h, _ptr(q), _ptr(t), q.size) == 0
+        return q, t
+
+    def reset(self):
+        assert self.L.orc_dqn_reset(self.h) == 0
+
+    def run(self, iterations):
+        st = _abi.crl_dqn_stats()
+        assert self.L.orc_dqn_run(self.h, int(iterations), C.byref(st)) == 0
+        return st
+
+    def read_buffer(self):
+        cap = self.cfg.buffer_size
+        out = {"state": np.zeros((cap, 4), np.float32), "action": np.zeros(cap, np.int32), "reward": np.zeros(cap, np.float32),
+               "next_state": np.zeros((cap, 4), np.float32), "terminal": np.zeros(cap, np.uint8)}
+        size, ptr = C.c_int32(), C.c_int32()
+        assert self.L.orc_dqn_read_buffer(self.h, _ptr(out["state"]), _ptr(out["action"]), _ptr(out["reward"]),
+                                          _ptr(out["next_state"]), _ptr(out["terminal"]), C.byref(size), C.byref(ptr)) == 0
+        out["size"], out["ptr"] = size.value, ptr.value
+        return out
+
+    def linear_schedule(self, s, e, d, t):
+        return self.L.orc_dqn_linear_schedule(s, e, d, t)
+
+    def forward(self, params, obs):
+        params = np.ascontiguousarray(params, np.float32)
+        obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 4)
+        q = np.zeros((obs.shape[0], 2), np.float32)
+        assert self.L.orc_dqn_forward_raw(_ptr(params), _ptr(obs), _ptr(q), obs.shape[0]) == 0
+        return q
+
+    def loss_raw(self, q_params, tgt_params, state, action, reward, next_state, terminal, gamma):
+        B = len(action)
+        arrs = [np.ascontiguousarray(q_params, np.float32), np.ascontiguousarray(tgt_params, np.float32),
+                np.ascontiguousarray(state, np.float32), np.ascontiguousarray(action, np.int32),
+                np.ascontiguousarray(reward, np.float32), np.ascontiguousarray(next_state, np.float32),
+                np.ascontiguousarray(terminal, np.uint8)]
+        g = np.zeros(_abi.CRL_DQN_PARAMS, np.float32)
+        loss = C.c_double()
+        assert self.L.orc_dqn_loss_raw(_ptr(arrs[0]), _ptr(arrs[1]), B, _ptr(arrs[2]), _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
+                                       _ptr(arrs[6]), float(gamma), _ptr(g), C.byref(loss)) == 0
+        return g, loss.value

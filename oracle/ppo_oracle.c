@@ -1150,3 +1150,271 @@ int orc_pop_episodes(orc_ctx* c, crl_episode* out, int32_t max_records, int32_t*
   return 0;
 }
 uint64_t orc_policy_step(orc_ctx* c) { return c->policy_step; }
+
+/* ================================================================== DQN (dqn.jl) =====
+ * CPU restatement of the vectorised DQN contract in include/cleanrl_cuda.h. TEST INFRASTRUCTURE like the rest of
+ * this file. Parity unpinned: Flux Dense/relu/mse/Adam and RLEnvs CartPole are restated from the pinned versions,
+ * the reference has no tests or golden vectors. What is pinned: linear_schedule (dqn.jl:28-31) by hand, the
+ * backward pass against a float64 NumPy restatement (tests/test_dqn.py). */
+#define DQ_H1 120
+#define DQ_H2 84
+#define DQ_A 2
+#define DQ_D 4
+#define DQ_W1 0
+#define DQ_B1 (DQ_W1 + DQ_H1 * DQ_D)
+#define DQ_W2 (DQ_B1 + DQ_H1)
+#define DQ_B2 (DQ_W2 + DQ_H2 * DQ_H1)
+#define DQ_W3 (DQ_B2 + DQ_H2)
+#define DQ_B3 (DQ_W3 + DQ_A * DQ_H2)
+#define DQ_P (DQ_B3 + DQ_A)
+#define ORC_STREAM_DQN_ACT 3u
+#define ORC_STREAM_DQN_BATCH 4u
+
+typedef struct orc_dqn_ctx {
+  crl_dqn_config cfg;
+  float q[DQ_P], tgt[DQ_P], m[DQ_P], v[DQ_P], g[DQ_P];
+  double bp1, bp2;
+  float* env_state; int32_t* env_t; double* ep_ret; int32_t* ep_len; uint32_t* resets;
+  float *b_state, *b_next, *b_reward; int32_t* b_action; uint8_t* b_term;
+  int32_t size, ptr;
+  int64_t it, learn_steps;
+  double last_loss;
+} orc_dqn_ctx;
+
+double orc_dqn_linear_schedule(double start_e, double end_e, double duration, double t) {
+  double slope = (end_e - start_e) / duration;   /* dqn.jl:29 */
+  double e = slope * t + start_e;
+  return e > end_e ? e : end_e;                  /* dqn.jl:30 */
+}
+/* Chain(Dense(4,120,relu), Dense(120,84,relu), Dense(84,2)), dqn.jl:25; W (out,in) column-major */
+static void dqn_forward(const float* p, const float* x, float* h1, float* h2, float* q) {
+  for (int j = 0; j < DQ_H1; j++) {
+    float acc = 0.0f;
+    for (int k = 0; k < DQ_D; k++) acc += p[DQ_W1 + j + DQ_H1 * k] * x[k];
+    acc += p[DQ_B1 + j];
+    h1[j] = acc > 0.0f ? acc : 0.0f;
+  }
+  for (int j = 0; j < DQ_H2; j++) {
+    float acc = 0.0f;
+    for (int k = 0; k < DQ_H1; k++) acc += p[DQ_W2 + j + DQ_H2 * k] * h1[k];
+    acc += p[DQ_B2 + j];
+    h2[j] = acc > 0.0f ? acc : 0.0f;
+  }
+  for (int o = 0; o < DQ_A; o++) {
+    float acc = 0.0f;
+    for (int k = 0; k < DQ_H2; k++) acc += p[DQ_W3 + o + DQ_A * k] * h2[k];
+    q[o] = acc + p[DQ_B3 + o];
+  }
+}
+int orc_dqn_forward_raw(const float* params, const float* obs, float* q_out, int64_t n) {
+  float h1[DQ_H1], h2[DQ_H2];
+  for (int64_t i = 0; i < n; i++) dqn_forward(params, obs + i * DQ_D, h1, h2, q_out + i * DQ_A);
+  return 0;
+}
+/* loss and gradient of one batch (dqn.jl:96-108); everything passed in, nothing sampled */
+int orc_dqn_loss_raw(const float* q_params, const float* tgt_params, int32_t B, const float* state, const int32_t* action,
+                     const float* reward, const float* next_state, const uint8_t* terminal, double gamma, float* grads,
+                     double* loss_out) {
+  float* h1 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H1);
+  float* h2 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H2);
+  float* dq = (float*)calloc((size_t)B * DQ_A, sizeof(float));
+  float* dz2 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H2);
+  float* dz1 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H1);
+  double loss = 0.0;
+  for (int i = 0; i < B; i++) {
+    float t1[DQ_H1], t2[DQ_H2], qn[DQ_A], qv[DQ_A];
+    dqn_forward(tgt_params, next_state + i * DQ_D, t1, t2, qn);
+    float next_q = qn[0] > qn[1] ? qn[0] : qn[1];                                       /* maximum, dqn.jl:99 */
+    double td = (double)reward[i] + gamma * (double)next_q * (1.0 - (double)terminal[i]); /* dqn.jl:100 */
+    dqn_forward(q_params, state + i * DQ_D, h1 + i * DQ_H1, h2 + i * DQ_H2, qv);
+    double diff = td - (double)qv[action[i]];
+    loss += diff * diff;                                                                 /* Flux.mse, dqn.jl:107 */
+    dq[i * DQ_A + action[i]] = (float)(-2.0 * diff / (double)B);
+  }
+  *loss_out = loss / (double)B;
+  memset(grads, 0, sizeof(float) * DQ_P);
+  /* backward, reductions over the batch in ascending sample order */
+  for (int o = 0; o < DQ_A; o++) {
+    float bs = 0.0f;
+    for (int i = 0; i < B; i++) bs += dq[i * DQ_A + o];
+    grads[DQ_B3 + o] = bs;
+    for (int k = 0; k < DQ_H2; k++) {
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += dq[i * DQ_A + o] * h2[i * DQ_H2 + k];
+      grads[DQ_W3 + o + DQ_A * k] = acc;
+    }
+  }
+  for (int i = 0; i < B; i++)
+    for (int k = 0; k < DQ_H2; k++) {
+      float dh = 0.0f;
+      for (int o = 0; o < DQ_A; o++) dh += q_params[DQ_W3 + o + DQ_A * k] * dq[i * DQ_A + o];
+      dz2[i * DQ_H2 + k] = h2[i * DQ_H2 + k] > 0.0f ? dh : 0.0f;
+    }
+  for (int j = 0; j < DQ_H2; j++) {
+    float bs = 0.0f;
+    for (int i = 0; i < B; i++) bs += dz2[i * DQ_H2 + j];
+    grads[DQ_B2 + j] = bs;
+    for (int k = 0; k < DQ_H1; k++) {
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += dz2[i * DQ_H2 + j] * h1[i * DQ_H1 + k];
+      grads[DQ_W2 + j + DQ_H2 * k] = acc;
+    }
+  }
+  for (int i = 0; i < B; i++)
+    for (int k = 0; k < DQ_H1; k++) {
+      float dh = 0.0f;
+      for (int j = 0; j < DQ_H2; j++) dh += q_params[DQ_W2 + j + DQ_H2 * k] * dz2[i * DQ_H2 + j];
+      dz1[i * DQ_H1 + k] = h1[i * DQ_H1 + k] > 0.0f ? dh : 0.0f;
+    }
+  for (int j = 0; j < DQ_H1; j++) {
+    float bs = 0.0f;
+    for (int i = 0; i < B; i++) bs += dz1[i * DQ_H1 + j];
+    grads[DQ_B1 + j] = bs;
+    for (int k = 0; k < DQ_D; k++) {
+      float acc = 0.0f;
+      for (int i = 0; i < B; i++) acc += dz1[i * DQ_H1 + j] * state[i * DQ_D + k];
+      grads[DQ_W1 + j + DQ_H1 * k] = acc;
+    }
+  }
+  free(h1); free(h2); free(dq); free(dz2); free(dz1);
+  return 0;
+}
+/* Flux.Adam(eta) [Flux 0.13.4], one shared (beta1^t, beta2^t) pair: every array is updated at every step */
+static void dqn_adam(orc_dqn_ctx* c) {
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8, lr = c->cfg.lr;
+  for (int k = 0; k < DQ_P; k++) {
+    float d = c->g[k];
+    float mt = (float)(b1 * (double)c->m[k] + (1.0 - b1) * (double)d);
+    float vt = (float)(b2 * (double)c->v[k] + (1.0 - b2) * (double)d * (double)d);
+    c->m[k] = mt; c->v[k] = vt;
+    double den = sqrt((double)vt / (1.0 - c->bp2)) + eps;
+    float step = (float)((double)mt / (1.0 - c->bp1) / den * lr);
+    c->q[k] = c->q[k] - step;
+  }
+  c->bp1 *= b1; c->bp2 *= b2;
+}
+int orc_dqn_create(const crl_dqn_config* cfg, orc_dqn_ctx** out) {
+  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(crl_dqn_config)) return -1;
+  if (cfg->num_envs < 1 || cfg->buffer_size < cfg->num_envs || cfg->batch_size < 1 || cfg->batch_size > 128 ||
+      cfg->train_freq < 1 || cfg->target_net_freq < 1) return -1;
+  orc_dqn_ctx* c = (orc_dqn_ctx*)calloc(1, sizeof(orc_dqn_ctx));
+  c->cfg = *cfg;
+  int N = cfg->num_envs, C = cfg->buffer_size;
+  c->env_state = (float*)calloc((size_t)N * 4, sizeof(float)); c->env_t = (int32_t*)calloc(N, sizeof(int32_t));
+  c->ep_ret = (double*)calloc(N, sizeof(double)); c->ep_len = (int32_t*)calloc(N, sizeof(int32_t));
+  c->resets = (uint32_t*)calloc(N, sizeof(uint32_t));
+  c->b_state = (float*)calloc((size_t)C * 4, sizeof(float)); c->b_next = (float*)calloc((size_t)C * 4, sizeof(float));
+  c->b_reward = (float*)calloc(C, sizeof(float)); c->b_action = (int32_t*)calloc(C, sizeof(int32_t));
+  c->b_term = (uint8_t*)calloc(C, 1);
+  c->bp1 = 0.9; c->bp2 = 0.999;
+  *out = c;
+  return 0;
+}
+int orc_dqn_destroy(orc_dqn_ctx* c) {
+  if (!c) return -1;
+  free(c->env_state); free(c->env_t); free(c->ep_ret); free(c->ep_len); free(c->resets);
+  free(c->b_state); free(c->b_next); free(c->b_reward); free(c->b_action); free(c->b_term); free(c);
+  return 0;
+}
+int orc_dqn_set_params(orc_dqn_ctx* c, const float* p, int32_t n) {
+  if (!c || n != DQ_P) return -1;
+  memcpy(c->q, p, sizeof(float) * DQ_P); memcpy(c->tgt, p, sizeof(float) * DQ_P);   /* deepcopy, dqn.jl:40 */
+  memset(c->m, 0, sizeof(c->m)); memset(c->v, 0, sizeof(c->v));
+  c->bp1 = 0.9; c->bp2 = 0.999;
+  return 0;
+}
+int orc_dqn_get_params(orc_dqn_ctx* c, float* q, float* tgt, int32_t n) {
+  if (!c || n != DQ_P) return -1;
+  if (q) memcpy(q, c->q, sizeof(float) * DQ_P);
+  if (tgt) memcpy(tgt, c->tgt, sizeof(float) * DQ_P);
+  return 0;
+}
+int orc_dqn_reset(orc_dqn_ctx* c) {
+  if (!c) return -1;
+  for (int n = 0; n < c->cfg.num_envs; n++) {
+    float u[4];
+    c->resets[n] = 0;
+    orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)n, c->resets[n], u);
+    c->resets[n] += 1;
+    orc_cartpole_reset(c->env_state + 4 * n, &c->env_t[n], u);
+    c->ep_ret[n] = 0.0; c->ep_len[n] = 0;
+  }
+  c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0; c->last_loss = 0.0;
+  return 0;
+}
+static void dqn_learn(orc_dqn_ctx* c) {
+  const int B = c->cfg.batch_size;
+  uint32_t keys[8];
+  philox_draw(c->cfg.seed, 0u, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys);
+  philox_draw(c->cfg.seed, 0x80000000u, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys + 4);
+  float st[128 * 4], nx[128 * 4], rw[128];
+  int32_t ac[128];
+  uint8_t tm[128];
+  for (int i = 0; i < B; i++) {
+    uint32_t idx = orc_perm_index((uint32_t)i, (uint32_t)c->size, keys);   /* sample(1:size, B, replace=false) */
+    memcpy(st + 4 * i, c->b_state + 4 * idx, 16); memcpy(nx + 4 * i, c->b_next + 4 * idx, 16);
+    rw[i] = c->b_reward[idx]; ac[i] = c->b_action[idx]; tm[i] = c->b_term[idx];
+  }
+  orc_dqn_loss_raw(c->q, c->tgt, B, st, ac, rw, nx, tm, c->cfg.gamma, c->g, &c->last_loss);
+  dqn_adam(c);
+  c->learn_steps += 1;
+}
+int orc_dqn_run(orc_dqn_ctx* c, int64_t iterations, crl_dqn_stats* stats) {
+  if (!c || iterations < 0) return -1;
+  const int N = c->cfg.num_envs, C = c->cfg.buffer_size;
+  double sum_ret = 0.0, sum_len = 0.0, eps = 0.0;
+  int64_t episodes = 0;
+  for (int64_t k = 0; k < iterations; k++) {
+    c->it += 1;
+    const double gs = (double)c->it * (double)N;
+    eps = orc_dqn_linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);
+    for (int n = 0; n < N; n++) {
+      float obs[4], h1[DQ_H1], h2[DQ_H2], q[DQ_A];
+      memcpy(obs, c->env_state + 4 * n, 16);                                    /* deepcopy(state(env)), dqn.jl:50 */
+      uint32_t r[4];
+      philox_draw(c->cfg.seed, (uint32_t)n, (uint64_t)c->it, ORC_STREAM_DQN_ACT, r);
+      const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+      int action;
+      if (u < eps) action = (int)(r[2] & 1u);                                   /* rand(action_space), dqn.jl:54 */
+      else { dqn_forward(c->q, obs, h1, h2, q); action = q[1] > q[0] ? 1 : 0; } /* argmax: first maximum */
+      float rew; uint8_t done;
+      orc_cartpole_step(c->env_state + 4 * n, &c->env_t[n], action, c->cfg.max_episode_steps, &rew, &done);
+      const int p = (c->ptr + n) % C;                                           /* add!, replay_buffer.jl:23-37 */
+      memcpy(c->b_state + 4 * p, obs, 16); memcpy(c->b_next + 4 * p, c->env_state + 4 * n, 16);
+      c->b_action[p] = action; c->b_reward[p] = rew; c->b_term[p] = done;
+      c->ep_ret[n] += (double)rew; c->ep_len[n] += 1;
+      if (done) {                                                               /* dqn.jl:80-86 */
+        episodes += 1; sum_ret += c->ep_ret[n]; sum_len += (double)c->ep_len[n];
+        c->ep_ret[n] = 0.0; c->ep_len[n] = 0;
+        float u4[4];
+        orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)n, c->resets[n], u4);
+        c->resets[n] += 1;
+        orc_cartpole_reset(c->env_state + 4 * n, &c->env_t[n], u4);
+      }
+    }
+    c->ptr = (c->ptr + N) % C;
+    c->size = c->size + N > C ? C : c->size + N;
+    if (gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size) {  /* dqn.jl:94 */
+      dqn_learn(c);
+      if (c->it % c->cfg.target_net_freq == 0) memcpy(c->tgt, c->q, sizeof(float) * DQ_P);   /* dqn.jl:111-113 */
+    }
+  }
+  if (stats) {
+    stats->last_loss = c->last_loss; stats->sum_return = sum_ret; stats->sum_length = sum_len; stats->epsilon = eps;
+    stats->episodes = episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
+  }
+  return 0;
+}
+int orc_dqn_read_buffer(orc_dqn_ctx* c, float* state, int32_t* action, float* reward, float* next_state, uint8_t* terminal,
+                        int32_t* size, int32_t* ptr) {
+  if (!c) return -1;
+  const size_t C = (size_t)c->cfg.buffer_size;
+  if (state) memcpy(state, c->b_state, C * 16);
+  if (next_state) memcpy(next_state, c->b_next, C * 16);
+  if (action) memcpy(action, c->b_action, C * 4);
+  if (reward) memcpy(reward, c->b_reward, C * 4);
+  if (terminal) memcpy(terminal, c->b_term, C);
+  if (size) *size = c->size;
+  if (ptr) *ptr = c->ptr;
+  return 0;
+}
