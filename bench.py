@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gae-n", type=int, default=1 << 20, help="envs in the GAE HBM measurement (T=128)")
     ap.add_argument("--local-stats", action="store_true")
-    ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c"],
+    ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c", "dqn"],
                     help="a2c = BASELINE.json configs[2]: A2C CartPole, 16384 envs, n-step returns + fused update (1 GPU)")
     return ap.parse_args()
 
@@ -249,7 +249,55 @@ def gae_roofline(torch, lib_mod, N, T=NUM_STEPS):
     return nbytes / (ms * 1e-3) / 1e9, ms, nbytes
 
 
+def run_dqn(args):
+    """BASELINE.json configs[4]-style secondary line: vectorised DQN with a 1M-transition HBM replay buffer on one GPU.
+    A step = 100 iterations (vector steps) of 4096 envs with the reference's schedule (learn every 10, target every 100)."""
+    import torch
+    from cleanrl_jl_b200 import _abi
+    from cleanrl_jl_b200.dqn_algo import DQNConfig, DQNHandle, dqn, init_q_params
+    from cleanrl_jl_b200 import logger as Logger
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback")
+    N, ITERS = 4096, 100
+    cfg = _abi.make_dqn_config(num_envs=N, buffer_size=1 << 20, min_buff_size=10_000, batch_size=120, train_freq=10,
+                               target_net_freq=100, epsilon_duration=5e6, seed=1)
+    h = DQNHandle(cfg)
+    h.set_params(init_q_params(1))
+    h.reset()
+    for _ in range(max(args.warmup, 3)):
+        h.run(ITERS)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps - 1):
+        h.lib.crl_dqn_run(h.h, ITERS, None)      # asynchronous: launches only
+    st = h.run(ITERS)                              # the last call reads the statistics back = stream synchronisation
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    h.close()
+    value = args.steps * ITERS * N / wall
+    tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
+    lg = Logger.make_logger("bench_dqn", to_terminal=False, to_tensorboard=False, to_json=True, log_dir=tmp)
+    res = dqn(DQNConfig(num_envs=N, total_timesteps=N * ITERS * 20, buffer_size=1 << 20, min_buff_size=10_000,
+                        epsilon_duration=5e6, log_frequencey=N * ITERS), logger=lg)
+    lg.close()
+    print(json.dumps({
+        "metric": "dqn_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DQN CartPole, %d vectorized envs, 1,048,576-transition HBM replay, batch 120, learn every 10 "
+                               "iterations, target copy every 100 (dqn.jl defaults); a step = %d iterations" % (N, ITERS),
+                   "timing": "host wall clock around asynchronous launches, closed by the statistics read-back"},
+        "clocks": clocks,
+        "e2e": {"value": res["steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 56,
+                "note": "dqn(config) public API with logging every %d iterations" % ITERS},
+        "gpu_launches": args.steps * (ITERS + ITERS // 10), "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
+    }), flush=True)
+
+
 def run_ours(args):
+    if args.algo == "dqn":
+        return run_dqn(args)
     import torch
     from cleanrl_jl_b200 import _abi, _lib, networks, parallel
     from cleanrl_jl_b200.config import PPOConfig

@@ -3,12 +3,13 @@
 // ring replay buffer, and one learning step (sample without replacement -> TD target from the target net -> MSE on
 // the taken action -> backward -> Adam -> optional target copy) every train_freq iterations.
 //
-//   dqn_act_kernel    one thread per env, 64 envs per CTA. The 10,934 parameters sit in shared memory; a thread walks
-//                     the three Dense layers with its activations in shared memory ([neuron][env lane]: conflict-free,
-//                     weight reads are warp broadcasts), draws epsilon / the random action from Philox, steps CartPole,
-//                     appends the transition at (ptr + env) % capacity and resets a finished env on the spot.
-//   dqn_learn_kernel  ONE CTA of 128 threads (batch_size <= 128 samples, one per thread): both parameter sets and the
-//                     batch activations live in shared memory (~195 KB); forward target net and q net per sample,
+//   dqn_act_kernel    32 envs per CTA of 256 threads: lane = env, warp = neuron group (neurons group, group + 8, ...).
+//                     The 10,934 parameters sit in shared memory; activations are [neuron][env lane] tiles in shared
+//                     memory (conflict-free, weight reads are warp broadcasts). Warp 0 then draws epsilon / the random
+//                     action from Philox, steps CartPole, appends the transition at (ptr + env) % capacity and resets a
+//                     finished env on the spot.
+//   dqn_learn_kernel  ONE CTA of 512 threads for the batch (<= 128 samples x 4 neuron groups): both parameter sets
+//                     and the batch activations live in shared memory (~197 KB); forward target net and q net,
 //                     gradient reductions over the batch by one thread per weight in ascending sample order
 //                     (deterministic, same order as the oracle), Adam and the target copy in the same launch.
 // Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?") is taken on
@@ -28,8 +29,12 @@ constexpr int DQ_W1 = 0, DQ_B1 = DQ_W1 + DQ_H1 * DQ_D, DQ_W2 = DQ_B1 + DQ_H1, DQ
               DQ_W3 = DQ_B2 + DQ_H2, DQ_B3 = DQ_W3 + DQ_A * DQ_H2, DQ_P = DQ_B3 + DQ_A;
 static_assert(DQ_P == CRL_DQN_PARAMS, "parameter count");
 constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
-constexpr int ACT_T = 64;     // envs (threads) per CTA in dqn_act_kernel
-constexpr int LEARN_T = 128;  // threads = max batch size in dqn_learn_kernel
+constexpr int ACT_E = 32;     // envs per CTA in dqn_act_kernel (one warp-width of samples)
+constexpr int ACT_G = 8;      // neuron groups: thread (lane = env, warp = group) computes neurons group, group + 8, ...
+constexpr int ACT_T = ACT_E * ACT_G;
+constexpr int LEARN_B = 128;  // max batch size = samples per tile in dqn_learn_kernel
+constexpr int LEARN_G = 4;    // neuron groups
+constexpr int LEARN_T = LEARN_B * LEARN_G;
 
 struct DqnDev {               // device-resident scalars
   double bp1, bp2;            // beta1^t, beta2^t of Adam
@@ -48,57 +53,63 @@ struct ActArgs {
   int N, C, ptr, max_steps;
 };
 
-// Dense -> relu -> Dense -> relu -> Dense for the sample of lane `l`; h1/h2 are [neuron][T] tiles in shared memory
-template <int T>
-__device__ __forceinline__ void q_forward(const float* __restrict__ p, const float x[DQ_D], float* h1, float* h2, int l,
-                                          float q[DQ_A]) {
-  for (int j = 0; j < DQ_H1; j++) {
+// Dense -> relu -> Dense -> relu -> Dense for a tile of S samples, neurons strided over G thread groups (CTA-wide
+// barriers between the layers: every thread of the CTA must call this). Activations are [neuron][S] tiles in shared
+// memory (conflict-free across the lanes of a warp; weight reads are warp broadcasts); each neuron is one fmaf chain
+// over ascending k, so the result does not depend on S or G. qo = [DQ_A][S].
+template <int S, int G>
+__device__ __forceinline__ void q_forward(const float* __restrict__ p, const float x[DQ_D], float* h1, float* h2, float* qo,
+                                          int l, int g) {
+  for (int j = g; j < DQ_H1; j += G) {
     float acc = 0.0f;
 #pragma unroll
     for (int k = 0; k < DQ_D; k++) acc = fmaf(p[DQ_W1 + j + DQ_H1 * k], x[k], acc);
     acc += p[DQ_B1 + j];
-    h1[j * T + l] = fmaxf(acc, 0.0f);
+    h1[j * S + l] = fmaxf(acc, 0.0f);
   }
-  for (int j = 0; j < DQ_H2; j++) {
+  __syncthreads();
+  for (int j = g; j < DQ_H2; j += G) {
     float acc = 0.0f;
 #pragma unroll 8
-    for (int k = 0; k < DQ_H1; k++) acc = fmaf(p[DQ_W2 + j + DQ_H2 * k], h1[k * T + l], acc);
+    for (int k = 0; k < DQ_H1; k++) acc = fmaf(p[DQ_W2 + j + DQ_H2 * k], h1[k * S + l], acc);
     acc += p[DQ_B2 + j];
-    h2[j * T + l] = fmaxf(acc, 0.0f);
+    h2[j * S + l] = fmaxf(acc, 0.0f);
   }
-#pragma unroll
-  for (int o = 0; o < DQ_A; o++) {
+  __syncthreads();
+  for (int o = g; o < DQ_A; o += G) {
     float acc = 0.0f;
 #pragma unroll 4
-    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * T + l], acc);
-    q[o] = acc + p[DQ_B3 + o];
+    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * S + l], acc);
+    qo[o * S + l] = acc + p[DQ_B3 + o];
   }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* p = smem;                       // [DQ_P]
-  float* h1 = p + ((DQ_P + 3) & ~3);     // [120][64]
-  float* h2 = h1 + DQ_H1 * ACT_T;        // [84][64]
+  float* h1 = p + ((DQ_P + 3) & ~3);     // [120][32]
+  float* h2 = h1 + DQ_H1 * ACT_E;        // [84][32]
+  float* qo = h2 + DQ_H2 * ACT_E;        // [2][32]
   for (int i = threadIdx.x; i < DQ_P; i += ACT_T) p[i] = a.q[i];
-  __syncthreads();
-  const int n = blockIdx.x * ACT_T + threadIdx.x;
-  if (n >= a.N) return;
-  float st[4];
+  const int e = threadIdx.x & (ACT_E - 1), g = threadIdx.x / ACT_E;
+  const int n = blockIdx.x * ACT_E + e;
+  const bool valid = n < a.N;
+  float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (valid) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+    for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+  }
+  __syncthreads();
+  q_forward<ACT_E, ACT_G>(p, st, h1, h2, qo, e, g);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
+  if (g != 0 || !valid) return;
   const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
   uint32_t r[4];
   philox_draw(a.seed, (uint32_t)n, a.it, STREAM_DQN_ACT, r);
   const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
   int action;
-  if (u < a.eps) {
-    action = (int)(r[2] & 1u);           // rand(action_space(env)), dqn.jl:54
-  } else {
-    float q[DQ_A];
-    q_forward<ACT_T>(p, st, h1, h2, threadIdx.x, q);
-    action = q[1] > q[0] ? 1 : 0;        // argmax: first maximum, dqn.jl:56-57
-  }
+  if (u < a.eps) action = (int)(r[2] & 1u);                     // rand(action_space(env)), dqn.jl:54
+  else action = qo[1 * ACT_E + e] > qo[0 * ACT_E + e] ? 1 : 0;  // argmax: first maximum, dqn.jl:56-57
   int t = a.env_t[n];
   float rew;
   bool done;
@@ -141,73 +152,80 @@ struct LearnArgs {
 
 __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int PP = (DQ_P + 3) & ~3;
+  constexpr int PP = (DQ_P + 3) & ~3, S = LEARN_B;
   float* pq = smem;                       // q_net parameters
   float* pt = pq + PP;                    // target_net parameters
   float* h1 = pt + PP;                    // [120][128]  (later dz1 in place)
-  float* h2 = h1 + DQ_H1 * LEARN_T;       // [84][128]   (later dz2 in place)
-  float* xs = h2 + DQ_H2 * LEARN_T;       // [4][128] states of the batch
-  float* dq = xs + DQ_D * LEARN_T;        // [2][128]
+  float* h2 = h1 + DQ_H1 * S;             // [84][128]   (later dz2 in place)
+  float* xs = h2 + DQ_H2 * S;             // [4][128] states of the batch
+  float* dq = xs + DQ_D * S;              // [2][128]
+  float* qo = dq + DQ_A * S;              // [2][128] network outputs
   __shared__ uint32_t keys[8];
-  __shared__ double red[LEARN_T / 32];
+  __shared__ double red[S / 32];
   const int tid = threadIdx.x, B = a.B;
-  for (int i = tid; i < DQ_P; i += LEARN_T) { pq[i] = a.q[i]; pt[i] = a.tgt[i]; }
+  const int i = tid & (S - 1), g = tid / S;   // sample, neuron group
+  for (int k = tid; k < DQ_P; k += LEARN_T) { pq[k] = a.q[k]; pt[k] = a.tgt[k]; }
   if (tid == 0) {
     philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
     philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
   }
   __syncthreads();
-  double sq = 0.0;
-  dq[0 * LEARN_T + tid] = 0.0f;
-  dq[1 * LEARN_T + tid] = 0.0f;
-#pragma unroll
-  for (int k = 0; k < DQ_D; k++) xs[k * LEARN_T + tid] = 0.0f;
-  if (tid < B) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, nx[4] = {0.f, 0.f, 0.f, 0.f};
+  int act = 0, term = 0;
+  float rew = 0.0f;
+  if (i < B) {
     // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
-    const uint32_t idx = perm_index((uint32_t)tid, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
+    const uint32_t idx = perm_index((uint32_t)i, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
     const float4 s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
     const float4 n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
-    const float s[4] = {s4.x, s4.y, s4.z, s4.w}, nx[4] = {n4.x, n4.y, n4.z, n4.w};
-    const int act = a.b_action[idx];
-    const float rew = a.b_reward[idx];
-    const int term = a.b_term[idx];
-    float qn[DQ_A], qv[DQ_A];
-    q_forward<LEARN_T>(pt, nx, h1, h2, tid, qn);                     // target_net(next_state), dqn.jl:99
-    const float next_q = fmaxf(qn[0], qn[1]);
-    const double td = (double)rew + a.gamma * (double)next_q * (1.0 - (double)term);   // dqn.jl:100
-    q_forward<LEARN_T>(pq, s, h1, h2, tid, qv);                      // q_net(state), dqn.jl:105
-    const double diff = td - (double)qv[act];
-    sq = diff * diff;                                                // Flux.mse, dqn.jl:107
-    dq[act * LEARN_T + tid] = (float)(-2.0 * diff / (double)B);
-#pragma unroll
-    for (int k = 0; k < DQ_D; k++) xs[k * LEARN_T + tid] = s[k];
+    s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+    nx[0] = n4.x; nx[1] = n4.y; nx[2] = n4.z; nx[3] = n4.w;
+    act = a.b_action[idx];
+    rew = a.b_reward[idx];
+    term = a.b_term[idx];
   }
-  // loss
-  sq = warp_sum(sq);
-  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  q_forward<S, LEARN_G>(pt, nx, h1, h2, qo, i, g);                   // target_net(next_state), dqn.jl:99
+  const float next_q = fmaxf(qo[0 * S + i], qo[1 * S + i]);
+  const double td = (double)rew + a.gamma * (double)next_q * (1.0 - (double)term);   // dqn.jl:100
+  __syncthreads();
+  q_forward<S, LEARN_G>(pq, s, h1, h2, qo, i, g);                    // q_net(state), dqn.jl:105
+  double sq = 0.0;
+  if (g == 0) {
+    dq[0 * S + i] = 0.0f;
+    dq[1 * S + i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DQ_D; k++) xs[k * S + i] = s[k];
+    if (i < B) {
+      const double diff = td - (double)qo[act * S + i];
+      sq = diff * diff;                                              // Flux.mse, dqn.jl:107
+      dq[act * S + i] = (float)(-2.0 * diff / (double)B);
+    }
+    sq = warp_sum(sq);
+    if ((tid & 31) == 0) red[tid >> 5] = sq;
+  }
   __syncthreads();
   if (tid == 0) a.dev->last_loss = ((red[0] + red[1]) + (red[2] + red[3])) / (double)B;
   // ---- backward; every reduction over the batch runs in ascending sample order in one thread
-  float* g = a.g;
+  float* gr = a.g;
   for (int w = tid; w < DQ_A * DQ_H2 + DQ_A; w += LEARN_T) {         // dW3(o,k), db3(o)
     if (w < DQ_A * DQ_H2) {
       const int o = w % DQ_A, k = w / DQ_A;
       float acc = 0.0f;
-      for (int i = 0; i < B; i++) acc = fmaf(dq[o * LEARN_T + i], h2[k * LEARN_T + i], acc);
-      g[DQ_W3 + w] = acc;
+      for (int b = 0; b < B; b++) acc = fmaf(dq[o * S + b], h2[k * S + b], acc);
+      gr[DQ_W3 + w] = acc;
     } else {
       const int o = w - DQ_A * DQ_H2;
       float acc = 0.0f;
-      for (int i = 0; i < B; i++) acc += dq[o * LEARN_T + i];
-      g[DQ_B3 + o] = acc;
+      for (int b = 0; b < B; b++) acc += dq[o * S + b];
+      gr[DQ_B3 + o] = acc;
     }
   }
   __syncthreads();
-  if (tid < B) {                                                     // dz2 = (W3^T dq) .* (h2 > 0), in place
-    const float d0 = dq[0 * LEARN_T + tid], d1 = dq[1 * LEARN_T + tid];
-    for (int k = 0; k < DQ_H2; k++) {
+  {                                                                  // dz2 = (W3^T dq) .* (h2 > 0), in place
+    const float d0 = dq[0 * S + i], d1 = dq[1 * S + i];
+    for (int k = g; k < DQ_H2; k += LEARN_G) {
       const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
-      h2[k * LEARN_T + tid] = h2[k * LEARN_T + tid] > 0.0f ? dh : 0.0f;
+      h2[k * S + i] = h2[k * S + i] > 0.0f ? dh : 0.0f;
     }
   }
   __syncthreads();
@@ -216,36 +234,34 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
       const int j = w % DQ_H2, k = w / DQ_H2;
       float acc = 0.0f;
 #pragma unroll 4
-      for (int i = 0; i < B; i++) acc = fmaf(h2[j * LEARN_T + i], h1[k * LEARN_T + i], acc);
-      g[DQ_W2 + w] = acc;
+      for (int b = 0; b < B; b++) acc = fmaf(h2[j * S + b], h1[k * S + b], acc);
+      gr[DQ_W2 + w] = acc;
     } else {
       const int j = w - DQ_H2 * DQ_H1;
       float acc = 0.0f;
-      for (int i = 0; i < B; i++) acc += h2[j * LEARN_T + i];
-      g[DQ_B2 + j] = acc;
+      for (int b = 0; b < B; b++) acc += h2[j * S + b];
+      gr[DQ_B2 + j] = acc;
     }
   }
   __syncthreads();
-  if (tid < B) {                                                     // dz1 = (W2^T dz2) .* (h1 > 0), in place
-    for (int k = 0; k < DQ_H1; k++) {
-      float dh = 0.0f;
+  for (int k = g; k < DQ_H1; k += LEARN_G) {                         // dz1 = (W2^T dz2) .* (h1 > 0), in place
+    float dh = 0.0f;
 #pragma unroll 4
-      for (int j = 0; j < DQ_H2; j++) dh = fmaf(pq[DQ_W2 + j + DQ_H2 * k], h2[j * LEARN_T + tid], dh);
-      h1[k * LEARN_T + tid] = h1[k * LEARN_T + tid] > 0.0f ? dh : 0.0f;
-    }
+    for (int j = 0; j < DQ_H2; j++) dh = fmaf(pq[DQ_W2 + j + DQ_H2 * k], h2[j * S + i], dh);
+    h1[k * S + i] = h1[k * S + i] > 0.0f ? dh : 0.0f;
   }
   __syncthreads();
   for (int w = tid; w < DQ_H1 * DQ_D + DQ_H1; w += LEARN_T) {        // dW1(j,k), db1(j)
     if (w < DQ_H1 * DQ_D) {
       const int j = w % DQ_H1, k = w / DQ_H1;
       float acc = 0.0f;
-      for (int i = 0; i < B; i++) acc = fmaf(h1[j * LEARN_T + i], xs[k * LEARN_T + i], acc);
-      g[DQ_W1 + w] = acc;
+      for (int b = 0; b < B; b++) acc = fmaf(h1[j * S + b], xs[k * S + b], acc);
+      gr[DQ_W1 + w] = acc;
     } else {
       const int j = w - DQ_H1 * DQ_D;
       float acc = 0.0f;
-      for (int i = 0; i < B; i++) acc += h1[j * LEARN_T + i];
-      g[DQ_B1 + j] = acc;
+      for (int b = 0; b < B; b++) acc += h1[j * S + b];
+      gr[DQ_B1 + j] = acc;
     }
   }
   __syncthreads();
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   const double bp1 = a.dev->bp1, bp2 = a.dev->bp2;
   __syncthreads();
   for (int k = tid; k < DQ_P; k += LEARN_T) {
-    const float d = g[k];
+    const float d = gr[k];
     const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[k]), __dmul_rn(1.0 - b1, (double)d));
     const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
     a.m[k] = mt;
@@ -268,8 +284,8 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   if (tid == 0) { a.dev->bp1 = bp1 * b1; a.dev->bp2 = bp2 * b2; }
 }
 
-constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2) * ACT_T) * sizeof(float);
-constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + DQ_A) * LEARN_T) * sizeof(float);
+constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_A) * ACT_E) * sizeof(float);
+constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + 2 * DQ_A) * LEARN_B) * sizeof(float);
 static_assert(LEARN_SMEM <= 227 * 1024, "dqn_learn shared memory");
 
 int dfail(int code, const std::string& msg) { return crl_internal_fail(code, msg.c_str()); }
@@ -322,7 +338,7 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   if (!cfg || !out) return dfail(CRL_ERR_INVALID, "NULL argument");
   if (cfg->struct_size != (int32_t)sizeof(crl_dqn_config)) return dfail(CRL_ERR_INVALID, "crl_dqn_config.struct_size mismatch");
   if (cfg->num_envs < 1 || cfg->buffer_size < cfg->num_envs) return dfail(CRL_ERR_INVALID, "need 1 <= num_envs <= buffer_size");
-  if (cfg->batch_size < 1 || cfg->batch_size > LEARN_T) return dfail(CRL_ERR_INVALID, "batch_size must be in [1, 128]");
+  if (cfg->batch_size < 1 || cfg->batch_size > LEARN_B) return dfail(CRL_ERR_INVALID, "batch_size must be in [1, 128]");
   if (cfg->train_freq < 1 || cfg->target_net_freq < 1 || cfg->max_episode_steps < 1 || !(cfg->epsilon_duration > 0.0))
     return dfail(CRL_ERR_INVALID, "train_freq, target_net_freq, max_episode_steps, epsilon_duration must be positive");
   int ndev = 0;
@@ -417,7 +433,7 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     a.b_state = c->b_state; a.b_next = c->b_next; a.b_reward = c->b_reward; a.b_action = c->b_action; a.b_term = c->b_term;
     a.dev = c->dev; a.seed = c->cfg.seed; a.it = (unsigned long long)c->it; a.eps = eps; a.N = N; a.C = C; a.ptr = c->ptr;
     a.max_steps = c->cfg.max_episode_steps;
-    dqn_act_kernel<<<(N + ACT_T - 1) / ACT_T, ACT_T, ACT_SMEM, c->stream>>>(a);
+    dqn_act_kernel<<<(N + ACT_E - 1) / ACT_E, ACT_T, ACT_SMEM, c->stream>>>(a);
     DCK(cudaGetLastError());
     c->ptr = (c->ptr + N) % C;
     c->size = c->size + N > C ? C : c->size + N;
