@@ -271,4 +271,73 @@ function a2c(config; actor, critic)
   get_params(h, length(p))
 end
 
+# ---- DQN (dqn.jl) over the crl_dqn_* entry points ------------------------------------------------------------
+struct CrlDqnConfig          # crl_dqn_config
+  struct_size::Int32
+  num_envs::Int32
+  buffer_size::Int32
+  min_buff_size::Int32
+  batch_size::Int32
+  train_freq::Int32
+  target_net_freq::Int32
+  max_episode_steps::Int32
+  device::Int32
+  _pad::Int32
+  lr::Float64
+  gamma::Float64
+  epsilon_start::Float64
+  epsilon_end::Float64
+  epsilon_duration::Float64
+  seed::UInt64
+end
+struct CrlDqnStats           # crl_dqn_stats
+  last_loss::Float64
+  sum_return::Float64
+  sum_length::Float64
+  epsilon::Float64
+  episodes::Int64
+  learn_steps::Int64
+  iterations::Int64
+end
+
+"""
+    dqn(config::DQNConfig; q_net, num_envs = 1, seed = 1)
+
+Drop-in for `CleanRL.dqn` (dqn.jl:34): same `DQNConfig`, same two `@info` records. `q_net` is the Flux chain of
+`make_nn` (dqn.jl:22-26), used only to initialise the device parameters. `num_envs = 1` reproduces the reference's
+schedule step for step; larger values step that many CartPole envs in lockstep on the GPU.
+"""
+function dqn(config; q_net, num_envs::Integer=1, seed::Integer=1)
+  cfg = CrlDqnConfig(Int32(sizeof(CrlDqnConfig)), num_envs, config.buffer_size, config.min_buff_size, config.batch_size,
+                     config.train_freq, config.target_net_freq, 200, 0, 0, config.lr, config.gamma, config.epsilon_start,
+                     config.epsilon_end, config.epsilon_duration, UInt64(seed))
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:crl_dqn_create, LIB), Cint, (Ref{CrlDqnConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+  h = out[]
+  p = reduce(vcat, [vec(Float32.(x)) for x in Flux_params(q_net)])                    # Flux.params(q_net), dqn.jl:103
+  GC.@preserve p check(ccall((:crl_dqn_set_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int32), h, p, length(p)))
+  check(ccall((:crl_dqn_reset, LIB), Cint, (Ptr{Cvoid},), h))                          # reset!(env), dqn.jl:48
+  chunk = max(1, config.log_frequencey ÷ num_envs)
+  n_iter = config.total_timesteps ÷ num_envs
+  done = 0
+  start_time = time()
+  while done < n_iter
+    k = min(chunk, n_iter - done)
+    st = Ref(CrlDqnStats(0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:crl_dqn_run, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{CrlDqnStats}), h, k, st))   # dqn.jl:49-118
+    done += k
+    global_step = done * num_envs
+    s = st[]
+    if s.episodes > 0
+      steps_per_sec = trunc(global_step / (time() - start_time))
+      @info "Episode Statistics" episode_return = s.sum_return / s.episodes episode_length = s.sum_length / s.episodes global_step ϵ = s.epsilon steps_per_sec   # dqn.jl:82
+    end
+    s.learn_steps > 0 && @info "Training Statistics" loss = s.last_loss                          # dqn.jl:116
+  end
+  q = Vector{Float32}(undef, length(p))
+  GC.@preserve q check(ccall((:crl_dqn_get_params, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32), h, q, C_NULL, length(q)))
+  check(ccall((:crl_dqn_destroy, LIB), Cint, (Ptr{Cvoid},), h))
+  q
+end
+
 end # module
