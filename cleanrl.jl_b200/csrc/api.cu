@@ -585,7 +585,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.grid_loss = loss_grad_grid(M, c->sm_count);
   ua.parts_in = c->parts; ua.n_parts_in = gs; ua.fin = c->fin; ua.world = 1;
   ua.gpart = c->gpart; ua.spart = c->spart; ua.gsum = c->gsum;
-  ua.mode = LG_EXACT; ua.fixup = 0; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
+  ua.mode = LG_EXACT; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
   ua.rank = c->cfg.rank;
   ua.algo = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
   ua.tc_net_a = c->L.critic - c->L.actor; ua.tc_net_c = (c->L.continuous ? c->L.logstd : c->L.P) - c->L.critic;
@@ -594,7 +594,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   AdamArgs aa = adam_args(c, M, lr_host, stats_slot);
   if (spec || ua.algo == 1) {  // the A2C losses have no minibatch-global scalars: the 3-kernel chain is already exact
     const bool p2p = multi && c->p2p_on;
-    ua.mode = LG_SPEC; ua.world = W; ua.defer_verify = 1;
+    ua.mode = LG_SPEC; ua.world = W;
     if (p2p) {
       ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq;
       ua.p2p_peers = c->p2p_peers_dev; ua.p2p_flags_off = c->p2p_flags_off; ua.p2p_count = c->p2p_count;
@@ -1103,8 +1103,7 @@ extern "C" CRL_API int crl_ppo_loss_raw(int32_t env_kind, const float* params, c
   ua.parts_in = g_raw.parts; ua.n_parts_in = gs; ua.fin = g_raw.fin; ua.world = 1;
   ua.gpart = g_raw.gpart; ua.spart = g_raw.spart; ua.grid_loss = loss_grad_grid(M, g_raw.sm); ua.gsum = g_raw.gsum;
   ua.advparts = g_raw.advparts; ua.mpart = g_raw.mpart;
-  ua.defer_verify = 0; ua.rank = 0; ua.p2p_data = nullptr; ua.p2p_stride = 0; ua.p2p_seq = nullptr;
-  ua.mode = LG_EXACT; ua.fixup = 0;
+  ua.mode = LG_EXACT;
   CK(launch_mb_stats(ua, gs, s));
   CK(launch_mb_count(ua, s));
   CK(launch_loss_grad(ua, s));

@@ -53,7 +53,7 @@ struct MbFinal {
   float adv_mean, adv_std, s_unclipped, min_vlc;
   double M_global;
   unsigned long long cnt;  // #{i : s > (clip_i - R_i)^2}, ppo.jl:236 (Q5)
-  int need_fixup;          // speculative pass found s > min (clip_i - R_i)^2: redo with the exact terms
+  int need_fixup;          // speculative pass found s > min (clip_i - R_i)^2: the host replays the update exactly
   int _pad;
 };
 
@@ -98,11 +98,9 @@ struct UpdateArgs {
   int grid_loss;
   double* gsum;          // [P + 4] reduced gradient (+ loss sums) in double: the allreduce buffer
   int mode;              // LG_EXACT | LG_SPEC
-  int fixup;             // 1: this launch is the verification re-run; exits at once unless fin->need_fixup
   const double* advparts;  // [ADV_CHUNKS][2] of this minibatch (LG_SPEC)
   float* mpart;          // [grid] per-CTA min (clip_i - R_i)^2 (LG_SPEC)
-  int defer_verify;      // multi-GPU: grad_reduce only packs (sum s, per-rank min) behind the gradient; verify_kernel
-  int rank;              //            checks the speculation after the allreduce
+  int rank;
   // peer-memory allreduce (NVLink/NVSwitch): grad_reduce PUSHES its sums into every rank's exchange buffer
   // (layout [2 slots][world][p2p_stride] doubles, then [world] arrival flags); the last block to finish raises this
   // rank's flag on every peer, and clip_adam only ever reads its own memory

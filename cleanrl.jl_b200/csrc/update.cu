@@ -126,25 +126,6 @@ __global__ void __launch_bounds__(CRL_THREADS) mb_count_kernel(UpdateArgs a) {
   __shared__ double red[8];
   __shared__ float mred[8];
   __shared__ uint32_t keys[8];
-  if (a.fixup) {
-    // verification re-run of the speculative path: fin already holds s; count only if it is needed
-    if (!a.fin->need_fixup) return;
-    if (threadIdx.x == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
-    __syncthreads();
-    const float s_fx = a.fin->s_unclipped;
-    unsigned int cf = 0;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += gridDim.x * blockDim.x) {
-      const int b = sample_index(a.idx, keys, m);
-      float d, vlc;
-      bool inside;
-      value_clip(a.vnew[m], a.values[b], a.returns[b], a.clip_coef, d, vlc, inside);
-      cf += (s_fx > vlc) ? 1u : 0u;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cf += __shfl_xor_sync(0xffffffffu, cf, o);
-    if ((threadIdx.x & 31) == 0 && cf) atomicAdd(&a.fin->cnt, (unsigned long long)cf);
-    return;
-  }
   double s_adv = 0.0, s_adv2 = 0.0, s_s = 0.0;
   float mn = INFINITY;
   for (int i = threadIdx.x; i < a.n_parts_in; i += blockDim.x) {
@@ -296,7 +277,6 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
   double* red = reinterpret_cast<double*>(smem + SM::RED);
   const ThreadCoord<G> tc;
   const int tid = threadIdx.x;
-  if (a.fixup && !a.fin->need_fixup) return;  // speculation held: nothing to redo
   // a new peer exchange begins with this minibatch: grad_reduce and the finishing kernel only READ the counter
   if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
   float* xin = smem + SM::XIN;
@@ -757,7 +737,6 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
 // min_i (clip_i - R_i)^2, otherwise the exact kernels that follow redo the minibatch.
 __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
   __shared__ double sh[4][64];
-  if (a.fixup && !a.fin->need_fixup) return;
   const int grid = a.grid_loss;
   // with the peer-memory allreduce the sums are pushed straight into every rank's exchange buffer
   const bool push = a.p2p_data != nullptr;
@@ -786,41 +765,22 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(UpdateArgs a, int P) {
     }
   };
   if (blockIdx.x == gridDim.x - 1) {
-    if (a.mode != LG_SPEC || a.fixup) { arrive(); return; }
-    __shared__ double red[8];
+    if (a.mode != LG_SPEC) { arrive(); return; }   // exact chain: mb_count has already produced the statistics
+    // speculative chain: sum s and this rank's min (clip_i - R_i)^2 ride behind the gradient (every other rank adds 0
+    // in this rank's min slot), so ONE sum-exchange delivers gradient, loss sums, sum s and every rank's min; the
+    // finishing kernel checks s <= min on the exchanged values
     __shared__ float mred[8];
-    double ss = 0.0;
     float mn = INFINITY;
-    for (int c = threadIdx.x; c < grid; c += blockDim.x) { ss += a.spart[(long long)c * 4 + 3]; mn = fminf(mn, a.mpart[c]); }
-    ss = warp_sum(ss);
+    for (int c = threadIdx.x; c < grid; c += blockDim.x) mn = fminf(mn, a.mpart[c]);
     mn = warp_min(mn);
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; mred[threadIdx.x >> 5] = mn; }
+    if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = mn;
     __syncthreads();
-    if (a.defer_verify) {
-      // multi-GPU: this rank's min rides behind the gradient in its own slot (the other ranks add 0 there),
-      // so ONE sum-allreduce delivers gradient, loss sums, sum s and every rank's min
-      if (threadIdx.x == 0) {
-        float m8 = mred[0];
-        for (int w = 0; w < 8; w++) m8 = fminf(m8, mred[w]);
-        for (int r = 0; r < a.world; r++) put(P + 4 + r, (r == a.rank) ? (double)m8 : 0.0);
-      }
-      arrive();
-      return;
-    }
     if (threadIdx.x == 0) {
-      double tot = 0.0;
       float m8 = mred[0];
-      for (int w = 0; w < 8; w++) { tot += red[w]; m8 = fminf(m8, mred[w]); }
-      double sa = 0.0, sa2 = 0.0;
-      for (int i = 0; i < ADV_CHUNKS; i++) { sa += a.advparts[2 * i]; sa2 += a.advparts[2 * i + 1]; }
-      const double Mg = (double)a.M * (double)a.world;
-      const double mean = sa / Mg;
-      double var = (sa2 - Mg * mean * mean) / (Mg - 1.0);
-      if (var < 0.0) var = 0.0;
-      const float s_f = (float)(tot / Mg);
-      a.fin->adv_mean = (float)mean; a.fin->adv_std = (float)sqrt(var); a.fin->s_unclipped = s_f; a.fin->min_vlc = m8;
-      a.fin->M_global = Mg; a.fin->cnt = 0ull; a.fin->need_fixup = (s_f > m8) ? 1 : 0;
+      for (int w = 1; w < 8; w++) m8 = fminf(m8, mred[w]);
+      for (int r = 0; r < a.world; r++) put(P + 4 + r, (r == a.rank) ? (double)m8 : 0.0);
     }
+    arrive();
     return;
   }
   const int el = threadIdx.x & 63, g = threadIdx.x >> 6;

@@ -824,7 +824,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
 #ifdef TC_TRACE
   const long long k_t0 = clock64();
 #endif
-  if (a.fixup && !a.fin->need_fixup) return;
   if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
   const int net = (int)blockIdx.x < a.tc_actor_ctas ? 0 : 1;
   uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SM::KEYS);
