@@ -1,18 +1,17 @@
-// update.cu — the clipped-surrogate minibatch update (ppo.jl:191-252) as five kernels:
+// update.cu — the minibatch update (ppo.jl:191-252) around the forward/loss/backward kernel:
 //
-//   mb_stats    critic forward over the minibatch -> v_new[M] + per-CTA sums for the three
-//               minibatch-global scalars the reference's loss needs before any gradient exists:
-//               mean/std of the advantages (ppo.jl:221) and s = mean(newvalue .- R.^2) (ppo.jl:232,
-//               quirk Q5), plus min_i (clip_i - R_i)^2 to short-cut the count below.
-//   mb_count    finalises those scalars and counts #{i : s > (clip_i - R_i)^2} (ppo.jl:236).
-//   loss_grad   fused forward (actor+critic) + loss + full backward for tiles of 128 samples;
-//               every 64x64 contraction is a register-tiled FFMA GEMM out of shared memory;
-//               weight gradients stay in registers for the whole kernel.
-//   grad_reduce sums the per-CTA partial gradients in a fixed order (deterministic) into the
-//               double-precision buffer that is also the NCCL allreduce payload.
-//   clip_adam   Flux.Optimiser(ClipNorm(0.5), Adam) per parameter array (ppo.jl:93,250).
-//
-// FP32 FFMA throughout (no TF32): results are within fp32 rounding of the oracle.
+//   adv_stats   advantage sums of every minibatch of an update in one launch (speculative chain).
+//   mb_stats    critic forward over the minibatch -> v_new[M] + per-CTA sums for the three minibatch-global scalars
+//               the reference's loss needs before any gradient exists: mean/std of the advantages (ppo.jl:221) and
+//               s = mean(newvalue .- R.^2) (ppo.jl:232, quirk Q5), plus min_i (clip_i - R_i)^2 (exact chain only).
+//   mb_count    finalises those scalars and counts #{i : s > (clip_i - R_i)^2} (ppo.jl:236) (exact chain only).
+//   loss_grad   the FP32 FFMA variant of the fused forward (actor+critic) + loss + full backward for tiles of 128
+//               samples: every 64x64 contraction is a register-tiled FFMA GEMM out of shared memory. The default
+//               variant is the tcgen05 kernel in update_tc.cu; this one serves the exact replay, the raw entry point,
+//               A2C through crl_update_minibatch and CRL_NO_TC=1.
+//   grad_reduce sums the per-CTA partial gradients in a fixed order (deterministic) into the double-precision vector
+//               that is exchanged between GPUs (pushed into every peer's memory), or reduced with NCCL.
+//   clip_adam   Flux.Optimiser(ClipNorm(0.5), Adam) per parameter array (ppo.jl:93,250) on thread-block clusters.
 #include "kernels.h"
 #include "mlp_tile.cuh"
 #include "update_common.cuh"
