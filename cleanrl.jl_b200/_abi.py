@@ -7,6 +7,7 @@ CRL_ENV_CARTPOLE, CRL_ENV_PENDULUM = 0, 1
 CRL_GAE_REF_COMPAT, CRL_GAE_FIXED, CRL_GAE_A2C_RETURNS = 0, 1, 2
 CRL_FLAG_LOCAL_STATS = 1
 CRL_FLAG_A2C = 2
+CRL_FLAG_NO_VCLIP = 4
 
 (CRL_F_STATE, CRL_F_ACTION, CRL_F_LOGPROB, CRL_F_REWARD, CRL_F_TERMINAL, CRL_F_VALUE,
  CRL_F_ADVANTAGE, CRL_F_RETURN, CRL_F_NEXT_OBS, CRL_F_NEXT_DONE, CRL_F_NEXT_VALUE,

@@ -588,6 +588,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.mode = LG_EXACT; ua.advparts = c->advparts + (size_t)set * ADV_CHUNKS * 2; ua.mpart = c->mpart;
   ua.rank = c->cfg.rank;
   ua.algo = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
+  ua.no_vclip = (c->cfg.flags & CRL_FLAG_NO_VCLIP) ? 1 : 0;
   ua.tc_net_a = c->L.critic - c->L.actor; ua.tc_net_c = (c->L.continuous ? c->L.logstd : c->L.P) - c->L.critic;
   ua.values_fresh = spec ? 1 : 0;       // throughput path: the rollout that filled `value` used the current parameters
   loss_grad_tc_plan(&ua, c->sm_count);  // tensor-core kernel when it applies: sets grid_loss / tc_actor_ctas

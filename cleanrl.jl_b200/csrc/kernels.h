@@ -73,6 +73,7 @@ struct AdvStatsArgs {
 struct UpdateArgs {
   int env_kind;
   int algo;            // 0 = PPO clipped surrogate (ppo.jl:213-243), 1 = A2C losses (a2c.jl:78-97)
+  int no_vclip;        // PPO with clip_value_loss = false: v_loss = 0.5 mean((newvalue - R)^2), ppo.jl:239-241
   const float* params;
   const float* image;  // shared-memory image of the parameters (see param_image_floats) or nullptr
   IdxSrc idx;

@@ -516,15 +516,21 @@ __global__ void __launch_bounds__(CRL_THREADS, 1) loss_grad_kernel(UpdateArgs a)
         float d_vcR, vlc;
         bool inside;
         value_clip(v, s_V, s_R, c, d_vcR, vlc, inside);
-        const bool s_wins = !spec && s_f > vlc;
-        st_vmax += (double)(s_wins ? s_f : vlc);
-        if (spec) {
+        const bool s_wins = !spec && s_f > vlc && !a.no_vclip;
+        double dv_d = cnt_over_M;
+        if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
+        if (a.no_vclip) {
+          // clip_value_loss = false: 0.5 * mean((newvalue - R).^2), ppo.jl:239-241 (no minibatch scalar, nothing to verify)
+          const float d = __fsub_rn(v, s_R);
+          vlc = __fmul_rn(d, d);
+          dv_d = 2.0 * (double)d;
+          if (spec) a.vnew[m0 + s] = v;
+        } else if (spec) {
           st_s += (double)__fsub_rn(v, __fmul_rn(s_R, s_R));  // newvalue .- mb_returns .^ 2, ppo.jl:232
           st_min = fminf(st_min, vlc);
           a.vnew[m0 + s] = v;
         }
-        double dv_d = cnt_over_M;
-        if (!s_wins && inside) dv_d += 2.0 * (double)d_vcR;
+        st_vmax += (double)(s_wins ? s_f : vlc);
         dv = (float)((double)a.v_coef * 0.5 / Mg * dv_d);
         st_ent += ent_sum;
         const double ent_scale = (double)a.ent_coeff / ((double)A * Mg);

@@ -594,6 +594,14 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
           const double advd = (double)cur.R - (double)z[0];
           if (own) st_vmax += advd * advd;
           dl[0] = (float)(-2.0 * advd * inv_Mg);
+        } else if (a.no_vclip) {
+          // clip_value_loss = false: 0.5 * mean((newvalue - R).^2), ppo.jl:239-241 (no minibatch scalar, nothing to verify)
+          const float d = __fsub_rn(z[0], cur.R);
+          if (own) {
+            st_vmax += (double)__fmul_rn(d, d);
+            if (spec) a.vnew[m0 + s] = z[0];
+          }
+          dl[0] = (float)(v_scale * 2.0 * (double)d);
         } else {
           // value loss (Q5): 0.5*mean(max.(s, (clip - R)^2)), s a minibatch scalar
           const float v = z[0];

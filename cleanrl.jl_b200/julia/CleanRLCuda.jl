@@ -22,6 +22,7 @@ const CRL_GAE_FIXED = Int32(1)
 const CRL_GAE_A2C_RETURNS = Int32(2)
 const CRL_FLAG_LOCAL_STATS = UInt32(1)
 const CRL_FLAG_A2C = UInt32(2)
+const CRL_FLAG_NO_VCLIP = UInt32(4)   # PPOConfig.clip_value_loss = false (ppo.jl:16)
 
 # field ids for crl_read_field / crl_write_field
 const F_STATE, F_ACTION, F_LOGPROB, F_REWARD, F_TERMINAL, F_VALUE, F_ADVANTAGE, F_RETURN = Int32.(0:7)
@@ -192,7 +193,7 @@ only to initialise the device parameters.
 """
 function ppo(config; actor, critic, log_episodes::Bool=false)
   nt = config.num_envs                                            # ppo.jl:76
-  h = Handle(make_config(config))
+  h = Handle(make_config(config; flags=config.clip_value_loss ? UInt32(0) : CRL_FLAG_NO_VCLIP))
   p = flat_params(actor, critic)                                  # ppo.jl:85-87,196
   set_params!(h, p)
   batch_size = config.num_steps * nt                              # ppo.jl:89

@@ -31,15 +31,13 @@ def make_crl_config(config, num_envs_local=None, device=0, world_size=1, rank=0,
         # ppo.jl:219-222: the `if` has no else branch, mb_advantages becomes `nothing` and the
         # next line throws. Keep the error behaviour.
         raise ValueError("normalize_advantages=false is not supported by the reference (ppo.jl:219-222 throws)")
-    if not config.clip_value_loss:
-        raise NotImplementedError("clip_value_loss=false (ppo.jl:239) is not built yet")
     kind = ENV_KINDS[config.env_id]
     max_steps = config.max_steps or (500 if kind == _abi.CRL_ENV_CARTPOLE else 200)
     return _abi.make_config(
         env_kind=kind, num_envs=num_envs_local if num_envs_local is not None else config.num_envs,
         num_steps=config.num_steps, num_minibatches=config.num_minibatches, update_epochs=config.update_epochs,
         max_episode_steps=max_steps, gae_mode=GAE_MODES[config.gae_mode], device=device, world_size=world_size,
-        rank=rank, env_id_base=env_id_base, flags=_abi.CRL_FLAG_LOCAL_STATS if config.local_stats else 0,
+        rank=rank, env_id_base=env_id_base, flags=(_abi.CRL_FLAG_LOCAL_STATS if config.local_stats else 0) | (0 if config.clip_value_loss else _abi.CRL_FLAG_NO_VCLIP),
         gamma=config.gamma, gae_lambda=config.gae_lambda, clip_coef=config.clip_coef, ent_coeff=config.ent_coeff,
         v_coef=config.v_coef, clip_norm=config.clip_norm, seed=config.seed)
 

@@ -69,6 +69,7 @@ extern "C" {
 #define CRL_FLAG_LOCAL_STATS 1u /* multi-GPU: per-shard minibatch statistics (no pre-backward exchange) */
 #define CRL_FLAG_A2C 2u         /* A2C losses (a2c.jl:78-97) instead of the PPO clipped surrogate: critic mean((ret-v)^2),
                                    actor -mean(logp * (ret - v)); use with CRL_GAE_A2C_RETURNS, 1 epoch x 1 minibatch */
+#define CRL_FLAG_NO_VCLIP 4u    /* PPOConfig.clip_value_loss = false (ppo.jl:16,239-241): v_loss = 0.5 mean((newvalue - R)^2) */
 
 /* buffer fields for crl_read_field / crl_write_field */
 #define CRL_F_STATE 0       /* float  [T][N][D]                                    */

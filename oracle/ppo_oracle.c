@@ -703,6 +703,11 @@ typedef struct {
   int P;
 } loss_args;
 
+/* clip_value_loss = false (ppo.jl:239-241, CRL_FLAG_NO_VCLIP): set around a loss evaluation; not thread-safe across
+ * contexts, which the tests do not need */
+static int g_no_vclip = 0;
+void orc_set_no_vclip(int on) { g_no_vclip = on ? 1 : 0; }
+
 /* per-thread slot layout after the P gradient doubles */
 #define SL_SUM_ADV 0
 #define SL_SUM_ADV2 1
@@ -790,9 +795,14 @@ static void loss_range(int64_t lo, int64_t hi, int tid, void* argp) {
       float vc = V + cl;
       float vlc = (vc - R) * (vc - R);
       float vmax = a->s_unclipped > vlc ? a->s_unclipped : vlc;
-      sl[SL_VMAX] += (double)vmax;
       double dv_d = a->inv_cnt_term; /* (1/M) * cnt: every v_new_j feeds s */
       if (!(a->s_unclipped > vlc) && dvv >= -c && dvv <= c) dv_d += 2.0 * (double)(vc - R);
+      if (g_no_vclip) {              /* clip_value_loss = false: 0.5 * mean((newvalue - R).^2), ppo.jl:239-241 */
+        float d = v - R;
+        vmax = d * d;
+        dv_d = 2.0 * (double)d;
+      }
+      sl[SL_VMAX] += (double)vmax;
       float dv = (float)((double)a->v_coef * 0.5 / a->Mg * dv_d);
       sl[SL_ENT] += ent_sum;
       /* back through the heads */
@@ -1013,9 +1023,12 @@ int orc_update_minibatch(orc_ctx* c, const int32_t* idx, int32_t M, double lr, c
   int rc;
   if (c->cfg.flags & CRL_FLAG_A2C)
     rc = orc_a2c_loss_raw(c->cfg.env_kind, c->params, idx, M, c->state, c->action, c->ret, c->grads, st);
-  else
+  else {
+    g_no_vclip = (c->cfg.flags & CRL_FLAG_NO_VCLIP) ? 1 : 0;
     rc = orc_ppo_loss_raw(c->cfg.env_kind, c->params, idx, M, c->state, c->action, c->logprob, c->advantage,
                           c->ret, c->value, c->cfg.clip_coef, c->cfg.ent_coeff, c->cfg.v_coef, c->grads, st, c->vnew);
+    g_no_vclip = 0;
+  }
   if (rc) return rc;
   if (stats) { stats->loss = st[0]; stats->pg_loss = st[1]; stats->v_loss = st[2]; stats->entropy_loss = st[3]; }
   return orc_clip_adam_raw(c->cfg.env_kind, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, lr, c->cfg.clip_norm);

@@ -468,3 +468,27 @@ def test_call_order_and_argument_errors(crl, olib, abi, torch_cuda):
     with pytest.raises(CleanRLCudaError) as e:
         PPOHandle(cfg)
     assert e.value.code == abi.CRL_ERR_CUDA
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_unclipped_value_loss_update_matches_oracle(crl, olib, abi, torch_cuda, kind):
+    """PPOConfig.clip_value_loss = false (ppo.jl:239-241): stage-by-stage update and the graph path against the oracle"""
+    h, o = make_pair(crl, olib, abi, kind, N=64, T=16, mb=4, epochs=2, seed=6, flags=abi.CRL_FLAG_NO_VCLIP)
+    for x in (h, o):
+        x.env_reset()
+    for u in range(2):
+        sh = h.train_update(2.5e-4) or h.fetch_update()[0]
+        so = o.train_update(2.5e-4)
+        np.testing.assert_allclose(sh, so, rtol=1e-4, atol=2e-6, err_msg="update %d" % u)
+        np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=1e-5, atol=1e-6)
+    assert h.spec_replays() == 0
+    # and the exact chain (crl_update_epochs) from identical buffers
+    for x in (h, o):
+        x.rollout(); x.gae()
+    for name in BUF_FIELDS + ["ADVANTAGE", "RETURN"]:
+        f = getattr(abi, "CRL_F_" + name)
+        o.write_field(f, h.read_field(f))
+    sh, so = h.update_epochs(None, 1e-4), o.update_epochs(None, 1e-4)
+    np.testing.assert_allclose(sh, so, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=1e-5, atol=1e-6)
+    h.close()

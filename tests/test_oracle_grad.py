@@ -30,7 +30,7 @@ class TanhFast(torch.autograd.Function):
         return g * (1 - y * y)
 
 
-def torch_loss(params, layout, dims, idx, states, actions, logprobs, adv, ret, val, c, ent_c, v_c, continuous):
+def torch_loss(params, layout, dims, idx, states, actions, logprobs, adv, ret, val, c, ent_c, v_c, continuous, clip_vloss=True):
     off, size = layout
     D, A = dims["D"], dims["A"]
     t = lambda a: torch.tensor(np.asarray(a, np.float64))
@@ -69,6 +69,8 @@ def torch_loss(params, layout, dims, idx, states, actions, logprobs, adv, ret, v
     s = (newvalue - mb_ret ** 2).mean()  # ppo.jl:232 (Q5: a scalar)
     v_clipped = mb_val + torch.clamp(newvalue - mb_val, -c, c)
     v_loss = 0.5 * torch.maximum(s, (v_clipped - mb_ret) ** 2).mean()  # ppo.jl:234-237
+    if not clip_vloss:
+        v_loss = 0.5 * ((newvalue - mb_ret) ** 2).mean()  # ppo.jl:239-241
     entropy_loss = entropy.mean()  # ppo.jl:242
     loss = pg_loss - ent_c * entropy_loss + v_c * v_loss  # ppo.jl:243
     return loss, pg_loss, v_loss, entropy_loss
@@ -139,3 +141,29 @@ def test_loss_rejects_tiny_minibatch(olib):
     with pytest.raises(AssertionError):
         olib.ppo_loss_raw(0, rand_params(olib, 0), np.array([0], np.int32), states, actions, logprobs, adv, ret, val,
                           0.2, 0.01, 0.5)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_oracle_unclipped_value_loss_matches_float64_autograd(olib, kind):
+    """PPOConfig.clip_value_loss = false (ppo.jl:16,239-241; CRL_FLAG_NO_VCLIP)"""
+    d = olib.dims(kind)
+    layout = olib.param_layout(kind)
+    B, M = 300, 96
+    p = rand_params(olib, kind, seed=5 + kind)
+    if kind == 1:
+        p[-1] = -0.3
+    states, actions, logprobs, adv, ret, val = make_batch(olib, kind, B, 13)
+    idx = np.random.default_rng(4).permutation(B)[:M].astype(np.int32)
+    c, ent_c, v_c = float(F(0.2)), float(F(0.01)), float(F(0.5))
+    olib.lib.orc_set_no_vclip(1)
+    try:
+        g, stats, vnew = olib.ppo_loss_raw(kind, p, idx, states, actions, logprobs, adv, ret, val, c, ent_c, v_c)
+    finally:
+        olib.lib.orc_set_no_vclip(0)
+    pt = torch.tensor(p.astype(np.float64), requires_grad=True)
+    loss, pg, vl, en = torch_loss(pt, layout, d, idx, states, actions, logprobs, adv, ret, val, c, ent_c, v_c, kind == 1,
+                                  clip_vloss=False)
+    loss.backward()
+    gt = pt.grad.numpy()
+    np.testing.assert_allclose(stats, [loss.item(), pg.item(), vl.item(), en.item()], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(g, gt, rtol=2e-3, atol=2e-5 * np.abs(gt).max())
