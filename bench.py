@@ -416,6 +416,20 @@ def run_ours(args):
                     "peak_source": "derived FP32 FFMA peak: 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json has no "
                                    "fp32 figure); FFMA kernel (A2C, CRL_NO_TC=1, exact replay)"}
 
+    # ---- rollout kernel: FP32 FFMA work (policy + value forward) and the buffer traffic it writes
+    ro = kernels.get("rollout")
+    roofline_rollout = None
+    if ro and ro["ms_per_update"] > 0 and args.algo == "ppo":
+        ro_s = ro["ms_per_update"] * 1e-3
+        ro_tf = FWD_FLOP * B_local / ro_s / 1e12
+        bytes_per_step = 33 if args.env == "CartPole" else 29
+        roofline_rollout = {"kernel": "rollout_kernel", "bound": "fp32", "achieved": ro_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": ro_tf / fp32_peak, "avg_launch_ms": ro["ms_per_update"],
+                            "algorithmic": "%d FLOP per env-step x %d env-steps per launch" % (FWD_FLOP, B_local),
+                            "buffer_write_gbs": bytes_per_step * B_local / ro_s / 1e9,
+                            "note": "a %d-step serial chain over %d envs per GPU: latency-bound (one CTA of 32 envs per SM), "
+                                    "neither the FFMA pipe nor HBM is the limit at this batch size" % (NUM_STEPS, args.envs_per_gpu)}
+
     # ---- GAE HBM roofline (the metric's second half) on rank 0
     roofline_gae = None
     if rank == 0:
@@ -478,7 +492,7 @@ def run_ours(args):
                                                                    "(L2-resident in production too); the GAE roofline uses a 2.29 GB input",
                                                                 arithmetic="fp32 results; the 64-wide contractions of the update run as 3xTF32 on "
                                                                            "tcgen05 (fp32-accurate to ~1e-6), everything else fp32/fp64 on the CUDA cores"),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gae": roofline_gae,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gae": roofline_gae, "roofline_rollout": roofline_rollout,
             "cpu_baseline": cpu_baseline, "kernels": kernels,
             "last_loss": float(stats[-1, 0]), "episodes_last_update": int(agg.count),
         }
