@@ -256,18 +256,28 @@ def run_dqn(args):
     from cleanrl_jl_b200 import _abi
     from cleanrl_jl_b200.dqn_algo import DQNConfig, DQNHandle, dqn, init_q_params
     from cleanrl_jl_b200 import logger as Logger
+    from cleanrl_jl_b200 import parallel
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback")
+    # N > 1: independent replicas, one per GPU (the DQN path has no exchange step)
+    rank, local_rank, world = parallel.dist_info()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
     N, ITERS = 4096, 100
     cfg = _abi.make_dqn_config(num_envs=N, buffer_size=1 << 20, min_buff_size=10_000, batch_size=120, train_freq=10,
-                               target_net_freq=100, epsilon_duration=5e6, seed=1)
+                               target_net_freq=100, epsilon_duration=5e6, seed=1 + rank, device=local_rank)
     h = DQNHandle(cfg)
     h.set_params(init_q_params(1))
     h.reset()
     for _ in range(max(args.warmup, 3)):
         h.run(ITERS)
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     sampler.start()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps - 1):
         h.lib.crl_dqn_run(h.h, ITERS, None)      # asynchronous: launches only
@@ -275,14 +285,20 @@ def run_dqn(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     h.close()
-    value = args.steps * ITERS * N / wall
+    wall = parallel.max_over_ranks(wall * 1e3) * 1e-3
+    value = args.steps * ITERS * N * world / wall
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
     lg = Logger.make_logger("bench_dqn", to_terminal=False, to_tensorboard=False, to_json=True, log_dir=tmp)
     res = dqn(DQNConfig(num_envs=N, total_timesteps=N * ITERS * 20, buffer_size=1 << 20, min_buff_size=10_000,
                         epsilon_duration=5e6, log_frequencey=N * ITERS), logger=lg)
     lg.close()
     print(json.dumps({
-        "metric": "dqn_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "metric": "dqn_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DQN CartPole, %d vectorized envs, 1,048,576-transition HBM replay, batch 120, learn every 10 "
@@ -292,7 +308,11 @@ def run_dqn(args):
         "e2e": {"value": res["steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 56,
                 "note": "dqn(config) public API with logging every %d iterations" % ITERS},
         "gpu_launches": args.steps * (ITERS + ITERS // 10), "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
+        "replicas": "independent replicas, one per GPU, no collective" if world > 1 else None,
     }), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_ours(args):
