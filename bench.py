@@ -9,6 +9,9 @@ update_epochs x num_minibatches clipped-surrogate minibatch updates (ppo.jl:117-
 Workload at N=1 = BASELINE.json configs[1]: CartPole, 4096 envs x 128 steps, 64-64 MLPs, the
 reference's default 4 epochs x 4 minibatches. Weak scaling: every GPU owns 4096 envs.
 Prints ONE JSON line on rank 0.
+
+Secondary lines (not the headline): --algo a2c (BASELINE configs[2], one GPU), --algo dqn (configs[4]: vectorised DQN
+with a 1M-transition replay buffer; N > 1 = independent replicas), --env Pendulum --envs-per-gpu 8192 (configs[3]).
 """
 import argparse
 import json
