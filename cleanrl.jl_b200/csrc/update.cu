@@ -924,6 +924,9 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   const int i = blockIdx.x / ADAM_CL;         // parameter array
   unsigned int crank;                          // rank of this CTA inside its cluster
   asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // Distributed shared memory of a peer CTA may only be written once that CTA is known to be running: arrive on the
+  // cluster barrier now, wait for it just before the remote stores (compute-sanitizer racecheck flags it otherwise).
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   const int o = L.off[i], n = L.size[i];
   int slot = 0;
   if (a.p2p_local) {
@@ -954,6 +957,7 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   }
   ss = block_sum<8>(ss, red);
   const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];  // read BEFORE the cluster barrier (rank 0 rewrites them after)
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started
   if (threadIdx.x < ADAM_CL) {
     // distributed shared memory: part[crank] of CTA `threadIdx.x` of this cluster
     unsigned int local = (unsigned int)__cvta_generic_to_shared(&part[crank]), remote;
