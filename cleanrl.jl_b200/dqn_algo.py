@@ -29,7 +29,7 @@ class DQNConfig:
     gamma: float = 0.99                 # dqn.jl:15
     epsilon_start: float = 1.0          # dqn.jl:17
     epsilon_end: float = 0.05           # dqn.jl:18
-    epsilon_duration: float = 10_000    # dqn.jl:19
+    epsilon_duration: float = 10_000.0  # dqn.jl:19 (Float64)
     # ---- not in the reference
     num_envs: int = 1                   # vectorised envs (the reference: one env, dqn.jl:38)
     seed: int = 1

@@ -113,6 +113,17 @@ def test_dqn_config_has_the_reference_fields():
         assert getattr(c, k) == v, k
 
 
+def test_dqn_config_through_the_cli_parser(monkeypatch):
+    """ConfigParser.argparse_struct (config_parser.jl:18-40) works on DQNConfig like on PPOConfig"""
+    import sys
+    from cleanrl_jl_b200 import DQNConfig, argparse_struct
+    monkeypatch.setattr(sys, "argv", ["dqn", "--num_envs", "64", "--lr", "0.001", "--epsilon_duration", "5000.5",
+                                      "--batch_size", "64"])
+    c = argparse_struct(DQNConfig())
+    assert (c.num_envs, c.lr, c.epsilon_duration, c.batch_size) == (64, 0.001, 5000.5, 64)
+    assert c.buffer_size == 10_000 and c.train_freq == 10      # untouched fields keep the reference defaults
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,iters", [(1, 400), (8, 120), (64, 60)])
