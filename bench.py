@@ -277,6 +277,7 @@ def run_dqn(args):
     h.reset()
     for _ in range(max(args.warmup, 3)):
         h.run(ITERS)
+    launches0 = int(h.run(0).kernel_launches)
     sampler = ClockSampler(local_rank)
     sampler.start()
     if dist is not None:
@@ -310,7 +311,7 @@ def run_dqn(args):
         "clocks": clocks,
         "e2e": {"value": res["steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 56,
                 "note": "dqn(config) public API with logging every %d iterations" % ITERS},
-        "gpu_launches": args.steps * (ITERS + ITERS // 10), "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
+        "gpu_launches": int(st.kernel_launches) - launches0, "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
         "replicas": "independent replicas, one per GPU, no collective" if world > 1 else None,
     }), flush=True)
     if dist is not None:

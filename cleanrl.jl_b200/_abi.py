@@ -79,7 +79,7 @@ class crl_dqn_config(C.Structure):
 
 class crl_dqn_stats(C.Structure):
     _fields_ = [("last_loss", C.c_double), ("sum_return", C.c_double), ("sum_length", C.c_double), ("epsilon", C.c_double),
-                ("episodes", C.c_int64), ("learn_steps", C.c_int64), ("iterations", C.c_int64)]
+                ("episodes", C.c_int64), ("learn_steps", C.c_int64), ("iterations", C.c_int64), ("kernel_launches", C.c_int64)]
 
 
 def make_dqn_config(num_envs=1, buffer_size=10_000, min_buff_size=200, batch_size=120, train_freq=10, target_net_freq=100,

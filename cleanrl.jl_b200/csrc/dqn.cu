@@ -3,15 +3,19 @@
 // ring replay buffer, and one learning step (sample without replacement -> TD target from the target net -> MSE on
 // the taken action -> backward -> Adam -> optional target copy) every train_freq iterations.
 //
-//   dqn_act_kernel    32 envs per CTA of 256 threads: lane = env, warp = neuron group (neurons group, group + 8, ...).
-//                     The 10,934 parameters sit in shared memory; activations are [neuron][env lane] tiles in shared
-//                     memory (conflict-free, weight reads are warp broadcasts). Warp 0 then draws epsilon / the random
-//                     action from Philox, steps CartPole, appends the transition at (ptr + env) % capacity and resets a
-//                     finished env on the spot.
+//   dqn_act_kernel    32 envs per CTA of 256 threads: lane = env, warp = neuron group. The 10,934 parameters sit in
+//                     shared memory; activations are [neuron][env lane] tiles in shared memory (conflict-free; the
+//                     weights of four consecutive neurons are one broadcast 128-bit load). Warp 0 then draws epsilon /
+//                     the random action from Philox, steps CartPole, appends the transition at
+//                     (ptr + step * N + env) % capacity and resets a finished env on the spot. The parameters only
+//                     change at a learning step, so ONE launch runs every iteration up to the next learning step
+//                     (train_freq of them, at most ACT_MAX_STEPS) with the env state in registers.
 //   dqn_learn_kernel  ONE CTA of 512 threads for the batch (<= 128 samples x 4 neuron groups): both parameter sets
-//                     and the batch activations live in shared memory (~197 KB); forward target net and q net,
-//                     gradient reductions over the batch by one thread per weight in ascending sample order
-//                     (deterministic, same order as the oracle), Adam and the target copy in the same launch.
+//                     and the batch activations live in shared memory (~197 KB, activation rows padded to 129 floats
+//                     so that the batch reductions, whose lanes walk down the neuron axis, are conflict-free);
+//                     forward target net and q net, gradient reductions over the batch as 4x4 register tiles, every
+//                     sum in ascending sample order (deterministic, same order as the oracle), Adam and the target
+//                     copy in the same launch.
 // Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?") is taken on
 // the host, so a run is a plain sequence of launches on one stream without any device-to-host read.
 #include <math.h>
@@ -32,7 +36,9 @@ constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
 constexpr int ACT_E = 32;     // envs per CTA in dqn_act_kernel (one warp-width of samples)
 constexpr int ACT_G = 8;      // neuron groups: thread (lane = env, warp = group) computes neurons group, group + 8, ...
 constexpr int ACT_T = ACT_E * ACT_G;
+constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bounded by the next learning step)
 constexpr int LEARN_B = 128;  // max batch size = samples per tile in dqn_learn_kernel
+constexpr int LEARN_SP = LEARN_B + 1;   // activation row stride in dqn_learn_kernel: odd, so rows fall on distinct banks
 constexpr int LEARN_G = 4;    // neuron groups
 constexpr int LEARN_T = LEARN_B * LEARN_G;
 
@@ -48,16 +54,20 @@ struct ActArgs {
   float* env_state; int* env_t; double* ep_ret; int* ep_len; uint32_t* resets;
   float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
   DqnDev* dev;
-  unsigned long long seed, it;
-  double eps;
+  unsigned long long seed, it0;   // it0 = iteration number (1-based) of step 0 of this launch
+  double eps[ACT_MAX_STEPS];      // epsilon of each step (dqn.jl:52, evaluated on the host)
+  int n_steps;
   int N, C, ptr, max_steps;
 };
 
-// Dense -> relu -> Dense -> relu -> Dense for a tile of S samples, neurons strided over G thread groups (CTA-wide
-// barriers between the layers: every thread of the CTA must call this). Activations are [neuron][S] tiles in shared
-// memory (conflict-free across the lanes of a warp; weight reads are warp broadcasts); each neuron is one fmaf chain
-// over ascending k, so the result does not depend on S or G. qo = [DQ_A][S].
-template <int S, int G>
+// Dense -> relu -> Dense -> relu -> Dense for a tile of samples, neurons spread over G thread groups (CTA-wide
+// barriers between the layers: every thread of the CTA must call this). Activations are [neuron][SP] tiles in shared
+// memory (row stride SP floats; conflict-free across the lanes of a warp, which are consecutive samples); weight reads
+// are warp broadcasts, and in the 120 -> 84 layer a thread owns four consecutive neurons so that their weights are
+// one 128-bit load per k (p must be 16-byte aligned). Each neuron is one fmaf chain over ascending k, so the result
+// does not depend on the tile shape or on G. qo = [DQ_A][SP].
+static_assert(DQ_H2 % 4 == 0 && DQ_W2 % 4 == 0, "128-bit weight loads of the second layer");
+template <int SP, int G>
 __device__ __forceinline__ void q_forward(const float* __restrict__ p, const float x[DQ_D], float* h1, float* h2, float* qo,
                                           int l, int g) {
   for (int j = g; j < DQ_H1; j += G) {
@@ -65,22 +75,31 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 #pragma unroll
     for (int k = 0; k < DQ_D; k++) acc = fmaf(p[DQ_W1 + j + DQ_H1 * k], x[k], acc);
     acc += p[DQ_B1 + j];
-    h1[j * S + l] = fmaxf(acc, 0.0f);
+    h1[j * SP + l] = fmaxf(acc, 0.0f);
   }
   __syncthreads();
-  for (int j = g; j < DQ_H2; j += G) {
-    float acc = 0.0f;
+  for (int j = 4 * g; j < DQ_H2; j += 4 * G) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 8
-    for (int k = 0; k < DQ_H1; k++) acc = fmaf(p[DQ_W2 + j + DQ_H2 * k], h1[k * S + l], acc);
-    acc += p[DQ_B2 + j];
-    h2[j * S + l] = fmaxf(acc, 0.0f);
+    for (int k = 0; k < DQ_H1; k++) {
+      const float4 w = *reinterpret_cast<const float4*>(p + DQ_W2 + j + DQ_H2 * k);
+      const float h = h1[k * SP + l];
+      a0 = fmaf(w.x, h, a0);
+      a1 = fmaf(w.y, h, a1);
+      a2 = fmaf(w.z, h, a2);
+      a3 = fmaf(w.w, h, a3);
+    }
+    h2[(j + 0) * SP + l] = fmaxf(a0 + p[DQ_B2 + j + 0], 0.0f);
+    h2[(j + 1) * SP + l] = fmaxf(a1 + p[DQ_B2 + j + 1], 0.0f);
+    h2[(j + 2) * SP + l] = fmaxf(a2 + p[DQ_B2 + j + 2], 0.0f);
+    h2[(j + 3) * SP + l] = fmaxf(a3 + p[DQ_B2 + j + 3], 0.0f);
   }
   __syncthreads();
   for (int o = g; o < DQ_A; o += G) {
     float acc = 0.0f;
 #pragma unroll 4
-    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * S + l], acc);
-    qo[o * S + l] = acc + p[DQ_B3 + o];
+    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * SP + l], acc);
+    qo[o * SP + l] = acc + p[DQ_B3 + o];
   }
   __syncthreads();
 }
@@ -91,54 +110,76 @@ __global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
   float* h1 = p + ((DQ_P + 3) & ~3);     // [120][32]
   float* h2 = h1 + DQ_H1 * ACT_E;        // [84][32]
   float* qo = h2 + DQ_H2 * ACT_E;        // [2][32]
+  float* xs = qo + DQ_A * ACT_E;         // [4][32] current observation of the CTA's envs
   for (int i = threadIdx.x; i < DQ_P; i += ACT_T) p[i] = a.q[i];
   const int e = threadIdx.x & (ACT_E - 1), g = threadIdx.x / ACT_E;
   const int n = blockIdx.x * ACT_E + e;
-  const bool valid = n < a.N;
+  const bool owner = g == 0, valid = n < a.N;   // warp 0: one lane per env, state in registers for the whole launch
   float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  if (valid) {
+  int t = 0, len = 0;
+  double ret = 0.0;
+  uint32_t rc = 0;
+  if (owner) {
+    if (valid) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+      for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+      t = a.env_t[n];
+      ret = a.ep_ret[n];
+      len = a.ep_len[n];
+      rc = a.resets[n];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) xs[k * ACT_E + e] = st[k];
   }
   __syncthreads();
-  q_forward<ACT_E, ACT_G>(p, st, h1, h2, qo, e, g);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
-  if (g != 0 || !valid) return;
-  const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
-  uint32_t r[4];
-  philox_draw(a.seed, (uint32_t)n, a.it, STREAM_DQN_ACT, r);
-  const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
-  int action;
-  if (u < a.eps) action = (int)(r[2] & 1u);                     // rand(action_space(env)), dqn.jl:54
-  else action = qo[1 * ACT_E + e] > qo[0 * ACT_E + e] ? 1 : 0;  // argmax: first maximum, dqn.jl:56-57
-  int t = a.env_t[n];
-  float rew;
-  bool done;
-  cartpole_step(st, t, action, a.max_steps, rew, done);
-  const int slot = (a.ptr + n) % a.C;    // add!, replay_buffer.jl:23-37, envs in order
-  reinterpret_cast<float4*>(a.b_state)[slot] = obs;
-  reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
-  a.b_action[slot] = action;
-  a.b_reward[slot] = rew;
-  a.b_term[slot] = done ? 1 : 0;
-  double ret = a.ep_ret[n] + (double)rew;
-  int len = a.ep_len[n] + 1;
-  if (done) {                            // dqn.jl:80-86
-    atomicAdd(&a.dev->episodes, 1ull);
-    atomicAdd(&a.dev->sum_return, ret);
-    atomicAdd(&a.dev->sum_length, (double)len);
-    ret = 0.0;
-    len = 0;
-    float u4[4];
-    uint32_t rc = a.resets[n];
-    rng_reset_uniforms(a.seed, (uint32_t)n, rc, u4);
-    a.resets[n] = rc + 1;
-    cartpole_reset(st, t, u4);
-  }
-  a.ep_ret[n] = ret;
-  a.ep_len[n] = len;
-  a.env_t[n] = t;
+  for (int s = 0; s < a.n_steps; s++) {
+    float x[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) a.env_state[4 * n + k] = st[k];
+    for (int k = 0; k < 4; k++) x[k] = xs[k * ACT_E + e];
+    q_forward<ACT_E, ACT_G>(p, x, h1, h2, qo, e, g);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
+    if (owner && valid) {
+      const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
+      uint32_t r[4];
+      philox_draw(a.seed, (uint32_t)n, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
+      const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+      int action;
+      if (u < a.eps[s]) action = (int)(r[2] & 1u);                  // rand(action_space(env)), dqn.jl:54
+      else action = qo[1 * ACT_E + e] > qo[0 * ACT_E + e] ? 1 : 0;  // argmax: first maximum, dqn.jl:56-57
+      float rew;
+      bool done;
+      cartpole_step(st, t, action, a.max_steps, rew, done);
+      const int slot = (int)(((long long)a.ptr + (long long)s * a.N + n) % a.C);   // add!, replay_buffer.jl:23-37, envs in order
+      reinterpret_cast<float4*>(a.b_state)[slot] = obs;
+      reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
+      a.b_action[slot] = action;
+      a.b_reward[slot] = rew;
+      a.b_term[slot] = done ? 1 : 0;
+      ret += (double)rew;
+      len += 1;
+      if (done) {                          // dqn.jl:80-86
+        atomicAdd(&a.dev->episodes, 1ull);
+        atomicAdd(&a.dev->sum_return, ret);
+        atomicAdd(&a.dev->sum_length, (double)len);
+        ret = 0.0;
+        len = 0;
+        float u4[4];
+        rng_reset_uniforms(a.seed, (uint32_t)n, rc, u4);
+        rc += 1;
+        cartpole_reset(st, t, u4);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) xs[k * ACT_E + e] = st[k];
+    }
+    __syncthreads();
+  }
+  if (owner && valid) {
+    a.ep_ret[n] = ret;
+    a.ep_len[n] = len;
+    a.env_t[n] = t;
+    a.resets[n] = rc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.env_state[4 * n + k] = st[k];
+  }
 }
 
 struct LearnArgs {
@@ -152,14 +193,14 @@ struct LearnArgs {
 
 __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int PP = (DQ_P + 3) & ~3, S = LEARN_B;
+  constexpr int PP = (DQ_P + 3) & ~3, S = LEARN_B, SP = LEARN_SP;
   float* pq = smem;                       // q_net parameters
   float* pt = pq + PP;                    // target_net parameters
-  float* h1 = pt + PP;                    // [120][128]  (later dz1 in place)
-  float* h2 = h1 + DQ_H1 * S;             // [84][128]   (later dz2 in place)
-  float* xs = h2 + DQ_H2 * S;             // [4][128] states of the batch
-  float* dq = xs + DQ_D * S;              // [2][128]
-  float* qo = dq + DQ_A * S;              // [2][128] network outputs
+  float* h1 = pt + PP;                    // [120][SP]  (later dz1 in place)
+  float* h2 = h1 + DQ_H1 * SP;            // [84][SP]   (later dz2 in place)
+  float* xs = h2 + DQ_H2 * SP;            // [4][SP] states of the batch
+  float* dq = xs + DQ_D * SP;             // [2][SP]
+  float* qo = dq + DQ_A * SP;             // [2][SP] network outputs
   __shared__ uint32_t keys[8];
   __shared__ double red[S / 32];
   const int tid = threadIdx.x, B = a.B;
@@ -184,83 +225,116 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
     rew = a.b_reward[idx];
     term = a.b_term[idx];
   }
-  q_forward<S, LEARN_G>(pt, nx, h1, h2, qo, i, g);                   // target_net(next_state), dqn.jl:99
-  const float next_q = fmaxf(qo[0 * S + i], qo[1 * S + i]);
+  q_forward<SP, LEARN_G>(pt, nx, h1, h2, qo, i, g);                  // target_net(next_state), dqn.jl:99
+  const float next_q = fmaxf(qo[0 * SP + i], qo[1 * SP + i]);
   const double td = (double)rew + a.gamma * (double)next_q * (1.0 - (double)term);   // dqn.jl:100
   __syncthreads();
-  q_forward<S, LEARN_G>(pq, s, h1, h2, qo, i, g);                    // q_net(state), dqn.jl:105
+  q_forward<SP, LEARN_G>(pq, s, h1, h2, qo, i, g);                   // q_net(state), dqn.jl:105
   double sq = 0.0;
   if (g == 0) {
-    dq[0 * S + i] = 0.0f;
-    dq[1 * S + i] = 0.0f;
+    dq[0 * SP + i] = 0.0f;
+    dq[1 * SP + i] = 0.0f;
 #pragma unroll
-    for (int k = 0; k < DQ_D; k++) xs[k * S + i] = s[k];
+    for (int k = 0; k < DQ_D; k++) xs[k * SP + i] = s[k];
     if (i < B) {
-      const double diff = td - (double)qo[act * S + i];
+      const double diff = td - (double)qo[act * SP + i];
       sq = diff * diff;                                              // Flux.mse, dqn.jl:107
-      dq[act * S + i] = (float)(-2.0 * diff / (double)B);
+      dq[act * SP + i] = (float)(-2.0 * diff / (double)B);
     }
     sq = warp_sum(sq);
     if ((tid & 31) == 0) red[tid >> 5] = sq;
   }
   __syncthreads();
   if (tid == 0) a.dev->last_loss = ((red[0] + red[1]) + (red[2] + red[3])) / (double)B;
-  // ---- backward; every reduction over the batch runs in ascending sample order in one thread
+  // ---- backward; every reduction over the batch runs in ascending sample order in one thread. The lanes of a warp
+  //      walk down the NEURON axis of the [neuron][SP] tiles here: SP is odd, so they hit distinct banks.
   float* gr = a.g;
   for (int w = tid; w < DQ_A * DQ_H2 + DQ_A; w += LEARN_T) {         // dW3(o,k), db3(o)
     if (w < DQ_A * DQ_H2) {
       const int o = w % DQ_A, k = w / DQ_A;
       float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc = fmaf(dq[o * S + b], h2[k * S + b], acc);
+      for (int b = 0; b < B; b++) acc = fmaf(dq[o * SP + b], h2[k * SP + b], acc);
       gr[DQ_W3 + w] = acc;
     } else {
       const int o = w - DQ_A * DQ_H2;
       float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += dq[o * S + b];
+      for (int b = 0; b < B; b++) acc += dq[o * SP + b];
       gr[DQ_B3 + o] = acc;
     }
   }
   __syncthreads();
   {                                                                  // dz2 = (W3^T dq) .* (h2 > 0), in place
-    const float d0 = dq[0 * S + i], d1 = dq[1 * S + i];
+    const float d0 = dq[0 * SP + i], d1 = dq[1 * SP + i];
     for (int k = g; k < DQ_H2; k += LEARN_G) {
       const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
-      h2[k * S + i] = h2[k * S + i] > 0.0f ? dh : 0.0f;
+      h2[k * SP + i] = h2[k * SP + i] > 0.0f ? dh : 0.0f;
     }
   }
   __syncthreads();
-  for (int w = tid; w < DQ_H2 * DQ_H1 + DQ_H2; w += LEARN_T) {       // dW2(j,k), db2(j)
-    if (w < DQ_H2 * DQ_H1) {
-      const int j = w % DQ_H2, k = w / DQ_H2;
+  {                                                                  // dW2(j,k) as 4x4 register tiles, db2(j)
+    constexpr int JQ = DQ_H2 / 4, KQ = DQ_H1 / 4;                    // tile = neurons j, j+21, j+42, j+63 x inputs k0..k0+3
+    static_assert(DQ_H2 % 4 == 0 && DQ_H1 % 4 == 0, "4x4 weight-gradient tiles");
+    for (int w = tid; w < JQ * KQ; w += LEARN_T) {
+      const int j = w % JQ, k0 = (w / JQ) * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[t][u] = 0.0f;
+#pragma unroll 2
+      for (int b = 0; b < B; b++) {
+        float z[4], hh[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) z[t] = h2[(j + JQ * t) * SP + b];
+#pragma unroll
+        for (int u = 0; u < 4; u++) hh[u] = h1[(k0 + u) * SP + b];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[t][u] = fmaf(z[t], hh[u], acc[t][u]);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) gr[DQ_W2 + (j + JQ * t) + DQ_H2 * (k0 + u)] = acc[t][u];
+    }
+    for (int j = tid; j < DQ_H2; j += LEARN_T) {
       float acc = 0.0f;
-#pragma unroll 4
-      for (int b = 0; b < B; b++) acc = fmaf(h2[j * S + b], h1[k * S + b], acc);
-      gr[DQ_W2 + w] = acc;
-    } else {
-      const int j = w - DQ_H2 * DQ_H1;
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += h2[j * S + b];
+      for (int b = 0; b < B; b++) acc += h2[j * SP + b];
       gr[DQ_B2 + j] = acc;
     }
   }
   __syncthreads();
-  for (int k = g; k < DQ_H1; k += LEARN_G) {                         // dz1 = (W2^T dz2) .* (h1 > 0), in place
-    float dh = 0.0f;
-#pragma unroll 4
-    for (int j = 0; j < DQ_H2; j++) dh = fmaf(pq[DQ_W2 + j + DQ_H2 * k], h2[j * S + i], dh);
-    h1[k * S + i] = h1[k * S + i] > 0.0f ? dh : 0.0f;
+  // dz1 = (W2^T dz2) .* (h1 > 0), in place; three inputs k per pass share the dz2 loads, four consecutive j are one
+  // 128-bit weight load (ascending j within each chain)
+  static_assert(DQ_H1 % (3 * LEARN_G) == 0, "dz1 passes");
+  for (int k0 = 3 * g; k0 < DQ_H1; k0 += 3 * LEARN_G) {
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+#pragma unroll 3
+    for (int j = 0; j < DQ_H2; j += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 0));
+      const float4 w1 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 1));
+      const float4 w2 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 2));
+      const float z0 = h2[(j + 0) * SP + i], z1 = h2[(j + 1) * SP + i], z2 = h2[(j + 2) * SP + i], z3 = h2[(j + 3) * SP + i];
+      d0 = fmaf(w0.x, z0, d0); d0 = fmaf(w0.y, z1, d0); d0 = fmaf(w0.z, z2, d0); d0 = fmaf(w0.w, z3, d0);
+      d1 = fmaf(w1.x, z0, d1); d1 = fmaf(w1.y, z1, d1); d1 = fmaf(w1.z, z2, d1); d1 = fmaf(w1.w, z3, d1);
+      d2 = fmaf(w2.x, z0, d2); d2 = fmaf(w2.y, z1, d2); d2 = fmaf(w2.z, z2, d2); d2 = fmaf(w2.w, z3, d2);
+    }
+    h1[(k0 + 0) * SP + i] = h1[(k0 + 0) * SP + i] > 0.0f ? d0 : 0.0f;
+    h1[(k0 + 1) * SP + i] = h1[(k0 + 1) * SP + i] > 0.0f ? d1 : 0.0f;
+    h1[(k0 + 2) * SP + i] = h1[(k0 + 2) * SP + i] > 0.0f ? d2 : 0.0f;
   }
   __syncthreads();
   for (int w = tid; w < DQ_H1 * DQ_D + DQ_H1; w += LEARN_T) {        // dW1(j,k), db1(j)
     if (w < DQ_H1 * DQ_D) {
       const int j = w % DQ_H1, k = w / DQ_H1;
       float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc = fmaf(h1[j * S + b], xs[k * S + b], acc);
+      for (int b = 0; b < B; b++) acc = fmaf(h1[j * SP + b], xs[k * SP + b], acc);
       gr[DQ_W1 + w] = acc;
     } else {
       const int j = w - DQ_H1 * DQ_D;
       float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += h1[j * S + b];
+      for (int b = 0; b < B; b++) acc += h1[j * SP + b];
       gr[DQ_B1 + j] = acc;
     }
   }
@@ -284,8 +358,8 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   if (tid == 0) { a.dev->bp1 = bp1 * b1; a.dev->bp2 = bp2 * b2; }
 }
 
-constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_A) * ACT_E) * sizeof(float);
-constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + 2 * DQ_A) * LEARN_B) * sizeof(float);
+constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_E) * sizeof(float);
+constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + 2 * DQ_A) * LEARN_SP) * sizeof(float);
 static_assert(LEARN_SMEM <= 227 * 1024, "dqn_learn shared memory");
 
 int dfail(int code, const std::string& msg) { return crl_internal_fail(code, msg.c_str()); }
@@ -312,7 +386,7 @@ struct crl_dqn_ctx {
   float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
   DqnDev* dev;
   int size, ptr;
-  long long it, learn_steps;
+  long long it, learn_steps, launches;
   bool params_set, reset_done;
 };
 
@@ -409,7 +483,7 @@ extern "C" CRL_API int crl_dqn_reset(crl_dqn_ctx* c) {
   const int N = c->cfg.num_envs;
   dqn_reset_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(N, c->cfg.seed, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets);
   DCK(cudaGetLastError());
-  c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0;
+  c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0;   /* launches keeps counting: it is a lifetime counter */
   c->reset_done = true;
   return CRL_OK;
 }
@@ -424,20 +498,33 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
   // per-call episode aggregate: clear the three accumulators, keep Adam's powers and the last loss
   DCK(cudaMemsetAsync(&c->dev->sum_return, 0, sizeof(double) * 2 + sizeof(unsigned long long), c->stream));
   double eps = 0.0;
-  for (int64_t k = 0; k < iterations; k++) {
-    c->it += 1;
-    const double gs = (double)c->it * (double)N;
-    eps = linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);   // dqn.jl:52
+  int64_t k = 0;
+  while (k < iterations) {
+    // One launch acts for every iteration up to (and including) the next learning step: the parameters are constant in
+    // between. Bounded by ACT_MAX_STEPS and by the ring capacity (steps of one launch must not share a slot).
     ActArgs a;
     a.q = c->q; a.env_state = c->env_state; a.env_t = c->env_t; a.ep_ret = c->ep_ret; a.ep_len = c->ep_len; a.resets = c->resets;
     a.b_state = c->b_state; a.b_next = c->b_next; a.b_reward = c->b_reward; a.b_action = c->b_action; a.b_term = c->b_term;
-    a.dev = c->dev; a.seed = c->cfg.seed; a.it = (unsigned long long)c->it; a.eps = eps; a.N = N; a.C = C; a.ptr = c->ptr;
+    a.dev = c->dev; a.seed = c->cfg.seed; a.it0 = (unsigned long long)(c->it + 1); a.N = N; a.C = C; a.ptr = c->ptr;
     a.max_steps = c->cfg.max_episode_steps;
+    int ns = 0;
+    bool learn = false;
+    while (k < iterations && ns < ACT_MAX_STEPS && (long long)(ns + 1) * N <= (long long)C && !learn) {
+      c->it += 1;
+      k += 1;
+      const double gs = (double)c->it * (double)N;
+      eps = linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);   // dqn.jl:52
+      a.eps[ns++] = eps;
+      c->ptr = (c->ptr + N) % C;
+      c->size = c->size + N > C ? C : c->size + N;
+      learn = gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size;   // dqn.jl:94
+    }
+    for (int i = ns; i < ACT_MAX_STEPS; i++) a.eps[i] = 0.0;
+    a.n_steps = ns;
     dqn_act_kernel<<<(N + ACT_E - 1) / ACT_E, ACT_T, ACT_SMEM, c->stream>>>(a);
     DCK(cudaGetLastError());
-    c->ptr = (c->ptr + N) % C;
-    c->size = c->size + N > C ? C : c->size + N;
-    if (gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size) {   // dqn.jl:94
+    c->launches += 1;
+    if (learn) {
       LearnArgs l;
       l.q = c->q; l.tgt = c->tgt; l.m = c->m; l.v = c->v; l.g = c->g;
       l.b_state = c->b_state; l.b_next = c->b_next; l.b_reward = c->b_reward; l.b_action = c->b_action; l.b_term = c->b_term;
@@ -447,6 +534,7 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
       dqn_learn_kernel<<<1, LEARN_T, LEARN_SMEM, c->stream>>>(l);
       DCK(cudaGetLastError());
       c->learn_steps += 1;
+      c->launches += 1;
     }
   }
   if (stats) {
@@ -455,6 +543,7 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     DCK(cudaStreamSynchronize(c->stream));
     stats->last_loss = d.last_loss; stats->sum_return = d.sum_return; stats->sum_length = d.sum_length; stats->epsilon = eps;
     stats->episodes = (int64_t)d.episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
+    stats->kernel_launches = c->launches;
   }
   return CRL_OK;
 }

@@ -299,6 +299,7 @@ struct CrlDqnStats           # crl_dqn_stats
   episodes::Int64
   learn_steps::Int64
   iterations::Int64
+  kernel_launches::Int64
 end
 
 """
@@ -324,7 +325,7 @@ function dqn(config; q_net, num_envs::Integer=1, seed::Integer=1)
   start_time = time()
   while done < n_iter
     k = min(chunk, n_iter - done)
-    st = Ref(CrlDqnStats(0, 0, 0, 0, 0, 0, 0))
+    st = Ref(CrlDqnStats(0, 0, 0, 0, 0, 0, 0, 0))
     check(ccall((:crl_dqn_run, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{CrlDqnStats}), h, k, st))   # dqn.jl:49-118
     done += k
     global_step = done * num_envs

@@ -312,6 +312,7 @@ typedef struct crl_dqn_stats {
   int64_t episodes;
   int64_t learn_steps;  /* learning steps so far */
   int64_t iterations;   /* iterations so far; global_step = iterations * num_envs */
+  int64_t kernel_launches; /* kernels launched so far (one acting launch covers the iterations up to the next learning step) */
 } crl_dqn_stats;
 CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** out);
 CRL_API int crl_dqn_destroy(crl_dqn_ctx* ctx);

@@ -1415,6 +1415,7 @@ int orc_dqn_run(orc_dqn_ctx* c, int64_t iterations, crl_dqn_stats* stats) {
   if (stats) {
     stats->last_loss = c->last_loss; stats->sum_return = sum_ret; stats->sum_length = sum_len; stats->epsilon = eps;
     stats->episodes = episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
+    stats->kernel_launches = 0;   /* the oracle launches nothing */
   }
   return 0;
 }

@@ -42,15 +42,15 @@ def test_library_does_not_link_the_oracle_or_nccl_at_load_time():
 
 def test_struct_layout_matches_the_c_header(tmp_path, abi):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cleanrl_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cleanrl_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(crl_config),offsetof(crl_config,seed),offsetof(crl_config,gamma),sizeof(crl_loss_stats),'
-                   'sizeof(crl_episode),sizeof(crl_episode_agg),sizeof(crl_kernel_times));return 0;}\n')
+                   'sizeof(crl_episode),sizeof(crl_episode_agg),sizeof(crl_kernel_times),sizeof(crl_dqn_config),sizeof(crl_dqn_stats));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert got == [C.sizeof(abi.crl_config), abi.crl_config.seed.offset, abi.crl_config.gamma.offset,
                    C.sizeof(abi.crl_loss_stats), C.sizeof(abi.crl_episode), C.sizeof(abi.crl_episode_agg),
-                   C.sizeof(abi.crl_kernel_times)]
+                   C.sizeof(abi.crl_kernel_times), C.sizeof(abi.crl_dqn_config), C.sizeof(abi.crl_dqn_stats)]
 
 
 @pytest.mark.skipif("torch" in sys.modules and sys.modules["torch"].cuda.is_available(), reason="CPU-box behaviour")
