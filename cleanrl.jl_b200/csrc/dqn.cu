@@ -19,6 +19,7 @@
 // Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?") is taken on
 // the host, so a run is a plain sequence of launches on one stream without any device-to-host read.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -34,11 +35,20 @@ constexpr int DQ_W1 = 0, DQ_B1 = DQ_W1 + DQ_H1 * DQ_D, DQ_W2 = DQ_B1 + DQ_H1, DQ
 static_assert(DQ_P == CRL_DQN_PARAMS, "parameter count");
 constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
 constexpr int ACT_E = 32;     // envs per CTA in dqn_act_kernel (one warp-width of samples)
-constexpr int ACT_G = 8;      // neuron groups: thread (lane = env, warp = group) computes neurons group, group + 8, ...
+constexpr int ACT_G = DQ_H2 / 4;   // 21 warps: warp g owns neurons 4g..4g+3 of the second layer (one pass) and g, g+21, .. of the first
 constexpr int ACT_T = ACT_E * ACT_G;
 constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bounded by the next learning step)
 constexpr int LEARN_B = 128;  // max batch size = samples per tile in dqn_learn_kernel
 constexpr int LEARN_SP = LEARN_B + 1;   // activation row stride in dqn_learn_kernel: odd, so rows fall on distinct banks
+// the learning step spread over several SMs (default): forward/backward for 16 samples per CTA, then one thread per
+// 4x4 tile of dW2 (or per single small-array element) which reduces over the batch and applies Adam on the spot
+constexpr int LF_S = 16, LF_G = 32, LF_T = LF_S * LF_G, LF_SP = LF_S + 1;
+constexpr int LF_MAX_BLOCKS = LEARN_B / LF_S;
+constexpr int LU_T = 64;
+constexpr int LU_TILES = (DQ_H2 / 4) * (DQ_H1 / 4);
+constexpr int LU_TILE_BLOCKS = (LU_TILES + LU_T - 1) / LU_T;
+constexpr int LU_SINGLES = DQ_H1 * DQ_D + DQ_H1 + DQ_H2 + DQ_A * DQ_H2 + DQ_A;   // dW1, db1, db2, dW3, db3
+constexpr int LU_SINGLE_BLOCKS = (LU_SINGLES + LU_T - 1) / LU_T;
 constexpr int LEARN_G = 4;    // neuron groups
 constexpr int LEARN_T = LEARN_B * LEARN_G;
 
@@ -79,20 +89,18 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
   }
   __syncthreads();
   for (int j = 4 * g; j < DQ_H2; j += 4 * G) {
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);   // packed FP32: two chains per instruction
 #pragma unroll 8
     for (int k = 0; k < DQ_H1; k++) {
       const float4 w = *reinterpret_cast<const float4*>(p + DQ_W2 + j + DQ_H2 * k);
       const float h = h1[k * SP + l];
-      a0 = fmaf(w.x, h, a0);
-      a1 = fmaf(w.y, h, a1);
-      a2 = fmaf(w.z, h, a2);
-      a3 = fmaf(w.w, h, a3);
+      a01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(h, h), a01);
+      a23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(h, h), a23);
     }
-    h2[(j + 0) * SP + l] = fmaxf(a0 + p[DQ_B2 + j + 0], 0.0f);
-    h2[(j + 1) * SP + l] = fmaxf(a1 + p[DQ_B2 + j + 1], 0.0f);
-    h2[(j + 2) * SP + l] = fmaxf(a2 + p[DQ_B2 + j + 2], 0.0f);
-    h2[(j + 3) * SP + l] = fmaxf(a3 + p[DQ_B2 + j + 3], 0.0f);
+    h2[(j + 0) * SP + l] = fmaxf(a01.x + p[DQ_B2 + j + 0], 0.0f);
+    h2[(j + 1) * SP + l] = fmaxf(a01.y + p[DQ_B2 + j + 1], 0.0f);
+    h2[(j + 2) * SP + l] = fmaxf(a23.x + p[DQ_B2 + j + 2], 0.0f);
+    h2[(j + 3) * SP + l] = fmaxf(a23.y + p[DQ_B2 + j + 3], 0.0f);
   }
   __syncthreads();
   for (int o = g; o < DQ_A; o += G) {
@@ -189,6 +197,10 @@ struct LearnArgs {
   unsigned long long seed, learn_step;
   double gamma, lr;
   int B, size, copy_target;
+  // multi-SM path: sample-major scratch [128][rows] between the two kernels, Adam's beta powers from the host
+  float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;
+  double* loss_part;
+  double bp1, bp2;
 };
 
 __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
@@ -358,9 +370,203 @@ __global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
   if (tid == 0) { a.dev->bp1 = bp1 * b1; a.dev->bp2 = bp2 * b2; }
 }
 
+
+// ---- the learning step on several SMs -------------------------------------------------------------------------------
+// dqn_learn_fwd_kernel: CTA c owns samples 16c..16c+15 of the batch (thread = sample x neuron group): gather, target
+// and q forward, TD target, loss, dz2, dz1; everything the weight gradients need is written sample-major to a global
+// scratch (L2-resident, 220 KB). dqn_learn_upd_kernel: one thread per 4x4 tile of dW2 (or per element of the small
+// arrays) sums over the batch in ascending sample order - the same fmaf chains as dqn_learn_kernel - and applies Adam
+// to the parameters it has just differentiated, so gradients never leave registers.
+__global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PP = (DQ_P + 3) & ~3, SP = LF_SP;
+  float* pq = smem;                       // q_net parameters
+  float* pt = pq + PP;                    // target_net parameters
+  float* h1 = pt + PP;                    // [120][SP]
+  float* h2 = h1 + DQ_H1 * SP;            // [84][SP]   (later dz2 in place)
+  float* qo = h2 + DQ_H2 * SP;            // [2][SP]
+  float* dq = qo + DQ_A * SP;             // [2][SP]
+  float* xin = dq + DQ_A * SP;            // [8][SP]: rows 0-3 state, rows 4-7 next_state
+  __shared__ uint32_t keys[8];
+  __shared__ float s_rew[LF_S];
+  __shared__ int s_act[LF_S], s_term[LF_S];
+  const int tid = threadIdx.x, B = a.B;
+  const int i = tid & (LF_S - 1), g = tid / LF_S;   // sample within the CTA, neuron group
+  const int b = blockIdx.x * LF_S + i;              // sample of the batch
+  for (int k = tid; k < DQ_P; k += LF_T) { pq[k] = a.q[k]; pt[k] = a.tgt[k]; }
+  if (tid == 0) {
+    philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
+    philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
+  }
+  __syncthreads();
+  if (g == 0) {
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = s4;
+    int act = 0, term = 0;
+    float rew = 0.0f;
+    if (b < B) {
+      // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
+      const uint32_t idx = perm_index((uint32_t)b, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
+      s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
+      n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
+      act = a.b_action[idx];
+      rew = a.b_reward[idx];
+      term = a.b_term[idx];
+    }
+    xin[0 * SP + i] = s4.x; xin[1 * SP + i] = s4.y; xin[2 * SP + i] = s4.z; xin[3 * SP + i] = s4.w;
+    xin[4 * SP + i] = n4.x; xin[5 * SP + i] = n4.y; xin[6 * SP + i] = n4.z; xin[7 * SP + i] = n4.w;
+    s_rew[i] = rew; s_act[i] = act; s_term[i] = term;
+  }
+  __syncthreads();
+  float s[4], nx[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { s[k] = xin[k * SP + i]; nx[k] = xin[(4 + k) * SP + i]; }
+  q_forward<SP, LF_G>(pt, nx, h1, h2, qo, i, g);                     // target_net(next_state), dqn.jl:99
+  const float next_q = fmaxf(qo[0 * SP + i], qo[1 * SP + i]);
+  const double td = (double)s_rew[i] + a.gamma * (double)next_q * (1.0 - (double)s_term[i]);   // dqn.jl:100
+  __syncthreads();
+  q_forward<SP, LF_G>(pq, s, h1, h2, qo, i, g);                      // q_net(state), dqn.jl:105
+  if (g == 0) {                                                      // lanes 0-15 of warp 0
+    float d0 = 0.0f, d1 = 0.0f;
+    double sq = 0.0;
+    if (b < B) {
+      const int act = s_act[i];
+      const double diff = td - (double)qo[act * SP + i];
+      sq = diff * diff;                                              // Flux.mse, dqn.jl:107
+      const float dd = (float)(-2.0 * diff / (double)B);
+      if (act == 0) d0 = dd; else d1 = dd;
+      a.dqT[b * DQ_A + 0] = d0;
+      a.dqT[b * DQ_A + 1] = d1;
+#pragma unroll
+      for (int k = 0; k < DQ_D; k++) a.xT[b * DQ_D + k] = s[k];
+    }
+    dq[0 * SP + i] = d0;
+    dq[1 * SP + i] = d1;
+#pragma unroll
+    for (int o = LF_S / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0x0000ffffu, sq, o);
+    if (i == 0) a.loss_part[blockIdx.x] = sq;
+  }
+  __syncthreads();
+  {                                                                  // dz2 = (W3^T dq) .* (h2 > 0), in place
+    const float d0 = dq[0 * SP + i], d1 = dq[1 * SP + i];
+    for (int k = g; k < DQ_H2; k += LF_G) {
+      const float hv = h2[k * SP + i];
+      const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
+      const float z = hv > 0.0f ? dh : 0.0f;
+      h2[k * SP + i] = z;
+      if (b < B) { a.h2T[b * DQ_H2 + k] = hv; a.z2T[b * DQ_H2 + k] = z; }
+    }
+    if (b < B)
+      for (int k = g; k < DQ_H1; k += LF_G) a.h1T[b * DQ_H1 + k] = h1[k * SP + i];
+  }
+  __syncthreads();
+  {                                                                  // dz1 = (W2^T dz2) .* (h1 > 0) for k = g, g+32, g+64, g+96
+    static_assert(4 * LF_G >= DQ_H1, "one dz1 pass covers the first hidden layer");
+    float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int kk[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) kk[t] = min(g + LF_G * t, DQ_H1 - 1);   // clamped for the loads; stores are guarded
+#pragma unroll 3
+    for (int j = 0; j < DQ_H2; j += 4) {
+      const float z0 = h2[(j + 0) * SP + i], z1 = h2[(j + 1) * SP + i], z2 = h2[(j + 2) * SP + i], z3 = h2[(j + 3) * SP + i];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float4 w = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * kk[t]);
+        d[t] = fmaf(w.x, z0, d[t]); d[t] = fmaf(w.y, z1, d[t]); d[t] = fmaf(w.z, z2, d[t]); d[t] = fmaf(w.w, z3, d[t]);
+      }
+    }
+    if (b < B) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = g + LF_G * t;
+        if (k < DQ_H1) a.z1T[b * DQ_H1 + k] = h1[k * SP + i] > 0.0f ? d[t] : 0.0f;
+      }
+    }
+  }
+}
+
+// Flux.Adam(lr) (dqn.jl:41,109) for one parameter, Float64 scalars as in clip_adam_kernel; then the target copy
+// (dqn.jl:111-113)
+__device__ __forceinline__ void dqn_adam_one(const LearnArgs& a, int k, float d) {
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[k]), __dmul_rn(1.0 - b1, (double)d));
+  const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
+  a.m[k] = mt;
+  a.v[k] = vt;
+  const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - a.bp2)), eps);
+  const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - a.bp1), den), a.lr);
+  const float pn = __fsub_rn(a.q[k], step);
+  a.q[k] = pn;
+  if (a.copy_target) a.tgt[k] = pn;
+}
+
+__global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_fwd_blocks) {
+  const int B = a.B;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double sq = 0.0;
+    for (int c = 0; c < n_fwd_blocks; c++) sq += a.loss_part[c];
+    a.dev->last_loss = sq / (double)B;
+  }
+  if (blockIdx.x < LU_TILE_BLOCKS) {                                 // dW2(j,k): neurons j, j+21, j+42, j+63 x inputs k0..k0+3
+    const int w = blockIdx.x * LU_T + threadIdx.x;
+    if (w >= LU_TILES) return;
+    constexpr int JQ = DQ_H2 / 4;
+    const int j = w % JQ, k0 = (w / JQ) * 4;
+    float2 acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+    for (int b = 0; b < B; b++) {
+      const float4 hh = *reinterpret_cast<const float4*>(a.h1T + b * DQ_H1 + k0);
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float z = a.z2T[b * DQ_H2 + j + JQ * t];
+        acc[t][0] = __ffma2_rn(make_float2(z, z), make_float2(hh.x, hh.y), acc[t][0]);
+        acc[t][1] = __ffma2_rn(make_float2(z, z), make_float2(hh.z, hh.w), acc[t][1]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int base = DQ_W2 + (j + JQ * t) + DQ_H2 * k0;
+      dqn_adam_one(a, base + DQ_H2 * 0, acc[t][0].x);
+      dqn_adam_one(a, base + DQ_H2 * 1, acc[t][0].y);
+      dqn_adam_one(a, base + DQ_H2 * 2, acc[t][1].x);
+      dqn_adam_one(a, base + DQ_H2 * 3, acc[t][1].y);
+    }
+    return;
+  }
+  const int w = (blockIdx.x - LU_TILE_BLOCKS) * LU_T + threadIdx.x;
+  if (w >= LU_SINGLES) return;
+  constexpr int N_W1 = DQ_H1 * DQ_D, N_B1 = N_W1 + DQ_H1, N_B2 = N_B1 + DQ_H2, N_W3 = N_B2 + DQ_A * DQ_H2;
+  float acc = 0.0f;
+  int pidx;
+  if (w < N_W1) {                                                    // dW1(j,k)
+    const int j = w % DQ_H1, k = w / DQ_H1;
+    for (int b = 0; b < B; b++) acc = fmaf(a.z1T[b * DQ_H1 + j], a.xT[b * DQ_D + k], acc);
+    pidx = DQ_W1 + w;
+  } else if (w < N_B1) {                                             // db1(j)
+    const int j = w - N_W1;
+    for (int b = 0; b < B; b++) acc += a.z1T[b * DQ_H1 + j];
+    pidx = DQ_B1 + j;
+  } else if (w < N_B2) {                                             // db2(j)
+    const int j = w - N_B1;
+    for (int b = 0; b < B; b++) acc += a.z2T[b * DQ_H2 + j];
+    pidx = DQ_B2 + j;
+  } else if (w < N_W3) {                                             // dW3(o,k)
+    const int ww = w - N_B2, o = ww % DQ_A, k = ww / DQ_A;
+    for (int b = 0; b < B; b++) acc = fmaf(a.dqT[b * DQ_A + o], a.h2T[b * DQ_H2 + k], acc);
+    pidx = DQ_W3 + ww;
+  } else {                                                           // db3(o)
+    const int o = w - N_W3;
+    for (int b = 0; b < B; b++) acc += a.dqT[b * DQ_A + o];
+    pidx = DQ_B3 + o;
+  }
+  dqn_adam_one(a, pidx, acc);
+}
+
 constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_E) * sizeof(float);
 constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + 2 * DQ_A) * LEARN_SP) * sizeof(float);
 static_assert(LEARN_SMEM <= 227 * 1024, "dqn_learn shared memory");
+constexpr size_t LF_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + 2 * DQ_A + 2 * DQ_D) * LF_SP) * sizeof(float);
 
 int dfail(int code, const std::string& msg) { return crl_internal_fail(code, msg.c_str()); }
 #define DCK(call)                                                                                          \
@@ -385,9 +591,12 @@ struct crl_dqn_ctx {
   float* env_state; int* env_t; double* ep_ret; int* ep_len; uint32_t* resets;
   float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
   DqnDev* dev;
+  float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;   // scratch between dqn_learn_fwd_kernel and dqn_learn_upd_kernel
+  double* loss_part;
+  double bp1, bp2;                            // beta1^t, beta2^t of Adam (multi-SM learning step: kept on the host)
   int size, ptr;
   long long it, learn_steps, launches;
-  bool params_set, reset_done;
+  bool params_set, reset_done, one_cta_learn;
 };
 
 __global__ void dqn_reset_kernel(int N, unsigned long long seed, float* env_state, int* env_t, double* ep_ret, int* ep_len,
@@ -432,6 +641,14 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   DCK(dzalloc(&c->resets, N));
   DCK(dzalloc(&c->b_state, 4 * C)); DCK(dzalloc(&c->b_next, 4 * C)); DCK(dzalloc(&c->b_reward, C)); DCK(dzalloc(&c->b_action, C));
   DCK(dzalloc(&c->b_term, C)); DCK(dzalloc(&c->dev, 1));
+  DCK(dzalloc(&c->h1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->h2T, (size_t)LEARN_B * DQ_H2)); DCK(dzalloc(&c->z2T, (size_t)LEARN_B * DQ_H2));
+  DCK(dzalloc(&c->z1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->xT, (size_t)LEARN_B * DQ_D)); DCK(dzalloc(&c->dqT, (size_t)LEARN_B * DQ_A));
+  DCK(dzalloc(&c->loss_part, LF_MAX_BLOCKS));
+  DCK(cudaFuncSetAttribute(dqn_learn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+  {
+    const char* e = getenv("CRL_DQN_ONE_CTA");   // A/B switch: the whole learning step in one CTA (dqn_learn_kernel)
+    c->one_cta_learn = e && atoi(e) != 0;
+  }
   DCK(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
   DCK(cudaFuncSetAttribute(dqn_learn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEARN_SMEM));
   *out = c;
@@ -443,7 +660,7 @@ extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->g, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
-                  c->b_reward, c->b_action, c->b_term, c->dev};
+                  c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -463,6 +680,7 @@ extern "C" CRL_API int crl_dqn_set_params(crl_dqn_ctx* c, const float* params, i
   d.bp1 = 0.9; d.bp2 = 0.999;
   DCK(cudaMemcpyAsync(c->dev, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream));
   DCK(cudaStreamSynchronize(c->stream));
+  c->bp1 = 0.9; c->bp2 = 0.999;
   c->params_set = true;
   return CRL_OK;
 }
@@ -526,15 +744,28 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     c->launches += 1;
     if (learn) {
       LearnArgs l;
+      memset(&l, 0, sizeof(l));
       l.q = c->q; l.tgt = c->tgt; l.m = c->m; l.v = c->v; l.g = c->g;
       l.b_state = c->b_state; l.b_next = c->b_next; l.b_reward = c->b_reward; l.b_action = c->b_action; l.b_term = c->b_term;
       l.dev = c->dev; l.seed = c->cfg.seed; l.learn_step = (unsigned long long)c->learn_steps; l.gamma = c->cfg.gamma;
       l.lr = c->cfg.lr; l.B = c->cfg.batch_size; l.size = c->size;
       l.copy_target = (c->it % c->cfg.target_net_freq == 0) ? 1 : 0;                                             // dqn.jl:111
-      dqn_learn_kernel<<<1, LEARN_T, LEARN_SMEM, c->stream>>>(l);
-      DCK(cudaGetLastError());
+      if (c->one_cta_learn) {
+        dqn_learn_kernel<<<1, LEARN_T, LEARN_SMEM, c->stream>>>(l);
+        DCK(cudaGetLastError());
+        c->launches += 1;
+      } else {
+        l.h1T = c->h1T; l.h2T = c->h2T; l.z2T = c->z2T; l.z1T = c->z1T; l.xT = c->xT; l.dqT = c->dqT;
+        l.loss_part = c->loss_part; l.bp1 = c->bp1; l.bp2 = c->bp2;
+        const int fwd_blocks = (l.B + LF_S - 1) / LF_S;
+        dqn_learn_fwd_kernel<<<fwd_blocks, LF_T, LF_SMEM, c->stream>>>(l);
+        DCK(cudaGetLastError());
+        dqn_learn_upd_kernel<<<LU_TILE_BLOCKS + LU_SINGLE_BLOCKS, LU_T, 0, c->stream>>>(l, fwd_blocks);
+        DCK(cudaGetLastError());
+        c->bp1 *= 0.9; c->bp2 *= 0.999;   // same Float64 products the one-CTA kernel keeps on the device
+        c->launches += 2;
+      }
       c->learn_steps += 1;
-      c->launches += 1;
     }
   }
   if (stats) {

@@ -1,5 +1,6 @@
 """Short, graph-free workload for ncu: 2 PPO updates at BASELINE configs[1] (CartPole, 4096 envs
-x 128 steps) and one GAE launch at N=2^20 (2.29 GB). Used by the ncu recipes in profiles/README.md."""
+x 128 steps) and one GAE launch at N=2^20 (2.29 GB); `dqn`: 40 DQN iterations at BASELINE configs[4]. Used by the ncu
+recipes in profiles/README.md."""
 import os
 import sys
 
@@ -34,4 +35,13 @@ if what in ("all", "gae"):
         _lib.check(lib.crl_gae_raw(_lib.ptr(v), _lib.ptr(r), _lib.ptr(d), None, None, _lib.ptr(adv), _lib.ptr(ret),
                                    T, N, 0.99, 0.95, 0, None))
     torch.cuda.synchronize()
+if what == "dqn":
+    from cleanrl_jl_b200.dqn_algo import DQNHandle, init_q_params  # noqa: E402
+    cfg = _abi.make_dqn_config(num_envs=4096, buffer_size=1 << 20, min_buff_size=10_000, batch_size=120, train_freq=10,
+                               target_net_freq=100, epsilon_duration=5e6, seed=1)
+    h = DQNHandle(cfg)
+    h.set_params(init_q_params(1))
+    h.reset()
+    h.run(40)   # 4 acting launches of 10 iterations + 4 learning steps
+    h.close()
 print("profile target done")
