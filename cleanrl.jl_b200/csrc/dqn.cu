@@ -3,21 +3,25 @@
 // ring replay buffer, and one learning step (sample without replacement -> TD target from the target net -> MSE on
 // the taken action -> backward -> Adam -> optional target copy) every train_freq iterations.
 //
-//   dqn_act_kernel    32 envs per CTA of 256 threads: lane = env, warp = neuron group. The 10,934 parameters sit in
-//                     shared memory; activations are [neuron][env lane] tiles in shared memory (conflict-free; the
-//                     weights of four consecutive neurons are one broadcast 128-bit load). Warp 0 then draws epsilon /
-//                     the random action from Philox, steps CartPole, appends the transition at
-//                     (ptr + step * N + env) % capacity and resets a finished env on the spot. The parameters only
-//                     change at a learning step, so ONE launch runs every iteration up to the next learning step
-//                     (train_freq of them, at most ACT_MAX_STEPS) with the env state in registers.
-//   dqn_learn_kernel  ONE CTA of 512 threads for the batch (<= 128 samples x 4 neuron groups): both parameter sets
-//                     and the batch activations live in shared memory (~197 KB, activation rows padded to 129 floats
-//                     so that the batch reductions, whose lanes walk down the neuron axis, are conflict-free);
-//                     forward target net and q net, gradient reductions over the batch as 4x4 register tiles, every
-//                     sum in ascending sample order (deterministic, same order as the oracle), Adam and the target
-//                     copy in the same launch.
-// Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?") is taken on
-// the host, so a run is a plain sequence of launches on one stream without any device-to-host read.
+// The 4-120-84-2 network is evaluated out of shared memory as register tiles of 4 neurons x 4 samples (q_forward):
+// per k one 128-bit weight load and one 128-bit activation load feed 16 FMAs (packed FP32). With one neuron per thread
+// and one sample per lane the kernels were bound by shared-memory wavefronts (ncu: profiles/r1_v7_ncu_dqn_summary.csv);
+// every neuron is still ONE fmaf chain over ascending k, so results do not depend on the tiling.
+//
+//   dqn_act_kernel        32 envs per CTA of 256 threads. Warp 0 (one lane per env, state in registers) draws epsilon /
+//                         the random action from Philox, steps CartPole, appends the transition at
+//                         (ptr + step * N + env) % capacity and resets a finished env on the spot. The parameters only
+//                         change at a learning step, so ONE launch runs every iteration up to the next learning step
+//                         (train_freq of them, at most ACT_MAX_STEPS).
+//   dqn_learn_fwd_kernel  the learning step, part 1: CTA c owns samples 16c..16c+15 of the batch: gather, target and q
+//                         forward, TD target, loss, dz2, dz1; everything the weight gradients need is written
+//                         sample-major to a global scratch (L2-resident, 220 KB).
+//   dqn_learn_upd_kernel  part 2: a block stages the scratch columns it needs in shared memory, one thread per 4x4
+//                         tile of dW2 (or per element of the small arrays) sums over the batch in ascending sample
+//                         order (deterministic, the oracle's order) and applies Adam to the parameters it has just
+//                         differentiated (plus the target copy), so gradients never leave registers.
+// Every decision that only depends on counters (epsilon, "learn on this iteration?", "copy the target?", Adam's beta
+// powers) is taken on the host, so a run is a plain sequence of launches on one stream without any device-to-host read.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,31 +33,37 @@
 
 namespace {
 
+// -DDQN_TRACE: clock stamps of one CTA printed from the kernels (development aid, like TC_TRACE in update_tc.cu)
+#ifdef DQN_TRACE
+#define DTR(i) do { if (dtrace) dtr[i] = clock64(); } while (0)
+#else
+#define DTR(i) do { } while (0)
+#endif
+
 constexpr int DQ_D = 4, DQ_H1 = 120, DQ_H2 = 84, DQ_A = 2;
 constexpr int DQ_W1 = 0, DQ_B1 = DQ_W1 + DQ_H1 * DQ_D, DQ_W2 = DQ_B1 + DQ_H1, DQ_B2 = DQ_W2 + DQ_H2 * DQ_H1,
               DQ_W3 = DQ_B2 + DQ_H2, DQ_B3 = DQ_W3 + DQ_A * DQ_H2, DQ_P = DQ_B3 + DQ_A;
+constexpr int DQ_PP = (DQ_P + 3) & ~3;
 static_assert(DQ_P == CRL_DQN_PARAMS, "parameter count");
+static_assert(DQ_H2 % 4 == 0 && DQ_H1 % 4 == 0 && DQ_W2 % 4 == 0, "128-bit weight loads of the second layer");
 constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
-constexpr int ACT_E = 32;     // envs per CTA in dqn_act_kernel (one warp-width of samples)
-constexpr int ACT_G = DQ_H2 / 4;   // 21 warps: warp g owns neurons 4g..4g+3 of the second layer (one pass) and g, g+21, .. of the first
-constexpr int ACT_T = ACT_E * ACT_G;
+constexpr int ACT_E = 32;           // envs per CTA in dqn_act_kernel
+constexpr int ACT_SP = ACT_E + 4;   // activation row stride (floats): rows stay 16-byte aligned
+constexpr int ACT_T = 256;
 constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bounded by the next learning step)
-constexpr int LEARN_B = 128;  // max batch size = samples per tile in dqn_learn_kernel
-constexpr int LEARN_SP = LEARN_B + 1;   // activation row stride in dqn_learn_kernel: odd, so rows fall on distinct banks
-// the learning step spread over several SMs (default): forward/backward for 16 samples per CTA, then one thread per
-// 4x4 tile of dW2 (or per single small-array element) which reduces over the batch and applies Adam on the spot
-constexpr int LF_S = 16, LF_G = 32, LF_T = LF_S * LF_G, LF_SP = LF_S + 1;
+constexpr int LEARN_B = 128;        // max batch size
+constexpr int LF_S = 16, LF_SP = LF_S + 4, LF_T = 256;   // dqn_learn_fwd_kernel: samples per CTA, row stride, threads
 constexpr int LF_MAX_BLOCKS = LEARN_B / LF_S;
-constexpr int LU_T = 64;
-constexpr int LU_TILES = (DQ_H2 / 4) * (DQ_H1 / 4);
-constexpr int LU_TILE_BLOCKS = (LU_TILES + LU_T - 1) / LU_T;
-constexpr int LU_SINGLES = DQ_H1 * DQ_D + DQ_H1 + DQ_H2 + DQ_A * DQ_H2 + DQ_A;   // dW1, db1, db2, dW3, db3
-constexpr int LU_SINGLE_BLOCKS = (LU_SINGLES + LU_T - 1) / LU_T;
-constexpr int LEARN_G = 4;    // neuron groups
-constexpr int LEARN_T = LEARN_B * LEARN_G;
+// dqn_learn_upd_kernel: block kinds (A) dW2 tiles of 24 input columns, (B) dW1/db1 of 24 neurons, (C) dW3/db2(/db3)
+// of 28 neurons
+constexpr int LU_T = 128;
+constexpr int LU_KA = 24, LU_A_BLOCKS = DQ_H1 / LU_KA;   // 5 blocks x (21 neuron quads x 6 input quads) = 630 tiles
+constexpr int LU_JB = 24, LU_B_BLOCKS = DQ_H1 / LU_JB;   // 5 blocks x 24 neurons x (4 inputs + bias)
+constexpr int LU_KC = 28, LU_C_BLOCKS = DQ_H2 / LU_KC;   // 3 blocks x 28 neurons x (2 outputs + bias)
+static_assert(DQ_H1 % LU_KA == 0 && DQ_H1 % LU_JB == 0 && DQ_H2 % LU_KC == 0, "upd block decomposition");
+static_assert((DQ_H2 / 4) * (LU_KA / 4) <= LU_T && LU_JB * (DQ_D + 1) <= LU_T && LU_KC * (DQ_A + 1) + DQ_A <= LU_T, "upd block size");
 
 struct DqnDev {               // device-resident scalars
-  double bp1, bp2;            // beta1^t, beta2^t of Adam
   double last_loss;
   double sum_return, sum_length;
   unsigned long long episodes;
@@ -70,42 +80,65 @@ struct ActArgs {
   int N, C, ptr, max_steps;
 };
 
-// Dense -> relu -> Dense -> relu -> Dense for a tile of samples, neurons spread over G thread groups (CTA-wide
-// barriers between the layers: every thread of the CTA must call this). Activations are [neuron][SP] tiles in shared
-// memory (row stride SP floats; conflict-free across the lanes of a warp, which are consecutive samples); weight reads
-// are warp broadcasts, and in the 120 -> 84 layer a thread owns four consecutive neurons so that their weights are
-// one 128-bit load per k (p must be 16-byte aligned). Each neuron is one fmaf chain over ascending k, so the result
-// does not depend on the tile shape or on G. qo = [DQ_A][SP].
-static_assert(DQ_H2 % 4 == 0 && DQ_W2 % 4 == 0, "128-bit weight loads of the second layer");
-template <int SP, int G>
-__device__ __forceinline__ void q_forward(const float* __restrict__ p, const float x[DQ_D], float* h1, float* h2, float* qo,
-                                          int l, int g) {
-  for (int j = g; j < DQ_H1; j += G) {
-    float acc = 0.0f;
+// global -> shared copy of one parameter vector (128-bit loads; cudaMalloc'ed source, 16-byte aligned destination)
+template <int NT> __device__ __forceinline__ void load_q_params(const float* __restrict__ g, float* sp, int tid) {
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* s4 = reinterpret_cast<float4*>(sp);
+  for (int i = tid; i < DQ_P / 4; i += NT) s4[i] = g4[i];
+  if (tid < DQ_P % 4) sp[(DQ_P / 4) * 4 + tid] = g[(DQ_P / 4) * 4 + tid];
+}
+
+// Dense -> relu -> Dense -> relu -> Dense for a tile of NS samples by NT threads (CTA-wide barriers between the
+// layers: every thread of the CTA must call this). p: parameters in shared memory (16-byte aligned); xs [4][SP] the
+// inputs, h1 [120][SP], h2 [84][SP], qo [2][SP] (SP a multiple of 4). A thread owns 4 consecutive samples of one
+// first-layer neuron, then 4 neurons x 4 samples of the second layer (one 128-bit weight load + one 128-bit activation
+// load per k for 16 FMAs), then one (output, sample) chain of the head.
+template <int NS, int SP, int NT>
+__device__ __forceinline__ void q_forward(const float* __restrict__ p, const float* xs, float* h1, float* h2, float* qo, int tid) {
+  constexpr int EQ = NS / 4;   // sample quads
+  static_assert(NS % 4 == 0 && SP % 4 == 0 && SP >= NS, "tile geometry");
+  static_assert((DQ_H2 / 4) * EQ <= NT && DQ_A * NS <= NT, "one pass for the second layer and the head");
+  for (int w = tid; w < DQ_H1 * EQ; w += NT) {
+    const int eq = w % EQ, j = w / EQ;
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-    for (int k = 0; k < DQ_D; k++) acc = fmaf(p[DQ_W1 + j + DQ_H1 * k], x[k], acc);
-    acc += p[DQ_B1 + j];
-    h1[j * SP + l] = fmaxf(acc, 0.0f);
+    for (int k = 0; k < DQ_D; k++) {
+      const float wt = p[DQ_W1 + j + DQ_H1 * k];
+      const float4 x = *reinterpret_cast<const float4*>(xs + k * SP + 4 * eq);
+      acc.x = fmaf(wt, x.x, acc.x); acc.y = fmaf(wt, x.y, acc.y); acc.z = fmaf(wt, x.z, acc.z); acc.w = fmaf(wt, x.w, acc.w);
+    }
+    const float b = p[DQ_B1 + j];
+    *reinterpret_cast<float4*>(h1 + j * SP + 4 * eq) =
+        make_float4(fmaxf(acc.x + b, 0.0f), fmaxf(acc.y + b, 0.0f), fmaxf(acc.z + b, 0.0f), fmaxf(acc.w + b, 0.0f));
   }
   __syncthreads();
-  for (int j = 4 * g; j < DQ_H2; j += 4 * G) {
-    float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);   // packed FP32: two chains per instruction
-#pragma unroll 8
+  if (tid < (DQ_H2 / 4) * EQ) {
+    const int eq = tid % EQ, j = 4 * (tid / EQ);
+    float2 acc[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; n++) acc[n][0] = acc[n][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
     for (int k = 0; k < DQ_H1; k++) {
       const float4 w = *reinterpret_cast<const float4*>(p + DQ_W2 + j + DQ_H2 * k);
-      const float h = h1[k * SP + l];
-      a01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(h, h), a01);
-      a23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(h, h), a23);
+      const float4 h = *reinterpret_cast<const float4*>(h1 + k * SP + 4 * eq);
+      const float2 h01 = make_float2(h.x, h.y), h23 = make_float2(h.z, h.w);
+      acc[0][0] = __ffma2_rn(make_float2(w.x, w.x), h01, acc[0][0]); acc[0][1] = __ffma2_rn(make_float2(w.x, w.x), h23, acc[0][1]);
+      acc[1][0] = __ffma2_rn(make_float2(w.y, w.y), h01, acc[1][0]); acc[1][1] = __ffma2_rn(make_float2(w.y, w.y), h23, acc[1][1]);
+      acc[2][0] = __ffma2_rn(make_float2(w.z, w.z), h01, acc[2][0]); acc[2][1] = __ffma2_rn(make_float2(w.z, w.z), h23, acc[2][1]);
+      acc[3][0] = __ffma2_rn(make_float2(w.w, w.w), h01, acc[3][0]); acc[3][1] = __ffma2_rn(make_float2(w.w, w.w), h23, acc[3][1]);
     }
-    h2[(j + 0) * SP + l] = fmaxf(a01.x + p[DQ_B2 + j + 0], 0.0f);
-    h2[(j + 1) * SP + l] = fmaxf(a01.y + p[DQ_B2 + j + 1], 0.0f);
-    h2[(j + 2) * SP + l] = fmaxf(a23.x + p[DQ_B2 + j + 2], 0.0f);
-    h2[(j + 3) * SP + l] = fmaxf(a23.y + p[DQ_B2 + j + 3], 0.0f);
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+      const float b = p[DQ_B2 + j + n];
+      *reinterpret_cast<float4*>(h2 + (j + n) * SP + 4 * eq) =
+          make_float4(fmaxf(acc[n][0].x + b, 0.0f), fmaxf(acc[n][0].y + b, 0.0f), fmaxf(acc[n][1].x + b, 0.0f), fmaxf(acc[n][1].y + b, 0.0f));
+    }
   }
   __syncthreads();
-  for (int o = g; o < DQ_A; o += G) {
+  if (tid < DQ_A * NS) {
+    const int l = tid % NS, o = tid / NS;
     float acc = 0.0f;
-#pragma unroll 4
+#pragma unroll 12
     for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * SP + l], acc);
     qo[o * SP + l] = acc + p[DQ_B3 + o];
   }
@@ -114,48 +147,57 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 
 __global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* p = smem;                       // [DQ_P]
-  float* h1 = p + ((DQ_P + 3) & ~3);     // [120][32]
-  float* h2 = h1 + DQ_H1 * ACT_E;        // [84][32]
-  float* qo = h2 + DQ_H2 * ACT_E;        // [2][32]
-  float* xs = qo + DQ_A * ACT_E;         // [4][32] current observation of the CTA's envs
-  for (int i = threadIdx.x; i < DQ_P; i += ACT_T) p[i] = a.q[i];
-  const int e = threadIdx.x & (ACT_E - 1), g = threadIdx.x / ACT_E;
+  constexpr int SP = ACT_SP;
+  float* p = smem;                       // [DQ_PP]
+  float* h1 = p + DQ_PP;                 // [120][SP]
+  float* h2 = h1 + DQ_H1 * SP;           // [84][SP]
+  float* qo = h2 + DQ_H2 * SP;           // [2][SP]
+  float* xs = qo + DQ_A * SP;            // [4][SP] current observation of the CTA's envs
+  const int tid = threadIdx.x;
+  load_q_params<ACT_T>(a.q, p, tid);
+  const int e = tid;                     // env lane, meaningful for warp 0
   const int n = blockIdx.x * ACT_E + e;
-  const bool owner = g == 0, valid = n < a.N;   // warp 0: one lane per env, state in registers for the whole launch
+  const bool owner = tid < ACT_E, valid = owner && n < a.N;   // warp 0: one lane per env, state in registers
   float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   int t = 0, len = 0;
   double ret = 0.0;
   uint32_t rc = 0;
   if (owner) {
     if (valid) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) st[k] = a.env_state[4 * n + k];
+      const float4 s4 = reinterpret_cast<const float4*>(a.env_state)[n];
+      st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
       t = a.env_t[n];
       ret = a.ep_ret[n];
       len = a.ep_len[n];
       rc = a.resets[n];
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) xs[k * ACT_E + e] = st[k];
+    for (int k = 0; k < 4; k++) xs[k * SP + e] = st[k];
   }
   __syncthreads();
+#ifdef DQN_TRACE
+  long long dtr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   for (int s = 0; s < a.n_steps; s++) {
-    float x[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) x[k] = xs[k * ACT_E + e];
-    q_forward<ACT_E, ACT_G>(p, x, h1, h2, qo, e, g);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
-    if (owner && valid) {
+#ifdef DQN_TRACE
+    const bool dtrace = blockIdx.x == 0 && s == 5 && (tid == 0 || tid == 5 * 32);
+#endif
+    DTR(0);
+    q_forward<ACT_E, SP, ACT_T>(p, xs, h1, h2, qo, tid);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
+    DTR(1);
+    if (valid) {
       const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
       uint32_t r[4];
       philox_draw(a.seed, (uint32_t)n, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
       const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
       int action;
-      if (u < a.eps[s]) action = (int)(r[2] & 1u);                  // rand(action_space(env)), dqn.jl:54
-      else action = qo[1 * ACT_E + e] > qo[0 * ACT_E + e] ? 1 : 0;  // argmax: first maximum, dqn.jl:56-57
+      if (u < a.eps[s]) action = (int)(r[2] & 1u);              // rand(action_space(env)), dqn.jl:54
+      else action = qo[1 * SP + e] > qo[0 * SP + e] ? 1 : 0;    // argmax: first maximum, dqn.jl:56-57
+      DTR(2);
       float rew;
       bool done;
       cartpole_step(st, t, action, a.max_steps, rew, done);
+      DTR(3);
       const int slot = (int)(((long long)a.ptr + (long long)s * a.N + n) % a.C);   // add!, replay_buffer.jl:23-37, envs in order
       reinterpret_cast<float4*>(a.b_state)[slot] = obs;
       reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
@@ -176,213 +218,45 @@ __global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
         cartpole_reset(st, t, u4);
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) xs[k * ACT_E + e] = st[k];
+      for (int k = 0; k < 4; k++) xs[k * SP + e] = st[k];
     }
+    DTR(4);
     __syncthreads();
+    DTR(5);
+#ifdef DQN_TRACE
+    if (dtrace)
+      printf("act warp %d: forward %lld | philox+choice %lld | cartpole %lld | store+reset %lld | barrier %lld | step %lld\n",
+             tid >> 5, dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2], dtr[4] - dtr[3], dtr[5] - dtr[4], dtr[5] - dtr[0]);
+#endif
   }
-  if (owner && valid) {
+  if (valid) {
     a.ep_ret[n] = ret;
     a.ep_len[n] = len;
     a.env_t[n] = t;
     a.resets[n] = rc;
-#pragma unroll
-    for (int k = 0; k < 4; k++) a.env_state[4 * n + k] = st[k];
+    reinterpret_cast<float4*>(a.env_state)[n] = make_float4(st[0], st[1], st[2], st[3]);
   }
 }
 
 struct LearnArgs {
-  float* q; float* tgt; float* m; float* v; float* g;
+  float* q; float* tgt; float* m; float* v;
   const float *b_state, *b_next, *b_reward; const int* b_action; const uint8_t* b_term;
   DqnDev* dev;
   unsigned long long seed, learn_step;
   double gamma, lr;
   int B, size, copy_target;
-  // multi-SM path: sample-major scratch [128][rows] between the two kernels, Adam's beta powers from the host
+  // sample-major scratch between the two kernels: [128][120], [128][84], [128][84], [128][120], [128][4], [128][2]
   float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;
-  double* loss_part;
-  double bp1, bp2;
+  double* loss_part;      // [LF_MAX_BLOCKS]
+  double bp1, bp2;        // beta1^t, beta2^t of Adam, kept on the host
 };
 
-__global__ void __launch_bounds__(LEARN_T) dqn_learn_kernel(LearnArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int PP = (DQ_P + 3) & ~3, S = LEARN_B, SP = LEARN_SP;
-  float* pq = smem;                       // q_net parameters
-  float* pt = pq + PP;                    // target_net parameters
-  float* h1 = pt + PP;                    // [120][SP]  (later dz1 in place)
-  float* h2 = h1 + DQ_H1 * SP;            // [84][SP]   (later dz2 in place)
-  float* xs = h2 + DQ_H2 * SP;            // [4][SP] states of the batch
-  float* dq = xs + DQ_D * SP;             // [2][SP]
-  float* qo = dq + DQ_A * SP;             // [2][SP] network outputs
-  __shared__ uint32_t keys[8];
-  __shared__ double red[S / 32];
-  const int tid = threadIdx.x, B = a.B;
-  const int i = tid & (S - 1), g = tid / S;   // sample, neuron group
-  for (int k = tid; k < DQ_P; k += LEARN_T) { pq[k] = a.q[k]; pt[k] = a.tgt[k]; }
-  if (tid == 0) {
-    philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
-    philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
-  }
-  __syncthreads();
-  float s[4] = {0.f, 0.f, 0.f, 0.f}, nx[4] = {0.f, 0.f, 0.f, 0.f};
-  int act = 0, term = 0;
-  float rew = 0.0f;
-  if (i < B) {
-    // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
-    const uint32_t idx = perm_index((uint32_t)i, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
-    const float4 s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
-    const float4 n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
-    s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
-    nx[0] = n4.x; nx[1] = n4.y; nx[2] = n4.z; nx[3] = n4.w;
-    act = a.b_action[idx];
-    rew = a.b_reward[idx];
-    term = a.b_term[idx];
-  }
-  q_forward<SP, LEARN_G>(pt, nx, h1, h2, qo, i, g);                  // target_net(next_state), dqn.jl:99
-  const float next_q = fmaxf(qo[0 * SP + i], qo[1 * SP + i]);
-  const double td = (double)rew + a.gamma * (double)next_q * (1.0 - (double)term);   // dqn.jl:100
-  __syncthreads();
-  q_forward<SP, LEARN_G>(pq, s, h1, h2, qo, i, g);                   // q_net(state), dqn.jl:105
-  double sq = 0.0;
-  if (g == 0) {
-    dq[0 * SP + i] = 0.0f;
-    dq[1 * SP + i] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < DQ_D; k++) xs[k * SP + i] = s[k];
-    if (i < B) {
-      const double diff = td - (double)qo[act * SP + i];
-      sq = diff * diff;                                              // Flux.mse, dqn.jl:107
-      dq[act * SP + i] = (float)(-2.0 * diff / (double)B);
-    }
-    sq = warp_sum(sq);
-    if ((tid & 31) == 0) red[tid >> 5] = sq;
-  }
-  __syncthreads();
-  if (tid == 0) a.dev->last_loss = ((red[0] + red[1]) + (red[2] + red[3])) / (double)B;
-  // ---- backward; every reduction over the batch runs in ascending sample order in one thread. The lanes of a warp
-  //      walk down the NEURON axis of the [neuron][SP] tiles here: SP is odd, so they hit distinct banks.
-  float* gr = a.g;
-  for (int w = tid; w < DQ_A * DQ_H2 + DQ_A; w += LEARN_T) {         // dW3(o,k), db3(o)
-    if (w < DQ_A * DQ_H2) {
-      const int o = w % DQ_A, k = w / DQ_A;
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc = fmaf(dq[o * SP + b], h2[k * SP + b], acc);
-      gr[DQ_W3 + w] = acc;
-    } else {
-      const int o = w - DQ_A * DQ_H2;
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += dq[o * SP + b];
-      gr[DQ_B3 + o] = acc;
-    }
-  }
-  __syncthreads();
-  {                                                                  // dz2 = (W3^T dq) .* (h2 > 0), in place
-    const float d0 = dq[0 * SP + i], d1 = dq[1 * SP + i];
-    for (int k = g; k < DQ_H2; k += LEARN_G) {
-      const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
-      h2[k * SP + i] = h2[k * SP + i] > 0.0f ? dh : 0.0f;
-    }
-  }
-  __syncthreads();
-  {                                                                  // dW2(j,k) as 4x4 register tiles, db2(j)
-    constexpr int JQ = DQ_H2 / 4, KQ = DQ_H1 / 4;                    // tile = neurons j, j+21, j+42, j+63 x inputs k0..k0+3
-    static_assert(DQ_H2 % 4 == 0 && DQ_H1 % 4 == 0, "4x4 weight-gradient tiles");
-    for (int w = tid; w < JQ * KQ; w += LEARN_T) {
-      const int j = w % JQ, k0 = (w / JQ) * 4;
-      float acc[4][4];
-#pragma unroll
-      for (int t = 0; t < 4; t++)
-#pragma unroll
-        for (int u = 0; u < 4; u++) acc[t][u] = 0.0f;
-#pragma unroll 2
-      for (int b = 0; b < B; b++) {
-        float z[4], hh[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) z[t] = h2[(j + JQ * t) * SP + b];
-#pragma unroll
-        for (int u = 0; u < 4; u++) hh[u] = h1[(k0 + u) * SP + b];
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-          for (int u = 0; u < 4; u++) acc[t][u] = fmaf(z[t], hh[u], acc[t][u]);
-      }
-#pragma unroll
-      for (int t = 0; t < 4; t++)
-#pragma unroll
-        for (int u = 0; u < 4; u++) gr[DQ_W2 + (j + JQ * t) + DQ_H2 * (k0 + u)] = acc[t][u];
-    }
-    for (int j = tid; j < DQ_H2; j += LEARN_T) {
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += h2[j * SP + b];
-      gr[DQ_B2 + j] = acc;
-    }
-  }
-  __syncthreads();
-  // dz1 = (W2^T dz2) .* (h1 > 0), in place; three inputs k per pass share the dz2 loads, four consecutive j are one
-  // 128-bit weight load (ascending j within each chain)
-  static_assert(DQ_H1 % (3 * LEARN_G) == 0, "dz1 passes");
-  for (int k0 = 3 * g; k0 < DQ_H1; k0 += 3 * LEARN_G) {
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-#pragma unroll 3
-    for (int j = 0; j < DQ_H2; j += 4) {
-      const float4 w0 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 0));
-      const float4 w1 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 1));
-      const float4 w2 = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k0 + 2));
-      const float z0 = h2[(j + 0) * SP + i], z1 = h2[(j + 1) * SP + i], z2 = h2[(j + 2) * SP + i], z3 = h2[(j + 3) * SP + i];
-      d0 = fmaf(w0.x, z0, d0); d0 = fmaf(w0.y, z1, d0); d0 = fmaf(w0.z, z2, d0); d0 = fmaf(w0.w, z3, d0);
-      d1 = fmaf(w1.x, z0, d1); d1 = fmaf(w1.y, z1, d1); d1 = fmaf(w1.z, z2, d1); d1 = fmaf(w1.w, z3, d1);
-      d2 = fmaf(w2.x, z0, d2); d2 = fmaf(w2.y, z1, d2); d2 = fmaf(w2.z, z2, d2); d2 = fmaf(w2.w, z3, d2);
-    }
-    h1[(k0 + 0) * SP + i] = h1[(k0 + 0) * SP + i] > 0.0f ? d0 : 0.0f;
-    h1[(k0 + 1) * SP + i] = h1[(k0 + 1) * SP + i] > 0.0f ? d1 : 0.0f;
-    h1[(k0 + 2) * SP + i] = h1[(k0 + 2) * SP + i] > 0.0f ? d2 : 0.0f;
-  }
-  __syncthreads();
-  for (int w = tid; w < DQ_H1 * DQ_D + DQ_H1; w += LEARN_T) {        // dW1(j,k), db1(j)
-    if (w < DQ_H1 * DQ_D) {
-      const int j = w % DQ_H1, k = w / DQ_H1;
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc = fmaf(h1[j * SP + b], xs[k * SP + b], acc);
-      gr[DQ_W1 + w] = acc;
-    } else {
-      const int j = w - DQ_H1 * DQ_D;
-      float acc = 0.0f;
-      for (int b = 0; b < B; b++) acc += h1[j * SP + b];
-      gr[DQ_B1 + j] = acc;
-    }
-  }
-  __syncthreads();
-  // ---- Flux.Adam(lr) (dqn.jl:41,109), Float64 scalars as in clip_adam_kernel; then the target copy (dqn.jl:111-113)
-  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-  const double bp1 = a.dev->bp1, bp2 = a.dev->bp2;
-  __syncthreads();
-  for (int k = tid; k < DQ_P; k += LEARN_T) {
-    const float d = gr[k];
-    const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[k]), __dmul_rn(1.0 - b1, (double)d));
-    const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
-    a.m[k] = mt;
-    a.v[k] = vt;
-    const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - bp2)), eps);
-    const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - bp1), den), a.lr);
-    const float pn = __fsub_rn(pq[k], step);
-    a.q[k] = pn;
-    if (a.copy_target) a.tgt[k] = pn;
-  }
-  if (tid == 0) { a.dev->bp1 = bp1 * b1; a.dev->bp2 = bp2 * b2; }
-}
-
-
-// ---- the learning step on several SMs -------------------------------------------------------------------------------
-// dqn_learn_fwd_kernel: CTA c owns samples 16c..16c+15 of the batch (thread = sample x neuron group): gather, target
-// and q forward, TD target, loss, dz2, dz1; everything the weight gradients need is written sample-major to a global
-// scratch (L2-resident, 220 KB). dqn_learn_upd_kernel: one thread per 4x4 tile of dW2 (or per element of the small
-// arrays) sums over the batch in ascending sample order - the same fmaf chains as dqn_learn_kernel - and applies Adam
-// to the parameters it has just differentiated, so gradients never leave registers.
 __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int PP = (DQ_P + 3) & ~3, SP = LF_SP;
+  constexpr int SP = LF_SP, EQ = LF_S / 4;
   float* pq = smem;                       // q_net parameters
-  float* pt = pq + PP;                    // target_net parameters
-  float* h1 = pt + PP;                    // [120][SP]
+  float* pt = pq + DQ_PP;                 // target_net parameters
+  float* h1 = pt + DQ_PP;                 // [120][SP]
   float* h2 = h1 + DQ_H1 * SP;            // [84][SP]   (later dz2 in place)
   float* qo = h2 + DQ_H2 * SP;            // [2][SP]
   float* dq = qo + DQ_A * SP;             // [2][SP]
@@ -391,15 +265,21 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   __shared__ float s_rew[LF_S];
   __shared__ int s_act[LF_S], s_term[LF_S];
   const int tid = threadIdx.x, B = a.B;
-  const int i = tid & (LF_S - 1), g = tid / LF_S;   // sample within the CTA, neuron group
-  const int b = blockIdx.x * LF_S + i;              // sample of the batch
-  for (int k = tid; k < DQ_P; k += LF_T) { pq[k] = a.q[k]; pt[k] = a.tgt[k]; }
-  if (tid == 0) {
+  const int b0 = blockIdx.x * LF_S;       // first sample of this CTA
+#ifdef DQN_TRACE
+  long long dtr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool dtrace = blockIdx.x == 0 && (tid == 0 || tid == 5 * 32);
+#endif
+  DTR(0);
+  load_q_params<LF_T>(a.q, pq, tid);
+  load_q_params<LF_T>(a.tgt, pt, tid);
+  if (tid == LF_S) {
     philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
     philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
   }
   __syncthreads();
-  if (g == 0) {
+  if (tid < LF_S) {
+    const int i = tid, b = b0 + i;
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = s4;
     int act = 0, term = 0;
     float rew = 0.0f;
@@ -411,21 +291,27 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
       act = a.b_action[idx];
       rew = a.b_reward[idx];
       term = a.b_term[idx];
+      reinterpret_cast<float4*>(a.xT)[b] = s4;
     }
     xin[0 * SP + i] = s4.x; xin[1 * SP + i] = s4.y; xin[2 * SP + i] = s4.z; xin[3 * SP + i] = s4.w;
     xin[4 * SP + i] = n4.x; xin[5 * SP + i] = n4.y; xin[6 * SP + i] = n4.z; xin[7 * SP + i] = n4.w;
     s_rew[i] = rew; s_act[i] = act; s_term[i] = term;
   }
+  DTR(1);
   __syncthreads();
-  float s[4], nx[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) { s[k] = xin[k * SP + i]; nx[k] = xin[(4 + k) * SP + i]; }
-  q_forward<SP, LF_G>(pt, nx, h1, h2, qo, i, g);                     // target_net(next_state), dqn.jl:99
-  const float next_q = fmaxf(qo[0 * SP + i], qo[1 * SP + i]);
-  const double td = (double)s_rew[i] + a.gamma * (double)next_q * (1.0 - (double)s_term[i]);   // dqn.jl:100
+  DTR(2);
+  q_forward<LF_S, SP, LF_T>(pt, xin + 4 * SP, h1, h2, qo, tid);      // target_net(next_state), dqn.jl:99
+  DTR(3);
+  double td = 0.0;
+  if (tid < LF_S) {
+    const float next_q = fmaxf(qo[0 * SP + tid], qo[1 * SP + tid]);
+    td = (double)s_rew[tid] + a.gamma * (double)next_q * (1.0 - (double)s_term[tid]);   // dqn.jl:100
+  }
   __syncthreads();
-  q_forward<SP, LF_G>(pq, s, h1, h2, qo, i, g);                      // q_net(state), dqn.jl:105
-  if (g == 0) {                                                      // lanes 0-15 of warp 0
+  q_forward<LF_S, SP, LF_T>(pq, xin, h1, h2, qo, tid);               // q_net(state), dqn.jl:105
+  DTR(4);
+  if (tid < LF_S) {                                                  // lanes 0-15 of warp 0
+    const int i = tid, b = b0 + i;
     float d0 = 0.0f, d1 = 0.0f;
     double sq = 0.0;
     if (b < B) {
@@ -434,10 +320,7 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
       sq = diff * diff;                                              // Flux.mse, dqn.jl:107
       const float dd = (float)(-2.0 * diff / (double)B);
       if (act == 0) d0 = dd; else d1 = dd;
-      a.dqT[b * DQ_A + 0] = d0;
-      a.dqT[b * DQ_A + 1] = d1;
-#pragma unroll
-      for (int k = 0; k < DQ_D; k++) a.xT[b * DQ_D + k] = s[k];
+      reinterpret_cast<float2*>(a.dqT)[b] = make_float2(d0, d1);
     }
     dq[0 * SP + i] = d0;
     dq[1 * SP + i] = d1;
@@ -446,127 +329,233 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
     if (i == 0) a.loss_part[blockIdx.x] = sq;
   }
   __syncthreads();
-  {                                                                  // dz2 = (W3^T dq) .* (h2 > 0), in place
-    const float d0 = dq[0 * SP + i], d1 = dq[1 * SP + i];
-    for (int k = g; k < DQ_H2; k += LF_G) {
-      const float hv = h2[k * SP + i];
-      const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], d1, pq[DQ_W3 + 0 + DQ_A * k] * d0);
-      const float z = hv > 0.0f ? dh : 0.0f;
-      h2[k * SP + i] = z;
-      if (b < B) { a.h2T[b * DQ_H2 + k] = hv; a.z2T[b * DQ_H2 + k] = z; }
-    }
-    if (b < B)
-      for (int k = g; k < DQ_H1; k += LF_G) a.h1T[b * DQ_H1 + k] = h1[k * SP + i];
+  DTR(5);
+  // dz2 = (W3^T dq) .* (h2 > 0), in place; h1, h2 (activations) and dz2 go to the scratch, neuron fastest
+  for (int w = tid; w < DQ_H2 * LF_S; w += LF_T) {
+    const int k = w % DQ_H2, i = w / DQ_H2, b = b0 + i;
+    const float hv = h2[k * SP + i];
+    const float dh = fmaf(pq[DQ_W3 + 1 + DQ_A * k], dq[1 * SP + i], pq[DQ_W3 + 0 + DQ_A * k] * dq[0 * SP + i]);
+    const float z = hv > 0.0f ? dh : 0.0f;
+    h2[k * SP + i] = z;
+    if (b < B) { a.h2T[b * DQ_H2 + k] = hv; a.z2T[b * DQ_H2 + k] = z; }
+  }
+  for (int w = tid; w < DQ_H1 * LF_S; w += LF_T) {
+    const int k = w % DQ_H1, i = w / DQ_H1, b = b0 + i;
+    if (b < B) a.h1T[b * DQ_H1 + k] = h1[k * SP + i];
   }
   __syncthreads();
-  {                                                                  // dz1 = (W2^T dz2) .* (h1 > 0) for k = g, g+32, g+64, g+96
-    static_assert(4 * LF_G >= DQ_H1, "one dz1 pass covers the first hidden layer");
-    float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    int kk[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) kk[t] = min(g + LF_G * t, DQ_H1 - 1);   // clamped for the loads; stores are guarded
+  DTR(6);
+  // dz1 = (W2^T dz2) .* (h1 > 0): a thread owns inputs k, k + 60 for 4 samples; four consecutive j are one 128-bit
+  // weight load (each chain in ascending j)
+  if (tid < (DQ_H1 / 2) * EQ) {
+    const int eq = tid % EQ, k = tid / EQ;
+    float4 d[2];
+    d[0] = d[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll 3
     for (int j = 0; j < DQ_H2; j += 4) {
-      const float z0 = h2[(j + 0) * SP + i], z1 = h2[(j + 1) * SP + i], z2 = h2[(j + 2) * SP + i], z3 = h2[(j + 3) * SP + i];
+      float4 z[4];
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const float4 w = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * kk[t]);
-        d[t] = fmaf(w.x, z0, d[t]); d[t] = fmaf(w.y, z1, d[t]); d[t] = fmaf(w.z, z2, d[t]); d[t] = fmaf(w.w, z3, d[t]);
+      for (int t = 0; t < 4; t++) z[t] = *reinterpret_cast<const float4*>(h2 + (j + t) * SP + 4 * eq);
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const float4 w = *reinterpret_cast<const float4*>(pq + DQ_W2 + j + DQ_H2 * (k + (DQ_H1 / 2) * c));
+        d[c].x = fmaf(w.x, z[0].x, d[c].x); d[c].y = fmaf(w.x, z[0].y, d[c].y); d[c].z = fmaf(w.x, z[0].z, d[c].z); d[c].w = fmaf(w.x, z[0].w, d[c].w);
+        d[c].x = fmaf(w.y, z[1].x, d[c].x); d[c].y = fmaf(w.y, z[1].y, d[c].y); d[c].z = fmaf(w.y, z[1].z, d[c].z); d[c].w = fmaf(w.y, z[1].w, d[c].w);
+        d[c].x = fmaf(w.z, z[2].x, d[c].x); d[c].y = fmaf(w.z, z[2].y, d[c].y); d[c].z = fmaf(w.z, z[2].z, d[c].z); d[c].w = fmaf(w.z, z[2].w, d[c].w);
+        d[c].x = fmaf(w.w, z[3].x, d[c].x); d[c].y = fmaf(w.w, z[3].y, d[c].y); d[c].z = fmaf(w.w, z[3].z, d[c].z); d[c].w = fmaf(w.w, z[3].w, d[c].w);
       }
     }
-    if (b < B) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const int kc = k + (DQ_H1 / 2) * c;
+      const float4 hv = *reinterpret_cast<const float4*>(h1 + kc * SP + 4 * eq);
+      const float dv[4] = {d[c].x, d[c].y, d[c].z, d[c].w}, hh[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
       for (int t = 0; t < 4; t++) {
-        const int k = g + LF_G * t;
-        if (k < DQ_H1) a.z1T[b * DQ_H1 + k] = h1[k * SP + i] > 0.0f ? d[t] : 0.0f;
+        const int b = b0 + 4 * eq + t;
+        if (b < B) a.z1T[b * DQ_H1 + kc] = hh[t] > 0.0f ? dv[t] : 0.0f;
       }
     }
+  }
+  DTR(7);
+#ifdef DQN_TRACE
+  if (dtrace)
+    printf("learn_fwd warp %d: params+gather %lld | barrier %lld | target fwd %lld | q fwd %lld | loss %lld | dz2+export %lld | dz1 %lld | total %lld\n",
+           tid >> 5, dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2], dtr[4] - dtr[3], dtr[5] - dtr[4], dtr[6] - dtr[5], dtr[7] - dtr[6], dtr[7] - dtr[0]);
+#endif
+}
+
+// Flux.Adam(lr) (dqn.jl:41,109) for NP parameters of one thread, Float64 scalars as in clip_adam_kernel; then the
+// target copy (dqn.jl:111-113). All loads are issued before the first store (the compiler cannot prove that the
+// arrays do not alias).
+template <int NP> __device__ __forceinline__ void dqn_adam(const LearnArgs& a, const int (&idx)[NP], const float (&g)[NP]) {
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  float m0[NP], v0[NP], q0[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) { m0[i] = a.m[idx[i]]; v0[i] = a.v[idx[i]]; q0[i] = a.q[idx[i]]; }
+  const double c1 = 1.0 - a.bp1, c2 = 1.0 - a.bp2;
+#pragma unroll
+  for (int i = 0; i < NP; i++) {
+    const float d = g[i];
+    const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)m0[i]), __dmul_rn(1.0 - b1, (double)d));
+    const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)v0[i]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
+    const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, c2)), eps);
+    const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, c1), den), a.lr);
+    const float pn = __fsub_rn(q0[i], step);
+    a.m[idx[i]] = mt;
+    a.v[idx[i]] = vt;
+    a.q[idx[i]] = pn;
+    if (a.copy_target) a.tgt[idx[i]] = pn;
   }
 }
 
-// Flux.Adam(lr) (dqn.jl:41,109) for one parameter, Float64 scalars as in clip_adam_kernel; then the target copy
-// (dqn.jl:111-113)
-__device__ __forceinline__ void dqn_adam_one(const LearnArgs& a, int k, float d) {
-  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-  const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[k]), __dmul_rn(1.0 - b1, (double)d));
-  const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[k]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
-  a.m[k] = mt;
-  a.v[k] = vt;
-  const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - a.bp2)), eps);
-  const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - a.bp1), den), a.lr);
-  const float pn = __fsub_rn(a.q[k], step);
-  a.q[k] = pn;
-  if (a.copy_target) a.tgt[k] = pn;
+// block-wide copy of `cols` consecutive columns starting at column c0 of a sample-major [rows][ld] scratch array into
+// shared memory [rows][cols] (128-bit loads; c0, cols, ld multiples of 4)
+__device__ __forceinline__ void stage_cols(const float* __restrict__ src, int ld, int c0, int cols, int rows, float* dst, int tid) {
+  const int q = cols / 4;
+  for (int i = tid; i < rows * q; i += LU_T) {
+    const int r = i / q, c = i % q;
+    reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(src + r * ld + c0 + 4 * c);
+  }
 }
 
 __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_fwd_blocks) {
-  const int B = a.B;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  extern __shared__ __align__(16) float smem[];
+  const int B = a.B, tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == LU_T - 1) {
     double sq = 0.0;
     for (int c = 0; c < n_fwd_blocks; c++) sq += a.loss_part[c];
     a.dev->last_loss = sq / (double)B;
   }
-  if (blockIdx.x < LU_TILE_BLOCKS) {                                 // dW2(j,k): neurons j, j+21, j+42, j+63 x inputs k0..k0+3
-    const int w = blockIdx.x * LU_T + threadIdx.x;
-    if (w >= LU_TILES) return;
+#ifdef DQN_TRACE
+  long long dtr[4] = {0, 0, 0, 0};
+  const bool dtrace = (blockIdx.x == 1 || blockIdx.x == LU_A_BLOCKS || blockIdx.x == LU_A_BLOCKS + LU_B_BLOCKS) && tid == 0;
+#endif
+  DTR(0);
+  if (blockIdx.x < LU_A_BLOCKS) {
+    // (A) dW2(j,k) for the 24 inputs k0..k0+23: thread = neurons j, j+21, j+42, j+63 x 4 consecutive inputs
     constexpr int JQ = DQ_H2 / 4;
-    const int j = w % JQ, k0 = (w / JQ) * 4;
+    const int k0 = blockIdx.x * LU_KA;
+    float* zs = smem;                     // [B][84]  dz2
+    float* hs = zs + LEARN_B * DQ_H2;     // [B][24]  h1 columns k0..
+    stage_cols(a.z2T, DQ_H2, 0, DQ_H2, B, zs, tid);
+    stage_cols(a.h1T, DQ_H1, k0, LU_KA, B, hs, tid);
+    __syncthreads();
+    DTR(1);
+    if (tid >= JQ * (LU_KA / 4)) return;
+    const int j = tid % JQ, kq = tid / JQ;
     float2 acc[4][2];
 #pragma unroll
     for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = make_float2(0.0f, 0.0f);
 #pragma unroll 4
     for (int b = 0; b < B; b++) {
-      const float4 hh = *reinterpret_cast<const float4*>(a.h1T + b * DQ_H1 + k0);
+      const float4 hh = *reinterpret_cast<const float4*>(hs + b * LU_KA + 4 * kq);
 #pragma unroll
       for (int t = 0; t < 4; t++) {
-        const float z = a.z2T[b * DQ_H2 + j + JQ * t];
+        const float z = zs[b * DQ_H2 + j + JQ * t];
         acc[t][0] = __ffma2_rn(make_float2(z, z), make_float2(hh.x, hh.y), acc[t][0]);
         acc[t][1] = __ffma2_rn(make_float2(z, z), make_float2(hh.z, hh.w), acc[t][1]);
       }
     }
+    DTR(2);
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int base = DQ_W2 + (j + JQ * t) + DQ_H2 * k0;
-      dqn_adam_one(a, base + DQ_H2 * 0, acc[t][0].x);
-      dqn_adam_one(a, base + DQ_H2 * 1, acc[t][0].y);
-      dqn_adam_one(a, base + DQ_H2 * 2, acc[t][1].x);
-      dqn_adam_one(a, base + DQ_H2 * 3, acc[t][1].y);
+    for (int half = 0; half < 2; half++) {   // two rounds of 8 parameters keep the register count down
+      int idx[8];
+      float g[8];
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int tt = 2 * half + t, base = DQ_W2 + (j + JQ * tt) + DQ_H2 * (k0 + 4 * kq);
+        idx[4 * t + 0] = base;              g[4 * t + 0] = acc[tt][0].x;
+        idx[4 * t + 1] = base + DQ_H2;      g[4 * t + 1] = acc[tt][0].y;
+        idx[4 * t + 2] = base + 2 * DQ_H2;  g[4 * t + 2] = acc[tt][1].x;
+        idx[4 * t + 3] = base + 3 * DQ_H2;  g[4 * t + 3] = acc[tt][1].y;
+      }
+      dqn_adam<8>(a, idx, g);
     }
+    DTR(3);
+#ifdef DQN_TRACE
+    if (dtrace) printf("learn_upd A: stage %lld | reduce %lld | adam x16 %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
+#endif
     return;
   }
-  const int w = (blockIdx.x - LU_TILE_BLOCKS) * LU_T + threadIdx.x;
-  if (w >= LU_SINGLES) return;
-  constexpr int N_W1 = DQ_H1 * DQ_D, N_B1 = N_W1 + DQ_H1, N_B2 = N_B1 + DQ_H2, N_W3 = N_B2 + DQ_A * DQ_H2;
-  float acc = 0.0f;
-  int pidx;
-  if (w < N_W1) {                                                    // dW1(j,k)
-    const int j = w % DQ_H1, k = w / DQ_H1;
-    for (int b = 0; b < B; b++) acc = fmaf(a.z1T[b * DQ_H1 + j], a.xT[b * DQ_D + k], acc);
-    pidx = DQ_W1 + w;
-  } else if (w < N_B1) {                                             // db1(j)
-    const int j = w - N_W1;
-    for (int b = 0; b < B; b++) acc += a.z1T[b * DQ_H1 + j];
-    pidx = DQ_B1 + j;
-  } else if (w < N_B2) {                                             // db2(j)
-    const int j = w - N_B1;
-    for (int b = 0; b < B; b++) acc += a.z2T[b * DQ_H2 + j];
-    pidx = DQ_B2 + j;
-  } else if (w < N_W3) {                                             // dW3(o,k)
-    const int ww = w - N_B2, o = ww % DQ_A, k = ww / DQ_A;
-    for (int b = 0; b < B; b++) acc = fmaf(a.dqT[b * DQ_A + o], a.h2T[b * DQ_H2 + k], acc);
-    pidx = DQ_W3 + ww;
-  } else {                                                           // db3(o)
-    const int o = w - N_W3;
-    for (int b = 0; b < B; b++) acc += a.dqT[b * DQ_A + o];
-    pidx = DQ_B3 + o;
+  if (blockIdx.x < LU_A_BLOCKS + LU_B_BLOCKS) {
+    // (B) dW1(j, 0..3) and db1(j) for the 24 first-layer neurons j0..j0+23
+    const int j0 = (blockIdx.x - LU_A_BLOCKS) * LU_JB;
+    float* z1s = smem;                    // [B][24]  dz1 columns j0..
+    float* xs = z1s + LEARN_B * LU_JB;    // [B][4]
+    stage_cols(a.z1T, DQ_H1, j0, LU_JB, B, z1s, tid);
+    stage_cols(a.xT, DQ_D, 0, DQ_D, B, xs, tid);
+    __syncthreads();
+    DTR(1);
+    if (tid >= LU_JB * (DQ_D + 1)) return;
+    const int jl = tid % LU_JB, kind = tid / LU_JB, j = j0 + jl;
+    float acc = 0.0f;
+    int idx[1];
+    if (kind < DQ_D) {
+#pragma unroll 8
+      for (int b = 0; b < B; b++) acc = fmaf(z1s[b * LU_JB + jl], xs[b * DQ_D + kind], acc);
+      idx[0] = DQ_W1 + j + DQ_H1 * kind;
+    } else {
+#pragma unroll 8
+      for (int b = 0; b < B; b++) acc += z1s[b * LU_JB + jl];
+      idx[0] = DQ_B1 + j;
+    }
+    DTR(2);
+    const float g[1] = {acc};
+    dqn_adam<1>(a, idx, g);
+    DTR(3);
+#ifdef DQN_TRACE
+    if (dtrace) printf("learn_upd B: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
+#endif
+    return;
   }
-  dqn_adam_one(a, pidx, acc);
+  {
+    // (C) dW3(0,k), dW3(1,k), db2(k) for the 28 second-layer neurons k0..k0+27; db3 in the first of these blocks
+    const int c = blockIdx.x - LU_A_BLOCKS - LU_B_BLOCKS, k0 = c * LU_KC;
+    float* h2s = smem;                    // [B][28]  h2 columns k0..
+    float* z2s = h2s + LEARN_B * LU_KC;   // [B][28]  dz2 columns k0..
+    float* dqs = z2s + LEARN_B * LU_KC;   // [B][2]
+    stage_cols(a.h2T, DQ_H2, k0, LU_KC, B, h2s, tid);
+    stage_cols(a.z2T, DQ_H2, k0, LU_KC, B, z2s, tid);
+    for (int i = tid; i < B * DQ_A; i += LU_T) dqs[i] = a.dqT[i];
+    __syncthreads();
+    DTR(1);
+    const int n_main = LU_KC * (DQ_A + 1);
+    if (tid >= n_main + (c == 0 ? DQ_A : 0)) return;
+    float acc = 0.0f;
+    int idx[1];
+    if (tid < n_main) {
+      const int kl = tid % LU_KC, kind = tid / LU_KC, k = k0 + kl;
+      if (kind < DQ_A) {
+#pragma unroll 8
+        for (int b = 0; b < B; b++) acc = fmaf(dqs[b * DQ_A + kind], h2s[b * LU_KC + kl], acc);
+        idx[0] = DQ_W3 + kind + DQ_A * k;
+      } else {
+#pragma unroll 8
+        for (int b = 0; b < B; b++) acc += z2s[b * LU_KC + kl];
+        idx[0] = DQ_B2 + k;
+      }
+    } else {
+      const int o = tid - n_main;
+#pragma unroll 8
+      for (int b = 0; b < B; b++) acc += dqs[b * DQ_A + o];
+      idx[0] = DQ_B3 + o;
+    }
+    DTR(2);
+    const float g[1] = {acc};
+    dqn_adam<1>(a, idx, g);
+    DTR(3);
+#ifdef DQN_TRACE
+    if (dtrace) printf("learn_upd C: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
+#endif
+  }
 }
 
-constexpr size_t ACT_SMEM = (((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_E) * sizeof(float);
-constexpr size_t LEARN_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + DQ_D + 2 * DQ_A) * LEARN_SP) * sizeof(float);
-static_assert(LEARN_SMEM <= 227 * 1024, "dqn_learn shared memory");
-constexpr size_t LF_SMEM = (2 * ((DQ_P + 3) & ~3) + (DQ_H1 + DQ_H2 + 2 * DQ_A + 2 * DQ_D) * LF_SP) * sizeof(float);
+constexpr size_t ACT_SMEM = (DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP) * sizeof(float);
+constexpr size_t LF_SMEM = (2 * DQ_PP + (DQ_H1 + DQ_H2 + 2 * DQ_A + 2 * DQ_D) * LF_SP) * sizeof(float);
+constexpr size_t LU_SMEM = (size_t)LEARN_B * (DQ_H2 + LU_KA) * sizeof(float);   // kind (A) is the largest
+static_assert(LEARN_B * (LU_JB + DQ_D) <= LEARN_B * (DQ_H2 + LU_KA) && LEARN_B * (2 * LU_KC + DQ_A) <= LEARN_B * (DQ_H2 + LU_KA), "upd smem");
+static_assert(ACT_SMEM <= 227 * 1024 && LF_SMEM <= 227 * 1024 && LU_SMEM <= 227 * 1024, "dqn shared memory");
 
 int dfail(int code, const std::string& msg) { return crl_internal_fail(code, msg.c_str()); }
 #define DCK(call)                                                                                          \
@@ -587,16 +576,16 @@ template <typename T> cudaError_t dzalloc(T** p, size_t n) {
 struct crl_dqn_ctx {
   crl_dqn_config cfg;
   cudaStream_t stream;
-  float *q, *tgt, *m, *v, *g;
+  float *q, *tgt, *m, *v;
   float* env_state; int* env_t; double* ep_ret; int* ep_len; uint32_t* resets;
   float *b_state, *b_next, *b_reward; int* b_action; uint8_t* b_term;
   DqnDev* dev;
   float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;   // scratch between dqn_learn_fwd_kernel and dqn_learn_upd_kernel
   double* loss_part;
-  double bp1, bp2;                            // beta1^t, beta2^t of Adam (multi-SM learning step: kept on the host)
+  double bp1, bp2;                            // beta1^t, beta2^t of Adam
   int size, ptr;
   long long it, learn_steps, launches;
-  bool params_set, reset_done, one_cta_learn;
+  bool params_set, reset_done;
 };
 
 __global__ void dqn_reset_kernel(int N, unsigned long long seed, float* env_state, int* env_t, double* ep_ret, int* ep_len,
@@ -636,7 +625,7 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   c->cfg = *cfg;
   const size_t N = cfg->num_envs, C = cfg->buffer_size;
   DCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  DCK(dzalloc(&c->q, DQ_P)); DCK(dzalloc(&c->tgt, DQ_P)); DCK(dzalloc(&c->m, DQ_P)); DCK(dzalloc(&c->v, DQ_P)); DCK(dzalloc(&c->g, DQ_P));
+  DCK(dzalloc(&c->q, DQ_P)); DCK(dzalloc(&c->tgt, DQ_P)); DCK(dzalloc(&c->m, DQ_P)); DCK(dzalloc(&c->v, DQ_P));
   DCK(dzalloc(&c->env_state, 4 * N)); DCK(dzalloc(&c->env_t, N)); DCK(dzalloc(&c->ep_ret, N)); DCK(dzalloc(&c->ep_len, N));
   DCK(dzalloc(&c->resets, N));
   DCK(dzalloc(&c->b_state, 4 * C)); DCK(dzalloc(&c->b_next, 4 * C)); DCK(dzalloc(&c->b_reward, C)); DCK(dzalloc(&c->b_action, C));
@@ -645,12 +634,8 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   DCK(dzalloc(&c->z1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->xT, (size_t)LEARN_B * DQ_D)); DCK(dzalloc(&c->dqT, (size_t)LEARN_B * DQ_A));
   DCK(dzalloc(&c->loss_part, LF_MAX_BLOCKS));
   DCK(cudaFuncSetAttribute(dqn_learn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
-  {
-    const char* e = getenv("CRL_DQN_ONE_CTA");   // A/B switch: the whole learning step in one CTA (dqn_learn_kernel)
-    c->one_cta_learn = e && atoi(e) != 0;
-  }
+  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
   DCK(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
-  DCK(cudaFuncSetAttribute(dqn_learn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEARN_SMEM));
   *out = c;
   return CRL_OK;
 }
@@ -659,7 +644,7 @@ extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
   if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
-  void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->g, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
+  void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
                   c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   cudaStreamDestroy(c->stream);
@@ -677,7 +662,6 @@ extern "C" CRL_API int crl_dqn_set_params(crl_dqn_ctx* c, const float* params, i
   DCK(cudaMemsetAsync(c->v, 0, sizeof(float) * DQ_P, c->stream));
   DqnDev d;
   memset(&d, 0, sizeof(d));
-  d.bp1 = 0.9; d.bp2 = 0.999;
   DCK(cudaMemcpyAsync(c->dev, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream));
   DCK(cudaStreamSynchronize(c->stream));
   c->bp1 = 0.9; c->bp2 = 0.999;
@@ -745,26 +729,20 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     if (learn) {
       LearnArgs l;
       memset(&l, 0, sizeof(l));
-      l.q = c->q; l.tgt = c->tgt; l.m = c->m; l.v = c->v; l.g = c->g;
+      l.q = c->q; l.tgt = c->tgt; l.m = c->m; l.v = c->v;
       l.b_state = c->b_state; l.b_next = c->b_next; l.b_reward = c->b_reward; l.b_action = c->b_action; l.b_term = c->b_term;
       l.dev = c->dev; l.seed = c->cfg.seed; l.learn_step = (unsigned long long)c->learn_steps; l.gamma = c->cfg.gamma;
       l.lr = c->cfg.lr; l.B = c->cfg.batch_size; l.size = c->size;
       l.copy_target = (c->it % c->cfg.target_net_freq == 0) ? 1 : 0;                                             // dqn.jl:111
-      if (c->one_cta_learn) {
-        dqn_learn_kernel<<<1, LEARN_T, LEARN_SMEM, c->stream>>>(l);
-        DCK(cudaGetLastError());
-        c->launches += 1;
-      } else {
-        l.h1T = c->h1T; l.h2T = c->h2T; l.z2T = c->z2T; l.z1T = c->z1T; l.xT = c->xT; l.dqT = c->dqT;
-        l.loss_part = c->loss_part; l.bp1 = c->bp1; l.bp2 = c->bp2;
-        const int fwd_blocks = (l.B + LF_S - 1) / LF_S;
-        dqn_learn_fwd_kernel<<<fwd_blocks, LF_T, LF_SMEM, c->stream>>>(l);
-        DCK(cudaGetLastError());
-        dqn_learn_upd_kernel<<<LU_TILE_BLOCKS + LU_SINGLE_BLOCKS, LU_T, 0, c->stream>>>(l, fwd_blocks);
-        DCK(cudaGetLastError());
-        c->bp1 *= 0.9; c->bp2 *= 0.999;   // same Float64 products the one-CTA kernel keeps on the device
-        c->launches += 2;
-      }
+      l.h1T = c->h1T; l.h2T = c->h2T; l.z2T = c->z2T; l.z1T = c->z1T; l.xT = c->xT; l.dqT = c->dqT;
+      l.loss_part = c->loss_part; l.bp1 = c->bp1; l.bp2 = c->bp2;
+      const int fwd_blocks = (l.B + LF_S - 1) / LF_S;
+      dqn_learn_fwd_kernel<<<fwd_blocks, LF_T, LF_SMEM, c->stream>>>(l);
+      DCK(cudaGetLastError());
+      dqn_learn_upd_kernel<<<LU_A_BLOCKS + LU_B_BLOCKS + LU_C_BLOCKS, LU_T, LU_SMEM, c->stream>>>(l, fwd_blocks);
+      DCK(cudaGetLastError());
+      c->bp1 *= 0.9; c->bp2 *= 0.999;
+      c->launches += 2;
       c->learn_steps += 1;
     }
   }
