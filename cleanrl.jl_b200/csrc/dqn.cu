@@ -54,10 +54,10 @@ constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bou
 constexpr int LEARN_B = 128;        // max batch size
 constexpr int LF_S = 16, LF_SP = LF_S + 4, LF_T = 256;   // dqn_learn_fwd_kernel: samples per CTA, row stride, threads
 constexpr int LF_MAX_BLOCKS = LEARN_B / LF_S;
-// dqn_learn_upd_kernel: block kinds (A) dW2 tiles of 24 input columns, (B) dW1/db1 of 24 neurons, (C) dW3/db2(/db3)
+// dqn_learn_upd_kernel: block kinds (A) dW2 tiles of 8 input columns, (B) dW1/db1 of 24 neurons, (C) dW3/db2(/db3)
 // of 28 neurons
-constexpr int LU_T = 128;
-constexpr int LU_KA = 24, LU_A_BLOCKS = DQ_H1 / LU_KA;   // 5 blocks x (21 neuron quads x 6 input quads) = 630 tiles
+constexpr int LU_T = 256;
+constexpr int LU_KA = 8, LU_A_BLOCKS = DQ_H1 / LU_KA;    // 15 blocks x (21 neuron quads x 2 input quads) = 630 tiles
 constexpr int LU_JB = 24, LU_B_BLOCKS = DQ_H1 / LU_JB;   // 5 blocks x 24 neurons x (4 inputs + bias)
 constexpr int LU_KC = 28, LU_C_BLOCKS = DQ_H2 / LU_KC;   // 3 blocks x 28 neurons x (2 outputs + bias)
 static_assert(DQ_H1 % LU_KA == 0 && DQ_H1 % LU_JB == 0 && DQ_H2 % LU_KC == 0, "upd block decomposition");
@@ -84,8 +84,13 @@ struct ActArgs {
 template <int NT> __device__ __forceinline__ void load_q_params(const float* __restrict__ g, float* sp, int tid) {
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* s4 = reinterpret_cast<float4*>(sp);
-  for (int i = tid; i < DQ_P / 4; i += NT) s4[i] = g4[i];
-  if (tid < DQ_P % 4) sp[(DQ_P / 4) * 4 + tid] = g[(DQ_P / 4) * 4 + tid];
+  constexpr int N4 = DQ_P / 4, PER = (N4 + NT - 1) / NT;
+  float4 tmp[PER];   // every load is in flight before the first store: one L2 round trip instead of PER
+#pragma unroll
+  for (int u = 0; u < PER; u++) if (tid + u * NT < N4) tmp[u] = g4[tid + u * NT];
+#pragma unroll
+  for (int u = 0; u < PER; u++) if (tid + u * NT < N4) s4[tid + u * NT] = tmp[u];
+  if (tid < DQ_P % 4) sp[N4 * 4 + tid] = g[N4 * 4 + tid];
 }
 
 // Dense -> relu -> Dense -> relu -> Dense for a tile of NS samples by NT threads (CTA-wide barriers between the
@@ -117,15 +122,39 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
     float2 acc[4][2];
 #pragma unroll
     for (int n = 0; n < 4; n++) acc[n][0] = acc[n][1] = make_float2(0.0f, 0.0f);
-#pragma unroll 4
-    for (int k = 0; k < DQ_H1; k++) {
-      const float4 w = *reinterpret_cast<const float4*>(p + DQ_W2 + j + DQ_H2 * k);
-      const float4 h = *reinterpret_cast<const float4*>(h1 + k * SP + 4 * eq);
-      const float2 h01 = make_float2(h.x, h.y), h23 = make_float2(h.z, h.w);
-      acc[0][0] = __ffma2_rn(make_float2(w.x, w.x), h01, acc[0][0]); acc[0][1] = __ffma2_rn(make_float2(w.x, w.x), h23, acc[0][1]);
-      acc[1][0] = __ffma2_rn(make_float2(w.y, w.y), h01, acc[1][0]); acc[1][1] = __ffma2_rn(make_float2(w.y, w.y), h23, acc[1][1]);
-      acc[2][0] = __ffma2_rn(make_float2(w.z, w.z), h01, acc[2][0]); acc[2][1] = __ffma2_rn(make_float2(w.z, w.z), h23, acc[2][1]);
-      acc[3][0] = __ffma2_rn(make_float2(w.w, w.w), h01, acc[3][0]); acc[3][1] = __ffma2_rn(make_float2(w.w, w.w), h23, acc[3][1]);
+    // software pipeline: the operands of the next U values of k are loaded while the current U are multiplied (the
+    // layer runs on one or two warps per scheduler, which cannot hide the shared-memory latency by themselves)
+    constexpr int U = 4;
+    static_assert(DQ_H1 % U == 0, "pipeline depth");
+    const float* wp = p + DQ_W2 + j;
+    const float* hp = h1 + 4 * eq;
+    float4 wn[U], hn[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      wn[u] = *reinterpret_cast<const float4*>(wp + DQ_H2 * u);
+      hn[u] = *reinterpret_cast<const float4*>(hp + SP * u);
+    }
+#pragma unroll 1
+    for (int k0 = 0; k0 < DQ_H1; k0 += U) {
+      float4 wc[U], hc[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { wc[u] = wn[u]; hc[u] = hn[u]; }
+      if (k0 + U < DQ_H1) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          wn[u] = *reinterpret_cast<const float4*>(wp + DQ_H2 * (k0 + U + u));
+          hn[u] = *reinterpret_cast<const float4*>(hp + SP * (k0 + U + u));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float4 w = wc[u];
+        const float2 h01 = make_float2(hc[u].x, hc[u].y), h23 = make_float2(hc[u].z, hc[u].w);
+        acc[0][0] = __ffma2_rn(make_float2(w.x, w.x), h01, acc[0][0]); acc[0][1] = __ffma2_rn(make_float2(w.x, w.x), h23, acc[0][1]);
+        acc[1][0] = __ffma2_rn(make_float2(w.y, w.y), h01, acc[1][0]); acc[1][1] = __ffma2_rn(make_float2(w.y, w.y), h23, acc[1][1]);
+        acc[2][0] = __ffma2_rn(make_float2(w.z, w.z), h01, acc[2][0]); acc[2][1] = __ffma2_rn(make_float2(w.z, w.z), h23, acc[2][1]);
+        acc[3][0] = __ffma2_rn(make_float2(w.w, w.w), h01, acc[3][0]); acc[3][1] = __ffma2_rn(make_float2(w.w, w.w), h23, acc[3][1]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < 4; n++) {
@@ -145,7 +174,7 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(ACT_T) dqn_act_kernel(ActArgs a) {
+__global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int SP = ACT_SP;
   float* p = smem;                       // [DQ_PP]
@@ -261,7 +290,6 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   float* qo = h2 + DQ_H2 * SP;            // [2][SP]
   float* dq = qo + DQ_A * SP;             // [2][SP]
   float* xin = dq + DQ_A * SP;            // [8][SP]: rows 0-3 state, rows 4-7 next_state
-  __shared__ uint32_t keys[8];
   __shared__ float s_rew[LF_S];
   __shared__ int s_act[LF_S], s_term[LF_S];
   const int tid = threadIdx.x, B = a.B;
@@ -271,28 +299,27 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   const bool dtrace = blockIdx.x == 0 && (tid == 0 || tid == 5 * 32);
 #endif
   DTR(0);
-  load_q_params<LF_T>(a.q, pq, tid);
-  load_q_params<LF_T>(a.tgt, pt, tid);
-  if (tid == LF_S) {
+  // the gather (HBM latency) is issued first and completes under the parameter loads
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = s4;
+  int act = 0, term = 0;
+  float rew = 0.0f;
+  if (tid < LF_S && b0 + tid < B) {
+    // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
+    uint32_t keys[8];
     philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
     philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
+    const uint32_t idx = perm_index((uint32_t)(b0 + tid), (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
+    s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
+    n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
+    act = a.b_action[idx];
+    rew = a.b_reward[idx];
+    term = a.b_term[idx];
   }
-  __syncthreads();
+  load_q_params<LF_T>(a.q, pq, tid);
+  load_q_params<LF_T>(a.tgt, pt, tid);
   if (tid < LF_S) {
     const int i = tid, b = b0 + i;
-    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = s4;
-    int act = 0, term = 0;
-    float rew = 0.0f;
-    if (b < B) {
-      // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
-      const uint32_t idx = perm_index((uint32_t)b, (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
-      s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
-      n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
-      act = a.b_action[idx];
-      rew = a.b_reward[idx];
-      term = a.b_term[idx];
-      reinterpret_cast<float4*>(a.xT)[b] = s4;
-    }
+    if (b < B) reinterpret_cast<float4*>(a.xT)[b] = s4;
     xin[0 * SP + i] = s4.x; xin[1 * SP + i] = s4.y; xin[2 * SP + i] = s4.z; xin[3 * SP + i] = s4.w;
     xin[4 * SP + i] = n4.x; xin[5 * SP + i] = n4.y; xin[6 * SP + i] = n4.z; xin[7 * SP + i] = n4.w;
     s_rew[i] = rew; s_act[i] = act; s_term[i] = term;
@@ -388,14 +415,19 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
 // Flux.Adam(lr) (dqn.jl:41,109) for NP parameters of one thread, Float64 scalars as in clip_adam_kernel; then the
 // target copy (dqn.jl:111-113). All loads are issued before the first store (the compiler cannot prove that the
 // arrays do not alias).
-template <int NP> __device__ __forceinline__ void dqn_adam(const LearnArgs& a, const int (&idx)[NP], const float (&g)[NP]) {
+template <int NP>
+__device__ __forceinline__ void dqn_adam(const LearnArgs& a, const int (&idx)[NP], const float (&g)[NP], const bool (&ok)[NP]) {
   const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
   float m0[NP], v0[NP], q0[NP];
 #pragma unroll
-  for (int i = 0; i < NP; i++) { m0[i] = a.m[idx[i]]; v0[i] = a.v[idx[i]]; q0[i] = a.q[idx[i]]; }
+  for (int i = 0; i < NP; i++) {
+    m0[i] = v0[i] = q0[i] = 0.0f;
+    if (ok[i]) { m0[i] = a.m[idx[i]]; v0[i] = a.v[idx[i]]; q0[i] = a.q[idx[i]]; }
+  }
   const double c1 = 1.0 - a.bp1, c2 = 1.0 - a.bp2;
 #pragma unroll
   for (int i = 0; i < NP; i++) {
+    if (!ok[i]) continue;
     const float d = g[i];
     const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)m0[i]), __dmul_rn(1.0 - b1, (double)d));
     const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)v0[i]), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
@@ -412,10 +444,20 @@ template <int NP> __device__ __forceinline__ void dqn_adam(const LearnArgs& a, c
 // block-wide copy of `cols` consecutive columns starting at column c0 of a sample-major [rows][ld] scratch array into
 // shared memory [rows][cols] (128-bit loads; c0, cols, ld multiples of 4)
 __device__ __forceinline__ void stage_cols(const float* __restrict__ src, int ld, int c0, int cols, int rows, float* dst, int tid) {
-  const int q = cols / 4;
-  for (int i = tid; i < rows * q; i += LU_T) {
-    const int r = i / q, c = i % q;
-    reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(src + r * ld + c0 + 4 * c);
+  const int q = cols / 4, total = rows * q;
+  constexpr int BATCH = 8;   // loads in flight per thread before the first store
+  for (int base = 0; base < total; base += BATCH * LU_T) {
+    float4 tmp[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+      const int i = base + u * LU_T + tid;
+      if (i < total) tmp[u] = *reinterpret_cast<const float4*>(src + (i / q) * ld + c0 + 4 * (i % q));
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+      const int i = base + u * LU_T + tid;
+      if (i < total) reinterpret_cast<float4*>(dst)[i] = tmp[u];
+    }
   }
 }
 
@@ -433,48 +475,56 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
 #endif
   DTR(0);
   if (blockIdx.x < LU_A_BLOCKS) {
-    // (A) dW2(j,k) for the 24 inputs k0..k0+23: thread = neurons j, j+21, j+42, j+63 x 4 consecutive inputs
-    constexpr int JQ = DQ_H2 / 4;
+    // (A) dW2(j,k) for the 8 inputs k0..k0+7: thread = neurons j, j+21, j+42, j+63 x 4 consecutive inputs; the block's
+    // 672 parameters W2(:, k0..k0+7) are contiguous in the flat vector, so Adam then runs block-wide and coalesced
+    constexpr int JQ = DQ_H2 / 4, NPAR = DQ_H2 * LU_KA, PER = (NPAR + LU_T - 1) / LU_T;
     const int k0 = blockIdx.x * LU_KA;
     float* zs = smem;                     // [B][84]  dz2
-    float* hs = zs + LEARN_B * DQ_H2;     // [B][24]  h1 columns k0..
+    float* hs = zs + LEARN_B * DQ_H2;     // [B][8]   h1 columns k0..
+    float* gs = hs + LEARN_B * LU_KA;     // [8][84]  gradient of this block's parameters
     stage_cols(a.z2T, DQ_H2, 0, DQ_H2, B, zs, tid);
     stage_cols(a.h1T, DQ_H1, k0, LU_KA, B, hs, tid);
     __syncthreads();
     DTR(1);
-    if (tid >= JQ * (LU_KA / 4)) return;
-    const int j = tid % JQ, kq = tid / JQ;
-    float2 acc[4][2];
+    if (tid < JQ * (LU_KA / 4)) {
+      const int j = tid % JQ, kq = tid / JQ;
+      float2 acc[4][2];
 #pragma unroll
-    for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = make_float2(0.0f, 0.0f);
+      for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = make_float2(0.0f, 0.0f);
 #pragma unroll 4
-    for (int b = 0; b < B; b++) {
-      const float4 hh = *reinterpret_cast<const float4*>(hs + b * LU_KA + 4 * kq);
+      for (int b = 0; b < B; b++) {
+        const float4 hh = *reinterpret_cast<const float4*>(hs + b * LU_KA + 4 * kq);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const float z = zs[b * DQ_H2 + j + JQ * t];
+          acc[t][0] = __ffma2_rn(make_float2(z, z), make_float2(hh.x, hh.y), acc[t][0]);
+          acc[t][1] = __ffma2_rn(make_float2(z, z), make_float2(hh.z, hh.w), acc[t][1]);
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 4; t++) {
-        const float z = zs[b * DQ_H2 + j + JQ * t];
-        acc[t][0] = __ffma2_rn(make_float2(z, z), make_float2(hh.x, hh.y), acc[t][0]);
-        acc[t][1] = __ffma2_rn(make_float2(z, z), make_float2(hh.z, hh.w), acc[t][1]);
+        float* gp = gs + (4 * kq) * DQ_H2 + j + JQ * t;
+        gp[0 * DQ_H2] = acc[t][0].x; gp[1 * DQ_H2] = acc[t][0].y; gp[2 * DQ_H2] = acc[t][1].x; gp[3 * DQ_H2] = acc[t][1].y;
       }
     }
+    __syncthreads();
     DTR(2);
+    {
+      int idx[PER];
+      float g[PER];
+      bool ok[PER];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {   // two rounds of 8 parameters keep the register count down
-      int idx[8];
-      float g[8];
-#pragma unroll
-      for (int t = 0; t < 2; t++) {
-        const int tt = 2 * half + t, base = DQ_W2 + (j + JQ * tt) + DQ_H2 * (k0 + 4 * kq);
-        idx[4 * t + 0] = base;              g[4 * t + 0] = acc[tt][0].x;
-        idx[4 * t + 1] = base + DQ_H2;      g[4 * t + 1] = acc[tt][0].y;
-        idx[4 * t + 2] = base + 2 * DQ_H2;  g[4 * t + 2] = acc[tt][1].x;
-        idx[4 * t + 3] = base + 3 * DQ_H2;  g[4 * t + 3] = acc[tt][1].y;
+      for (int u = 0; u < PER; u++) {
+        const int i = tid + u * LU_T;
+        ok[u] = i < NPAR;
+        idx[u] = DQ_W2 + DQ_H2 * k0 + i;
+        g[u] = ok[u] ? gs[i] : 0.0f;
       }
-      dqn_adam<8>(a, idx, g);
+      dqn_adam<PER>(a, idx, g, ok);
     }
     DTR(3);
 #ifdef DQN_TRACE
-    if (dtrace) printf("learn_upd A: stage %lld | reduce %lld | adam x16 %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
+    if (dtrace) printf("learn_upd A: stage %lld | reduce %lld | adam x3 %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
 #endif
     return;
   }
@@ -502,7 +552,8 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     }
     DTR(2);
     const float g[1] = {acc};
-    dqn_adam<1>(a, idx, g);
+    const bool ok[1] = {true};
+    dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
     if (dtrace) printf("learn_upd B: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
@@ -543,7 +594,8 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     }
     DTR(2);
     const float g[1] = {acc};
-    dqn_adam<1>(a, idx, g);
+    const bool ok[1] = {true};
+    dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
     if (dtrace) printf("learn_upd C: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
@@ -553,7 +605,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
 
 constexpr size_t ACT_SMEM = (DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP) * sizeof(float);
 constexpr size_t LF_SMEM = (2 * DQ_PP + (DQ_H1 + DQ_H2 + 2 * DQ_A + 2 * DQ_D) * LF_SP) * sizeof(float);
-constexpr size_t LU_SMEM = (size_t)LEARN_B * (DQ_H2 + LU_KA) * sizeof(float);   // kind (A) is the largest
+constexpr size_t LU_SMEM = ((size_t)LEARN_B * (DQ_H2 + LU_KA) + DQ_H2 * LU_KA) * sizeof(float);   // kind (A) is the largest
 static_assert(LEARN_B * (LU_JB + DQ_D) <= LEARN_B * (DQ_H2 + LU_KA) && LEARN_B * (2 * LU_KC + DQ_A) <= LEARN_B * (DQ_H2 + LU_KA), "upd smem");
 static_assert(ACT_SMEM <= 227 * 1024 && LF_SMEM <= 227 * 1024 && LU_SMEM <= 227 * 1024, "dqn shared memory");
 
