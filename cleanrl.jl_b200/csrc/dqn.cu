@@ -4,9 +4,11 @@
 // the taken action -> backward -> Adam -> optional target copy) every train_freq iterations.
 //
 // The 4-120-84-2 network is evaluated out of shared memory as register tiles of 4 neurons x 4 samples (q_forward):
-// per k one 128-bit weight load and one 128-bit activation load feed 16 FMAs (packed FP32). With one neuron per thread
-// and one sample per lane the kernels were bound by shared-memory wavefronts (ncu: profiles/r1_v7_ncu_dqn_summary.csv);
-// every neuron is still ONE fmaf chain over ascending k, so results do not depend on the tiling.
+// per k one 128-bit weight load and one 128-bit activation load feed 16 independent FMA chains, software-pipelined.
+// With one neuron per thread and one sample per lane the kernels were bound by shared-memory wavefronts (ncu:
+// profiles/r1_v7_ncu_dqn_summary.csv); every neuron is still ONE fmaf chain over ascending k, so results do not
+// depend on the tiling. What is left in the 120 -> 84 layer is the FMA pipe of the busiest scheduler: 21 x 8 tiles are
+// 5.25 warps, so two schedulers carry two warps each (measured 44 cycles per k for 32 envs, -DDQN_TRACE).
 //
 //   dqn_act_kernel        32 envs per CTA of 256 threads. Warp 0 (one lane per env, state in registers) draws epsilon /
 //                         the random action from Philox, steps CartPole, appends the transition at
@@ -54,10 +56,10 @@ constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bou
 constexpr int LEARN_B = 128;        // max batch size
 constexpr int LF_S = 16, LF_SP = LF_S + 4, LF_T = 256;   // dqn_learn_fwd_kernel: samples per CTA, row stride, threads
 constexpr int LF_MAX_BLOCKS = LEARN_B / LF_S;
-// dqn_learn_upd_kernel: block kinds (A) dW2 tiles of 8 input columns, (B) dW1/db1 of 24 neurons, (C) dW3/db2(/db3)
+// dqn_learn_upd_kernel: block kinds (A) dW2 tiles of 4 input columns, (B) dW1/db1 of 24 neurons, (C) dW3/db2(/db3)
 // of 28 neurons
 constexpr int LU_T = 256;
-constexpr int LU_KA = 8, LU_A_BLOCKS = DQ_H1 / LU_KA;    // 15 blocks x (21 neuron quads x 2 input quads) = 630 tiles
+constexpr int LU_KA = 4, LU_A_BLOCKS = DQ_H1 / LU_KA;    // 30 blocks x (21 neuron quads x 1 input quad) = 630 tiles
 constexpr int LU_JB = 24, LU_B_BLOCKS = DQ_H1 / LU_JB;   // 5 blocks x 24 neurons x (4 inputs + bias)
 constexpr int LU_KC = 28, LU_C_BLOCKS = DQ_H2 / LU_KC;   // 3 blocks x 28 neurons x (2 outputs + bias)
 static_assert(DQ_H1 % LU_KA == 0 && DQ_H1 % LU_JB == 0 && DQ_H2 % LU_KC == 0, "upd block decomposition");
@@ -102,6 +104,9 @@ template <int NS, int SP, int NT>
 __device__ __forceinline__ void q_forward(const float* __restrict__ p, const float* xs, float* h1, float* h2, float* qo, int tid) {
   constexpr int EQ = NS / 4;   // sample quads
   static_assert(NS % 4 == 0 && SP % 4 == 0 && SP >= NS, "tile geometry");
+#ifdef DQN_TRACE
+  const long long q_t0 = clock64();
+#endif
   static_assert((DQ_H2 / 4) * EQ <= NT && DQ_A * NS <= NT, "one pass for the second layer and the head");
   for (int w = tid; w < DQ_H1 * EQ; w += NT) {
     const int eq = w % EQ, j = w / EQ;
@@ -116,16 +121,25 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
     *reinterpret_cast<float4*>(h1 + j * SP + 4 * eq) =
         make_float4(fmaxf(acc.x + b, 0.0f), fmaxf(acc.y + b, 0.0f), fmaxf(acc.z + b, 0.0f), fmaxf(acc.w + b, 0.0f));
   }
+#ifdef DQN_TRACE
+  const long long q_t1 = clock64();
+#endif
   __syncthreads();
+#ifdef DQN_TRACE
+  const long long q_t2 = clock64();
+#endif
   if (tid < (DQ_H2 / 4) * EQ) {
     const int eq = tid % EQ, j = 4 * (tid / EQ);
-    float2 acc[4][2];
+    // 16 independent scalar chains (packed FP32 would need a register-pair move per operand, and with one or two
+    // warps per scheduler and in-order issue each move stalls the FMA behind it: measured 45 cycles per k).
+    // Software pipeline: the operands of the next U values of k are loaded while the current U are multiplied.
+    float acc[4][4];
 #pragma unroll
-    for (int n = 0; n < 4; n++) acc[n][0] = acc[n][1] = make_float2(0.0f, 0.0f);
-    // software pipeline: the operands of the next U values of k are loaded while the current U are multiplied (the
-    // layer runs on one or two warps per scheduler, which cannot hide the shared-memory latency by themselves)
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[n][c] = 0.0f;
     constexpr int U = 4;
-    static_assert(DQ_H1 % U == 0, "pipeline depth");
+    static_assert(DQ_H1 % (2 * U) == 0, "pipeline depth");
     const float* wp = p + DQ_W2 + j;
     const float* hp = h1 + 4 * eq;
     float4 wn[U], hn[U];
@@ -134,7 +148,7 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
       wn[u] = *reinterpret_cast<const float4*>(wp + DQ_H2 * u);
       hn[u] = *reinterpret_cast<const float4*>(hp + SP * u);
     }
-#pragma unroll 1
+#pragma unroll 2
     for (int k0 = 0; k0 < DQ_H1; k0 += U) {
       float4 wc[U], hc[U];
 #pragma unroll
@@ -148,30 +162,61 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const float4 w = wc[u];
-        const float2 h01 = make_float2(hc[u].x, hc[u].y), h23 = make_float2(hc[u].z, hc[u].w);
-        acc[0][0] = __ffma2_rn(make_float2(w.x, w.x), h01, acc[0][0]); acc[0][1] = __ffma2_rn(make_float2(w.x, w.x), h23, acc[0][1]);
-        acc[1][0] = __ffma2_rn(make_float2(w.y, w.y), h01, acc[1][0]); acc[1][1] = __ffma2_rn(make_float2(w.y, w.y), h23, acc[1][1]);
-        acc[2][0] = __ffma2_rn(make_float2(w.z, w.z), h01, acc[2][0]); acc[2][1] = __ffma2_rn(make_float2(w.z, w.z), h23, acc[2][1]);
-        acc[3][0] = __ffma2_rn(make_float2(w.w, w.w), h01, acc[3][0]); acc[3][1] = __ffma2_rn(make_float2(w.w, w.w), h23, acc[3][1]);
+        const float wv[4] = {wc[u].x, wc[u].y, wc[u].z, wc[u].w}, hv[4] = {hc[u].x, hc[u].y, hc[u].z, hc[u].w};
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[n][c] = fmaf(wv[n], hv[c], acc[n][c]);
       }
     }
 #pragma unroll
     for (int n = 0; n < 4; n++) {
       const float b = p[DQ_B2 + j + n];
       *reinterpret_cast<float4*>(h2 + (j + n) * SP + 4 * eq) =
-          make_float4(fmaxf(acc[n][0].x + b, 0.0f), fmaxf(acc[n][0].y + b, 0.0f), fmaxf(acc[n][1].x + b, 0.0f), fmaxf(acc[n][1].y + b, 0.0f));
+          make_float4(fmaxf(acc[n][0] + b, 0.0f), fmaxf(acc[n][1] + b, 0.0f), fmaxf(acc[n][2] + b, 0.0f), fmaxf(acc[n][3] + b, 0.0f));
     }
   }
+#ifdef DQN_TRACE
+  const long long q_t3 = clock64();
+#endif
   __syncthreads();
+#ifdef DQN_TRACE
+  const long long q_t4 = clock64();
+#endif
   if (tid < DQ_A * NS) {
     const int l = tid % NS, o = tid / NS;
+    // one chain of 84 dependent FMAs: the next 12 operand pairs are loaded under the current 12 FMAs
+    constexpr int UH = 12;
+    static_assert(DQ_H2 % UH == 0, "head pipeline depth");
+    const float* wp = p + DQ_W3 + o;
+    const float* hp = h2 + l;
+    float wn[UH], hn[UH];
+#pragma unroll
+    for (int u = 0; u < UH; u++) { wn[u] = wp[DQ_A * u]; hn[u] = hp[SP * u]; }
     float acc = 0.0f;
-#pragma unroll 12
-    for (int k = 0; k < DQ_H2; k++) acc = fmaf(p[DQ_W3 + o + DQ_A * k], h2[k * SP + l], acc);
+#pragma unroll
+    for (int k0 = 0; k0 < DQ_H2; k0 += UH) {
+      float wc[UH], hc[UH];
+#pragma unroll
+      for (int u = 0; u < UH; u++) { wc[u] = wn[u]; hc[u] = hn[u]; }
+      if (k0 + UH < DQ_H2) {
+#pragma unroll
+        for (int u = 0; u < UH; u++) { wn[u] = wp[DQ_A * (k0 + UH + u)]; hn[u] = hp[SP * (k0 + UH + u)]; }
+      }
+#pragma unroll
+      for (int u = 0; u < UH; u++) acc = fmaf(wc[u], hc[u], acc);
+    }
     qo[o * SP + l] = acc + p[DQ_B3 + o];
   }
+#ifdef DQN_TRACE
+  const long long q_t5 = clock64();
+#endif
   __syncthreads();
+#ifdef DQN_TRACE
+  if (tid == 0 && blockIdx.x == 0)
+    printf("q_forward<%d>: layer1 %lld | barrier %lld | layer2 %lld | barrier %lld | head %lld | barrier %lld\n", NS, q_t1 - q_t0,
+           q_t2 - q_t1, q_t3 - q_t2, q_t4 - q_t3, q_t5 - q_t4, clock64() - q_t5);
+#endif
 }
 
 __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
@@ -475,37 +520,39 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
 #endif
   DTR(0);
   if (blockIdx.x < LU_A_BLOCKS) {
-    // (A) dW2(j,k) for the 8 inputs k0..k0+7: thread = neurons j, j+21, j+42, j+63 x 4 consecutive inputs; the block's
-    // 672 parameters W2(:, k0..k0+7) are contiguous in the flat vector, so Adam then runs block-wide and coalesced
+    // (A) dW2(j,k) for the 4 inputs k0..k0+3: thread = neurons j, j+21, j+42, j+63 x 4 consecutive inputs; the block's
+    // 336 parameters W2(:, k0..k0+3) are contiguous in the flat vector, so Adam then runs block-wide and coalesced
     constexpr int JQ = DQ_H2 / 4, NPAR = DQ_H2 * LU_KA, PER = (NPAR + LU_T - 1) / LU_T;
     const int k0 = blockIdx.x * LU_KA;
     float* zs = smem;                     // [B][84]  dz2
-    float* hs = zs + LEARN_B * DQ_H2;     // [B][8]   h1 columns k0..
-    float* gs = hs + LEARN_B * LU_KA;     // [8][84]  gradient of this block's parameters
+    float* hs = zs + LEARN_B * DQ_H2;     // [B][4]   h1 columns k0..
+    float* gs = hs + LEARN_B * LU_KA;     // [4][84]  gradient of this block's parameters
     stage_cols(a.z2T, DQ_H2, 0, DQ_H2, B, zs, tid);
     stage_cols(a.h1T, DQ_H1, k0, LU_KA, B, hs, tid);
     __syncthreads();
     DTR(1);
     if (tid < JQ * (LU_KA / 4)) {
       const int j = tid % JQ, kq = tid / JQ;
-      float2 acc[4][2];
+      float acc[4][4];   // 16 independent scalar chains (see q_forward)
 #pragma unroll
-      for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = make_float2(0.0f, 0.0f);
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[t][u] = 0.0f;
 #pragma unroll 4
       for (int b = 0; b < B; b++) {
         const float4 hh = *reinterpret_cast<const float4*>(hs + b * LU_KA + 4 * kq);
+        const float hv[4] = {hh.x, hh.y, hh.z, hh.w};
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           const float z = zs[b * DQ_H2 + j + JQ * t];
-          acc[t][0] = __ffma2_rn(make_float2(z, z), make_float2(hh.x, hh.y), acc[t][0]);
-          acc[t][1] = __ffma2_rn(make_float2(z, z), make_float2(hh.z, hh.w), acc[t][1]);
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[t][u] = fmaf(z, hv[u], acc[t][u]);
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        float* gp = gs + (4 * kq) * DQ_H2 + j + JQ * t;
-        gp[0 * DQ_H2] = acc[t][0].x; gp[1 * DQ_H2] = acc[t][0].y; gp[2 * DQ_H2] = acc[t][1].x; gp[3 * DQ_H2] = acc[t][1].y;
-      }
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) gs[(4 * kq + u) * DQ_H2 + j + JQ * t] = acc[t][u];
     }
     __syncthreads();
     DTR(2);
@@ -524,7 +571,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     }
     DTR(3);
 #ifdef DQN_TRACE
-    if (dtrace) printf("learn_upd A: stage %lld | reduce %lld | adam x3 %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
+    if (dtrace) printf("learn_upd A: stage %lld | reduce %lld | adam x2 %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
 #endif
     return;
   }
