@@ -126,10 +126,13 @@ def test_dqn_config_through_the_cli_parser(monkeypatch):
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,iters", [(1, 400), (8, 120), (64, 60)])
-def test_dqn_cuda_matches_oracle(crl, olib, abi, torch_cuda, N, iters):
+@pytest.mark.parametrize("N,iters,batch", [(1, 400, 32), (8, 120, 32), (64, 60, 32),
+                                           # batch sizes that leave the last 16-sample CTA of the learning step partly
+                                           # filled (120 = dqn.jl default, 33), fill all eight (128), or hold one sample
+                                           (16, 80, 120), (16, 80, 33), (32, 40, 128), (8, 60, 1)])
+def test_dqn_cuda_matches_oracle(crl, olib, abi, torch_cuda, N, iters, batch):
     from cleanrl_jl_b200.dqn_algo import DQNHandle, init_q_params
-    cfg = abi.make_dqn_config(num_envs=N, buffer_size=max(512, 4 * N), min_buff_size=64, batch_size=32, train_freq=4,
+    cfg = abi.make_dqn_config(num_envs=N, buffer_size=max(512, 4 * N), min_buff_size=max(64, batch), batch_size=batch, train_freq=4,
                               target_net_freq=12, epsilon_duration=float(iters * N), seed=9)
     h, o = DQNHandle(cfg), OracleDQN(olib, cfg)
     p = init_q_params(3)
