@@ -414,6 +414,24 @@ class OracleDQN:
         assert self.L.orc_dqn_run(self.h, int(iterations), C.byref(st)) == 0
         return st
 
+    def set_shard(self, world, rank, env_id_base):
+        """make this context rank `rank` of a data-parallel world (it then only steps through dqn_group_run)"""
+        self.L.orc_dqn_set_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        assert self.L.orc_dqn_set_shard(self.h, int(world), int(rank), int(env_id_base)) == 0
+
+    @staticmethod
+    def group_run(shards, iterations):
+        """orc_dqn_group_run: all shards of a data-parallel world in lockstep; returns one crl_dqn_stats per shard"""
+        L = shards[0].L
+        k = len(shards)
+        hs = (C.c_void_p * k)(*[s.h for s in shards])
+        st = (_abi.crl_dqn_stats * k)()
+        L.orc_dqn_group_run.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+        rc = L.orc_dqn_group_run(hs, k, int(iterations), st)
+        if rc != 0:
+            raise ValueError("orc_dqn_group_run failed: %d" % rc)
+        return list(st)
+
     def read_buffer(self):
         cap = self.cfg.buffer_size
         out = {"state": np.zeros((cap, 4), np.float32), "action": np.zeros(cap, np.int32), "reward": np.zeros(cap, np.float32),

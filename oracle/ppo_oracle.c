@@ -1192,6 +1192,8 @@ typedef struct orc_dqn_ctx {
   int32_t size, ptr;
   int64_t it, learn_steps;
   double last_loss;
+  /* data-parallel shard (orc_dqn_set_shard): world ranks, this one owns the envs env_id_base .. env_id_base + num_envs - 1 */
+  int32_t world, rank, env_id_base;
 } orc_dqn_ctx;
 
 double orc_dqn_linear_schedule(double start_e, double end_e, double duration, double t) {
@@ -1225,9 +1227,11 @@ int orc_dqn_forward_raw(const float* params, const float* obs, float* q_out, int
   return 0;
 }
 /* loss and gradient of one batch (dqn.jl:96-108); everything passed in, nothing sampled */
-int orc_dqn_loss_raw(const float* q_params, const float* tgt_params, int32_t B, const float* state, const int32_t* action,
-                     const float* reward, const float* next_state, const uint8_t* terminal, double gamma, float* grads,
-                     double* loss_out) {
+/* B_scale = size of the GLOBAL batch the mean is taken over (= B unless the batch is one shard of a data-parallel
+ * step); sq_sum_out receives the plain sum of squared TD errors of these B samples */
+static int dqn_loss_grad(const float* q_params, const float* tgt_params, int32_t B, int32_t B_scale, const float* state,
+                         const int32_t* action, const float* reward, const float* next_state, const uint8_t* terminal,
+                         double gamma, float* grads, double* sq_sum_out) {
   float* h1 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H1);
   float* h2 = (float*)malloc(sizeof(float) * (size_t)B * DQ_H2);
   float* dq = (float*)calloc((size_t)B * DQ_A, sizeof(float));
@@ -1242,9 +1246,9 @@ int orc_dqn_loss_raw(const float* q_params, const float* tgt_params, int32_t B, 
     dqn_forward(q_params, state + i * DQ_D, h1 + i * DQ_H1, h2 + i * DQ_H2, qv);
     double diff = td - (double)qv[action[i]];
     loss += diff * diff;                                                                 /* Flux.mse, dqn.jl:107 */
-    dq[i * DQ_A + action[i]] = (float)(-2.0 * diff / (double)B);
+    dq[i * DQ_A + action[i]] = (float)(-2.0 * diff / (double)B_scale);
   }
-  *loss_out = loss / (double)B;
+  *sq_sum_out = loss;
   memset(grads, 0, sizeof(float) * DQ_P);
   /* backward, reductions over the batch in ascending sample order */
   for (int o = 0; o < DQ_A; o++) {
@@ -1292,6 +1296,14 @@ int orc_dqn_loss_raw(const float* q_params, const float* tgt_params, int32_t B, 
   free(h1); free(h2); free(dq); free(dz2); free(dz1);
   return 0;
 }
+int orc_dqn_loss_raw(const float* q_params, const float* tgt_params, int32_t B, const float* state, const int32_t* action,
+                     const float* reward, const float* next_state, const uint8_t* terminal, double gamma, float* grads,
+                     double* loss_out) {
+  double sq = 0.0;
+  int rc = dqn_loss_grad(q_params, tgt_params, B, B, state, action, reward, next_state, terminal, gamma, grads, &sq);
+  *loss_out = sq / (double)B;
+  return rc;
+}
 /* Flux.Adam(eta) [Flux 0.13.4], one shared (beta1^t, beta2^t) pair: every array is updated at every step */
 static void dqn_adam(orc_dqn_ctx* c) {
   const double b1 = 0.9, b2 = 0.999, eps = 1e-8, lr = c->cfg.lr;
@@ -1320,6 +1332,7 @@ int orc_dqn_create(const crl_dqn_config* cfg, orc_dqn_ctx** out) {
   c->b_reward = (float*)calloc(C, sizeof(float)); c->b_action = (int32_t*)calloc(C, sizeof(int32_t));
   c->b_term = (uint8_t*)calloc(C, 1);
   c->bp1 = 0.9; c->bp2 = 0.999;
+  c->world = 1; c->rank = 0; c->env_id_base = 0;
   *out = c;
   return 0;
 }
@@ -1347,7 +1360,7 @@ int orc_dqn_reset(orc_dqn_ctx* c) {
   for (int n = 0; n < c->cfg.num_envs; n++) {
     float u[4];
     c->resets[n] = 0;
-    orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)n, c->resets[n], u);
+    orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)(c->env_id_base + n), c->resets[n], u);
     c->resets[n] += 1;
     orc_cartpole_reset(c->env_state + 4 * n, &c->env_t[n], u);
     c->ep_ret[n] = 0.0; c->ep_len[n] = 0;
@@ -1355,11 +1368,13 @@ int orc_dqn_reset(orc_dqn_ctx* c) {
   c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0; c->last_loss = 0.0;
   return 0;
 }
-static void dqn_learn(orc_dqn_ctx* c) {
+/* this shard's part of a learning step: gradient of its batch_size samples scaled by 1 / (world * batch_size) into
+ * c->g, and the sum of its squared TD errors */
+static double dqn_learn_grad(orc_dqn_ctx* c) {
   const int B = c->cfg.batch_size;
   uint32_t keys[8];
-  philox_draw(c->cfg.seed, 0u, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys);
-  philox_draw(c->cfg.seed, 0x80000000u, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys + 4);
+  philox_draw(c->cfg.seed, (uint32_t)c->rank, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys);
+  philox_draw(c->cfg.seed, 0x80000000u | (uint32_t)c->rank, (uint64_t)c->learn_steps, ORC_STREAM_DQN_BATCH, keys + 4);
   float st[128 * 4], nx[128 * 4], rw[128];
   int32_t ac[128];
   uint8_t tm[128];
@@ -1368,56 +1383,99 @@ static void dqn_learn(orc_dqn_ctx* c) {
     memcpy(st + 4 * i, c->b_state + 4 * idx, 16); memcpy(nx + 4 * i, c->b_next + 4 * idx, 16);
     rw[i] = c->b_reward[idx]; ac[i] = c->b_action[idx]; tm[i] = c->b_term[idx];
   }
-  orc_dqn_loss_raw(c->q, c->tgt, B, st, ac, rw, nx, tm, c->cfg.gamma, c->g, &c->last_loss);
-  dqn_adam(c);
-  c->learn_steps += 1;
+  double sq = 0.0;
+  dqn_loss_grad(c->q, c->tgt, B, B * c->world, st, ac, rw, nx, tm, c->cfg.gamma, c->g, &sq);
+  return sq;
 }
-int orc_dqn_run(orc_dqn_ctx* c, int64_t iterations, crl_dqn_stats* stats) {
-  if (!c || iterations < 0) return -1;
+/* one vector step of this shard's envs (dqn.jl:49-92); gs = global step after it */
+static void dqn_act_iteration(orc_dqn_ctx* c, double eps, double* sum_ret, double* sum_len, int64_t* episodes) {
   const int N = c->cfg.num_envs, C = c->cfg.buffer_size;
-  double sum_ret = 0.0, sum_len = 0.0, eps = 0.0;
-  int64_t episodes = 0;
-  for (int64_t k = 0; k < iterations; k++) {
-    c->it += 1;
-    const double gs = (double)c->it * (double)N;
-    eps = orc_dqn_linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);
-    for (int n = 0; n < N; n++) {
-      float obs[4], h1[DQ_H1], h2[DQ_H2], q[DQ_A];
-      memcpy(obs, c->env_state + 4 * n, 16);                                    /* deepcopy(state(env)), dqn.jl:50 */
-      uint32_t r[4];
-      philox_draw(c->cfg.seed, (uint32_t)n, (uint64_t)c->it, ORC_STREAM_DQN_ACT, r);
-      const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
-      int action;
-      if (u < eps) action = (int)(r[2] & 1u);                                   /* rand(action_space), dqn.jl:54 */
-      else { dqn_forward(c->q, obs, h1, h2, q); action = q[1] > q[0] ? 1 : 0; } /* argmax: first maximum */
-      float rew; uint8_t done;
-      orc_cartpole_step(c->env_state + 4 * n, &c->env_t[n], action, c->cfg.max_episode_steps, &rew, &done);
-      const int p = (c->ptr + n) % C;                                           /* add!, replay_buffer.jl:23-37 */
-      memcpy(c->b_state + 4 * p, obs, 16); memcpy(c->b_next + 4 * p, c->env_state + 4 * n, 16);
-      c->b_action[p] = action; c->b_reward[p] = rew; c->b_term[p] = done;
-      c->ep_ret[n] += (double)rew; c->ep_len[n] += 1;
-      if (done) {                                                               /* dqn.jl:80-86 */
-        episodes += 1; sum_ret += c->ep_ret[n]; sum_len += (double)c->ep_len[n];
-        c->ep_ret[n] = 0.0; c->ep_len[n] = 0;
-        float u4[4];
-        orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)n, c->resets[n], u4);
-        c->resets[n] += 1;
-        orc_cartpole_reset(c->env_state + 4 * n, &c->env_t[n], u4);
-      }
+  for (int n = 0; n < N; n++) {
+    const uint32_t gid = (uint32_t)(c->env_id_base + n);
+    float obs[4], h1[DQ_H1], h2[DQ_H2], q[DQ_A];
+    memcpy(obs, c->env_state + 4 * n, 16);                                    /* deepcopy(state(env)), dqn.jl:50 */
+    uint32_t r[4];
+    philox_draw(c->cfg.seed, gid, (uint64_t)c->it, ORC_STREAM_DQN_ACT, r);
+    const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+    int action;
+    if (u < eps) action = (int)(r[2] & 1u);                                   /* rand(action_space), dqn.jl:54 */
+    else { dqn_forward(c->q, obs, h1, h2, q); action = q[1] > q[0] ? 1 : 0; } /* argmax: first maximum */
+    float rew; uint8_t done;
+    orc_cartpole_step(c->env_state + 4 * n, &c->env_t[n], action, c->cfg.max_episode_steps, &rew, &done);
+    const int p = (c->ptr + n) % C;                                           /* add!, replay_buffer.jl:23-37 */
+    memcpy(c->b_state + 4 * p, obs, 16); memcpy(c->b_next + 4 * p, c->env_state + 4 * n, 16);
+    c->b_action[p] = action; c->b_reward[p] = rew; c->b_term[p] = done;
+    c->ep_ret[n] += (double)rew; c->ep_len[n] += 1;
+    if (done) {                                                               /* dqn.jl:80-86 */
+      *episodes += 1; *sum_ret += c->ep_ret[n]; *sum_len += (double)c->ep_len[n];
+      c->ep_ret[n] = 0.0; c->ep_len[n] = 0;
+      float u4[4];
+      orc_rng_reset_uniforms(c->cfg.seed, gid, c->resets[n], u4);
+      c->resets[n] += 1;
+      orc_cartpole_reset(c->env_state + 4 * n, &c->env_t[n], u4);
     }
-    c->ptr = (c->ptr + N) % C;
-    c->size = c->size + N > C ? C : c->size + N;
-    if (gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size) {  /* dqn.jl:94 */
-      dqn_learn(c);
+  }
+  c->ptr = (c->ptr + N) % C;
+  c->size = c->size + N > C ? C : c->size + N;
+}
+/* Data-parallel DQN over `world` shards in lockstep (an extension: the reference has one env and one buffer). Every
+ * shard acts with the shared parameters on its own envs (Philox keyed by the GLOBAL env id, so the union of the
+ * shards' transitions equals a single run over all envs as long as the parameters agree), keeps its own ring, and
+ * contributes batch_size samples of it to a global batch of world * batch_size: the partial gradients are summed in
+ * rank order (a library allreduce may use another order: compare with a tolerance), Adam is applied identically
+ * everywhere. world = 1 is orc_dqn_run. stats: one per shard, or NULL. */
+int orc_dqn_group_run(orc_dqn_ctx** cs, int32_t world, int64_t iterations, crl_dqn_stats* stats) {
+  if (!cs || world < 1 || iterations < 0) return -1;
+  for (int r = 0; r < world; r++)
+    if (!cs[r] || cs[r]->world != world || cs[r]->rank != r || cs[r]->it != cs[0]->it ||
+        cs[r]->cfg.num_envs != cs[0]->cfg.num_envs || cs[r]->cfg.batch_size != cs[0]->cfg.batch_size) return -1;
+  double sum_ret[64] = {0}, sum_len[64] = {0}, eps = 0.0;
+  int64_t episodes[64] = {0};
+  if (world > 64) return -1;
+  const double n_global = (double)cs[0]->cfg.num_envs * (double)world;
+  for (int64_t k = 0; k < iterations; k++) {
+    int learn = 1;
+    for (int r = 0; r < world; r++) {
+      orc_dqn_ctx* c = cs[r];
+      c->it += 1;
+      const double gs = (double)c->it * n_global;
+      eps = orc_dqn_linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);
+      dqn_act_iteration(c, eps, &sum_ret[r], &sum_len[r], &episodes[r]);
+      learn = learn && gs > (double)c->cfg.min_buff_size && c->it % c->cfg.train_freq == 0 && c->size >= c->cfg.batch_size;  /* dqn.jl:94 */
+    }
+    if (!learn) continue;
+    double sq = 0.0;
+    float gsum[DQ_P];
+    for (int r = 0; r < world; r++) {
+      sq += dqn_learn_grad(cs[r]);
+      for (int i = 0; i < DQ_P; i++) gsum[i] = r == 0 ? cs[r]->g[i] : gsum[i] + cs[r]->g[i];
+    }
+    for (int r = 0; r < world; r++) {
+      orc_dqn_ctx* c = cs[r];
+      memcpy(c->g, gsum, sizeof(gsum));
+      c->last_loss = sq / ((double)c->cfg.batch_size * (double)world);
+      dqn_adam(c);
+      c->learn_steps += 1;
       if (c->it % c->cfg.target_net_freq == 0) memcpy(c->tgt, c->q, sizeof(float) * DQ_P);   /* dqn.jl:111-113 */
     }
   }
-  if (stats) {
-    stats->last_loss = c->last_loss; stats->sum_return = sum_ret; stats->sum_length = sum_len; stats->epsilon = eps;
-    stats->episodes = episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
-    stats->kernel_launches = 0;   /* the oracle launches nothing */
-  }
+  if (stats)
+    for (int r = 0; r < world; r++) {
+      orc_dqn_ctx* c = cs[r];
+      stats[r].last_loss = c->last_loss; stats[r].sum_return = sum_ret[r]; stats[r].sum_length = sum_len[r]; stats[r].epsilon = eps;
+      stats[r].episodes = episodes[r]; stats[r].learn_steps = c->learn_steps; stats[r].iterations = c->it;
+      stats[r].kernel_launches = 0;   /* the oracle launches nothing */
+    }
   return 0;
+}
+int orc_dqn_set_shard(orc_dqn_ctx* c, int32_t world, int32_t rank, int32_t env_id_base) {
+  if (!c || world < 1 || rank < 0 || rank >= world || env_id_base < 0) return -1;
+  c->world = world; c->rank = rank; c->env_id_base = env_id_base;
+  return 0;
+}
+int orc_dqn_run(orc_dqn_ctx* c, int64_t iterations, crl_dqn_stats* stats) {
+  if (!c || c->world != 1) return -1;   /* a shard of a larger world only steps through orc_dqn_group_run */
+  return orc_dqn_group_run(&c, 1, iterations, stats);
 }
 int orc_dqn_read_buffer(orc_dqn_ctx* c, float* state, int32_t* action, float* reward, float* next_state, uint8_t* terminal,
                         int32_t* size, int32_t* ptr) {

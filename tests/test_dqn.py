@@ -104,6 +104,71 @@ def test_oracle_run_schedule_matches_reference_counters(olib, abi):
     o.close()
 
 
+def _dqn_shards(olib, abi, world, n_local, **kw):
+    shards = []
+    for r in range(world):
+        o = OracleDQN(olib, abi.make_dqn_config(num_envs=n_local, **kw))
+        o.set_shard(world, r, r * n_local)
+        shards.append(o)
+    return shards
+
+
+def test_sharded_dqn_acts_like_one_process_until_the_first_learning_step(olib, abi):
+    """data-parallel extension: Philox is keyed by the GLOBAL env id and epsilon by the global step, so with equal
+    parameters the union of the shards' transitions is the single-process run over all envs, env for env"""
+    from cleanrl_jl_b200.dqn_algo import init_q_params
+    kw = dict(buffer_size=4096, min_buff_size=10 ** 6, batch_size=16, train_freq=4, target_net_freq=12, epsilon_duration=500.0, seed=4)
+    world, n_local, iters = 4, 6, 40
+    single = OracleDQN(olib, abi.make_dqn_config(num_envs=world * n_local, **kw))
+    shards = _dqn_shards(olib, abi, world, n_local, **kw)
+    p = init_q_params(2)
+    for o in [single] + shards:
+        o.set_params(p); o.reset()
+    s1 = single.run(iters)
+    ss = OracleDQN.group_run(shards, iters)
+    b1 = single.read_buffer()
+    assert s1.learn_steps == 0 and all(s.learn_steps == 0 for s in ss)
+    assert s1.episodes == sum(s.episodes for s in ss) and s1.sum_return == sum(s.sum_return for s in ss)
+    assert all(s.epsilon == s1.epsilon for s in ss)
+    N = world * n_local
+    for r, o in enumerate(shards):
+        b = o.read_buffer()
+        assert b["size"] == iters * n_local
+        for f in ("state", "action", "reward", "next_state", "terminal"):
+            glob = b1[f][:iters * N].reshape((iters, N) + b1[f].shape[1:])[:, r * n_local:(r + 1) * n_local]
+            np.testing.assert_array_equal(b[f][:iters * n_local].reshape(glob.shape), glob)
+    for o in [single] + shards:
+        o.close()
+
+
+def test_sharded_dqn_learning_keeps_the_replicas_identical(olib, abi):
+    """every shard applies Adam to the same rank-ordered gradient sum: parameters, target copies and losses agree bit for
+    bit across the shards; world = 1 through the group entry point is the plain run"""
+    from cleanrl_jl_b200.dqn_algo import init_q_params
+    kw = dict(buffer_size=512, min_buff_size=64, batch_size=16, train_freq=4, target_net_freq=12, epsilon_duration=2000.0, seed=6)
+    shards = _dqn_shards(olib, abi, 2, 8, **kw)
+    p = init_q_params(5)
+    for o in shards:
+        o.set_params(p); o.reset()
+    st = OracleDQN.group_run(shards, 60) and OracleDQN.group_run(shards, 40)      # two calls: state carries over
+    assert st[0].learn_steps == st[1].learn_steps > 10 and st[0].iterations == 100
+    assert st[0].last_loss == st[1].last_loss and np.isfinite(st[0].last_loss)
+    (q0, t0), (q1, t1) = shards[0].get_params(), shards[1].get_params()
+    np.testing.assert_array_equal(q0, q1)
+    np.testing.assert_array_equal(t0, t1)
+    assert np.abs(q0 - p).max() > 1e-4 and not np.array_equal(q0, t0)
+    with pytest.raises(AssertionError):
+        shards[0].run(1)                      # a shard of a larger world cannot step alone
+    a, b = OracleDQN(olib, abi.make_dqn_config(num_envs=8, **kw)), OracleDQN(olib, abi.make_dqn_config(num_envs=8, **kw))
+    for o in (a, b):
+        o.set_params(p); o.reset()
+    sa, sb = a.run(100), OracleDQN.group_run([b], 100)[0]
+    assert (sa.last_loss, sa.learn_steps, sa.episodes) == (sb.last_loss, sb.learn_steps, sb.episodes)
+    np.testing.assert_array_equal(a.get_params()[0], b.get_params()[0])
+    for o in shards + [a, b]:
+        o.close()
+
+
 def test_dqn_config_has_the_reference_fields():
     from cleanrl_jl_b200 import DQNConfig
     c = DQNConfig()
