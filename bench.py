@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gae-n", type=int, default=1 << 20, help="envs in the GAE HBM measurement (T=128)")
     ap.add_argument("--local-stats", action="store_true")
+    ap.add_argument("--dqn-mode", default="replicas", choices=["replicas", "sharded"],
+                    help="--algo dqn --gpus N: independent replicas (default) or one data-parallel learner "
+                         "(crl_dqn_comm_init: envs, replay and batch sharded, one gradient allreduce per learning step)")
     ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c", "dqn"],
                     help="a2c = BASELINE.json configs[2]: A2C CartPole, 16384 envs, n-step returns + fused update (1 GPU)")
     return ap.parse_args()
@@ -270,10 +273,16 @@ def run_dqn(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
     N, ITERS = 4096, 100
-    cfg = _abi.make_dqn_config(num_envs=N, buffer_size=1 << 20, min_buff_size=10_000, batch_size=120, train_freq=10,
-                               target_net_freq=100, epsilon_duration=5e6, seed=1 + rank, device=local_rank)
+    sharded = world > 1 and args.dqn_mode == "sharded"
+    # sharded: 4096 envs, a 1M-transition ring and 120 / world (rounded up to a multiple of 8) samples PER GPU (weak scaling)
+    batch = 120 if not sharded else max(8, (120 // world + 7) // 8 * 8)
+    cfg = _abi.make_dqn_config(num_envs=N, buffer_size=1 << 20, min_buff_size=10_000, batch_size=batch, train_freq=10,
+                               target_net_freq=100, epsilon_duration=5e6, seed=1 if sharded else 1 + rank, device=local_rank)
     h = DQNHandle(cfg)
     h.set_params(init_q_params(1))
+    if sharded:
+        from cleanrl_jl_b200.handle import comm_unique_id
+        h.comm_init(parallel.exchange_unique_id(comm_unique_id), world, rank, rank * N)
     h.reset()
     for _ in range(max(args.warmup, 3)):
         h.run(ITERS)
@@ -299,7 +308,7 @@ def run_dqn(args):
     tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
     lg = Logger.make_logger("bench_dqn", to_terminal=False, to_tensorboard=False, to_json=True, log_dir=tmp)
     res = dqn(DQNConfig(num_envs=N, total_timesteps=N * ITERS * 20, buffer_size=1 << 20, min_buff_size=10_000,
-                        epsilon_duration=5e6, log_frequencey=N * ITERS), logger=lg)
+                        epsilon_duration=5e6, log_frequencey=N * ITERS), logger=lg, distributed=False)
     lg.close()
     print(json.dumps({
         "metric": "dqn_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -312,7 +321,9 @@ def run_dqn(args):
         "e2e": {"value": res["steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 56,
                 "note": "dqn(config) public API with logging every %d iterations" % ITERS},
         "gpu_launches": int(st.kernel_launches) - launches0, "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
-        "replicas": "independent replicas, one per GPU, no collective" if world > 1 else None,
+        "replicas": (("one data-parallel learner: envs, replay and a global batch of %d sharded over the GPUs, one gradient "
+                      "allreduce per learning step; e2e is a single-GPU dqn(config) call on rank 0" % (batch * world)) if sharded
+                     else "independent replicas, one per GPU, no collective") if world > 1 else None,
     }), flush=True)
     if dist is not None:
         dist.barrier()

@@ -69,6 +69,7 @@ SIGNATURES = {
     "crl_dqn_get_params": (C.c_int, [V, V, V, I32]),
     "crl_dqn_reset": (C.c_int, [V]),
     "crl_dqn_run": (C.c_int, [V, I64, V]),
+    "crl_dqn_comm_init": (C.c_int, [V, V, I32, I32, I32]),
     "crl_dqn_read_buffer": (C.c_int, [V] * 8),
 }
 

@@ -73,6 +73,24 @@ static int nccl_load() {
     if (r__ != ncclSuccess) return fail(CRL_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
   } while (0)
 
+// NCCL for the other translation units of the library (dqn.cu): communicator as an opaque pointer
+int crl_internal_nccl_comm_init(void** comm, int world, int rank, const void* id128) {
+  CKRC(nccl_load());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t cm = nullptr;
+  CKN(g_nccl.CommInitRank(&cm, world, id, rank));
+  *comm = cm;
+  return CRL_OK;
+}
+int crl_internal_nccl_allreduce_sum(void* comm, void* buf, size_t count, int is_double, cudaStream_t s) {
+  CKN(g_nccl.AllReduce(buf, buf, count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, static_cast<ncclComm_t>(comm), s));
+  return CRL_OK;
+}
+void crl_internal_nccl_comm_destroy(void* comm) {
+  if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(comm));
+}
+
 // ------------------------------------------------------------------ context
 struct ProfEvent {
   int k;

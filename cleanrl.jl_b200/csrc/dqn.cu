@@ -80,6 +80,7 @@ struct ActArgs {
   double eps[ACT_MAX_STEPS];      // epsilon of each step (dqn.jl:52, evaluated on the host)
   int n_steps;
   int N, C, ptr, max_steps;
+  int env_id_base;                // global id of local env 0 (data-parallel shards; 0 on one GPU)
 };
 
 // global -> shared copy of one parameter vector (128-bit loads; cudaMalloc'ed source, 16-byte aligned destination)
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
   const int e = tid;                     // env lane, meaningful for warp 0
   const int n = blockIdx.x * ACT_E + e;
   const bool owner = tid < ACT_E, valid = owner && n < a.N;   // warp 0: one lane per env, state in registers
+  const uint32_t gid = (uint32_t)(a.env_id_base + n);         // Philox is keyed by the global env id
   float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   int t = 0, len = 0;
   double ret = 0.0;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
     if (valid) {
       const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
       uint32_t r[4];
-      philox_draw(a.seed, (uint32_t)n, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
+      philox_draw(a.seed, gid, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
       const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
       int action;
       if (u < a.eps[s]) action = (int)(r[2] & 1u);              // rand(action_space(env)), dqn.jl:54
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
         ret = 0.0;
         len = 0;
         float u4[4];
-        rng_reset_uniforms(a.seed, (uint32_t)n, rc, u4);
+        rng_reset_uniforms(a.seed, gid, rc, u4);
         rc += 1;
         cartpole_reset(st, t, u4);
       }
@@ -323,6 +325,11 @@ struct LearnArgs {
   float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;
   double* loss_part;      // [LF_MAX_BLOCKS]
   double bp1, bp2;        // beta1^t, beta2^t of Adam, kept on the host
+  // data-parallel shards: the mean is over B_scale = world * B samples, the batch permutation is keyed by the rank, and
+  // the update kernel leaves its gradient in gbuf / its squared-error sum in lbuf for the allreduce (dqn_adam_kernel)
+  int B_scale, rank;
+  float* gbuf;            // [DQ_P]
+  double* lbuf;           // [1]
 };
 
 __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
@@ -351,8 +358,8 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   if (tid < LF_S && b0 + tid < B) {
     // sample(1:size, B, replace=false), replay_buffer.jl:43: the first B entries of a keyed permutation of [0,size)
     uint32_t keys[8];
-    philox_draw(a.seed, 0u, a.learn_step, STREAM_DQN_BATCH, keys);
-    philox_draw(a.seed, 0x80000000u, a.learn_step, STREAM_DQN_BATCH, keys + 4);
+    philox_draw(a.seed, (uint32_t)a.rank, a.learn_step, STREAM_DQN_BATCH, keys);
+    philox_draw(a.seed, 0x80000000u | (uint32_t)a.rank, a.learn_step, STREAM_DQN_BATCH, keys + 4);
     const uint32_t idx = perm_index((uint32_t)(b0 + tid), (uint32_t)a.size, perm_half_bits((uint32_t)a.size), keys);
     s4 = reinterpret_cast<const float4*>(a.b_state)[idx];
     n4 = reinterpret_cast<const float4*>(a.b_next)[idx];
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
       const int act = s_act[i];
       const double diff = td - (double)qo[act * SP + i];
       sq = diff * diff;                                              // Flux.mse, dqn.jl:107
-      const float dd = (float)(-2.0 * diff / (double)B);
+      const float dd = (float)(-2.0 * diff / (double)a.B_scale);
       if (act == 0) d0 = dd; else d1 = dd;
       reinterpret_cast<float2*>(a.dqT)[b] = make_float2(d0, d1);
     }
@@ -506,13 +513,17 @@ __device__ __forceinline__ void stage_cols(const float* __restrict__ src, int ld
   }
 }
 
+// EXCH = false: Adam on the spot (one GPU). EXCH = true: the gradient goes to a.gbuf and the squared-error sum to a.lbuf;
+// after the allreduce dqn_adam_kernel finishes the step.
+template <bool EXCH>
 __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_fwd_blocks) {
   extern __shared__ __align__(16) float smem[];
   const int B = a.B, tid = threadIdx.x;
   if (blockIdx.x == 0 && tid == LU_T - 1) {
     double sq = 0.0;
     for (int c = 0; c < n_fwd_blocks; c++) sq += a.loss_part[c];
-    a.dev->last_loss = sq / (double)B;
+    if (EXCH) a.lbuf[0] = sq;
+    else a.dev->last_loss = sq / (double)B;
   }
 #ifdef DQN_TRACE
   long long dtr[4] = {0, 0, 0, 0};
@@ -566,8 +577,9 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
         ok[u] = i < NPAR;
         idx[u] = DQ_W2 + DQ_H2 * k0 + i;
         g[u] = ok[u] ? gs[i] : 0.0f;
+        if (EXCH && ok[u]) a.gbuf[idx[u]] = g[u];
       }
-      dqn_adam<PER>(a, idx, g, ok);
+      if (!EXCH) dqn_adam<PER>(a, idx, g, ok);
     }
     DTR(3);
 #ifdef DQN_TRACE
@@ -600,7 +612,8 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     DTR(2);
     const float g[1] = {acc};
     const bool ok[1] = {true};
-    dqn_adam<1>(a, idx, g, ok);
+    if (EXCH) a.gbuf[idx[0]] = acc;
+    else dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
     if (dtrace) printf("learn_upd B: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
@@ -642,12 +655,24 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     DTR(2);
     const float g[1] = {acc};
     const bool ok[1] = {true};
-    dqn_adam<1>(a, idx, g, ok);
+    if (EXCH) a.gbuf[idx[0]] = acc;
+    else dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
     if (dtrace) printf("learn_upd C: stage %lld | reduce %lld | adam %lld\n", dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2]);
 #endif
   }
+}
+
+// data-parallel shards: Adam on the allreduced gradient (every rank holds the same sums, so the replicas stay identical)
+__global__ void __launch_bounds__(256) dqn_adam_kernel(LearnArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) a.dev->last_loss = a.lbuf[0] / (double)a.B_scale;
+  if (k >= DQ_P) return;
+  const int idx[1] = {k};
+  const float g[1] = {a.gbuf[k]};
+  const bool ok[1] = {true};
+  dqn_adam<1>(a, idx, g, ok);
 }
 
 constexpr size_t ACT_SMEM = (DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP) * sizeof(float);
@@ -682,18 +707,21 @@ struct crl_dqn_ctx {
   float *h1T, *h2T, *z2T, *z1T, *xT, *dqT;   // scratch between dqn_learn_fwd_kernel and dqn_learn_upd_kernel
   double* loss_part;
   double bp1, bp2;                            // beta1^t, beta2^t of Adam
+  int world, rank, env_id_base;               // data-parallel shard (crl_dqn_comm_init); 1, 0, 0 on one GPU
+  void* comm;                                 // NCCL communicator when world > 1
+  float* gbuf; double* lbuf;                  // allreduce payload: gradient, squared-error sum
   int size, ptr;
   long long it, learn_steps, launches;
   bool params_set, reset_done;
 };
 
-__global__ void dqn_reset_kernel(int N, unsigned long long seed, float* env_state, int* env_t, double* ep_ret, int* ep_len,
+__global__ void dqn_reset_kernel(int N, unsigned long long seed, int env_id_base, float* env_state, int* env_t, double* ep_ret, int* ep_len,
                                  uint32_t* resets) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float u4[4], st[4];
   int t;
-  rng_reset_uniforms(seed, (uint32_t)n, 0, u4);
+  rng_reset_uniforms(seed, (uint32_t)(env_id_base + n), 0, u4);
   cartpole_reset(st, t, u4);
   for (int k = 0; k < 4; k++) env_state[4 * n + k] = st[k];
   env_t[n] = t; ep_ret[n] = 0.0; ep_len[n] = 0; resets[n] = 1;
@@ -732,8 +760,11 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   DCK(dzalloc(&c->h1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->h2T, (size_t)LEARN_B * DQ_H2)); DCK(dzalloc(&c->z2T, (size_t)LEARN_B * DQ_H2));
   DCK(dzalloc(&c->z1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->xT, (size_t)LEARN_B * DQ_D)); DCK(dzalloc(&c->dqT, (size_t)LEARN_B * DQ_A));
   DCK(dzalloc(&c->loss_part, LF_MAX_BLOCKS));
+  DCK(dzalloc(&c->gbuf, DQ_P)); DCK(dzalloc(&c->lbuf, 1));
+  c->world = 1; c->rank = 0; c->env_id_base = 0; c->comm = nullptr;
   DCK(cudaFuncSetAttribute(dqn_learn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
-  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
+  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
+  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
   DCK(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
   *out = c;
   return CRL_OK;
@@ -744,8 +775,9 @@ extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
-                  c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part};
+                  c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part, c->gbuf, c->lbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
+  crl_internal_nccl_comm_destroy(c->comm);
   cudaStreamDestroy(c->stream);
   delete c;
   return CRL_OK;
@@ -782,10 +814,31 @@ extern "C" CRL_API int crl_dqn_reset(crl_dqn_ctx* c) {
   if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
   DCK(cudaSetDevice(c->cfg.device));
   const int N = c->cfg.num_envs;
-  dqn_reset_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(N, c->cfg.seed, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets);
+  dqn_reset_kernel<<<(N + 127) / 128, 128, 0, c->stream>>>(N, c->cfg.seed, c->env_id_base, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets);
   DCK(cudaGetLastError());
   c->size = 0; c->ptr = 0; c->it = 0; c->learn_steps = 0;   /* launches keeps counting: it is a lifetime counter */
   c->reset_done = true;
+  return CRL_OK;
+}
+
+extern "C" CRL_API int crl_dqn_comm_init(crl_dqn_ctx* c, const void* id128, int32_t world_size, int32_t rank, int32_t env_id_base) {
+  if (!c || !id128) return dfail(CRL_ERR_INVALID, "NULL argument");
+  if (world_size < 2 || rank < 0 || rank >= world_size || env_id_base < 0)
+    return dfail(CRL_ERR_INVALID, "need world_size >= 2, 0 <= rank < world_size, env_id_base >= 0");
+  if (c->comm) return dfail(CRL_ERR_STATE, "crl_dqn_comm_init called twice");
+  if (c->reset_done) return dfail(CRL_ERR_STATE, "crl_dqn_comm_init must precede crl_dqn_reset (the env ids change)");
+  DCK(cudaSetDevice(c->cfg.device));
+  int rc = crl_internal_nccl_comm_init(&c->comm, world_size, rank, id128);
+  if (rc != CRL_OK) return rc;
+  c->world = world_size; c->rank = rank; c->env_id_base = env_id_base;
+  // NCCL connects its channels lazily on the first collective: do that here, not inside the first learning step
+  DCK(cudaMemsetAsync(c->lbuf, 0, sizeof(double), c->stream));
+  rc = crl_internal_nccl_allreduce_sum(c->comm, c->lbuf, 1, 1, c->stream);
+  if (rc != CRL_OK) return rc;
+  DCK(cudaMemsetAsync(c->gbuf, 0, sizeof(float) * DQ_P, c->stream));
+  rc = crl_internal_nccl_allreduce_sum(c->comm, c->gbuf, DQ_P, 0, c->stream);
+  if (rc != CRL_OK) return rc;
+  DCK(cudaStreamSynchronize(c->stream));
   return CRL_OK;
 }
 
@@ -794,6 +847,7 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
   if (iterations < 0) return dfail(CRL_ERR_INVALID, "iterations must be >= 0");
   if (!c->params_set) return dfail(CRL_ERR_STATE, "crl_dqn_run called before crl_dqn_set_params");
   if (!c->reset_done) return dfail(CRL_ERR_STATE, "crl_dqn_run called before crl_dqn_reset");
+  if (c->world > 1 && !c->comm) return dfail(CRL_ERR_STATE, "world_size > 1 but crl_dqn_comm_init did not complete");
   DCK(cudaSetDevice(c->cfg.device));
   const int N = c->cfg.num_envs, C = c->cfg.buffer_size;
   // per-call episode aggregate: clear the three accumulators, keep Adam's powers and the last loss
@@ -807,13 +861,13 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     a.q = c->q; a.env_state = c->env_state; a.env_t = c->env_t; a.ep_ret = c->ep_ret; a.ep_len = c->ep_len; a.resets = c->resets;
     a.b_state = c->b_state; a.b_next = c->b_next; a.b_reward = c->b_reward; a.b_action = c->b_action; a.b_term = c->b_term;
     a.dev = c->dev; a.seed = c->cfg.seed; a.it0 = (unsigned long long)(c->it + 1); a.N = N; a.C = C; a.ptr = c->ptr;
-    a.max_steps = c->cfg.max_episode_steps;
+    a.max_steps = c->cfg.max_episode_steps; a.env_id_base = c->env_id_base;
     int ns = 0;
     bool learn = false;
     while (k < iterations && ns < ACT_MAX_STEPS && (long long)(ns + 1) * N <= (long long)C && !learn) {
       c->it += 1;
       k += 1;
-      const double gs = (double)c->it * (double)N;
+      const double gs = (double)c->it * (double)N * (double)c->world;   // global step over all shards
       eps = linear_schedule(c->cfg.epsilon_start, c->cfg.epsilon_end, c->cfg.epsilon_duration, gs);   // dqn.jl:52
       a.eps[ns++] = eps;
       c->ptr = (c->ptr + N) % C;
@@ -835,13 +889,27 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
       l.copy_target = (c->it % c->cfg.target_net_freq == 0) ? 1 : 0;                                             // dqn.jl:111
       l.h1T = c->h1T; l.h2T = c->h2T; l.z2T = c->z2T; l.z1T = c->z1T; l.xT = c->xT; l.dqT = c->dqT;
       l.loss_part = c->loss_part; l.bp1 = c->bp1; l.bp2 = c->bp2;
+      l.B_scale = l.B * c->world; l.rank = c->rank; l.gbuf = c->gbuf; l.lbuf = c->lbuf;
       const int fwd_blocks = (l.B + LF_S - 1) / LF_S;
       dqn_learn_fwd_kernel<<<fwd_blocks, LF_T, LF_SMEM, c->stream>>>(l);
       DCK(cudaGetLastError());
-      dqn_learn_upd_kernel<<<LU_A_BLOCKS + LU_B_BLOCKS + LU_C_BLOCKS, LU_T, LU_SMEM, c->stream>>>(l, fwd_blocks);
-      DCK(cudaGetLastError());
+      if (c->world == 1) {
+        dqn_learn_upd_kernel<false><<<LU_A_BLOCKS + LU_B_BLOCKS + LU_C_BLOCKS, LU_T, LU_SMEM, c->stream>>>(l, fwd_blocks);
+        DCK(cudaGetLastError());
+        c->launches += 2;
+      } else {
+        // one gradient allreduce per learning step (NCCL, on the handle's stream), then Adam on the sums
+        dqn_learn_upd_kernel<true><<<LU_A_BLOCKS + LU_B_BLOCKS + LU_C_BLOCKS, LU_T, LU_SMEM, c->stream>>>(l, fwd_blocks);
+        DCK(cudaGetLastError());
+        int rc = crl_internal_nccl_allreduce_sum(c->comm, c->gbuf, DQ_P, 0, c->stream);
+        if (rc != CRL_OK) return rc;
+        rc = crl_internal_nccl_allreduce_sum(c->comm, c->lbuf, 1, 1, c->stream);
+        if (rc != CRL_OK) return rc;
+        dqn_adam_kernel<<<(DQ_P + 255) / 256, 256, 0, c->stream>>>(l);
+        DCK(cudaGetLastError());
+        c->launches += 3;
+      }
       c->bp1 *= 0.9; c->bp2 *= 0.999;
-      c->launches += 2;
       c->learn_steps += 1;
     }
   }

@@ -13,6 +13,19 @@ import numpy as np
 from . import _abi
 from . import _lib as L
 from . import logger as Logger
+from . import parallel
+from .handle import comm_unique_id
+
+
+def _dist():
+    """torch.distributed when it is initialised with more than one rank, else None (torch is only plumbing)"""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except ImportError:
+        pass
+    return None
 
 
 @dataclasses.dataclass
@@ -85,6 +98,12 @@ class DQNHandle:
     def reset(self):
         L.check(self.lib.crl_dqn_reset(self.h))
 
+    def comm_init(self, unique_id: bytes, world_size, rank, env_id_base):
+        """make this handle rank `rank` of a data-parallel world (collective; after set_params, before reset)"""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        L.check(self.lib.crl_dqn_comm_init(self.h, buf, int(world_size), int(rank), int(env_id_base)))
+
     def run(self, iterations):
         st = _abi.crl_dqn_stats()
         L.check(self.lib.crl_dqn_run(self.h, int(iterations), C.byref(st)))
@@ -109,16 +128,33 @@ def make_crl_dqn_config(config, device=0):
                                 epsilon_end=config.epsilon_end, epsilon_duration=config.epsilon_duration, seed=config.seed)
 
 
-def dqn(config=None, logger=None, params=None, device=0):
+def dqn(config=None, logger=None, params=None, device=0, distributed=None):
     """Runs `total_timesteps` env steps (dqn.jl:49) and returns a summary dict. Logs the reference's two records:
     "Episode Statistics" (episode_return, episode_length, global_step, ϵ, steps_per_sec: dqn.jl:82) aggregated over the
     episodes that ended since the last log, and "Training Statistics" (loss: dqn.jl:116) every `log_frequencey` steps."""
     config = config or DQNConfig()
-    own_logger = logger is None
-    if logger is None:
+    # Data-parallel over the GPUs of one box when torch.distributed is initialised (one process per GPU): every rank owns
+    # num_envs / k envs, its own ring of buffer_size / k transitions and batch_size / k samples of each learning step;
+    # one gradient allreduce per learning step. Only rank 0 logs (its own shard's episodes).
+    # `distributed=False` keeps this call on one GPU even inside a torchrun job (independent replicas).
+    dist = _dist() if distributed in (None, True) else None
+    if distributed and dist is None:
+        raise ValueError("distributed=True needs an initialised torch.distributed process group with more than one rank")
+    rank, local_rank, world = (dist.get_rank(), parallel.dist_info()[1], dist.get_world_size()) if dist else (0, device, 1)
+    own_logger = logger is None and rank == 0
+    if logger is None and rank == 0:
         logger = Logger.make_logger("dqn|%s" % config.run_name, to_terminal=False)   # dqn.jl:35
-    h = DQNHandle(make_crl_dqn_config(config, device))
+    local = config
+    if world > 1:
+        env_base, n_local = parallel.shard_envs(config.num_envs, world, rank)
+        if config.batch_size % world or config.buffer_size % world:
+            raise ValueError("batch_size and buffer_size must be divisible by the number of GPUs")
+        local = dataclasses.replace(config, num_envs=n_local, batch_size=config.batch_size // world,
+                                    buffer_size=config.buffer_size // world)
+    h = DQNHandle(make_crl_dqn_config(local, local_rank))
     h.set_params(init_q_params(config.seed) if params is None else params)
+    if world > 1:
+        h.comm_init(parallel.exchange_unique_id(comm_unique_id), world, rank, env_base)
     h.reset()
     n_iter = config.total_timesteps // config.num_envs
     chunk = max(1, config.log_frequencey // config.num_envs)
@@ -129,6 +165,8 @@ def dqn(config=None, logger=None, params=None, device=0):
         last = h.run(k)
         done_iter += k
         global_step = done_iter * config.num_envs
+        if logger is None:
+            continue
         if last.episodes > 0:
             episodes += last.episodes
             logger.info("Episode Statistics", episode_return=last.sum_return / last.episodes,

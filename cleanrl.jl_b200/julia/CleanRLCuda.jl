@@ -303,6 +303,30 @@ struct CrlDqnStats           # crl_dqn_stats
 end
 
 """
+    comm_unique_id() -> Vector{UInt8}
+
+The 128 bytes of `crl_comm_unique_id` (rank 0 calls it and ships them to the other ranks: MPI.jl, a file, sockets).
+"""
+function comm_unique_id()
+  id = zeros(UInt8, 128)
+  GC.@preserve id check(ccall((:crl_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+  id
+end
+
+"""
+    dqn_comm_init(h, unique_id::Vector{UInt8}, world_size, rank, env_id_base)
+
+Data-parallel DQN over the GPUs of one box (`crl_dqn_comm_init`): one handle per GPU and Julia process, called on all
+ranks after `crl_dqn_set_params` and before `crl_dqn_reset` with the 128 bytes rank 0 got from `comm_unique_id()`.
+`num_envs`, `buffer_size` and `batch_size` of the handle are then per rank.
+"""
+function dqn_comm_init(h::Ptr{Cvoid}, unique_id::Vector{UInt8}, world_size::Integer, rank::Integer, env_id_base::Integer)
+  length(unique_id) == 128 || error("unique id must have 128 bytes")
+  GC.@preserve unique_id check(ccall((:crl_dqn_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Int32),
+                                     h, unique_id, world_size, rank, env_id_base))
+end
+
+"""
     dqn(config::DQNConfig; q_net, num_envs = 1, seed = 1)
 
 Drop-in for `CleanRL.dqn` (dqn.jl:34): same `DQNConfig`, same two `@info` records. `q_net` is the Flux chain of

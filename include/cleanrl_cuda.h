@@ -322,6 +322,14 @@ CRL_API int crl_dqn_get_params(crl_dqn_ctx* ctx, float* q_params, float* target_
 CRL_API int crl_dqn_reset(crl_dqn_ctx* ctx);   /* reset!(env) for every env, empty buffer, iteration counter 0 */
 /* `iterations` vector steps with the learning steps that fall on them; stats may be NULL */
 CRL_API int crl_dqn_run(crl_dqn_ctx* ctx, int64_t iterations, crl_dqn_stats* stats);
+/* Data-parallel DQN over the GPUs of one box (an extension: dqn.jl has one env and one buffer; BASELINE configs[4]).
+ * One handle per GPU and rank; call after crl_dqn_create / crl_dqn_set_params (same parameters on every rank) and
+ * BEFORE crl_dqn_reset, on all ranks (collective), with the 128 bytes of crl_comm_unique_id from rank 0. Rank r then
+ * owns the envs env_id_base .. env_id_base + num_envs - 1 (Philox is keyed by the global env id; the epsilon schedule
+ * and the learning gate count world_size * num_envs steps per iteration), keeps its own ring of buffer_size
+ * transitions and contributes batch_size samples of it to a global batch of world_size * batch_size; the gradient is
+ * summed with ONE allreduce per learning step and Adam is applied identically on every rank. */
+CRL_API int crl_dqn_comm_init(crl_dqn_ctx* ctx, const void* id128, int32_t world_size, int32_t rank, int32_t env_id_base);
 /* replay buffer contents (host pointers, each may be NULL): state/next_state float [capacity][4], action int32,
  * reward float, terminal uint8; size/ptr as in replay_buffer.jl:11-12 (ptr 0-based) */
 CRL_API int crl_dqn_read_buffer(crl_dqn_ctx* ctx, float* state, int32_t* action, float* reward, float* next_state,

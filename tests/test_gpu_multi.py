@@ -39,3 +39,22 @@ def test_multi_gpu_sharded_update_matches_single_process_oracle(tmp_path, torch_
             assert f["bit_identical"], (kind, f)                        # a failed speculation is replayed exactly
         else:
             assert f["maxerr"] < 2e-5, (kind, f)
+
+
+def test_multi_gpu_sharded_dqn_matches_oracle_group(tmp_path, torch_cuda):
+    """data-parallel DQN (crl_dqn_comm_init): every rank's shard against the oracle's group run of all shards"""
+    ngpu = torch_cuda.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2|4|8)")
+    nproc = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    out = tmp_path / "dqn.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+           "--master-port", "29546", os.path.join(ROOT, "tests", "dqn_multi_worker.py"), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
+    r = json.load(open(out))
+    assert r["learn_steps"] > 10, r
+    assert r["exact"], r                    # actions, rewards, terminals, ring order, counters: bit-exact per shard
+    assert r["ranks_agree"], r              # replicated parameters stay bit-identical across ranks
+    assert r["param_maxerr"] < 2e-5, r      # vs the oracle's rank-ordered gradient sum
+    assert r["loss_relerr"] < 1e-4, r
