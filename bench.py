@@ -305,6 +305,24 @@ def run_dqn(args):
             dist.barrier()
             dist.destroy_process_group()
         return
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        # the oracle's restatement of the vectorised DQN contract, one host thread, epsilon pinned to its final value
+        # (the GPU evaluates the network for every env; the CPU loop skips it for random actions)
+        from oracle.oracle import OracleDQN, OracleLib
+        ocfg = _abi.make_dqn_config(num_envs=N, buffer_size=1 << 20, min_buff_size=10_000, batch_size=120, train_freq=10,
+                                    target_net_freq=100, epsilon_start=0.05, epsilon_end=0.05, epsilon_duration=1.0, seed=1)
+        o = OracleDQN(OracleLib(), ocfg)
+        o.set_params(init_q_params(1))
+        o.reset()
+        o.run(10)
+        c0 = time.perf_counter()
+        o.run(50)
+        cdt = time.perf_counter() - c0
+        o.close()
+        cpu_baseline = {"value": 50 * N / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": "50 iterations of %d envs (5 learning steps) at epsilon = 0.05, %.1f s" % (N, cdt),
+                        "note": "oracle/ppo_oracle.c, orc_dqn_run: scalar C restatement, not the Julia program"}
     tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
     lg = Logger.make_logger("bench_dqn", to_terminal=False, to_tensorboard=False, to_json=True, log_dir=tmp)
     res = dqn(DQNConfig(num_envs=N, total_timesteps=N * ITERS * 20, buffer_size=1 << 20, min_buff_size=10_000,
@@ -320,6 +338,7 @@ def run_dqn(args):
         "clocks": clocks,
         "e2e": {"value": res["steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 56,
                 "note": "dqn(config) public API with logging every %d iterations" % ITERS},
+        "cpu_baseline": cpu_baseline,
         "gpu_launches": int(st.kernel_launches) - launches0, "learn_steps": int(st.learn_steps), "last_loss": st.last_loss,
         "replicas": (("one data-parallel learner: envs, replay and a global batch of %d sharded over the GPUs, one gradient "
                       "allreduce per learning step; e2e is a single-GPU dqn(config) call on rank 0" % (batch * world)) if sharded
