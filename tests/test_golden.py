@@ -58,6 +58,24 @@ def test_oracle_reproduces_frozen_outputs(olib, abi, gold):
     np.testing.assert_array_equal(u, gold["philox_reset_u"])
 
 
+def test_oracle_dqn_reproduces_frozen_outputs():
+    """tests/golden/golden_dqn_v1.npz (make_golden_dqn.py): the oracle's DQN, single process and two-shard group.
+    Discrete outputs bit-exact; parameters to 1e-6 (libm sin/cos may differ by an ulp between hosts)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_dqn", os.path.join(HERE, "golden", "make_golden_dqn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now, gold = mod.generate(), np.load(os.path.join(HERE, "golden", "golden_dqn_v1.npz"))
+    assert set(now) == set(gold.files)
+    for k in gold.files:
+        if k.endswith(("_action", "_terminal", "_reward")):
+            np.testing.assert_array_equal(now[k], gold[k], err_msg=k)
+        else:
+            np.testing.assert_allclose(now[k], gold[k], rtol=1e-6, atol=1e-7, err_msg=k)
+    assert gold["single_scalars"][5] > 10 and gold["group0_scalars"][3] > 10          # learning steps happened
+    np.testing.assert_array_equal(gold["group0_q"], gold["group1_q"])                  # replicas agree
+
+
 @pytest.mark.gpu
 def test_cuda_path_matches_frozen_outputs(crl, abi, gold, torch_cuda):
     from cleanrl_jl_b200.handle import PPOHandle
