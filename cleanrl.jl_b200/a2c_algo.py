@@ -7,7 +7,9 @@ CRL_GAE_A2C_RETURNS scan), the two loss expressions (critic `mean(advantage .^ 2
 names/keys (a2c.jl:100,106). What differs, because the reference is single-env and episodic: the rollout is a fixed
 `num_steps` over `num_envs` vectorised envs (bootstrapped with the critic at the cut), and the two `update!` calls
 are one combined step (identical, the parameter sets are disjoint). Parity is therefore claimed only for the return
-scan and the two loss expressions, against the oracle."""
+scan and the two loss expressions, against the oracle. As in a2c.jl:108 then :52, the observation after a termination is
+the RESET state (`CRL_FLAG_A2C` makes the rollout kernel refresh it; the PPO path keeps ppo.jl's stale terminal
+observation), so no sample pairs a terminal observation with a new episode's return."""
 import time
 from dataclasses import dataclass
 

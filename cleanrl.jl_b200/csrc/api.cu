@@ -178,6 +178,13 @@ static int use_device(const crl_ctx* c) {
   return CRL_OK;
 }
 
+// Speculative updates (crl_train_update) are repaired lazily by validate_updates(). Every entry point that reads or
+// mutates handle state settles them first, so that no caller can observe -- or build on -- the output of a failed
+// speculation (a failed one is rare: it costs a stream synchronisation only when updates are pending).
+static int validate_updates(crl_ctx* c, uint64_t upto);
+static int settle(crl_ctx* c);
+#define SETTLE(c) CKRC(settle(c))
+
 template <typename T> static int dalloc(T** p, size_t n) {
   CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
   CK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
@@ -249,6 +256,11 @@ static int check_cfg(const crl_config* c) {
   if (c->world_size > CRL_MAX_WORLD) return fail(CRL_ERR_INVALID, "world_size > %d is not supported", CRL_MAX_WORLD);
   if (c->gae_mode != CRL_GAE_REF_COMPAT && c->gae_mode != CRL_GAE_FIXED && c->gae_mode != CRL_GAE_A2C_RETURNS)
     return fail(CRL_ERR_INVALID, "bad gae_mode");
+  // A2C (a2c.jl:78-97) steps once per rollout on the whole batch: the actor's advantage is the return minus the critic
+  // output recorded by that rollout, which is only the current critic for the first (and only) minibatch
+  if ((c->flags & CRL_FLAG_A2C) &&
+      (c->num_minibatches != 1 || c->update_epochs != 1 || c->gae_mode != CRL_GAE_A2C_RETURNS))
+    return fail(CRL_ERR_INVALID, "CRL_FLAG_A2C needs num_minibatches = 1, update_epochs = 1 and gae_mode = CRL_GAE_A2C_RETURNS");
   return CRL_OK;
 }
 
@@ -360,6 +372,7 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
 extern "C" CRL_API int crl_sync(crl_ctx* c) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   CKRC(use_device(c));
+  SETTLE(c);
   CK(cudaStreamSynchronize(c->stream));
   return CRL_OK;
 }
@@ -391,6 +404,7 @@ static int copy_vec(crl_ctx* c, void* dst, const void* src, size_t bytes, cudaMe
 extern "C" CRL_API int crl_set_params(crl_ctx* c, const float* host, int32_t n) {
   if (!c || !host || n != c->L.P) return fail(CRL_ERR_INVALID, "crl_set_params: expected %d floats", c ? c->L.P : -1);
   CKRC(use_device(c));
+  SETTLE(c);
   CK(cudaMemcpyAsync(c->params, host, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   {
     KernelScope ks(c, CRL_K_OTHER);
@@ -401,20 +415,24 @@ extern "C" CRL_API int crl_set_params(crl_ctx* c, const float* host, int32_t n) 
 }
 extern "C" CRL_API int crl_get_params(crl_ctx* c, float* host, int32_t n) {
   if (!c || !host || n != c->L.P) return fail(CRL_ERR_INVALID, "crl_get_params: expected %d floats", c ? c->L.P : -1);
+  SETTLE(c);
   return copy_vec(c, host, c->params, 4 * (size_t)n, cudaMemcpyDeviceToHost);
 }
 extern "C" CRL_API int crl_get_grads(crl_ctx* c, float* host, int32_t n) {
   if (!c || !host || n != c->L.P) return fail(CRL_ERR_INVALID, "crl_get_grads: expected %d floats", c ? c->L.P : -1);
+  SETTLE(c);
   return copy_vec(c, host, c->grads, 4 * (size_t)n, cudaMemcpyDeviceToHost);
 }
 extern "C" CRL_API int crl_get_adam_state(crl_ctx* c, float* m, float* v, double* beta_pow) {
   if (!c || !m || !v || !beta_pow) return fail(CRL_ERR_INVALID, "NULL argument");
+  SETTLE(c);
   CKRC(copy_vec(c, m, c->adam_m, 4 * (size_t)c->L.P, cudaMemcpyDeviceToHost));
   CKRC(copy_vec(c, v, c->adam_v, 4 * (size_t)c->L.P, cudaMemcpyDeviceToHost));
   return copy_vec(c, beta_pow, c->beta_pow, 16 * (size_t)c->L.n_arrays, cudaMemcpyDeviceToHost);
 }
 extern "C" CRL_API int crl_set_adam_state(crl_ctx* c, const float* m, const float* v, const double* beta_pow) {
   if (!c || !m || !v || !beta_pow) return fail(CRL_ERR_INVALID, "NULL argument");
+  SETTLE(c);
   CKRC(copy_vec(c, c->adam_m, m, 4 * (size_t)c->L.P, cudaMemcpyHostToDevice));
   CKRC(copy_vec(c, c->adam_v, v, 4 * (size_t)c->L.P, cudaMemcpyHostToDevice));
   return copy_vec(c, c->beta_pow, beta_pow, 16 * (size_t)c->L.n_arrays, cudaMemcpyHostToDevice);
@@ -424,6 +442,7 @@ extern "C" CRL_API int crl_set_adam_state(crl_ctx* c, const float* m, const floa
 extern "C" CRL_API int crl_env_reset(crl_ctx* c) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   CKRC(use_device(c));
+  SETTLE(c);
   {
     KernelScope ks(c, CRL_K_OTHER);
     CK(launch_env_reset(c->cfg.env_kind, c->N, c->cfg.seed, c->cfg.env_id_base, c->env_state, c->env_t, c->ep_return,
@@ -434,6 +453,7 @@ extern "C" CRL_API int crl_env_reset(crl_ctx* c) {
 extern "C" CRL_API int crl_env_set_state(crl_ctx* c, const float* state, const int32_t* t) {
   if (!c || !state) return fail(CRL_ERR_INVALID, "NULL argument");
   CKRC(use_device(c));
+  SETTLE(c);
   CK(cudaMemcpyAsync(c->env_state, state, 4 * (size_t)c->N * c->L.S, cudaMemcpyHostToDevice, c->stream));
   if (t) CK(cudaMemcpyAsync(c->env_t, t, 4 * (size_t)c->N, cudaMemcpyHostToDevice, c->stream));
   else CK(cudaMemsetAsync(c->env_t, 0, 4 * (size_t)c->N, c->stream));
@@ -455,6 +475,7 @@ static RolloutArgs rollout_args(crl_ctx* c, const double* an, const float* rn) {
   a.state = c->state; a.action = c->action; a.logprob = c->logprob; a.reward = c->reward; a.value = c->value;
   a.terminal = c->terminal; a.action_noise = an; a.reset_noise = rn; a.eb = c->eb; a.records = c->records;
   a.ep_capacity = c->ep_capacity;
+  a.fresh_obs_after_reset = (c->cfg.flags & CRL_FLAG_A2C) ? 1 : 0;
   return a;
 }
 
@@ -471,6 +492,7 @@ static int enqueue_rollout(crl_ctx* c, const double* an_dev, const float* rn_dev
 extern "C" CRL_API int crl_rollout(crl_ctx* c, const double* action_noise, const float* reset_noise) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   CKRC(use_device(c));
+  SETTLE(c);
   const size_t B = c->B;
   const double* an = nullptr;
   const float* rn = nullptr;
@@ -507,6 +529,7 @@ extern "C" CRL_API int crl_gae(crl_ctx* c) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   if (!c->rolled) return fail(CRL_ERR_STATE, "crl_gae called before crl_rollout");
   CKRC(use_device(c));
+  SETTLE(c);
   CKRC(enqueue_gae(c));
   c->gae_done = true;
   return CRL_OK;
@@ -670,6 +693,7 @@ extern "C" CRL_API int crl_update_minibatch(crl_ctx* c, const int32_t* idx, int3
   if (M > c->M) return fail(CRL_ERR_INVALID, "M = %d exceeds the configured minibatch size %d", M, c->M);
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(use_device(c));
+  SETTLE(c);
   CK(cudaMemcpyAsync(c->idx_dev, idx, 4 * (size_t)M, cudaMemcpyHostToDevice, c->stream));
   CKRC(enqueue_minibatch(c, idx_array(c, c->idx_dev), M, lr, c->stats_dev, 0));
   double s4[4];
@@ -710,6 +734,7 @@ extern "C" CRL_API int crl_update_epochs(crl_ctx* c, const int32_t* perms, doubl
   if (!c->gae_done) return fail(CRL_ERR_STATE, "crl_update_epochs called before crl_gae");
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
   CKRC(use_device(c));
+  SETTLE(c);
   const size_t nmb = (size_t)c->cfg.update_epochs * c->cfg.num_minibatches;
   if (perms) CK(cudaMemcpyAsync(c->perm_dev, perms, 4 * (size_t)c->cfg.update_epochs * c->B, cudaMemcpyHostToDevice, c->stream));
   CKRC(enqueue_epochs(c, perms ? c->perm_dev : nullptr, lr));
@@ -820,6 +845,11 @@ static int validate_updates(crl_ctx* c, uint64_t upto) {
   return CRL_OK;
 }
 
+static int settle(crl_ctx* c) {
+  if (c->validated_seq < c->update_seq) return validate_updates(c, c->update_seq - 1);
+  return CRL_OK;
+}
+
 extern "C" CRL_API int crl_train_update(crl_ctx* c, double lr) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   if (!(lr >= 0.0)) return fail(CRL_ERR_INVALID, "lr must be >= 0");
@@ -891,6 +921,8 @@ extern "C" CRL_API int crl_read_field(crl_ctx* c, int32_t field, void* host, siz
   void* p; size_t nb;
   CKRC(field_info(c, field, &p, &nb));
   if (bytes != nb) return fail(CRL_ERR_INVALID, "field %d holds %zu bytes, caller passed %zu", field, nb, bytes);
+  CKRC(use_device(c));
+  SETTLE(c);
   return copy_vec(c, host, p, nb, cudaMemcpyDeviceToHost);
 }
 extern "C" CRL_API int crl_write_field(crl_ctx* c, int32_t field, const void* host, size_t bytes) {
@@ -898,6 +930,8 @@ extern "C" CRL_API int crl_write_field(crl_ctx* c, int32_t field, const void* ho
   void* p; size_t nb;
   CKRC(field_info(c, field, &p, &nb));
   if (bytes != nb) return fail(CRL_ERR_INVALID, "field %d holds %zu bytes, caller passed %zu", field, nb, bytes);
+  CKRC(use_device(c));
+  SETTLE(c);
   CKRC(copy_vec(c, p, host, nb, cudaMemcpyHostToDevice));
   if (field <= CRL_F_VALUE) c->rolled = true;
   if (field == CRL_F_ADVANTAGE || field == CRL_F_RETURN) c->gae_done = true;
@@ -907,6 +941,7 @@ extern "C" CRL_API int crl_write_field(crl_ctx* c, int32_t field, const void* ho
 extern "C" CRL_API int crl_pop_episodes(crl_ctx* c, crl_episode* out, int32_t max_records, int32_t* n_out, crl_episode_agg* agg) {
   if (!c) return fail(CRL_ERR_INVALID, "ctx is NULL");
   CKRC(use_device(c));
+  SETTLE(c);
   EpisodeBuf e;
   CKRC(copy_vec(c, &e, c->eb, sizeof(e), cudaMemcpyDeviceToHost));
   const int have = (int)std::min<unsigned>(e.count, (unsigned)c->ep_capacity);

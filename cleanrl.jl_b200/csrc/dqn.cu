@@ -749,23 +749,33 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
   if (prop.major != 10) return dfail(CRL_ERR_CUDA, "libcleanrl_cuda is built for sm_100a only");
   crl_dqn_ctx* c = new crl_dqn_ctx();
   memset(c, 0, sizeof(*c));
+  // from here on a failure must release what was allocated so far (crl_dqn_destroy skips null members)
+#define DCKC(call)                                                                                           \
+  do {                                                                                                       \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess) {                                                                                \
+      crl_dqn_destroy(c);                                                                                    \
+      return dfail(CRL_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (dqn.cu)"); \
+    }                                                                                                        \
+  } while (0)
   c->cfg = *cfg;
   const size_t N = cfg->num_envs, C = cfg->buffer_size;
-  DCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  DCK(dzalloc(&c->q, DQ_P)); DCK(dzalloc(&c->tgt, DQ_P)); DCK(dzalloc(&c->m, DQ_P)); DCK(dzalloc(&c->v, DQ_P));
-  DCK(dzalloc(&c->env_state, 4 * N)); DCK(dzalloc(&c->env_t, N)); DCK(dzalloc(&c->ep_ret, N)); DCK(dzalloc(&c->ep_len, N));
-  DCK(dzalloc(&c->resets, N));
-  DCK(dzalloc(&c->b_state, 4 * C)); DCK(dzalloc(&c->b_next, 4 * C)); DCK(dzalloc(&c->b_reward, C)); DCK(dzalloc(&c->b_action, C));
-  DCK(dzalloc(&c->b_term, C)); DCK(dzalloc(&c->dev, 1));
-  DCK(dzalloc(&c->h1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->h2T, (size_t)LEARN_B * DQ_H2)); DCK(dzalloc(&c->z2T, (size_t)LEARN_B * DQ_H2));
-  DCK(dzalloc(&c->z1T, (size_t)LEARN_B * DQ_H1)); DCK(dzalloc(&c->xT, (size_t)LEARN_B * DQ_D)); DCK(dzalloc(&c->dqT, (size_t)LEARN_B * DQ_A));
-  DCK(dzalloc(&c->loss_part, LF_MAX_BLOCKS));
-  DCK(dzalloc(&c->gbuf, DQ_P)); DCK(dzalloc(&c->lbuf, 1));
+  DCKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  DCKC(dzalloc(&c->q, DQ_P)); DCKC(dzalloc(&c->tgt, DQ_P)); DCKC(dzalloc(&c->m, DQ_P)); DCKC(dzalloc(&c->v, DQ_P));
+  DCKC(dzalloc(&c->env_state, 4 * N)); DCKC(dzalloc(&c->env_t, N)); DCKC(dzalloc(&c->ep_ret, N)); DCKC(dzalloc(&c->ep_len, N));
+  DCKC(dzalloc(&c->resets, N));
+  DCKC(dzalloc(&c->b_state, 4 * C)); DCKC(dzalloc(&c->b_next, 4 * C)); DCKC(dzalloc(&c->b_reward, C)); DCKC(dzalloc(&c->b_action, C));
+  DCKC(dzalloc(&c->b_term, C)); DCKC(dzalloc(&c->dev, 1));
+  DCKC(dzalloc(&c->h1T, (size_t)LEARN_B * DQ_H1)); DCKC(dzalloc(&c->h2T, (size_t)LEARN_B * DQ_H2)); DCKC(dzalloc(&c->z2T, (size_t)LEARN_B * DQ_H2));
+  DCKC(dzalloc(&c->z1T, (size_t)LEARN_B * DQ_H1)); DCKC(dzalloc(&c->xT, (size_t)LEARN_B * DQ_D)); DCKC(dzalloc(&c->dqT, (size_t)LEARN_B * DQ_A));
+  DCKC(dzalloc(&c->loss_part, LF_MAX_BLOCKS));
+  DCKC(dzalloc(&c->gbuf, DQ_P)); DCKC(dzalloc(&c->lbuf, 1));
   c->world = 1; c->rank = 0; c->env_id_base = 0; c->comm = nullptr;
-  DCK(cudaFuncSetAttribute(dqn_learn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
-  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
-  DCK(cudaFuncSetAttribute(dqn_learn_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
-  DCK(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
+  DCKC(cudaFuncSetAttribute(dqn_learn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+  DCKC(cudaFuncSetAttribute(dqn_learn_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
+  DCKC(cudaFuncSetAttribute(dqn_learn_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_SMEM));
+  DCKC(cudaFuncSetAttribute(dqn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
+#undef DCKC
   *out = c;
   return CRL_OK;
 }
@@ -773,12 +783,12 @@ extern "C" CRL_API int crl_dqn_create(const crl_dqn_config* cfg, crl_dqn_ctx** o
 extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
   if (!c) return dfail(CRL_ERR_INVALID, "ctx is NULL");
   cudaSetDevice(c->cfg.device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
                   c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part, c->gbuf, c->lbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
   crl_internal_nccl_comm_destroy(c->comm);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return CRL_OK;
 }

@@ -39,6 +39,9 @@ struct RolloutArgs {
   EpisodeBuf* eb;
   crl_episode* records;
   int ep_capacity;
+  // A2C (a2c.jl:52,108): obs = deepcopy(state(env)) is taken AFTER reset!(env), so the step after a termination
+  // observes the reset state; PPO keeps the stale terminal observation (Q2, ppo.jl:143 before :164)
+  int fresh_obs_after_reset;
 };
 
 // where the minibatch sample indices come from: an explicit device array, or the

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
           }
           resets += 1;
           env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
+          if (a.fresh_obs_after_reset) env_obs<ENV>(st, obs);  // a2c.jl:108 then :52 (PPO: stale obs, Q2)
         }
       }
 #pragma unroll

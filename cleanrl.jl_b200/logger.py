@@ -78,8 +78,10 @@ class TeeLogger:
         self.records = 0
 
     def info(self, message, **kwargs):
-        """@info message key=value ... ; `log_step_increment` advances the TensorBoard step."""
-        self.step += int(kwargs.get("log_step_increment", 0))
+        """@info message key=value ... ; `log_step_increment` advances the TensorBoard step. A record without the key
+        advances it by 1, TensorBoardLogger.jl's default `step_increment` (the DQN and A2C records, dqn.jl:82,116 and
+        a2c.jl:100,106, carry none); the PPO records pass it explicitly, 0 included (ppo.jl:156-157,246-247)."""
+        self.step += int(kwargs.get("log_step_increment", 1))
         self.records += 1
         for s in self.sinks:
             s.write(message, self.step, kwargs)

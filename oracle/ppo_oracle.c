@@ -651,6 +651,9 @@ static void rollout_range(int64_t lo, int64_t hi, int tid, void* argp) {
         else orc_rng_reset_uniforms(c->cfg.seed, (uint32_t)(c->cfg.env_id_base + n), c->reset_count[n], u);
         c->reset_count[n] += 1;
         reset_one(c, (int)n, u); /* reset!(env) resets only terminated envs, multi_thread_env.jl:105-111 */
+        /* A2C: obs = deepcopy(state(env)) is read after reset!(env) (a2c.jl:108 then :52), so the next transition
+         * starts from the reset state; PPO keeps the stale terminal observation (Q2) */
+        if (c->cfg.flags & CRL_FLAG_A2C) env_obs(kind, c->env_state + S * n, obs);
       }
     }
     for (int d = 0; d < D; d++) c->next_obs[D * n + d] = obs[d];

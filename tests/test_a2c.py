@@ -86,6 +86,48 @@ def test_a2c_loss_gradient_matches_float64_autograd(olib, kind):
     np.testing.assert_allclose(g, gt, rtol=2e-3, atol=2e-5 * np.abs(gt).max())
 
 
+@pytest.mark.parametrize("a2c_flag", [True, False])
+def test_a2c_rollout_observes_the_reset_state_after_a_termination(olib, abi, a2c_flag):
+    """a2c.jl:108 resets the env and a2c.jl:52 then copies state(env): the transition after a termination starts from
+    the RESET state. PPO (ppo.jl:143 before :164, quirk Q2) keeps the stale terminal observation instead."""
+    N, T = 48, 24
+    kw = dict(num_minibatches=1, update_epochs=1, gae_mode=abi.CRL_GAE_A2C_RETURNS, flags=abi.CRL_FLAG_A2C, gae_lambda=1.0) \
+        if a2c_flag else dict(num_minibatches=4, update_epochs=1)
+    o = olib.create(abi.make_config(env_kind=0, num_envs=N, num_steps=T, seed=3, **kw))
+    from conftest import rand_params
+    o.set_params(rand_params(olib, 0, seed=2))
+    rng = np.random.default_rng(5)
+    st = (rng.random((N, 4)) * 0.1 - 0.05).astype(F)
+    st[:, 2] = rng.uniform(0.15, 0.2, N)   # about to fall
+    st[:, 3] = 1.5
+    o.env_set_state(st, np.zeros(N, np.int32))
+    o.rollout(rng.random((T, N)), rng.random((T, N, 4)).astype(F))
+    term, states = o.read_field(abi.CRL_F_TERMINAL), o.read_field(abi.CRL_F_STATE)
+    tt, nn = np.nonzero(term[1:])
+    assert len(tt) > 20
+    after = states[tt + 1, nn]
+    fresh = np.all(np.abs(after) <= 0.05, axis=1)   # reset!: 0.1 rand - 0.05 per component
+    fallen = (np.abs(after[:, 0]) > 2.4) | (np.abs(after[:, 2]) > 0.2094395)
+    if a2c_flag:
+        assert fresh.all() and not fallen.any()
+    else:
+        assert fallen.all() and not fresh.any()
+
+
+def test_a2c_flag_is_rejected_with_several_minibatches_or_epochs(olib, abi):
+    """the recorded values are the current critic's output for the first minibatch only (a2c.jl:79-85)"""
+    from cleanrl_jl_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    for bad in (dict(num_minibatches=2, update_epochs=1, gae_mode=abi.CRL_GAE_A2C_RETURNS),
+                dict(num_minibatches=1, update_epochs=2, gae_mode=abi.CRL_GAE_A2C_RETURNS),
+                dict(num_minibatches=1, update_epochs=1, gae_mode=abi.CRL_GAE_FIXED)):
+        cfg = abi.make_config(env_kind=0, num_envs=8, num_steps=8, flags=abi.CRL_FLAG_A2C, **bad)
+        h = C.c_void_p()
+        assert lib.crl_create(C.byref(cfg), C.byref(h)) == abi.CRL_ERR_INVALID
+        assert b"CRL_FLAG_A2C" in lib.crl_last_error()
+
+
 def test_a2c_config_defaults_match_a2c_jl():
     from cleanrl_jl_b200.a2c_algo import A2CConfig, make_crl_config
     c = A2CConfig()

@@ -123,6 +123,23 @@ def test_logger_records_and_step_increment(tmp_path):
     null.info("anything", a=1)
 
 
+def test_logger_record_without_step_increment_advances_by_one(tmp_path):
+    """TensorBoardLogger.jl advances its step by 1 per record unless `log_step_increment` says otherwise: the DQN and A2C
+    records (dqn.jl:82,116; a2c.jl:100,106) carry no such key, so each of them gets its own step"""
+    lg = Logger.make_logger("dq", to_terminal=False, to_tensorboard=True, to_json=False, log_dir=str(tmp_path))
+    lg.info("Training Statistics", actor_loss=0.1, critic_loss=0.2)
+    lg.info("Episode Statistics", episode_return=9.0, episode_length=9, global_step=9, steps_per_sec=10.0)
+    lg.info("Training Statistics", loss=0.5, log_step_increment=0)   # PPO-style explicit zero still means zero
+    lg.close()
+    assert lg.step == 2 and lg.records == 3
+    scal = tmp_path / "dq" / "scalars.jsonl"
+    if scal.exists():
+        rows = [json.loads(l) for l in open(scal)]
+        assert {"tag": "Training Statistics/actor_loss", "step": 1, "value": 0.1} in rows
+        assert {"tag": "Episode Statistics/episode_return", "step": 2, "value": 9.0} in rows
+        assert {"tag": "Training Statistics/loss", "step": 2, "value": 0.5} in rows
+
+
 def test_shard_envs():
     assert parallel.shard_envs(65536, 8, 3) == (3 * 8192, 8192)
     assert parallel.shard_envs(4, 1, 0) == (0, 4)
