@@ -44,12 +44,14 @@ UNIT = "env-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--env", default="CartPole", choices=["CartPole", "Pendulum"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary objects (multi_parity at N > 1, default_config, pendulum_65536, a2c, dqn)")
     ap.add_argument("--gae-n", type=int, default=1 << 20, help="envs in the GAE HBM measurement (T=128)")
     ap.add_argument("--local-stats", action="store_true")
     ap.add_argument("--dqn-mode", default="replicas", choices=["replicas", "sharded"],
@@ -60,7 +62,20 @@ def parse():
     return ap.parse_args()
 
 
+L2_NOTE = ("not flushed: every step regenerates its 16.5 MB rollout buffer on the device (L2-resident in production too); "
+           "the GAE roofline uses a 2.29 GB input, far larger than the 126 MB L2")
+ARITH_NOTE = ("fp32 results; GPU arm: the 64-wide contractions of the update run as 3xTF32 on tcgen05 (fp32-accurate to ~1e-6), "
+              "everything else fp32/fp64 on the CUDA cores; CPU arm: fp32/fp64 scalar + AVX2")
+
+
 def workload_config(args, world):
+    c = _workload_config(args, world)
+    c["l2"] = L2_NOTE
+    c["arithmetic"] = ARITH_NOTE
+    return c
+
+
+def _workload_config(args, world):
     if args.algo == "a2c":
         return {"workload": "A2C %s, %d vectorized envs x %d steps, 64-64 MLP, n-step returns + one fused update per rollout "
                             "(BASELINE.json configs[2])" % (args.env, A2C_ENVS, A2C_STEPS), "env": args.env,
@@ -113,7 +128,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
@@ -135,8 +150,9 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_ppo_throughput(env_kind, n_envs, steps, warmup, threads):
+def cpu_ppo_throughput(env_kind, n_envs, steps, warmup, threads, num_steps=None):
     """times the C restatement of the reference's PPO (oracle, -O3 -mavx2 build) on the host cores"""
+    T = num_steps or NUM_STEPS
     from cleanrl_jl_b200 import _abi, networks
     from oracle.oracle import OracleLib
     fast = False
@@ -147,7 +163,7 @@ def cpu_ppo_throughput(env_kind, n_envs, steps, warmup, threads):
         pass
     olib = OracleLib(fast=fast)
     olib.set_threads(threads)
-    cfg = _abi.make_config(env_kind=env_kind, num_envs=n_envs, num_steps=NUM_STEPS, num_minibatches=NUM_MINIBATCHES,
+    cfg = _abi.make_config(env_kind=env_kind, num_envs=n_envs, num_steps=T, num_minibatches=NUM_MINIBATCHES,
                            update_epochs=UPDATE_EPOCHS, seed=1)
     o = olib.create(cfg)
     d = olib.dims(env_kind)
@@ -161,7 +177,38 @@ def cpu_ppo_throughput(env_kind, n_envs, steps, warmup, threads):
         o.train_update(lr)
     dt = time.perf_counter() - t0
     o.close()
-    return n_envs * NUM_STEPS * steps / dt, dt / steps, "avx2" if fast else "sse2"
+    return n_envs * T * steps / dt, dt / steps, "avx2" if fast else "sse2"
+
+
+# ------------------------------------------------------------------ the reference's own default shape (ppo.jl:2-6)
+DEFAULT_SHAPE = "PPOConfig() defaults: CartPole, 4 envs x 32 steps, 4 epochs x 4 minibatches of 32 (ppo.jl:2-6; BASELINE.json configs[0])"
+
+
+def default_config_cpu(updates=400):
+    """CPU restatement at PPOConfig() defaults, best of 1 and 4 host threads (the reference spawns one task per env)"""
+    from cleanrl_jl_b200 import _abi
+    best = None
+    for th in (1, 4):
+        v, spu, build = cpu_ppo_throughput(_abi.CRL_ENV_CARTPOLE, 4, updates, 20, th, num_steps=32)
+        if best is None or v > best["value"]:
+            best = {"value": v, "unit": UNIT, "ms_per_update": spu * 1e3, "cores": th, "kind": "port",
+                    "sample": "%d updates of 128 env-steps (%s build)" % (updates, build)}
+    return best
+
+
+def default_config_gpu(device, updates=2000):
+    """ppo(PPOConfig()) through the public API: what a drop-in user calling ppo() with no arguments runs"""
+    from cleanrl_jl_b200 import logger as Logger
+    from cleanrl_jl_b200.config import PPOConfig
+    from cleanrl_jl_b200.ppo_algo import ppo
+    tmp = tempfile.mkdtemp(prefix="crl_bench_logs_")
+    lg = Logger.make_logger("bench_default", to_terminal=False, to_tensorboard=True, log_dir=tmp)
+    d = PPOConfig()
+    res = ppo(PPOConfig(total_timesteps=updates * d.num_envs * d.num_steps), logger=lg, device=device)
+    lg.close()
+    return {"value": res["global_step"] / res["elapsed_s"], "unit": UNIT, "ms_per_update": res["elapsed_s"] / res["num_updates"] * 1e3,
+            "updates": res["num_updates"], "note": "ppo(PPOConfig()) public API, wall clock as ppo.jl:111,148 defines it (set-up of the "
+                                                   "CUDA graph and all logging included); 128 samples per update: launch-latency bound"}
 
 
 def run_reference(args):
@@ -179,8 +226,12 @@ def run_reference(args):
     n_envs = int(min(args.envs_per_gpu * max(args.gpus, 1), max(64, per_step // NUM_STEPS)))
     n_envs = max(4, (n_envs // 4) * 4)
     value, sec_per_step, build = cpu_ppo_throughput(kind, n_envs, args.steps, args.warmup, cores)
-    sample = "%d envs x %d steps per update (%d env-steps), %d epochs x %d minibatches, %d updates timed" % (
-        n_envs, NUM_STEPS, n_envs * NUM_STEPS, UPDATE_EPOCHS, NUM_MINIBATCHES, args.steps)
+    n_stated = args.envs_per_gpu * max(args.gpus, 1)
+    sample = "%d envs x %d steps per update (%d env-steps), %d epochs x %d minibatches, %d updates timed%s" % (
+        n_envs, NUM_STEPS, n_envs * NUM_STEPS, UPDATE_EPOCHS, NUM_MINIBATCHES, args.steps,
+        "" if n_envs == n_stated else
+        "; a BOUNDED SAMPLE of the %d envs `config` states (a ~150 s budget for the whole run): env-steps/s of this CPU "
+        "path does not depend on the env count at these sizes" % n_stated)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -189,7 +240,10 @@ def run_reference(args):
                          "note": "C restatement of the reference's multi-threaded CPU PPO (oracle/ppo_oracle.c, %s build); "
                                  "Julia is not installed in this image so the Julia original cannot be timed" % build},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_envs": n_envs, "stated_envs": n_stated,
     }
+    if args.gpus <= 1 and not args.no_secondary and args.env == "CartPole":
+        line["default_config"] = {"workload": DEFAULT_SHAPE, "cpu_port": default_config_cpu()}
     print(json.dumps(line), flush=True)
 
 
@@ -349,6 +403,155 @@ def run_dqn(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ secondary measurements carried by the same JSON line
+def _sync_all(torch, dist, h=None):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if h is not None and h.h:
+        h.sync()
+
+
+def _time_updates(torch, dist, parallel, h, lr, warm, steps):
+    """ms for `steps` crl_train_update calls: CUDA events on the handle's stream, barrier on both sides, max over ranks"""
+    for _ in range(warm):
+        h.train_update(lr)
+    _sync_all(torch, dist, h)
+    stream = torch.cuda.ExternalStream(h.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        h.train_update(lr)
+    e1.record(stream)
+    _sync_all(torch, dist, h)
+    return parallel.max_over_ranks(e0.elapsed_time(e1))
+
+
+def secondary_pendulum(torch, dist, rank, local_rank, world, steps=10):
+    """north_star's multi-GPU configuration (BASELINE.json configs[3]): PPO Pendulum, Gaussian policy, 65,536 envs sharded
+    over the N GPUs (STRONG scaling: the global env count is fixed), one gradient exchange per minibatch"""
+    from cleanrl_jl_b200 import networks, parallel
+    from cleanrl_jl_b200.config import PPOConfig
+    from cleanrl_jl_b200.handle import PPOHandle, comm_unique_id
+    from cleanrl_jl_b200.ppo_algo import make_crl_config
+    n_global = 65536
+    n_local = n_global // world
+    pcfg = PPOConfig(total_timesteps=10 ** 12, num_steps=NUM_STEPS, num_envs=n_global, num_minibatches=NUM_MINIBATCHES,
+                     update_epochs=UPDATE_EPOCHS, env_id="Pendulum", seed=1)
+    h = PPOHandle(make_crl_config(pcfg, n_local, local_rank, world, rank, rank * n_local))
+    if world > 1:
+        h.comm_init(parallel.exchange_unique_id(comm_unique_id))
+    h.set_params(networks.init_params(True, h.d["D"], h.d["A"], seed=1))
+    h.env_reset()
+    ms = _time_updates(torch, dist, parallel, h, float(np.float32(2.5e-4)), 3, steps)
+    replays = h.spec_replays()
+    h.close()
+    return {"metric": METRIC, "value": steps * n_global * NUM_STEPS / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "steps": steps, "warmup": 3, "n_gpus": world, "scaling": "strong", "spec_replays": int(replays),
+            "config": {"workload": "PPO Pendulum (continuous Gaussian policy), 65536 envs sharded over %d GPU(s) x %d steps, 64-64 MLP, "
+                                   "%d epochs x %d minibatches (BASELINE.json configs[3])" % (world, NUM_STEPS, UPDATE_EPOCHS, NUM_MINIBATCHES),
+                       "num_envs_global": n_global, "num_envs_per_gpu": n_local}}
+
+
+def secondary_a2c(torch, local_rank, steps=30):
+    """BASELINE.json configs[2]: A2C CartPole, 16384 envs x 32 steps, n-step returns + one fused update per rollout, 1 GPU"""
+    from cleanrl_jl_b200 import a2c_algo, networks, parallel
+    from cleanrl_jl_b200.handle import PPOHandle
+    acfg = a2c_algo.A2CConfig(num_envs=A2C_ENVS, num_steps=A2C_STEPS, total_timesteps=10 ** 12)
+    h = PPOHandle(a2c_algo.make_crl_config(acfg, local_rank))
+    h.set_params(networks.init_params(False, h.d["D"], h.d["A"], seed=1))
+    h.env_reset()
+    ms = _time_updates(torch, None, parallel, h, acfg.lr, 3, steps)
+    h.close()
+    return {"metric": "a2c_env_steps_per_sec", "value": steps * A2C_ENVS * A2C_STEPS / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms / steps, "steps": steps, "warmup": 3, "n_gpus": 1,
+            "config": {"workload": "A2C CartPole, %d vectorized envs x %d steps, 64-64 MLP, n-step returns + one fused update per "
+                                   "rollout (BASELINE.json configs[2])" % (A2C_ENVS, A2C_STEPS)}}
+
+
+def secondary_dqn(torch, dist, rank, local_rank, world, steps=20):
+    """BASELINE.json configs[4]: DQN CartPole, 4096 envs per GPU, 1M-transition HBM replay per GPU. N > 1: ONE data-parallel
+    learner (crl_dqn_comm_init: envs, replay and the batch sharded, one gradient allreduce per learning step). Also a line
+    at the reference's update-to-data ratio (one gradient step per 10 env steps, dqn.jl:94), which 4096 lock-stepped envs
+    cannot have: 10 envs, learning every iteration."""
+    from cleanrl_jl_b200 import _abi, parallel
+    from cleanrl_jl_b200.dqn_algo import DQNHandle, init_q_params
+    from cleanrl_jl_b200.handle import comm_unique_id
+    N, ITERS = 4096, 100
+    batch = 120 if world == 1 else max(8, (120 // world + 7) // 8 * 8)
+
+    def run(num_envs, train_freq, min_buff, iters, n_steps, shard):
+        cfg = _abi.make_dqn_config(num_envs=num_envs, buffer_size=1 << 20, min_buff_size=min_buff, batch_size=batch if shard else 120,
+                                   train_freq=train_freq, target_net_freq=100, epsilon_duration=5e6, seed=1, device=local_rank)
+        h = DQNHandle(cfg)
+        h.set_params(init_q_params(1))
+        if shard:
+            h.comm_init(parallel.exchange_unique_id(comm_unique_id), world, rank, rank * num_envs)
+        h.reset()
+        for _ in range(3):
+            h.run(iters)
+        l0 = h.run(0)
+        _sync_all(torch, dist)
+        t0 = time.perf_counter()
+        for _ in range(n_steps - 1):
+            h.lib.crl_dqn_run(h.h, iters, None)   # asynchronous: launches only
+        st = h.run(iters)                          # reads the statistics back = stream synchronisation
+        wall = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+        h.close()
+        return wall, int(st.learn_steps) - int(l0.learn_steps)
+
+    wall, learn = run(N, 10, 10_000, ITERS, steps, world > 1)
+    out = {"metric": "dqn_env_steps_per_sec", "value": steps * ITERS * N * world / wall, "unit": UNIT, "n_gpus": world,
+           "learner_steps_per_sec": learn / wall, "env_steps_per_learner_step": ITERS * N * world * steps / max(learn, 1),
+           "ms_per_step": wall / steps * 1e3, "steps": steps, "scaling": "weak",
+           "config": {"workload": "DQN CartPole, %d vectorized envs per GPU, 1,048,576-transition HBM replay per GPU, global batch %d, "
+                                  "learn every 10 iterations, target copy every 100 (dqn.jl schedule in iterations); a step = %d iterations"
+                                  % (N, batch * world if world > 1 else 120, ITERS),
+                      "mode": "one data-parallel learner over %d GPUs, one gradient allreduce per learning step" % world if world > 1 else "single GPU",
+                      "timing": "host wall clock around asynchronous launches, closed by the statistics read-back, max over ranks"}}
+    if rank == 0 and world == 1:
+        w2, l2 = run(10, 1, 200, 1000, 5, False)
+        out["reference_update_to_data_ratio"] = {
+            "value": 5 * 1000 * 10 / w2, "unit": UNIT, "learner_steps_per_sec": l2 / w2, "env_steps_per_learner_step": 5 * 1000 * 10 / max(l2, 1),
+            "workload": "10 envs, a learning step (batch 120) every iteration = one gradient step per 10 env steps as at dqn.jl:94"}
+    return out
+
+
+def multi_parity(dist, rank):
+    """N > 1: the checks of tests/test_gpu_multi.py in-process, BEFORE timing, so that the driver's scaling record carries a
+    correctness verdict for the sharded path: union-of-shards rollout == single-process oracle, parameters bit-identical
+    across ranks, post-step parameters vs the oracle on the union minibatches, speculative == exact, and one forced
+    speculation failure replayed exactly. The oracle is the checker here, never the thing measured."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multi_gpu_checks import run_checks, verdict
+    from oracle.oracle import OracleLib
+    t0 = time.time()
+    try:
+        res = run_checks(dist, OracleLib())
+    except Exception as e:  # pragma: no cover
+        return {"ok": False, "failures": ["exception: %r" % (e,)]}
+    if rank != 0:
+        return None
+    bad = verdict(res)
+    return {"ok": not bad, "failures": bad, "seconds": time.time() - t0,
+            "checks": "tests/multi_gpu_checks.py: CartPole + Pendulum, 64 envs x 16 steps over all ranks, vs the single-process oracle",
+            "results": res}
+
+
+def measured_tf32_peak():
+    """tools/tf32_peak (tcgen05.mma kind::tf32 M128 N256 K8 issued back to back on every SM): the roofline denominator of
+    the update kernel. Returns the parsed JSON or None when the binary is missing."""
+    exe = os.path.join(ROOT, "tools", "tf32_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        import subprocess
+        out = subprocess.run([exe, "1.0"], capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception:  # pragma: no cover
+        return None
+
+
 def run_ours(args):
     if args.algo == "dqn":
         return run_dqn(args)
@@ -367,6 +570,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    secondary = (not args.no_secondary and args.algo == "ppo" and args.env == "CartPole" and
+                 args.envs_per_gpu == ENVS_PER_GPU and not args.local_stats)
+    parity = multi_parity(dist, rank) if (world > 1 and secondary) else None   # correctness of the sharded path, before timing
     kind = _abi.CRL_ENV_CARTPOLE if args.env == "CartPole" else _abi.CRL_ENV_PENDULUM
     n_local = args.envs_per_gpu
     pcfg = PPOConfig(total_timesteps=10 ** 12, num_steps=NUM_STEPS, num_envs=n_local * world,
@@ -444,7 +650,8 @@ def run_ours(args):
         # TC_EXEC_FLOP per sample for UPDATE_FLOP algorithmic fp32 FLOP. MEASURED_PEAKS.json holds a bf16 figure only;
         # the TF32 peak is that measurement scaled by the nominal TF32:bf16 ratio (1.1 : 2.25 PFLOP/s dense).
         bf16 = (peaks or {}).get("bf16_tflops")
-        tf32_peak = (bf16 if bf16 else 2250.0) * 1.1 / 2.25
+        tf32_meas = measured_tf32_peak() if rank == 0 else None
+        tf32_peak = tf32_meas["tf32_tflops"] if tf32_meas else (bf16 if bf16 else 2250.0) * 1.1 / 2.25
         exec_tf = TC_EXEC_FLOP * M_local / (lg_ms * 1e-3) / 1e12 if lg_ms else None
         tc_traffic, tc_tfile = ncu_traffic("loss_grad_tc_kernel")
         roofline = {"kernel": "loss_grad_tc_kernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
@@ -458,8 +665,13 @@ def run_ours(args):
                     "executed_tensor_tflops": exec_tf, "executed_frac": exec_tf / tf32_peak if exec_tf else None,
                     "executed": "%d FLOP/sample on the tensor pipe: 3xTF32 = 3-4 TF32 products per fp32 product" % TC_EXEC_FLOP,
                     "fp32_equiv_frac_of_ffma_peak": ach / fp32_peak if ach else None,
-                    "peak_source": ("TF32 dense peak = MEASURED_PEAKS.json bf16_tflops x 1.1/2.25 (nominal TF32:bf16 ratio; no "
-                                    "TF32 measurement exists)" if bf16 else "nominal 1.1 PFLOP/s TF32 dense (no MEASURED_PEAKS.json)"),
+                    "peak_source": ("measured in this run by tools/tf32_peak (burst; sustained %.1f): tcgen05.mma kind::tf32 M128 N256 K8 "
+                                    "issued back to back on all SMs (MEASURED_PEAKS.json holds no TF32 figure; its bf16 %s x 1.1/2.25 "
+                                    "nominal ratio would give %.1f)" % (tf32_meas["tf32_tflops_sustained"], bf16, (bf16 or 2250.0) * 1.1 / 2.25)
+                                    if tf32_meas else
+                                    "TF32 dense peak = MEASURED_PEAKS.json bf16_tflops x 1.1/2.25 (nominal TF32:bf16 ratio; tools/tf32_peak "
+                                    "not built)" if bf16 else "nominal 1.1 PFLOP/s TF32 dense (no MEASURED_PEAKS.json)"),
+                    "tf32_peak_probe": tf32_meas,
                     "note": "the kernel is bound by its CUDA-core work (tanh_fast on 2x64 activations per sample and layer, "
                             "hi/lo splitting, feature-major operand stores), not by the tensor pipe: see DESIGN.md section 5"}
     else:
@@ -535,21 +747,33 @@ def run_ours(args):
                         "sample": "1 PPO update of %d envs x %d steps (%d env-steps, 4 epochs x 4 minibatches), %.1f s" % (
                             n_s, NUM_STEPS, n_s * NUM_STEPS, spu),
                         "note": "C restatement of the reference's multi-threaded CPU PPO (%s build); not the Julia program" % build}
+    extra = {}
+    if secondary:
+        def guarded(name, fn):
+            try:
+                extra[name] = fn()
+            except Exception as e:  # pragma: no cover  (a failing secondary must not take the headline line down)
+                extra[name] = {"error": repr(e)}
+        guarded("pendulum_65536", lambda: secondary_pendulum(torch, dist, rank, local_rank, world))
+        guarded("dqn", lambda: secondary_dqn(torch, dist, rank, local_rank, world))
+        if world == 1:
+            guarded("a2c", lambda: secondary_a2c(torch, local_rank))
+            guarded("default_config", lambda: {"workload": DEFAULT_SHAPE, "gpu": default_config_gpu(local_rank),
+                                               "cpu_port": None if args.no_cpu_baseline else default_config_cpu()})
+        if parity is not None:
+            extra["multi_parity"] = parity
     if dist is not None:
         dist.barrier()
     if rank == 0:
         line = {
             "metric": METRIC if args.algo == "ppo" else "a2c_env_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world),
-                                                                l2="not flushed: every step regenerates its 16.5 MB rollout buffer on the device "
-                                                                   "(L2-resident in production too); the GAE roofline uses a 2.29 GB input",
-                                                                arithmetic="fp32 results; the 64-wide contractions of the update run as 3xTF32 on "
-                                                                           "tcgen05 (fp32-accurate to ~1e-6), everything else fp32/fp64 on the CUDA cores"),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gae": roofline_gae, "roofline_rollout": roofline_rollout,
             "cpu_baseline": cpu_baseline, "kernels": kernels,
             "last_loss": float(stats[-1, 0]), "episodes_last_update": int(agg.count),
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -22,23 +22,12 @@ def test_multi_gpu_sharded_update_matches_single_process_oracle(tmp_path, torch_
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     res = json.load(open(out))
-    for kind in ("kind0", "kind1"):
-        r = res[kind]
-        assert r["rollout_ok"], r             # union of the shards' rollouts == single-process rollout
-        assert r["ranks_agree"], r            # replicated parameters stay bit-identical across ranks
-        assert r["param_maxerr"] < 2e-5, r    # post-step parameters vs the oracle on the union minibatches
-        assert r["stats_maxerr"] < 1e-4, r
-        n, f = r["normal"], r["fail"]
-        assert n["ranks_agree"] and n["finite"] and n["replays"] == 0, n
-        assert n["maxerr"] < 2e-5 and n["stats_maxerr"] < 1e-4, n      # speculative == exact within fp32 tolerance
-        assert f["ranks_agree"] and f["finite"] and f["replays_exact_mode"] == 0, (kind, f)
-        if kind == "kind0":
-            # CartPole with gamma = 0: R in {0, 1, v} so s = mean(v - R^2) > min (clip - R)^2 = 0: verification fails
-            assert f["replays"] >= 1, (kind, f)
-        if f["replays"] >= 1:
-            assert f["bit_identical"], (kind, f)                        # a failed speculation is replayed exactly
-        else:
-            assert f["maxerr"] < 2e-5, (kind, f)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multi_gpu_checks import verdict
+    assert set(res) == {"kind0", "kind1"} and all("normal" in r and "fail" in r for r in res.values()), res
+    # union-of-shards rollout == single-process oracle; ranks bit-identical; post-step parameters and loss statistics vs
+    # the oracle on the union minibatches; speculative == exact; a forced speculation failure is replayed exactly
+    assert verdict(res) == [], res
 
 
 def test_multi_gpu_sharded_dqn_matches_oracle_group(tmp_path, torch_cuda):
