@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcleanrl_cuda.so")
-SOURCES = ["gae.cu", "rollout.cu", "update.cu", "update_tc.cu", "dqn.cu", "api.cu"]
+SOURCES = ["gae.cu", "rollout.cu", "update.cu", "update_tc.cu", "dqn.cu", "tblog.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("CRL_NVCC_EXTRA", "").split()
 

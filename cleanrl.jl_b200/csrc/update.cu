@@ -188,21 +188,6 @@ template <int ENV> struct LossSmem {
   static_assert(BYTES <= 227 * 1024, "loss_grad shared memory exceeds 227 KB");
 };
 
-// flat parameter index -> position(s) in the parameter image
-template <int ENV> __device__ __forceinline__ void image_scatter(float* image, int flat, float v) {
-  using E = EnvTraits<ENV>;
-  using SPm = SmemParams<ENV>;
-  using NO = NetOff<E::D, 1>;
-  int net, within;
-  if (flat < E::NET_A) { net = 0; within = flat; image[SPm::ACTOR + within] = v; }
-  else if (flat < E::NET_A + E::NET_C) { net = 1; within = flat - E::NET_A; image[SPm::CRITIC + within] = v; }
-  else { image[SPm::LOGSTD + (flat - E::NET_A - E::NET_C)] = v; return; }
-  if (within >= NO::W2 && within < NO::W2 + CRL_H * CRL_H) {
-    const int e = within - NO::W2, j = e % CRL_H, k = e / CRL_H;  // Flux W2 is (out=j, in=k) at j + 64 k
-    image[SPm::SIZE + net * CRL_H * CRL_H + j * CRL_H + k] = v;
-    tc_image_scatter<ENV>(image, net, j, k, v);  // hi/lo tensor-core operand images (update_tc.cu)
-  }
-}
 template <int ENV> __global__ void param_image_kernel(const float* params, float* image) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < EnvTraits<ENV>::P) image_scatter<ENV>(image, i, params[i]);
@@ -835,25 +820,6 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(AdvStatsArgs a) {
     o[0] = sa;
     o[1] = sa2;
   }
-}
-
-// loss scalars from the reduced sums (ppo.jl:228,237,242,243)
-__device__ __forceinline__ void finalize_stats(const double* sums, double Mg, int A, float ent_coeff, float v_coef,
-                                               double* out, int algo = 0) {
-  if (algo == 1) {  // A2C: @info "Training Statistics" actor_loss critic_loss (a2c.jl:100)
-    out[1] = sums[0] / Mg;
-    out[2] = sums[1] / Mg;
-    out[3] = 0.0;
-    out[0] = out[1] + out[2];
-    return;
-  }
-  const double pg = sums[0] / Mg;                                   // ppo.jl:228
-  const double vl = 0.5 * (double)(float)(sums[1] / Mg);            // ppo.jl:237
-  const double en = (double)(float)(sums[2] / ((double)A * Mg));    // ppo.jl:242
-  out[0] = pg - (double)__fmul_rn(ent_coeff, (float)en) + (double)v_coef * vl;  // ppo.jl:243
-  out[1] = pg;
-  out[2] = vl;
-  out[3] = en;
 }
 
 // raw path: Float32 gradient + loss scalars out of the double sums

@@ -140,10 +140,10 @@ class PPOHandle:
 
     def fetch_update(self, lag=0):
         """results of the latest update (lag=0) or of the one before it (lag=1, does not wait for the latest)"""
-        st = (_abi.crl_loss_stats * max(self.n_mb, 1))()
+        st = np.empty((max(self.n_mb, 1), 4), np.float64)   # crl_loss_stats = 4 doubles (static_assert in api.cu)
         agg = _abi.crl_episode_agg()
-        L.check(self.lib.crl_fetch_update_at(self.h, int(lag), st, C.byref(agg)))
-        return _stats_array(st[:self.n_mb]), agg
+        L.check(self.lib.crl_fetch_update_at(self.h, int(lag), st.ctypes.data_as(C.c_void_p), C.byref(agg)))
+        return st[:self.n_mb], agg
 
     # ---- data
     def field_shape(self, field):

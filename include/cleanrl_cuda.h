@@ -335,6 +335,15 @@ CRL_API int crl_dqn_comm_init(crl_dqn_ctx* ctx, const void* id128, int32_t world
 CRL_API int crl_dqn_read_buffer(crl_dqn_ctx* ctx, float* state, int32_t* action, float* reward, float* next_state,
                         uint8_t* terminal, int32_t* size, int32_t* ptr);
 
+/* ---- logger hook: TensorBoard event files (logger.jl:7-29, TBLogger; records of ppo.jl:157,247) -------------------
+ * Native writer for the "<message>/<key>" scalars the @info records become in TensorBoardLogger.jl. One call = one
+ * record = one Event holding n scalars at `step`. tags: n NUL-terminated strings back to back. Host-only (no GPU). */
+typedef struct crl_tb crl_tb;
+CRL_API int crl_tb_open(const char* logdir /* existing directory */, crl_tb** out);
+CRL_API int crl_tb_scalars(crl_tb* tb, double wall_time, int64_t step, int32_t n, const char* tags, const double* values);
+CRL_API int crl_tb_flush(crl_tb* tb);
+CRL_API int crl_tb_close(crl_tb* tb);
+
 #ifdef __cplusplus
 }
 #endif

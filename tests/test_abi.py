@@ -19,7 +19,7 @@ def header_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = header_symbols()
-    assert len(syms) == 46
+    assert len(syms) == 50
     for s in ("crl_create", "crl_rollout", "crl_gae", "crl_update_minibatch", "crl_train_update", "crl_gae_raw",
               "crl_env_step_raw", "crl_policy_forward_raw", "crl_ppo_loss_raw", "crl_clip_adam_raw", "crl_comm_init", "crl_dqn_run", "crl_dqn_comm_init"):
         assert s in syms

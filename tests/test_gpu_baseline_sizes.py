@@ -210,8 +210,14 @@ def test_dqn_at_baseline_size_matches_oracle(crl, olib, abi, torch_cuda):
         np.testing.assert_array_equal(bh["action"][:n], bo["action"][:n])      # epsilon draws, argmax, ring order
         np.testing.assert_array_equal(bh["terminal"][:n], bo["terminal"][:n])
         np.testing.assert_array_equal(bh["reward"][:n], bo["reward"][:n])
-        np.testing.assert_allclose(bh["state"][:n], bo["state"][:n], rtol=RTOL, atol=2e-6)
-        np.testing.assert_allclose(bh["next_state"][:n], bo["next_state"][:n], rtol=RTOL, atol=2e-6)
+        # trajectory level: episodes run up to 200 chained steps without teacher forcing, and CartPole amplifies a rounding
+        # difference by ~e^0.08 per step (23 of 2.6 M elements exceed 1e-5 relative, the largest by 2e-5 absolute)
+        np.testing.assert_allclose(bh["state"][:n], bo["state"][:n], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(bh["next_state"][:n], bo["next_state"][:n], rtol=1e-3, atol=1e-4)
+        # step level (north_star's rtol 1e-5 per step): every stored transition re-derived from the GPU's own state
+        s1, _, r1, _ = olib.env_step_raw(0, bh["state"][:n], np.zeros(n, np.int32), bh["action"][:n], 10 ** 6)
+        np.testing.assert_allclose(bh["next_state"][:n], s1, rtol=RTOL, atol=1e-6)
+        np.testing.assert_array_equal(bh["reward"][:n], r1)
         qh, th = h.get_params()
         qo, to = o.get_params()
         np.testing.assert_allclose(qh, qo, rtol=1e-4, atol=2e-6)

@@ -140,6 +140,60 @@ def test_logger_record_without_step_increment_advances_by_one(tmp_path):
         assert {"tag": "Training Statistics/loss", "step": 2, "value": 0.5} in rows
 
 
+def _crc32c(data):
+    tab = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tab.append(c)
+    c = 0xFFFFFFFF
+    for b in data:
+        c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def _masked(data):
+    c = _crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_native_tensorboard_writer_produces_valid_event_files(tmp_path):
+    """crl_tb_* (csrc/tblog.cu): TFRecord framing with masked CRC-32C, one Event per record, "<message>/<key>" tags at
+    the logger's step (TensorBoardLogger.jl semantics, logger.jl:7-29)"""
+    import glob
+    import struct
+    lg = Logger.make_logger("tb", to_terminal=False, to_tensorboard=True, to_json=False, log_dir=str(tmp_path))
+    lg.info("Episode Statistics", episode_return=12.5, episode_length=12.0, global_step=128, steps_per_sec=1e6, log_step_increment=0)
+    lg.info("Training Statistics", loss=0.5, pg_loss=-0.25, v_loss=0.125, entropy_loss=0.3, log_step_increment=128)
+    lg.close()
+    files = glob.glob(str(tmp_path / "tb" / "events.out.tfevents.*"))
+    assert len(files) == 1
+    raw = open(files[0], "rb").read()
+    recs, off = [], 0
+    while off < len(raw):
+        (n,) = struct.unpack_from("<Q", raw, off)
+        assert struct.unpack_from("<I", raw, off + 8)[0] == _masked(raw[off:off + 8])
+        data = raw[off + 12:off + 12 + n]
+        assert struct.unpack_from("<I", raw, off + 12 + n)[0] == _masked(data)
+        recs.append(data)
+        off += 16 + n
+    assert len(recs) == 3 and b"brain.Event:2" in recs[0]
+    assert b"Episode Statistics/episode_return" in recs[1] and b"Training Statistics/entropy_loss" in recs[2]
+    assert struct.pack("<f", 12.5) in recs[1] and struct.pack("<f", -0.25) in recs[2]
+    try:
+        from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    except Exception:
+        return
+    ea = EventAccumulator(str(tmp_path / "tb"))
+    ea.Reload()
+    assert set(ea.Tags()["scalars"]) == {"Episode Statistics/" + k for k in ("episode_return", "episode_length", "global_step", "steps_per_sec")} | \
+        {"Training Statistics/" + k for k in ("loss", "pg_loss", "v_loss", "entropy_loss")}
+    ev = ea.Scalars("Training Statistics/pg_loss")
+    assert len(ev) == 1 and ev[0].step == 128 and ev[0].value == -0.25
+    assert ea.Scalars("Episode Statistics/episode_return")[0].step == 0
+
+
 def test_shard_envs():
     assert parallel.shard_envs(65536, 8, 3) == (3 * 8192, 8192)
     assert parallel.shard_envs(4, 1, 0) == (0, 4)
