@@ -164,6 +164,13 @@ struct crl_ctx {
   int p2p_stride;
   size_t p2p_flags_off;
   bool p2p_on;
+  size_t ll_off;                   // flag-in-data region of the exchange buffer (fused tail), [2 slots][world][ll_stride] x 16 B
+  int ll_stride;
+  long long p2p_timeout_cycles;
+  // fused tail of the tcgen05 update kernel
+  unsigned long long* grid_bar;
+  double* normpart;
+  int fused_grid;                  // grid size the barrier counter is used with (constant per handle)
   // instrumentation
   uint64_t launches;
   bool profiling;
@@ -294,7 +301,7 @@ extern "C" CRL_API int crl_create(const crl_config* cfg, crl_ctx** out) {
   cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { delete c; return fail(CRL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
   A_(dalloc(&c->params, L.P)); A_(dalloc(&c->grads, L.P)); A_(dalloc(&c->adam_m, L.P)); A_(dalloc(&c->adam_v, L.P));
-  A_(dalloc(&c->beta_pow, 2 * CRL_MAX_ARRAYS)); A_(dalloc(&c->ds, 1));
+  A_(dalloc(&c->beta_pow, 2 * CRL_MAX_ARRAYS)); A_(dalloc(&c->ds, 1)); A_(dalloc(&c->grid_bar, 1)); A_(dalloc(&c->normpart, (size_t)CRL_MAX_ARRAYS * prop.multiProcessorCount));
   A_(dalloc(&c->image, param_image_floats(cfg->env_kind)));
   A_(dalloc(&c->env_state, N * L.S)); A_(dalloc(&c->env_t, N)); A_(dalloc(&c->ep_return, N)); A_(dalloc(&c->ep_length, N));
   A_(dalloc(&c->reset_count, N)); A_(dalloc(&c->next_obs, N * L.D)); A_(dalloc(&c->next_done, N)); A_(dalloc(&c->next_value, N));
@@ -350,7 +357,7 @@ extern "C" CRL_API int crl_destroy(crl_ctx* c) {
   { void* pp[] = {c->p2p_buf, c->p2p_peers_dev, c->p2p_seq, c->p2p_err, c->p2p_count}; for (void* q : pp) if (q) cudaFree(q); }
   for (auto& p : c->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
-  void* ptrs[] = {c->image, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
+  void* ptrs[] = {c->grid_bar, c->normpart, c->image, c->params, c->grads, c->adam_m, c->adam_v, c->beta_pow, c->ds, c->env_state, c->env_t, c->ep_return,
                   c->ep_length, c->reset_count, c->next_obs, c->next_done, c->next_value, c->state, c->action, c->logprob,
                   c->reward, c->value, c->advantage, c->ret, c->terminal, c->eb, c->records, c->vnew, c->parts,
                   c->parts_send, c->parts_recv, c->fin, c->gpart, c->mpart, c->advparts, c->spart, c->gsum, c->stats_dev, c->idx_dev,
@@ -641,16 +648,35 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
       ua.p2p_data = reinterpret_cast<double*>(c->p2p_buf); ua.p2p_stride = c->p2p_stride; ua.p2p_seq = c->p2p_seq;
       ua.p2p_peers = c->p2p_peers_dev; ua.p2p_flags_off = c->p2p_flags_off; ua.p2p_count = c->p2p_count;
     }
+    aa.M_global = (double)M * W; aa.world = W; aa.verify = 1;
+    // Fused tail: the tcgen05 kernel reduces, exchanges and applies clip + Adam itself (one cooperative launch per
+    // minibatch). Needs the peer-memory exchange when there are several ranks; CRL_NO_FUSED_TAIL=1 keeps the 3-kernel chain.
+    static const bool fuse_off = getenv("CRL_NO_FUSED_TAIL") != nullptr;
+    if (ua.tc_actor_ctas > 0 && !fuse_off && (!multi || p2p) && ua.grid_loss <= c->sm_count &&
+        (c->fused_grid == 0 || c->fused_grid == ua.grid_loss)) {
+      c->fused_grid = ua.grid_loss;
+      ua.fuse_tail = 1;
+      aa.grid_bar = c->grid_bar;
+      aa.normpart = c->normpart;
+      aa.p2p_err = c->p2p_err;
+      if (p2p) {
+        aa.ll_peers = c->p2p_peers_dev; aa.ll_local = c->p2p_buf; aa.ll_off = c->ll_off; aa.ll_stride = c->ll_stride;
+        aa.timeout_cycles = c->p2p_timeout_cycles;
+      }
+      ua.adam = aa;
+      KernelScope ks(c, CRL_K_LOSS_GRAD);
+      CK(launch_loss_grad(ua, c->stream));
+      return CRL_OK;
+    }
     { KernelScope ks(c, CRL_K_LOSS_GRAD); CK(launch_loss_grad(ua, c->stream)); }
     { KernelScope ks(c, CRL_K_GRAD_REDUCE); CK(launch_grad_reduce(ua, c->L.P, c->stream)); }
     if (multi && !p2p) {
       KernelScope ks(c, CRL_K_ALLREDUCE, false);
       CKN(g_nccl.AllReduce(c->gsum, c->gsum, (size_t)c->L.P + 4 + W, ncclFloat64, ncclSum, c->comm, c->stream));
     }
-    aa.M_global = (double)M * W; aa.world = W; aa.verify = 1;
     if (p2p) {
       aa.p2p_local = reinterpret_cast<const double*>(c->p2p_buf); aa.p2p_seq = c->p2p_seq; aa.p2p_err = c->p2p_err; aa.p2p_stride = c->p2p_stride;
-      aa.p2p_flags_off = c->p2p_flags_off;
+      aa.p2p_flags_off = c->p2p_flags_off; aa.timeout_cycles = c->p2p_timeout_cycles;
     }
     KernelScope ks(c, CRL_K_CLIP_ADAM);
     CK(launch_clip_adam(aa, c->stream));
@@ -992,7 +1018,19 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
     const int W = c->cfg.world_size;
     c->p2p_stride = (c->L.P + 4 + CRL_MAX_WORLD + 1) & ~1;
     c->p2p_flags_off = (size_t)2 * W * c->p2p_stride * sizeof(double);   // [2 slots][W ranks][stride] doubles, then the flags
-    const size_t bytes = c->p2p_flags_off + CRL_MAX_WORLD * sizeof(unsigned long long);
+    // behind them: the flag-in-data region of the fused tail, 16-byte packets {lo, seq, hi, seq} (gradient, 4 loss sums, min)
+    c->ll_stride = (c->L.P + 4 + 1 + 7) & ~7;
+    c->ll_off = (c->p2p_flags_off + CRL_MAX_WORLD * sizeof(unsigned long long) + 255) & ~size_t(255);
+    const size_t bytes = c->ll_off + (size_t)2 * W * c->ll_stride * 16;
+    {
+      // how long a kernel waits for a peer's data before it gives up (error, no update applied): a peer may legitimately
+      // be seconds late (first CUDA-graph instantiation, a host stall on the rank that logs). CRL_P2P_TIMEOUT_MS overrides.
+      const char* e = getenv("CRL_P2P_TIMEOUT_MS");
+      const double ms = e ? atof(e) : 30000.0;
+      int khz = 1965000;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->cfg.device);
+      c->p2p_timeout_cycles = (long long)(ms * (double)khz);
+    }
     bool ok = cudaMalloc(reinterpret_cast<void**>(&c->p2p_buf), bytes) == cudaSuccess &&
               cudaMemset(c->p2p_buf, 0, bytes) == cudaSuccess;
     cudaIpcMemHandle_t mine;

@@ -77,6 +77,50 @@ struct AdvStatsArgs {
   double* advparts;         // [n_sets][ADV_CHUNKS][2] = (sum adv, sum adv^2)
 };
 
+#define CRL_MAX_WORLD 16
+
+struct AdamArgs {
+  int env_kind;
+  float* params;
+  const double* gsum;  // [P+4] reduced sums (double), or nullptr to read gf
+  const float* gf;     // [P] Float32 gradient (raw entry point)
+  double grad_scale;   // 1, or 1/world with CRL_FLAG_LOCAL_STATS
+  double stat_ranks;   // ranks whose loss sums were added into gsum[P..] when M_global is local
+  float* image;        // parameter image kept in sync with params (may be nullptr)
+  float* grads_out;    // [P] un-clipped Float32 gradient (may be nullptr)
+  float* m;
+  float* v;
+  double* beta_pow;    // [n_arrays][2]
+  const DevState* ds;  // lr read from device when lr_host < 0
+  double lr_host;
+  float clip_norm;
+  float ent_coeff, v_coef;
+  double M_global;
+  int A;
+  double* stats_out;   // 4 doubles: loss, pg_loss, v_loss, entropy_loss (may be nullptr)
+  // ---- speculative throughput path: the finishing kernel also exchanges the reduced sums with the peers
+  //      (NVLink peer memory), verifies the speculation and records a failure for the host
+  const double* p2p_local;              // this rank's exchange buffer (every rank pushes into it), or nullptr
+  const unsigned long long* p2p_seq;    // exchange sequence number (advanced by loss_grad)
+  int* p2p_err;
+  int p2p_stride;
+  size_t p2p_flags_off;
+  int world, rank;
+  int algo;                             // 0 = PPO loss scalars, 1 = A2C (actor_loss, critic_loss)
+  int verify;                           // 1: check s <= min (clip-R)^2 and set ds_rw->spec_failed otherwise
+  int M, P;
+  DevState* ds_rw;
+  MbFinal* fin;
+  // ---- fused tail (loss_grad_tc_kernel finishes the minibatch itself, see UpdateArgs::fuse_tail)
+  unsigned long long* grid_bar;         // monotonic arrival counter of the grid barriers
+  double* normpart;                     // [n_arrays][grid] per-CTA partial sums of squares of the Float32 gradient
+  unsigned char* const* ll_peers;       // device array [world]: every rank's exchange buffer (this rank's included)
+  const unsigned char* ll_local;        // this rank's exchange buffer, or nullptr (single GPU)
+  size_t ll_off;                        // byte offset of the flag-in-data ("LL") region inside an exchange buffer
+  int ll_stride;                        // 16-byte packets per (slot, rank) row of that region
+  long long timeout_cycles;             // give up waiting for a peer after this many clock64 ticks (error, no update)
+};
+
 struct UpdateArgs {
   int env_kind;
   int algo;            // 0 = PPO clipped surrogate (ppo.jl:213-243), 1 = A2C losses (a2c.jl:78-97)
@@ -124,42 +168,12 @@ struct UpdateArgs {
   int tc_net_a, tc_net_c;               // sizes of the actor / critic slices of the flat parameter vector
   int values_fresh;                     // `values` holds the critic's output under the CURRENT parameters (rollout ->
                                         // one update, crl_train_update): lets the A2C actor CTAs take R - v from it
-};
-
-#define CRL_MAX_WORLD 16
-
-struct AdamArgs {
-  int env_kind;
-  float* params;
-  const double* gsum;  // [P+4] reduced sums (double), or nullptr to read gf
-  const float* gf;     // [P] Float32 gradient (raw entry point)
-  double grad_scale;   // 1, or 1/world with CRL_FLAG_LOCAL_STATS
-  double stat_ranks;   // ranks whose loss sums were added into gsum[P..] when M_global is local
-  float* image;        // parameter image kept in sync with params (may be nullptr)
-  float* grads_out;    // [P] un-clipped Float32 gradient (may be nullptr)
-  float* m;
-  float* v;
-  double* beta_pow;    // [n_arrays][2]
-  const DevState* ds;  // lr read from device when lr_host < 0
-  double lr_host;
-  float clip_norm;
-  float ent_coeff, v_coef;
-  double M_global;
-  int A;
-  double* stats_out;   // 4 doubles: loss, pg_loss, v_loss, entropy_loss (may be nullptr)
-  // ---- speculative throughput path: the finishing kernel also exchanges the reduced sums with the peers
-  //      (NVLink peer memory), verifies the speculation and records a failure for the host
-  const double* p2p_local;              // this rank's exchange buffer (every rank pushes into it), or nullptr
-  const unsigned long long* p2p_seq;    // exchange sequence number (advanced by loss_grad)
-  int* p2p_err;
-  int p2p_stride;
-  size_t p2p_flags_off;
-  int world, rank;
-  int algo;                             // 0 = PPO loss scalars, 1 = A2C (actor_loss, critic_loss)
-  int verify;                           // 1: check s <= min (clip-R)^2 and set ds_rw->spec_failed otherwise
-  int M, P;
-  DevState* ds_rw;
-  MbFinal* fin;
+  // Fused tail (tcgen05 kernel, speculative chain): after writing its partial gradient every CTA crosses a grid barrier,
+  // reduces ITS slab of the gradient over all CTAs' partials in the fixed order of grad_reduce, exchanges the slab with
+  // the peers (flag-in-data packets pushed over NVLink, no fence, no counter), and after a second grid barrier applies
+  // per-array clip + Adam to the slab: ONE cooperative launch per minibatch instead of three kernels.
+  int fuse_tail;
+  AdamArgs adam;
 };
 
 // per-device opt-in to large dynamic shared memory; call once per device outside stream capture

@@ -885,6 +885,7 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   // cluster barrier, then everybody adds the 8 partials in the same order.
   __shared__ double red[8];
   __shared__ double part[ADAM_CL];
+  __shared__ int badpart[ADAM_CL];
   Layout L;
   make_layout(a.env_kind, &L);
   const int i = blockIdx.x / ADAM_CL;         // parameter array
@@ -895,19 +896,21 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   const int o = L.off[i], n = L.size[i];
   int slot = 0;
+  int bad = 0;   // a peer never delivered (now or in an earlier minibatch): nobody applies an update built on partial sums
   if (a.p2p_local) {
     const unsigned long long q = *a.p2p_seq;
     slot = (int)(q & 1ull);
-    if (threadIdx.x < a.world) {   // wait until every rank's grad_reduce has pushed this minibatch's sums here
+    if (*reinterpret_cast<volatile int*>(a.p2p_err) != 0) bad = 1;   // sticky: the host reports CRL_ERR_NCCL at the next fetch
+    if (!bad && threadIdx.x < a.world) {   // wait until every rank's grad_reduce has pushed this minibatch's sums here
       const volatile unsigned long long* mine =
           reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const unsigned char*>(a.p2p_local) + a.p2p_flags_off) + threadIdx.x;
       const long long t0 = clock64();
       while (*mine < q) {
-        if (clock64() - t0 > 4000000000ll) { *a.p2p_err = 1; break; }  // ~2 s: a peer is gone; fail instead of hanging
+        if (clock64() - t0 > a.timeout_cycles) { atomicExch(a.p2p_err, 1); bad = 1; break; }  // fail instead of hanging
       }
       __threadfence_system();
     }
-    __syncthreads();
+    bad = __syncthreads_or(bad);
   }
   // this CTA's slice of the array: elements crank*512 + tid + c*256, c < 2
   float g[2];
@@ -925,15 +928,19 @@ __global__ void __cluster_dims__(ADAM_CL, 1, 1) __launch_bounds__(ADAM_NT) clip_
   const double bp1 = a.beta_pow[2 * i], bp2 = a.beta_pow[2 * i + 1];  // read BEFORE the cluster barrier (rank 0 rewrites them after)
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started
   if (threadIdx.x < ADAM_CL) {
-    // distributed shared memory: part[crank] of CTA `threadIdx.x` of this cluster
+    // distributed shared memory: part[crank] (and the error flag) of CTA `threadIdx.x` of this cluster
     unsigned int local = (unsigned int)__cvta_generic_to_shared(&part[crank]), remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(threadIdx.x));
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(ss) : "memory");
+    local = (unsigned int)__cvta_generic_to_shared(&badpart[crank]);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(threadIdx.x));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(bad) : "memory");
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   double tot = 0.0;
 #pragma unroll
-  for (int r = 0; r < ADAM_CL; r++) tot += part[r];
+  for (int r = 0; r < ADAM_CL; r++) { tot += part[r]; bad |= badpart[r]; }
+  if (bad) return;   // the whole cluster (= the whole parameter array) agrees: no Adam step, no beta powers, no statistics
   const float nrm = (float)sqrt(tot);  // norm(Δ::Array{Float32})::Float32
   const bool clip = (double)nrm > (double)a.clip_norm;
   const double scale = clip ? (double)a.clip_norm / (double)nrm : 1.0;

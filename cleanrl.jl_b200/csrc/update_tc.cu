@@ -819,8 +819,298 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   }
 }
 
+
+// ---------------------------------------------------------------- fused tail: reduce -> exchange -> clip + Adam
+// Runs at the end of loss_grad_tc_kernel when UpdateArgs::fuse_tail is set (cooperative launch: all CTAs co-resident).
+//   barrier 1   every CTA's partial gradient (gpart / spart / mpart) is in L2
+//   reduce      CTA j owns the slab [j*slab, (j+1)*slab) of the P gradient elements + 4 loss sums and adds the partials
+//               of all CTAs that hold them in the fixed order of grad_reduce_kernel (deterministic, same bits)
+//   exchange    [multi-GPU] the slab is PUSHED into every peer's exchange buffer as 16-byte {lo, seq, hi, seq} packets
+//               (the flag travels inside the data word, so no fence, no counter and no separate flag store is needed);
+//               the same CTA on every rank then polls ITS OWN memory for the slab of every peer and adds the world
+//               vectors in rank order: all ranks hold bit-identical sums. This rank's min (clip-R)^2 rides behind the
+//               loss sums for the verification of the speculation.
+//   barrier 2   the Float32 gradient of every array is complete in `grads_out`
+//   clip+Adam   every CTA recomputes the norm of the arrays its slab touches (Float64 sum of squares in a fixed order:
+//               identical in every CTA and on every rank), then Flux.Optimiser(ClipNorm, Adam) on its slab exactly as
+//               clip_adam_kernel does it, parameter image included.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: the CTA's writes (ordered before this point by the barrier above) become visible first
+    const unsigned long long old = atomicAdd(ctr, 1ull);
+    const unsigned long long target = (old / gridDim.x + 1ull) * gridDim.x;
+    while (ld_acquire_u64(ctr) < target) { }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void ll_store(uint4* p, double v, uint32_t flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(flag), "r"((uint32_t)(b >> 32)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int FT_EL = 64;  // elements per reduction pass (x 4 partial groups = 256 threads)
+// -DFT_TRACE: clock stamps of the tail's phases, printed by thread 0 of the first and the last CTA (development aid)
+#ifdef FT_TRACE
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FTR(i) do { if (ft_on) ftr[i] = gtime(); } while (0)
+#else
+#define FTR(i) do { } while (0)
+#endif
+
 template <int ENV>
-__global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs a) {
+__device__ __noinline__ void fused_tail(const UpdateArgs& a, float* scratch, const unsigned long long seq) {
+  using E = EnvTraits<ENV>;
+  static_assert(TC_THREADS == 4 * FT_EL, "the fused tail splits the partials over 4 thread groups of 64 elements");
+  constexpr int P = E::P;
+  const AdamArgs& f = a.adam;
+  const int tid = threadIdx.x, G = (int)gridDim.x;
+  const int lane_id = tid & 31, warp_id = tid >> 5;
+  // CTA j owns the gradient elements [j*slab, (j+1)*slab); the LAST CTA (whose slab is empty at the benchmark sizes)
+  // also owns the four loss sums and the min (clip-R)^2 of the verification, kept behind its gradient elements
+  const int slab = (((P + G - 1) / G) + FT_EL - 1) & ~(FT_EL - 1);
+  const int lo = (int)blockIdx.x * slab;
+  const int ngrad = min(P, lo + slab) > lo ? min(P, lo + slab) - lo : 0;
+  const bool tail_owner = (int)blockIdx.x == G - 1;
+  const bool multi = f.ll_local != nullptr;
+  const int W = multi ? f.world : 1;
+  // scratch (the operand buffers are free): reduced sums (+ 4 loss sums + min) | 4 x 64 pass buffer | small per-array
+  // state | Float32 gradient
+  double* gs = reinterpret_cast<double*>(scratch);
+  double* sh = gs + slab + 8;                          // [4][64]
+  double* red = sh + 4 * FT_EL;                        // 16 doubles (block min)
+  double* bp_s = red + 16;                             // [CRL_MAX_ARRAYS][2] beta powers BEFORE this step
+  double* scale_s = bp_s + 2 * CRL_MAX_ARRAYS;         // [CRL_MAX_ARRAYS] clip factor, 1.0 = no clip
+  float* gfl = reinterpret_cast<float*>(scale_s + CRL_MAX_ARRAYS);   // [slab]
+  int* clip_s = reinterpret_cast<int*>(gfl + slab);    // [CRL_MAX_ARRAYS]
+  __shared__ float all_min_s;
+  Layout L;
+  make_layout(ENV, &L);
+#ifdef FT_TRACE
+  const bool ft_on = tid == 0;
+  long long ftr[8];
+#endif
+  FTR(0);
+  if (tid < 2 * L.n_arrays) bp_s[tid] = f.beta_pow[tid];   // read before anybody can rewrite them (after barrier 2)
+  const double lr = f.lr_host >= 0.0 ? f.lr_host : f.ds->lr;
+
+  grid_barrier(f.grid_bar);
+  FTR(1);
+  if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq = seq;   // every CTA has read the old value at kernel start
+
+  // ---- reduce this slab over the per-CTA partials (order of grad_reduce_kernel)
+  const int el = tid & (FT_EL - 1), g = tid >> 6;
+  for (int base = 0; base < ngrad; base += FT_EL) {
+    const int e = lo + base + el;
+    double s = 0.0;
+    if (base + el < ngrad) {
+      int c_lo = 0, c_hi = G;
+      const bool critic = e >= a.tc_net_a && e < a.tc_net_a + a.tc_net_c;
+      if (critic) c_lo = a.tc_actor_ctas; else c_hi = a.tc_actor_ctas;
+      // ten partials requested before the first is added (one L2 round trip per batch); same summation order as the
+      // plain loop: adding the +0.0f of a padded slot changes nothing
+      for (int c0 = c_lo + g; c0 < c_hi; c0 += 40) {
+        float v[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) {   // unconditional (clamped) loads: a predicated load would be a branch, i.e. serialised
+          const int c = c0 + 4 * j;
+          const float x = __ldcg(a.gpart + (long long)min(c, c_hi - 1) * P + e);
+          v[j] = c < c_hi ? x : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 10; j++) s += (double)v[j];
+      }
+    }
+    sh[g * FT_EL + el] = s;
+    __syncthreads();
+    if (g == 0 && base + el < ngrad) gs[base + el] = (sh[el] + sh[FT_EL + el]) + (sh[2 * FT_EL + el] + sh[3 * FT_EL + el]);
+    __syncthreads();
+  }
+  int next = ngrad;   // entries of this CTA that take part in the exchange
+  if (tail_owner) {
+    // the four loss sums (same order as grad_reduce_kernel) and this rank's min_i (clip_i - R_i)^2 over all CTAs
+    const int q = tid & 3, gg = (tid >> 2) & 3;      // threads 0..15: (sum q, group gg); the partials of a group in batches
+    double s = 0.0;
+    if (tid < 16) {
+      for (int c0 = gg; c0 < G; c0 += 40) {
+        double v[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+          const int c = c0 + 4 * j;
+          const double x = __ldcg(a.spart + (long long)min(c, G - 1) * 4 + q);
+          v[j] = c < G ? x : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 10; j++) s += v[j];
+      }
+      sh[gg * 4 + q] = s;
+    }
+    float mn = INFINITY;
+    if (f.verify) {
+      for (int c = tid; c < G; c += TC_THREADS) mn = fminf(mn, __ldcg(a.mpart + c));
+      mn = warp_min(mn);
+      float* mred = reinterpret_cast<float*>(red);
+      if (lane_id == 0) mred[warp_id] = mn;
+    }
+    __syncthreads();
+    if (tid < 4) gs[ngrad + tid] = (sh[tid] + sh[4 + tid]) + (sh[8 + tid] + sh[12 + tid]);
+    if (tid == 0) {
+      const float* mred = reinterpret_cast<const float*>(red);
+      float m8 = INFINITY;
+      if (f.verify)
+        for (int w = 0; w < TC_WARPS; w++) m8 = fminf(m8, mred[w]);
+      all_min_s = m8;
+      gs[ngrad + 4] = (double)m8;
+    }
+    next = ngrad + 5;
+    __syncthreads();
+  }
+  FTR(2);
+
+  // ---- exchange with the peers (NVLink peer memory, flag-in-data packets). Position in a rank's row: gradient element
+  //      e at e, the loss sums at P..P+3, the min at P+4.
+  if (multi) {
+    const uint32_t flag = (uint32_t)seq;
+    const int slot = (int)(seq & 1ull);
+    auto pos = [&](int k) { return k < ngrad ? lo + k : P + (k - ngrad); };
+    for (int i = tid; i < next * W; i += TC_THREADS) {
+      const int r = i / next, k = i - r * next;
+      if (r == f.rank) continue;
+      uint4* dst = reinterpret_cast<uint4*>(f.ll_peers[r] + f.ll_off) + ((size_t)slot * W + f.rank) * f.ll_stride + pos(k);
+      ll_store(dst, gs[k], flag);
+    }
+    __syncthreads();
+    bool bad = false;
+    for (int k = tid; k < next; k += TC_THREADS) {
+      const uint4* src = reinterpret_cast<const uint4*>(f.ll_local + f.ll_off) + (size_t)slot * W * f.ll_stride + pos(k);
+      uint4 pk[CRL_MAX_WORLD];
+      const long long t0 = clock64();
+      bool all = false;
+      while (!all) {    // all peers' packets are requested before any is inspected: one round trip when they have arrived
+        all = true;
+#pragma unroll
+        for (int r = 0; r < CRL_MAX_WORLD; r++)
+          if (r < W && r != f.rank) pk[r] = ll_load(src + (size_t)r * f.ll_stride);
+#pragma unroll
+        for (int r = 0; r < CRL_MAX_WORLD; r++)
+          if (r < W && r != f.rank && (pk[r].y != flag || pk[r].w != flag)) all = false;
+        if (!all && clock64() - t0 > f.timeout_cycles) { bad = true; break; }
+      }
+      double tot = 0.0;
+      float mn = INFINITY;
+#pragma unroll
+      for (int r = 0; r < CRL_MAX_WORLD; r++) {
+        if (r >= W) continue;
+        const double v = r == f.rank ? gs[k] : __longlong_as_double((long long)(((unsigned long long)pk[r].z << 32) | pk[r].x));
+        tot += v;                       // rank order: bit-identical on every rank
+        mn = fminf(mn, (float)v);
+      }
+      if (tail_owner && k == ngrad + 4) all_min_s = mn; else gs[k] = tot;
+    }
+    if (bad) atomicExch(f.p2p_err, 1);
+    __syncthreads();
+  }
+
+  // ---- Float32 gradient (what Zygote returns), loss scalars, verification of the speculation
+  for (int k = tid; k < ngrad; k += TC_THREADS) {
+    const float gv = (float)gs[k];
+    gfl[k] = gv;
+    if (f.grads_out) f.grads_out[lo + k] = gv;
+  }
+  if (tail_owner && tid == 0) {
+    const double* tl = gs + ngrad;
+    if (f.stats_out) finalize_stats(tl, f.M_global, f.A, f.ent_coeff, f.v_coef, f.stats_out, f.algo);
+    if (f.verify) {
+      const float m = all_min_s;
+      const float s_f = (float)(tl[3] / f.M_global);
+      f.fin->s_unclipped = s_f; f.fin->min_vlc = m; f.fin->M_global = f.M_global; f.fin->cnt = 0ull;
+      f.fin->need_fixup = (s_f > m) ? 1 : 0;
+      if (s_f > m) f.ds_rw->spec_failed = 1;   // the host replays this update exactly
+    }
+  }
+  // partial sums of squares of this slab per parameter array it touches -> normpart[array][cta] (ClipNorm is per array)
+  __syncthreads();
+  for (int ai = warp_id; ai < L.n_arrays; ai += TC_WARPS) {
+    const int o = L.off[ai], n = L.size[ai];
+    if (ngrad == 0 || !(o < lo + ngrad && o + n > lo)) continue;
+    const int k0 = max(o, lo) - lo, k1 = min(o + n, lo + ngrad) - lo;
+    double ss = 0.0;
+    for (int k = k0 + lane_id; k < k1; k += 32) ss += (double)gfl[k] * (double)gfl[k];
+    ss = warp_sum(ss);
+    if (lane_id == 0) f.normpart[ai * G + (int)blockIdx.x] = ss;
+  }
+  // this thread's Adam operands are requested before the barrier (their values cannot change behind it)
+  const bool pre = ngrad <= TC_THREADS;
+  float pre_m = 0.0f, pre_v = 0.0f, pre_p = 0.0f;
+  if (pre && tid < ngrad) { pre_m = f.m[lo + tid]; pre_v = f.v[lo + tid]; pre_p = f.params[lo + tid]; }
+  FTR(3);
+  grid_barrier(f.grid_bar);
+  FTR(4);
+  // a peer that never delivered: nobody applies this (or any later) minibatch; the host reports CRL_ERR_NCCL
+  if (multi && (*reinterpret_cast<volatile int*>(f.p2p_err) != 0)) return;
+
+  // ---- per-array norms of the arrays this slab touches (ClipNorm is per array, ppo.jl:93): one warp per array adds the
+  //      partials of the CTAs that cover it, in an order that depends on nothing but the grid size
+  for (int ai = warp_id; ai < L.n_arrays; ai += TC_WARPS) {
+    const int o = L.off[ai], n = L.size[ai];
+    if (ngrad == 0 || !(o < lo + ngrad && o + n > lo)) continue;
+    const int c_first = o / slab, c_last = (o + n - 1) / slab;
+    double ss = 0.0;
+    for (int c = c_first + lane_id; c <= c_last; c += 32) ss += __ldcg(f.normpart + ai * G + c);
+    ss = warp_sum(ss);
+    if (lane_id == 0) {
+      const float nrm = (float)sqrt(ss);   // norm(Δ::Array{Float32})::Float32
+      const bool clip = (double)nrm > (double)f.clip_norm;
+      clip_s[ai] = clip ? 1 : 0;
+      scale_s[ai] = clip ? (double)f.clip_norm / (double)nrm : 1.0;
+    }
+  }
+  __syncthreads();
+
+  FTR(5);
+  // ---- Adam on the slab (same arithmetic as clip_adam_kernel: Float64 scalars, _rn intrinsics)
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  for (int k = tid; k < ngrad; k += TC_THREADS) {
+    const int e = lo + k;
+    int ai = 0;
+    while (ai + 1 < L.n_arrays && e >= L.off[ai + 1]) ai++;
+    const double bp1 = bp_s[2 * ai], bp2 = bp_s[2 * ai + 1];
+    float d = gfl[k];
+    if (clip_s[ai]) d = (float)__dmul_rn((double)d, scale_s[ai]);  // rmul!(Δ, thresh/nrm)
+    const float m_old = pre ? pre_m : f.m[e], v_old = pre ? pre_v : f.v[e], p_old = pre ? pre_p : f.params[e];
+    const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)m_old), __dmul_rn(1.0 - b1, (double)d));
+    const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)v_old), __dmul_rn(__dmul_rn(1.0 - b2, (double)d), (double)d));
+    f.m[e] = mt;
+    f.v[e] = vt;
+    const double den = __dadd_rn(sqrt(__ddiv_rn((double)vt, 1.0 - bp2)), eps);
+    const float step = (float)__dmul_rn(__ddiv_rn(__ddiv_rn((double)mt, 1.0 - bp1), den), lr);
+    const float pnew = __fsub_rn(p_old, step);
+    f.params[e] = pnew;
+    if (f.image) image_scatter<ENV>(f.image, e, pnew);
+    if (e == L.off[ai]) {   // the CTA that owns an array's first element advances its beta powers
+      f.beta_pow[2 * ai] = bp1 * b1;
+      f.beta_pow[2 * ai + 1] = bp2 * b2;
+    }
+  }
+#ifdef FT_TRACE
+  FTR(6);
+  if (ft_on)
+    printf("FT %d %lld %lld %lld %lld %lld %lld %lld\n", (int)blockIdx.x, ftr[0], ftr[1], ftr[2], ftr[3], ftr[4], ftr[5], ftr[6]);
+#endif
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(const __grid_constant__ UpdateArgs a) {
   using E = EnvTraits<ENV>;
   using SM = TcSmem<ENV>;
   using NO = NetOff<E::D, 1>;
@@ -832,7 +1122,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
 #ifdef TC_TRACE
   const long long k_t0 = clock64();
 #endif
-  if (a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq += 1ull;
+  // exchange sequence number of this minibatch. Unfused chain: CTA 0 advances it here for grad_reduce / clip_adam. Fused
+  // tail: every CTA needs it, so all read the old value now and CTA 0 stores the new one behind the first grid barrier.
+  const unsigned long long seq_next = a.p2p_seq ? *a.p2p_seq + 1ull : 0ull;
+  if (!a.fuse_tail && a.p2p_seq && blockIdx.x == 0 && tid == 0) *a.p2p_seq = seq_next;
   const int net = (int)blockIdx.x < a.tc_actor_ctas ? 0 : 1;
   uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SM::KEYS);
   if (tid == 0 && !a.idx.arr) perm_keys(a.idx.seed, a.idx.ds->update_index, a.idx.epoch, a.idx.rank, keys);
@@ -898,6 +1191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(UpdateArgs 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  if (a.fuse_tail) fused_tail<ENV>(a, smem + SM::FZ, seq_next);
 }
 
 }  // namespace
@@ -945,7 +1239,26 @@ int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   return 1;
 }
 
+template <int ENV> static cudaError_t launch_fused_t(const UpdateArgs& a, cudaStream_t s) {
+  // the grid barriers of the fused tail need every CTA resident: cooperative launch (grid <= SM count, 1 CTA per SM)
+  static int no_coop = -1;
+  if (no_coop < 0) { const char* e = getenv("CRL_NO_COOP"); no_coop = (e && atoi(e) != 0) ? 1 : 0; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a.grid_loss);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcSmem<ENV>::BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = no_coop ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, loss_grad_tc_kernel<ENV>, a);
+}
+
 cudaError_t launch_loss_grad_tc(const UpdateArgs& a, cudaStream_t s) {
+  if (a.fuse_tail)
+    return a.env_kind == CRL_ENV_CARTPOLE ? launch_fused_t<CRL_ENV_CARTPOLE>(a, s) : launch_fused_t<CRL_ENV_PENDULUM>(a, s);
   if (a.env_kind == CRL_ENV_CARTPOLE)
     loss_grad_tc_kernel<CRL_ENV_CARTPOLE><<<a.grid_loss, TC_THREADS, TcSmem<CRL_ENV_CARTPOLE>::BYTES, s>>>(a);
   else
