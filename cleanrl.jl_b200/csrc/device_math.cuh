@@ -105,6 +105,42 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return x2 < 66.0f ? y : copysignf(1.0f, x);
 }
 
+// packed FP32 (fma.rn.f32x2 / FFMA2: two FMAs per lane per issued instruction)
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+// tanh_fast on two values at once: same operations, same roundings per lane (bit-identical to tanh_fast). The numerator
+// is evaluated with negated coefficients and the reciprocal taken of -d, so both Newton FMAs and the final products
+// are plain packed instructions (the two sign flips cancel exactly).
+__device__ __forceinline__ float2 tanh_fast2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 n = __ffma2_rn(x2, f2s(-1.587199e-8f), f2s(-2.2332108e-5f));
+  n = __ffma2_rn(x2, n, f2s(-0.0035974074f));
+  n = __ffma2_rn(x2, n, f2s(-0.1346604f));
+  n = __ffma2_rn(x2, n, f2s(-1.0f));
+  float2 d = __ffma2_rn(x2, f2s(8.7767893e-7f), f2s(0.0003453992f));
+  d = __ffma2_rn(x2, d, f2s(0.026262015f));
+  d = __ffma2_rn(x2, d, f2s(0.4679937f));
+  d = __ffma2_rn(x2, d, f2s(1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(-d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(-d.y));
+  r = __ffma2_rn(__ffma2_rn(d, r, f2s(1.0f)), r, r);  // Newton step on -1/d
+  float2 y = __fmul2_rn(x, __fmul2_rn(n, r));
+  y.x = x2.x < 66.0f ? y.x : copysignf(1.0f, x.x);
+  y.y = x2.y < 66.0f ? y.y : copysignf(1.0f, x.y);
+  return y;
+}
+
+// Float64 division by a compile-time constant, correctly rounded (same bits as __ddiv_rn) in six dependent FMA-class
+// operations instead of the ~400-cycle division sequence: q0 = RN(a y) with y = RN(1/c), then two residual corrections
+// q <- q + (a - q c) y with exact residuals (Markstein; 4e8 random operands checked against IEEE division on the CPU).
+__device__ __forceinline__ double ddiv_const(double a, double c, double y) {
+  double q = __dmul_rn(a, y);
+  q = __fma_rn(__fma_rn(-q, c, a), y, q);
+  q = __fma_rn(__fma_rn(-q, c, a), y, q);
+  return q;
+}
+
 // ---------------------------------------------------------------- environments
 // CartPoleEnv(T=Float32) step [RLEnvs 0.6.12, called at multi_thread_env.jl:91]. Float32 params,
 // but the Float64 literal 4/3 promotes thetaacc, xacc and the velocity updates to Float64
@@ -119,13 +155,16 @@ __device__ inline void cartpole_step(float s[4], int& t, int action, int max_ste
   t += 1;
   const float force = action == 1 ? forcemag : -forcemag;
   const float xdot = s[1], theta = s[2], thetadot = s[3];
-  const float costheta = cosf(theta), sintheta = sinf(theta);
+  float sintheta, costheta;
+  sincosf(theta, &sintheta, &costheta);
   const float tmp = __fdiv_rn(__fadd_rn(force, __fmul_rn(__fmul_rn(polemasslength, __fmul_rn(thetadot, thetadot)), sintheta)), totalmass);
   const float num = __fsub_rn(__fmul_rn(gravity, sintheta), __fmul_rn(costheta, tmp));
   const float mc = __fdiv_rn(__fmul_rn(masspole, __fmul_rn(costheta, costheta)), totalmass);
   const double den = __dmul_rn((double)halflength, __dsub_rn(4.0 / 3.0, (double)mc));
   const double thetaacc = __ddiv_rn((double)num, den);
-  const double xacc = __dsub_rn((double)tmp, __ddiv_rn(__dmul_rn(__dmul_rn((double)polemasslength, thetaacc), (double)costheta), (double)totalmass));
+  // division by the constant totalmass: correctly rounded without the division sequence (ddiv_const)
+  constexpr double tm_d = (double)(1.0f + 0.1f), tm_inv = 1.0 / tm_d;
+  const double xacc = __dsub_rn((double)tmp, ddiv_const(__dmul_rn(__dmul_rn((double)polemasslength, thetaacc), (double)costheta), tm_d, tm_inv));
   s[0] = __fadd_rn(s[0], __fmul_rn(dt, xdot));
   s[1] = (float)__dadd_rn((double)s[1], __dmul_rn((double)dt, xacc));
   s[2] = __fadd_rn(s[2], __fmul_rn(dt, thetadot));

@@ -170,31 +170,7 @@ template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float
   if (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 
-// ---------------------------------------------------------------- packed FP32 (fma.rn.f32x2) helpers
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
-// tanh_fast (device_math.cuh) on two values at once: same operations, same roundings per lane. The numerator is
-// evaluated with negated coefficients and the reciprocal taken of -d, so both Newton FMAs and the final products
-// are plain packed instructions (the two sign flips cancel exactly).
-__device__ __forceinline__ float2 tanh_fast2(float2 x) {
-  const float2 x2 = __fmul2_rn(x, x);
-  float2 n = __ffma2_rn(x2, f2s(-1.587199e-8f), f2s(-2.2332108e-5f));
-  n = __ffma2_rn(x2, n, f2s(-0.0035974074f));
-  n = __ffma2_rn(x2, n, f2s(-0.1346604f));
-  n = __ffma2_rn(x2, n, f2s(-1.0f));
-  float2 d = __ffma2_rn(x2, f2s(8.7767893e-7f), f2s(0.0003453992f));
-  d = __ffma2_rn(x2, d, f2s(0.026262015f));
-  d = __ffma2_rn(x2, d, f2s(0.4679937f));
-  d = __ffma2_rn(x2, d, f2s(1.0f));
-  float2 r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(-d.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(-d.y));
-  r = __ffma2_rn(__ffma2_rn(d, r, f2s(1.0f)), r, r);  // Newton step on -1/d
-  float2 y = __fmul2_rn(x, __fmul2_rn(n, r));
-  y.x = x2.x < 66.0f ? y.x : copysignf(1.0f, x.x);
-  y.y = x2.y < 66.0f ? y.y : copysignf(1.0f, x.y);
-  return y;
-}
+// ---------------------------------------------------------------- packed FP32 helpers (f2, f2s, tanh_fast2: device_math.cuh)
 // x = hi + lo with hi = TF32(x) (see tf32_hi), two values at once
 __device__ __forceinline__ void split2(float2 v, float2& hi, float2& lo) {
   hi = f2(tf32_hi(v.x), tf32_hi(v.y));
