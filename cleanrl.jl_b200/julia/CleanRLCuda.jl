@@ -8,9 +8,13 @@
 #
 # Usage inside the reference repo:
 #   include("utils/CleanRLCuda.jl")          # after logger.jl / networks.jl in src/CleanRL.jl
+#   CleanRL.CleanRLCuda.ppo()                                         # PPOConfig() defaults, as ppo.jl:75
 #   CleanRL.CleanRLCuda.ppo(PPOConfig(num_envs=4096, num_steps=128))
+#   julia --project run_ppo.jl --num_envs 4096 --num_steps 128         # argparse_struct(PPOConfig()) |> ppo
 module CleanRLCuda
 
+import LinearAlgebra
+import Random
 using Random: shuffle
 
 const LIB = get(ENV, "CLEANRL_CUDA_LIB", "libcleanrl_cuda.so")
@@ -184,17 +188,49 @@ end
 # the reference, Project.toml:9.)
 #   crl_gae_raw(values[1:k], rewards, terminals[1:k], values[k+1:k+1], terminals[k+1:k+1], adv, ret, k, 1, γ, λ, mode, C_NULL)
 
-"""
-    ppo(config::PPOConfig = PPOConfig(); actor, critic, logger_info)
+# orthogonal initialisation of networks.jl:36-49 without Flux, so that `ppo()` needs no keyword argument: two separate
+# 64-64 tanh MLPs, gains sqrt(2) on the hidden layers, 0.01 on the actor head, 1.0 on the critic head, zero biases
+# (Flux.orthogonal = Q of a QR of a Gaussian matrix, signs fixed by diag(R)). Flat Flux.params(actor, critic) order.
+function default_params(D::Integer, A::Integer; continuous::Bool=false, seed::Integer=1)
+  rng = Random.Xoshiro(seed)
+  function orth(rows, cols, gain)
+    flat = randn(rng, Float64, max(rows, cols), min(rows, cols))
+    Q, R = LinearAlgebra.qr(flat)
+    Qm = Matrix(Q) * LinearAlgebra.Diagonal(sign.(LinearAlgebra.diag(R)))
+    W = rows >= cols ? Qm : Qm'
+    Float32.(gain .* W[1:rows, 1:cols])
+  end
+  function net(out, head_gain)
+    [vec(orth(64, D, sqrt(2.0))); zeros(Float32, 64); vec(orth(64, 64, sqrt(2.0))); zeros(Float32, 64);
+     vec(orth(out, 64, head_gain)); zeros(Float32, out)]
+  end
+  p = [net(A, 0.01); net(1, 1.0)]
+  continuous ? [p; zeros(Float32, A)] : p     # Gaussian head: state-independent log-std, initialised to 0
+end
 
-Drop-in for `CleanRL.ppo` (ppo.jl:75). Same config struct, same `@info` record names and keys.
-`actor`/`critic` are the Flux chains from `Networks.make_actor_critic` (networks.jl:36-49); they are used
-only to initialise the device parameters.
 """
-function ppo(config; actor, critic, log_episodes::Bool=false)
+    ppo(config::PPOConfig = PPOConfig(); actor = nothing, critic = nothing, env_id = "CartPole", seed = 1,
+        log_episodes = false)
+
+Drop-in for `CleanRL.ppo` (ppo.jl:75): `ppo()` with no arguments trains CartPole with the reference's defaults. Same
+config struct, same `@info` record names and keys. `actor`/`critic` may be the Flux chains of
+`Networks.make_actor_critic` (networks.jl:36-49), used only to initialise the device parameters; without them the same
+orthogonal initialisation is done here. The loop is the one of `cleanrl.jl_b200/ppo_algo.py` (the executed and tested
+host): one asynchronous `crl_train_update` per update, and the records of update u-1 are fetched (lag = 1) and logged
+while update u runs, so the stream never waits for the logger.
+"""
+function ppo(config=nothing; actor=nothing, critic=nothing, env_id::String="CartPole", seed::Integer=1,
+             log_episodes::Bool=false)
+  config === nothing && (config = Main.CleanRL.PPOConfig())       # ppo.jl:75 default argument
+  config.normalize_advantages || error("normalize_advantages=false is not supported by the reference (ppo.jl:219-222 throws)")
   nt = config.num_envs                                            # ppo.jl:76
-  h = Handle(make_config(config; flags=config.clip_value_loss ? UInt32(0) : CRL_FLAG_NO_VCLIP))
-  p = flat_params(actor, critic)                                  # ppo.jl:85-87,196
+  continuous = env_id == "Pendulum"
+  h = Handle(make_config(config; env_kind=continuous ? CRL_ENV_PENDULUM : CRL_ENV_CARTPOLE,
+                         max_steps=continuous ? 200 : 500, seed=UInt64(seed),
+                         flags=config.clip_value_loss ? UInt32(0) : CRL_FLAG_NO_VCLIP))
+  p = (actor === nothing || critic === nothing) ?
+      default_params(continuous ? 3 : 4, continuous ? 1 : 2; continuous=continuous, seed=seed) :
+      flat_params(actor, critic)                                  # ppo.jl:85-87,196
   set_params!(h, p)
   batch_size = config.num_steps * nt                              # ppo.jl:89
   num_updates = config.total_timesteps ÷ batch_size               # ppo.jl:91
@@ -202,6 +238,22 @@ function ppo(config; actor, critic, log_episodes::Bool=false)
   last_log_step = 0
   start_time = time()                                             # ppo.jl:111
   env_reset!(h)                                                   # ppo.jl:112-115
+
+  function log_update(stats, agg, gs)                             # records of one finished update
+    if agg !== nothing && agg.count > 0
+      steps_per_sec = trunc(gs / (time() - start_time))           # ppo.jl:148
+      log_step_inc = last_log_step == 0 ? 0 : gs - last_log_step  # ppo.jl:156
+      @info "Episode Statistics" episode_return = agg.sum_return / agg.count episode_length = agg.sum_length / agg.count global_step = gs steps_per_sec log_step_increment = log_step_inc
+      last_log_step = gs
+    end
+    for s in stats                                                # ppo.jl:246-248, one record per minibatch
+      log_step_inc = last_log_step == 0 ? 0 : gs - last_log_step
+      @info "Training Statistics" loss = s.loss pg_loss = s.pg_loss v_loss = s.v_loss entropy_loss = s.entropy_loss log_step_increment = log_step_inc
+      last_log_step = gs
+    end
+  end
+
+  pending = 0                                                     # global_step of the update not logged yet (0 = none)
   for update in 1:num_updates                                     # ppo.jl:117
     lr_now = Float64(config.lr)
     if config.anneal_lr
@@ -210,6 +262,7 @@ function ppo(config; actor, critic, log_episodes::Bool=false)
     end
     step_base = global_step
     if log_episodes
+      # stage-by-stage path: same call sequence as the reference's loop body, one record per episode
       rollout!(h)                                                 # ppo.jl:123-166 in one launch
       recs, _ = pop_episodes(h)
       for r in recs                                               # (step, env) order == ppo.jl:149
@@ -221,23 +274,20 @@ function ppo(config; actor, critic, log_episodes::Bool=false)
       end
       global_step += batch_size
       gae!(h)                                                     # ppo.jl:169-181
-      stats = update_epochs!(h, nothing, lr_now)                  # ppo.jl:191-252 (device permutation)
+      log_update(update_epochs!(h, nothing, lr_now), nothing, global_step)   # ppo.jl:191-252 (device permutation)
     else
-      train_update!(h, lr_now)                                    # whole update, one CUDA-graph launch
+      train_update!(h, lr_now)                                    # whole update, one CUDA-graph launch, asynchronous
       global_step += batch_size
-      stats, agg = fetch_update(h)
-      if agg.count > 0
-        steps_per_sec = trunc(global_step / (time() - start_time))
-        log_step_inc = last_log_step == 0 ? 0 : global_step - last_log_step
-        @info "Episode Statistics" episode_return = agg.sum_return / agg.count episode_length = agg.sum_length / agg.count global_step steps_per_sec log_step_increment = log_step_inc
-        last_log_step = global_step
+      if pending != 0
+        stats, agg = fetch_update(h, 1)                           # update u-1: does not wait for update u
+        log_update(stats, agg, pending)
       end
+      pending = global_step
     end
-    for s in stats                                                # ppo.jl:246-248
-      log_step_inc = last_log_step == 0 ? 0 : global_step - last_log_step
-      @info "Training Statistics" loss = s.loss pg_loss = s.pg_loss v_loss = s.v_loss entropy_loss = s.entropy_loss log_step_increment = log_step_inc
-      last_log_step = global_step
-    end
+  end
+  if pending != 0
+    stats, agg = fetch_update(h, 0)
+    log_update(stats, agg, pending)
   end
   get_params(h, length(p))
 end

@@ -10,3 +10,7 @@ _spec = importlib.util.spec_from_file_location(
 _mod = importlib.util.module_from_spec(_spec)
 sys.modules["cleanrl_jl_b200"] = _mod
 _spec.loader.exec_module(_mod)
+
+if __name__ == "__main__":  # `python -m cleanrl_jl_b200 ppo --num_envs 4096 ...` (see cleanrl.jl_b200/cli.py)
+    from cleanrl_jl_b200 import cli
+    sys.exit(cli.main())

@@ -88,3 +88,33 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in text.replace("the oracle", "").replace("oracle's", "").replace("ppo_oracle.c", "").lower() \
                     or f in ("device_math.cuh", "gae.cu", "update.cu"), (dirpath, f)
                 assert "import oracle" not in text and "from oracle" not in text and "libppo_oracle" not in text, f
+
+
+def _build_c_smoke(tmp_path):
+    exe = tmp_path / "c_abi_smoke"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", str(exe), "-ldl", "-lm"])
+    return str(exe)
+
+
+def test_pure_c_consumer_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/c_abi_smoke.c uses nothing but include/cleanrl_cuda.h + dlopen; on a CPU-only box crl_create must fail with
+    CRL_ERR_CUDA and a message (no CPU fallback), after the bad configuration has been rejected with CRL_ERR_INVALID"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible")
+    except ImportError:
+        pass
+    exe = _build_c_smoke(tmp_path)
+    p = subprocess.run([exe, os.path.join(ROOT, "cleanrl.jl_b200", "libcleanrl_cuda.so")], capture_output=True, text=True)
+    assert p.returncode == 1 and "-> -2" in p.stderr and "bad config was not rejected" not in p.stderr, p.stderr
+
+
+@pytest.mark.gpu
+def test_pure_c_consumer_trains_through_the_header_alone(tmp_path, torch_cuda):
+    """create -> set_params -> env_reset -> train_update x 3 with lag-1 fetches -> get_params -> destroy, from plain C"""
+    exe = _build_c_smoke(tmp_path)
+    p = subprocess.run([exe, os.path.join(ROOT, "cleanrl.jl_b200", "libcleanrl_cuda.so")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "c_abi_smoke ok" in p.stdout
