@@ -2,7 +2,14 @@
 
 The reference steps ONE CartPole env; here `num_envs` envs step in lockstep on the GPU (num_envs = 1 reproduces the
 reference's schedule exactly: see include/cleanrl_cuda.h, "DQN"). `DQNConfig` keeps the reference's field names,
-types and defaults (dqn.jl:1-20, including the `log_frequencey` spelling) and adds `num_envs` and `seed`."""
+types and defaults (dqn.jl:1-20, including the `log_frequencey` spelling) and adds `num_envs` and `seed`.
+
+Arithmetic: dqn.jl:37 builds `CartPoleEnv()` with its default T = Float64, so the reference's env state (and the replay
+buffer rows typed after it) are Float64. The kernels step the Float32 env of the PPO path (ppo.jl:82), whose accelerations
+are already evaluated in Float64 (the `4/3` literal promotes them), so only the stored state is rounded: per step
+|s32 - s64| <= 4e-7 + 3e-7 |s64| per component, every discrete quantity (action, reward, termination away from a threshold,
+counters) identical; `tests/test_dqn.py::test_float32_env_substitute_for_the_float64_cartpole_of_dqn_and_a2c` asserts it.
+The same holds for a2c.jl:33."""
 import ctypes as C
 import dataclasses
 import datetime

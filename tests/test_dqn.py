@@ -255,3 +255,57 @@ def test_dqn_argument_errors(crl, abi, torch_cuda):
     with pytest.raises(crl.CleanRLCudaError):
         h.run(1)                                  # before set_params / reset
     h.close()
+
+
+def test_float32_env_substitute_for_the_float64_cartpole_of_dqn_and_a2c(olib, abi):
+    """dqn.jl:37 `CartPoleEnv()` and a2c.jl:33 `CartPoleEnv(max_steps=500)` default to T = Float64 states, while the
+    kernels (and the oracle) step the Float32 env of the PPO path (ppo.jl:82 `T=Float32`). The substitute is exact in
+    everything discrete and within Float32 rounding per step in the state:
+      * per step, from the same Float32-representable state: |s32 - s64| <= 4e-7 + 3e-7 |s64| per component
+        (the Float32 step already evaluates the accelerations in Float64, SURVEY 8a row 5u, so only the stores round);
+      * the termination test agrees unless the Float64 state lies within that distance of a threshold;
+      * over a whole episode under a fixed action sequence the two trajectories stay within 1e-4 (chaotic growth
+        ~e^0.08 per step of the per-step rounding) and end at the same step in >= 99 % of the episodes.
+    Rewards (0/1), actions and the episode bookkeeping are integers in both."""
+    rng = np.random.default_rng(11)
+    n = 20000
+
+    def step64(s, a):
+        g, mc, mp, l, fm, dt = 9.8, 1.0, 0.1, 0.5, 10.0, 0.02
+        x, xd, th, thd = s.T
+        force = np.where(a == 1, fm, -fm)
+        tmp = (force + mp * l * thd ** 2 * np.sin(th)) / (mc + mp)
+        thacc = (g * np.sin(th) - np.cos(th) * tmp) / (l * (4.0 / 3.0 - mp * np.cos(th) ** 2 / (mc + mp)))
+        xacc = tmp - mp * l * thacc * np.cos(th) / (mc + mp)
+        return np.stack([x + dt * xd, xd + dt * xacc, th + dt * thd, thd + dt * thacc], 1)
+
+    s0 = (rng.random((n, 4)) * np.array([4.0, 4.0, 0.4, 4.0]) - np.array([2.0, 2.0, 0.2, 2.0])).astype(F)
+    a = rng.integers(0, 2, n).astype(np.int32)
+    s32, _, r32, d32 = olib.env_step_raw(0, s0, np.zeros(n, np.int32), a, 200)
+    s64 = step64(s0.astype(np.float64), a)
+    assert np.all(np.abs(s32 - s64) <= 4e-7 + 3e-7 * np.abs(s64))
+    d64 = (np.abs(s64[:, 0]) > 2.4) | (np.abs(s64[:, 2]) > 12 * 2 * np.pi / 360)
+    near = (np.abs(np.abs(s64[:, 0]) - 2.4) < 1e-6) | (np.abs(np.abs(s64[:, 2]) - 12 * 2 * np.pi / 360) < 1e-6)
+    assert np.array_equal(d32[~near].astype(bool), d64[~near]) and near.sum() < 5
+    assert np.array_equal(r32[~near], np.where(d64[~near], 0.0, 1.0).astype(F))
+    # whole episodes, fixed action sequences
+    m, T = 2000, 200
+    s = (rng.random((m, 4)) * 0.1 - 0.05).astype(F)
+    sf, sd = s.copy(), s.astype(np.float64)
+    acts = rng.integers(0, 2, (T, m)).astype(np.int32)
+    alive32, alive64 = np.ones(m, bool), np.ones(m, bool)
+    end32, end64 = np.full(m, T), np.full(m, T)
+    worst = 0.0
+    for t in range(T):
+        nf, _, _, df = olib.env_step_raw(0, sf, np.zeros(m, np.int32), acts[t], 10 ** 6)
+        nd = step64(sd, acts[t])
+        dd = (np.abs(nd[:, 0]) > 2.4) | (np.abs(nd[:, 2]) > 12 * 2 * np.pi / 360)
+        both = alive32 & alive64
+        worst = max(worst, float(np.max(np.abs(nf[both] - nd[both]), initial=0.0)))
+        end32[alive32 & df.astype(bool)] = t
+        end64[alive64 & dd] = t
+        alive32 &= ~df.astype(bool)
+        alive64 &= ~dd
+        sf, sd = nf, nd
+    assert worst < 1e-4
+    assert np.mean(end32 == end64) >= 0.99 and np.max(np.abs(end32 - end64)) <= 1
