@@ -87,6 +87,10 @@ int crl_internal_nccl_allreduce_sum(void* comm, void* buf, size_t count, int is_
   CKN(g_nccl.AllReduce(buf, buf, count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, static_cast<ncclComm_t>(comm), s));
   return CRL_OK;
 }
+int crl_internal_nccl_allgather(void* comm, const void* send, void* recv, size_t bytes, cudaStream_t s) {
+  CKN(g_nccl.AllGather(send, recv, bytes, ncclChar, static_cast<ncclComm_t>(comm), s));
+  return CRL_OK;
+}
 void crl_internal_nccl_comm_destroy(void* comm) {
   if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(comm));
 }

@@ -88,3 +88,19 @@ struct MbScalars {
 #define CRL_STREAM_ACTION 0u
 #define CRL_STREAM_RESET 1u
 #define CRL_STREAM_PERM 2u
+
+// ---- flag-in-data ("LL") packets for the peer-memory exchanges (NVLink / NVSwitch) ----------------------------------
+// A Float64 travels as one 16-byte store {lo, flag, hi, flag}: each 8-byte half is written atomically, so a reader that
+// sees `flag` in both halves has the whole value -- no fence, no separate flag store, no counter. flag = the exchange's
+// sequence number (never 0, never the value two exchanges ago, which is what the slot held before).
+#ifdef __CUDACC__
+__device__ __forceinline__ void ll_store(uint4* p, double v, uint32_t flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(flag), "r"((uint32_t)(b >> 32)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+#endif

@@ -330,7 +330,26 @@ struct LearnArgs {
   int B_scale, rank;
   float* gbuf;            // [DQ_P]
   double* lbuf;           // [1]
+  // peer-memory exchange (crl_dqn_comm_init): the update kernel also PUSHES every gradient element (and the loss sum)
+  // into every peer's exchange buffer as a flag-in-data packet; dqn_adam_kernel polls this rank's own buffer and adds
+  // the world values in rank order (the oracle's order). Row layout [2 slots][world][x_stride] packets of 16 bytes.
+  unsigned char* const* x_peers;   // device array [world] of all ranks' exchange buffers, or nullptr (NCCL allreduce)
+  const unsigned char* x_local;
+  int x_world, x_stride, x_slot;
+  unsigned int x_flag;
+  int* x_err;
+  long long x_timeout;
 };
+
+// push element k of this rank's contribution (gradient k < DQ_P, squared-error sum k = DQ_P) to every peer
+__device__ __forceinline__ void x_push(const LearnArgs& a, int k, double v) {
+  if (!a.x_peers) return;
+  for (int r = 0; r < a.x_world; r++) {
+    if (r == a.rank) continue;
+    uint4* dst = reinterpret_cast<uint4*>(a.x_peers[r]) + ((size_t)a.x_slot * a.x_world + a.rank) * a.x_stride + k;
+    ll_store(dst, v, a.x_flag);
+  }
+}
 
 __global__ void __launch_bounds__(LF_T) dqn_learn_fwd_kernel(LearnArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -522,7 +541,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
   if (blockIdx.x == 0 && tid == LU_T - 1) {
     double sq = 0.0;
     for (int c = 0; c < n_fwd_blocks; c++) sq += a.loss_part[c];
-    if (EXCH) a.lbuf[0] = sq;
+    if (EXCH) { a.lbuf[0] = sq; x_push(a, DQ_P, sq); }
     else a.dev->last_loss = sq / (double)B;
   }
 #ifdef DQN_TRACE
@@ -577,7 +596,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
         ok[u] = i < NPAR;
         idx[u] = DQ_W2 + DQ_H2 * k0 + i;
         g[u] = ok[u] ? gs[i] : 0.0f;
-        if (EXCH && ok[u]) a.gbuf[idx[u]] = g[u];
+        if (EXCH && ok[u]) { a.gbuf[idx[u]] = g[u]; x_push(a, idx[u], (double)g[u]); }
       }
       if (!EXCH) dqn_adam<PER>(a, idx, g, ok);
     }
@@ -612,7 +631,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     DTR(2);
     const float g[1] = {acc};
     const bool ok[1] = {true};
-    if (EXCH) a.gbuf[idx[0]] = acc;
+    if (EXCH) { a.gbuf[idx[0]] = acc; x_push(a, idx[0], (double)acc); }
     else dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
@@ -655,7 +674,7 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
     DTR(2);
     const float g[1] = {acc};
     const bool ok[1] = {true};
-    if (EXCH) a.gbuf[idx[0]] = acc;
+    if (EXCH) { a.gbuf[idx[0]] = acc; x_push(a, idx[0], (double)acc); }
     else dqn_adam<1>(a, idx, g, ok);
     DTR(3);
 #ifdef DQN_TRACE
@@ -664,13 +683,41 @@ __global__ void __launch_bounds__(LU_T) dqn_learn_upd_kernel(LearnArgs a, int n_
   }
 }
 
-// data-parallel shards: Adam on the allreduced gradient (every rank holds the same sums, so the replicas stay identical)
+// data-parallel shards: Adam on the summed gradient (every rank holds the same sums, so the replicas stay identical).
+// With the peer-memory exchange this kernel IS the second half of the allreduce: thread k waits for every peer's packet
+// k of this learning step in this rank's own memory and adds the world values in rank order, Float32 as the oracle's
+// group run does (the loss sum in Float64). Without it (x_local == nullptr) gbuf / lbuf hold NCCL's sums.
 __global__ void __launch_bounds__(256) dqn_adam_kernel(LearnArgs a) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) a.dev->last_loss = a.lbuf[0] / (double)a.B_scale;
-  if (k >= DQ_P) return;
+  if (k > DQ_P) return;
+  float gsum = k < DQ_P ? a.gbuf[k] : 0.0f;
+  double lsum = k == DQ_P ? a.lbuf[0] : 0.0;
+  if (a.x_local) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.x_local) + (size_t)a.x_slot * a.x_world * a.x_stride + k;
+    const float mine_g = gsum;
+    const double mine_l = lsum;
+    const long long t0 = clock64();
+    bool bad = *reinterpret_cast<volatile int*>(a.x_err) != 0;   // sticky: an earlier exchange timed out
+    for (int r = 0; r < a.x_world && !bad; r++) {
+      double v;
+      if (r == a.rank) {
+        v = k < DQ_P ? (double)mine_g : mine_l;
+      } else {
+        uint4 pk = ll_load(src + (size_t)r * a.x_stride);
+        while (pk.y != a.x_flag || pk.w != a.x_flag) {
+          if (clock64() - t0 > a.x_timeout) { bad = true; break; }
+          pk = ll_load(src + (size_t)r * a.x_stride);
+        }
+        v = __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | pk.x));
+      }
+      if (k < DQ_P) gsum = r == 0 ? (float)v : __fadd_rn(gsum, (float)v);
+      else lsum = r == 0 ? v : lsum + v;
+    }
+    if (bad) { atomicExch(a.x_err, 1); return; }   // no step on partial sums; the host reports CRL_ERR_NCCL
+  }
+  if (k == DQ_P) { a.dev->last_loss = lsum / (double)a.B_scale; return; }
   const int idx[1] = {k};
-  const float g[1] = {a.gbuf[k]};
+  const float g[1] = {gsum};
   const bool ok[1] = {true};
   dqn_adam<1>(a, idx, g, ok);
 }
@@ -710,6 +757,9 @@ struct crl_dqn_ctx {
   int world, rank, env_id_base;               // data-parallel shard (crl_dqn_comm_init); 1, 0, 0 on one GPU
   void* comm;                                 // NCCL communicator when world > 1
   float* gbuf; double* lbuf;                  // allreduce payload: gradient, squared-error sum
+  // peer-memory exchange of that payload (NVLink): own buffer, the peers' mappings, device copy of the pointer table
+  unsigned char* x_buf; unsigned char* x_peer[CRL_MAX_WORLD]; unsigned char** x_peers_dev; int* x_err; int x_stride; bool x_on;
+  long long x_timeout;
   int size, ptr;
   long long it, learn_steps, launches;
   bool params_set, reset_done;
@@ -787,6 +837,9 @@ extern "C" CRL_API int crl_dqn_destroy(crl_dqn_ctx* c) {
   void* ptrs[] = {c->q, c->tgt, c->m, c->v, c->env_state, c->env_t, c->ep_ret, c->ep_len, c->resets, c->b_state, c->b_next,
                   c->b_reward, c->b_action, c->b_term, c->dev, c->h1T, c->h2T, c->z2T, c->z1T, c->xT, c->dqT, c->loss_part, c->gbuf, c->lbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int r = 0; r < CRL_MAX_WORLD; r++)
+    if (c->x_peer[r] && c->x_peer[r] != c->x_buf) cudaIpcCloseMemHandle(c->x_peer[r]);
+  { void* xp[] = {c->x_buf, c->x_peers_dev, c->x_err}; for (void* q : xp) if (q) cudaFree(q); }
   crl_internal_nccl_comm_destroy(c->comm);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -849,6 +902,49 @@ extern "C" CRL_API int crl_dqn_comm_init(crl_dqn_ctx* c, const void* id128, int3
   rc = crl_internal_nccl_allreduce_sum(c->comm, c->gbuf, DQ_P, 0, c->stream);
   if (rc != CRL_OK) return rc;
   DCK(cudaStreamSynchronize(c->stream));
+  if (world_size > CRL_MAX_WORLD) return dfail(CRL_ERR_INVALID, "world_size exceeds CRL_MAX_WORLD");
+  if (getenv("CRL_NO_P2P") == nullptr) {
+    // peer-memory exchange buffers (same scheme as crl_comm_init): cudaIpc handles travel through one NCCL all-gather,
+    // every rank maps all peers; a failure anywhere leaves the NCCL allreduce in place on ALL ranks (one more collective
+    // carries the verdict)
+    const int W = world_size;
+    c->x_stride = (DQ_P + 1 + 7) & ~7;
+    const size_t bytes = (size_t)2 * W * c->x_stride * 16;
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&c->x_buf), bytes) == cudaSuccess && cudaMemset(c->x_buf, 0, bytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    ok = ok && cudaIpcGetMemHandle(&mine, c->x_buf) == cudaSuccess;
+    unsigned char* stage = nullptr;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&stage), (size_t)(W + 1) * sizeof(mine)) == cudaSuccess;
+    cudaIpcMemHandle_t all[CRL_MAX_WORLD];
+    if (ok) {
+      ok = cudaMemcpy(stage, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && crl_internal_nccl_allgather(c->comm, stage, stage + sizeof(mine), sizeof(mine), c->stream) == CRL_OK;
+      ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+      ok = ok && cudaMemcpy(all, stage + sizeof(mine), (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (stage) cudaFree(stage);
+    for (int r = 0; r < W && ok; r++) {
+      if (r == rank) { c->x_peer[r] = c->x_buf; continue; }
+      void* ptr = nullptr;
+      ok = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      c->x_peer[r] = static_cast<unsigned char*>(ptr);
+    }
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&c->x_peers_dev), CRL_MAX_WORLD * sizeof(void*)) == cudaSuccess;
+    ok = ok && cudaMemcpy(c->x_peers_dev, c->x_peer, CRL_MAX_WORLD * sizeof(void*), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && dzalloc(&c->x_err, 1) == cudaSuccess;
+    double verdict = ok ? 1.0 : 0.0;
+    DCK(cudaMemcpy(c->lbuf, &verdict, sizeof(double), cudaMemcpyHostToDevice));
+    rc = crl_internal_nccl_allreduce_sum(c->comm, c->lbuf, 1, 1, c->stream);
+    if (rc != CRL_OK) return rc;
+    DCK(cudaStreamSynchronize(c->stream));
+    DCK(cudaMemcpy(&verdict, c->lbuf, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaGetLastError();
+    c->x_on = verdict > W - 0.5;
+    const char* e = getenv("CRL_P2P_TIMEOUT_MS");
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->cfg.device);
+    c->x_timeout = (long long)((e ? atof(e) : 30000.0) * (double)khz);
+  }
   return CRL_OK;
 }
 
@@ -908,14 +1004,23 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
         DCK(cudaGetLastError());
         c->launches += 2;
       } else {
-        // one gradient allreduce per learning step (NCCL, on the handle's stream), then Adam on the sums
+        // one gradient exchange per learning step, then Adam on the sums. Peer memory (default): the update kernel pushes
+        // its gradient into every peer's buffer and dqn_adam_kernel collects: no collective call, two launches.
+        // Fallback (CRL_NO_P2P=1 or no peer access): two NCCL allreduces on the handle's stream in between.
+        if (c->x_on) {
+          l.x_peers = c->x_peers_dev; l.x_local = c->x_buf; l.x_world = c->world; l.x_stride = c->x_stride;
+          l.x_flag = (unsigned int)(c->learn_steps + 1); l.x_slot = (int)((c->learn_steps + 1) & 1);
+          l.x_err = c->x_err; l.x_timeout = c->x_timeout;
+        }
         dqn_learn_upd_kernel<true><<<LU_A_BLOCKS + LU_B_BLOCKS + LU_C_BLOCKS, LU_T, LU_SMEM, c->stream>>>(l, fwd_blocks);
         DCK(cudaGetLastError());
-        int rc = crl_internal_nccl_allreduce_sum(c->comm, c->gbuf, DQ_P, 0, c->stream);
-        if (rc != CRL_OK) return rc;
-        rc = crl_internal_nccl_allreduce_sum(c->comm, c->lbuf, 1, 1, c->stream);
-        if (rc != CRL_OK) return rc;
-        dqn_adam_kernel<<<(DQ_P + 255) / 256, 256, 0, c->stream>>>(l);
+        if (!c->x_on) {
+          int rc = crl_internal_nccl_allreduce_sum(c->comm, c->gbuf, DQ_P, 0, c->stream);
+          if (rc != CRL_OK) return rc;
+          rc = crl_internal_nccl_allreduce_sum(c->comm, c->lbuf, 1, 1, c->stream);
+          if (rc != CRL_OK) return rc;
+        }
+        dqn_adam_kernel<<<(DQ_P + 1 + 255) / 256, 256, 0, c->stream>>>(l);
         DCK(cudaGetLastError());
         c->launches += 3;
       }
@@ -930,6 +1035,11 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     stats->last_loss = d.last_loss; stats->sum_return = d.sum_return; stats->sum_length = d.sum_length; stats->epsilon = eps;
     stats->episodes = (int64_t)d.episodes; stats->learn_steps = c->learn_steps; stats->iterations = c->it;
     stats->kernel_launches = c->launches;
+    if (c->x_on) {
+      int err = 0;
+      DCK(cudaMemcpy(&err, c->x_err, sizeof(int), cudaMemcpyDeviceToHost));
+      if (err) return dfail(CRL_ERR_NCCL, "peer-memory gradient exchange timed out waiting for another rank");
+    }
   }
   return CRL_OK;
 }

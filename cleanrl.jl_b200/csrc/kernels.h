@@ -8,6 +8,7 @@ int crl_internal_fail(int code, const char* msg);
 // NCCL (resolved with dlopen in api.cu) for the other translation units: opaque communicator, in-place sum
 int crl_internal_nccl_comm_init(void** comm, int world, int rank, const void* id128);
 int crl_internal_nccl_allreduce_sum(void* comm, void* buf, size_t count, int is_double, cudaStream_t s);
+int crl_internal_nccl_allgather(void* comm, const void* send, void* recv, size_t bytes, cudaStream_t s);   // device buffers
 void crl_internal_nccl_comm_destroy(void* comm);
 
 struct RolloutArgs {

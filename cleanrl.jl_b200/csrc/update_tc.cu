@@ -825,16 +825,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr) {
   }
   __syncthreads();
 }
-__device__ __forceinline__ void ll_store(uint4* p, double v, uint32_t flag) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(flag), "r"((uint32_t)(b >> 32)), "r"(flag) : "memory");
-}
-__device__ __forceinline__ uint4 ll_load(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-
 constexpr int FT_EL = 64;  // elements per reduction pass (x 4 partial groups = 256 threads)
 // -DFT_TRACE: clock stamps of the tail's phases, printed by thread 0 of the first and the last CTA (development aid)
 #ifdef FT_TRACE
