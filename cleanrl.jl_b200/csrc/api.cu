@@ -170,6 +170,8 @@ struct crl_ctx {
   bool p2p_on;
   size_t ll_off;                   // flag-in-data region of the exchange buffer (fused tail), [2 slots][world][ll_stride] x 16 B
   int ll_stride;
+  size_t adv_off;                  // same for the per-update advantage sums (adv_stats), [2 slots][world][adv_stride] x 16 B
+  int adv_stride;
   long long p2p_timeout_cycles;
   // fused tail of the tcgen05 update kernel
   unsigned long long* grid_bar;
@@ -594,6 +596,11 @@ static int enqueue_adv_stats(crl_ctx* c, const int32_t* arr_base, int M, int nmb
   aa.idx.epoch = 0; aa.idx.rank = (uint32_t)c->cfg.rank; aa.idx.seed = c->cfg.seed; aa.idx.ds = c->ds;
   aa.arr_base = arr_base; aa.B = c->B; aa.M = M; aa.nmb = nmb; aa.n_sets = n_sets;
   aa.advantages = c->advantage; aa.advparts = c->advparts;
+  aa.x_peers = nullptr; aa.x_local = nullptr; aa.x_off = 0; aa.x_world = 1; aa.x_rank = 0; aa.x_stride = 0; aa.x_err = nullptr; aa.x_timeout = 0;
+  if (c->cfg.world_size > 1 && c->p2p_on && n_sets * ADV_CHUNKS * 2 <= c->adv_stride) {
+    aa.x_peers = c->p2p_peers_dev; aa.x_local = c->p2p_buf; aa.x_off = c->adv_off; aa.x_world = c->cfg.world_size;
+    aa.x_rank = c->cfg.rank; aa.x_stride = c->adv_stride; aa.x_err = c->p2p_err; aa.x_timeout = c->p2p_timeout_cycles;
+  }
   KernelScope ks(c, CRL_K_MB_STATS);
   CK(launch_adv_stats(aa, c->stream));
   return CRL_OK;
@@ -745,7 +752,8 @@ static int enqueue_epochs(crl_ctx* c, const int32_t* perm_dev, double lr_host, b
     perm_dev = c->perm_dev;
   }
   if (spec && !a2c) CKRC(enqueue_adv_stats(c, perm_dev, c->M, c->cfg.num_minibatches, n_sets));
-  if (spec && !a2c && c->cfg.world_size > 1) {  // global advantage sums for all minibatches of the update: one collective per update
+  if (spec && !a2c && c->cfg.world_size > 1 && !c->p2p_on) {  // global advantage sums for all minibatches of the update: one
+                                                               // collective per update (peer memory: adv_stats exchanged them itself)
     KernelScope ks(c, CRL_K_ALLREDUCE, false);
     CKN(g_nccl.AllReduce(c->advparts, c->advparts, (size_t)n_sets * ADV_CHUNKS * 2, ncclFloat64, ncclSum, c->comm, c->stream));
   }
@@ -1025,7 +1033,9 @@ extern "C" CRL_API int crl_comm_init(crl_ctx* c, const void* id128) {
     // behind them: the flag-in-data region of the fused tail, 16-byte packets {lo, seq, hi, seq} (gradient, 4 loss sums, min)
     c->ll_stride = (c->L.P + 4 + 1 + 7) & ~7;
     c->ll_off = (c->p2p_flags_off + CRL_MAX_WORLD * sizeof(unsigned long long) + 255) & ~size_t(255);
-    const size_t bytes = c->ll_off + (size_t)2 * W * c->ll_stride * 16;
+    c->adv_stride = std::max(1, c->cfg.update_epochs) * c->cfg.num_minibatches * ADV_CHUNKS * 2;
+    c->adv_off = c->ll_off + (size_t)2 * W * c->ll_stride * 16;
+    const size_t bytes = c->adv_off + (size_t)2 * W * c->adv_stride * 16;
     {
       // how long a kernel waits for a peer's data before it gives up (error, no update applied): a peer may legitimately
       // be seconds late (first CUDA-graph instantiation, a host stall on the rank that logs). CRL_P2P_TIMEOUT_MS overrides.

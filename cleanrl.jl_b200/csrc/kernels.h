@@ -76,6 +76,15 @@ struct AdvStatsArgs {
   int B, M, nmb, n_sets;
   const float* advantages;
   double* advparts;         // [n_sets][ADV_CHUNKS][2] = (sum adv, sum adv^2)
+  // multi-GPU: the sums of all ranks are exchanged by this kernel itself over peer memory (flag-in-data packets, rows
+  // [2 slots][world][x_stride] at byte offset x_off of the exchange buffers; slot/flag from the update index) and added
+  // in rank order, so advparts holds the GLOBAL sums on every rank when the kernel ends. nullptr = local sums only.
+  unsigned char* const* x_peers;
+  const unsigned char* x_local;
+  size_t x_off;
+  int x_world, x_rank, x_stride;
+  int* x_err;
+  long long x_timeout;
 };
 
 #define CRL_MAX_WORLD 16

@@ -815,10 +815,36 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(AdvStatsArgs a) {
   }
   sa = block_sum<8>(sa, red);
   sa2 = block_sum<8>(sa2, red);
-  if (threadIdx.x == 0) {
-    double* o = a.advparts + ((long long)set * ADV_CHUNKS + blockIdx.x) * 2;
-    o[0] = sa;
-    o[1] = sa2;
+  if (threadIdx.x < 2) {
+    const int pos = (set * ADV_CHUNKS + (int)blockIdx.x) * 2 + (int)threadIdx.x;
+    double v = threadIdx.x ? sa2 : sa;
+    if (a.x_local) {
+      // global sums over the ranks: push this block's value to every peer, collect the peers' values of the same block
+      // from this rank's own memory, add in rank order (identical on every rank). No other block is waited for.
+      const unsigned long long u = a.idx.ds->update_index;
+      const uint32_t flag = (uint32_t)(u + 1ull);
+      const size_t row0 = (size_t)(u & 1ull) * a.x_world * a.x_stride;
+      for (int r = 0; r < a.x_world; r++)
+        if (r != a.x_rank)
+          ll_store(reinterpret_cast<uint4*>(a.x_peers[r] + a.x_off) + row0 + (size_t)a.x_rank * a.x_stride + pos, v, flag);
+      const uint4* src = reinterpret_cast<const uint4*>(a.x_local + a.x_off) + row0 + pos;
+      const long long t0 = clock64();
+      double tot = 0.0;
+      for (int r = 0; r < a.x_world; r++) {
+        double x = v;
+        if (r != a.x_rank) {
+          uint4 pk = ll_load(src + (size_t)r * a.x_stride);
+          while (pk.y != flag || pk.w != flag) {
+            if (clock64() - t0 > a.x_timeout) { atomicExch(a.x_err, 1); break; }   // no update is applied after this
+            pk = ll_load(src + (size_t)r * a.x_stride);
+          }
+          x = __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | pk.x));
+        }
+        tot += x;
+      }
+      v = tot;
+    }
+    a.advparts[pos] = v;
   }
 }
 
