@@ -68,10 +68,14 @@ constexpr int XT_GROUP = F_SBO / 4;  // floats per 8-row group
 
 // TMEM columns (fp32): z2/dh1 accumulator (A W_hi^T | A_hi W_lo^T: 128) | A operand hi (64) | A operand lo (64) |
 // dW2 accumulator (x h1_hi | x h1_lo | x x~: 144) | dW1,db1 accumulator (x x~_hi | x x~_lo: 16)
-constexpr uint32_t COL_D = 0, COL_AH = 128, COL_AL = 192, COL_D2 = 256, COL_D4 = 400, TMEM_COLS = 512;
+constexpr uint32_t COL_D = 0, COL_AH = 128, COL_AL = 192, COL_D2 = 256, COL_D4 = 400, COL_P = 416, TMEM_COLS = 512;
+// TC_PARK: h1^2 - 1 (the tanh derivative E3 needs) waits in 64 spare TMEM columns from the start of the tile instead of
+// being rebuilt from the hi/lo rows of h1^T in shared memory (4 scalar loads + an add per feature pair)
+#ifndef TC_PARK
+#define TC_PARK 1
+#endif
 // named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4 = head exchange
 constexpr int BAR_G1 = 1, BAR_G3 = 2, BAR_G4 = 3, BAR_X = 4;
-
 template <int ENV> struct TcSmem {
   static constexpr int WB = 0;                      // [4][4096] weight images of this CTA's net
   static constexpr int FZ = WB + 4 * TC_W_FLOATS;   // dz2^T, rows 0-63 hi, 64-127 lo
@@ -158,6 +162,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// two N-column rows (an accumulator's hi*W_hi and hi*W_lo halves) requested back to back behind ONE wait: the second
+// load's latency hides behind the first instead of following it
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+template <int N> __device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, float* va, float* vb) {
+  static_assert(N == 16 || N == 32, "");
+  uint32_t ra[N], rb[N];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16_issue(ta + i, ra + i);
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16_issue(tb + i, rb + i);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i++) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+}
+
+template <int N> __device__ __forceinline__ void tmem_ld_triple(uint32_t ta, uint32_t tb, uint32_t tc, float* va, float* vb, float* vc) {
+  static_assert(N == 16 || N == 32, "");
+  uint32_t ra[N], rb[N], rc[N];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16_issue(ta + i, ra + i);
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16_issue(tb + i, rb + i);
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16_issue(tc + i, rc + i);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i++) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); vc[i] = __uint_as_float(rc[i]); }
 }
 
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float* v) {
@@ -435,6 +474,15 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       float h1h[TC_FG], h1l[TC_FG];
       TR(1);
       split_to_tmem(h1, h1h, h1l);
+      if (TC_PARK) {
+        float dt[TC_FG];
+#pragma unroll
+        for (int i = 0; i < TC_FG / 2; i++) {
+          const float2 d = __ffma2_rn(h1[i], h1[i], f2s(-1.0f));
+          dt[2 * i] = d.x; dt[2 * i + 1] = d.y;
+        }
+        tmem_st_n<TC_FG>(lane_addr + COL_P + f0, dt);   // the previous tile's E3 has read its copy (program order)
+      }
       tmem_st_wait();
       tc_fence_before();
       TR(2);
@@ -464,8 +512,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       float2 h2[TC_FG / 2];
       {
         float z2[TC_FG], z2b[TC_FG];
-        tmem_ld_n<TC_FG>(lane_addr + COL_D + f0, z2);
-        tmem_ld_n<TC_FG>(lane_addr + COL_D + CRL_H + f0, z2b);
+        tmem_ld_pair<TC_FG>(lane_addr + COL_D + f0, lane_addr + COL_D + CRL_H + f0, z2, z2b);
         float2 part[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; o++) part[o] = f2s(0.0f);
@@ -631,14 +678,21 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       TR(11);
       tc_fence_after();
       float ndh1[TC_FG], ndh1b[TC_FG];
-      tmem_ld_n<TC_FG>(lane_addr + COL_D + f0, ndh1);
-      tmem_ld_n<TC_FG>(lane_addr + COL_D + CRL_H + f0, ndh1b);
       float2 dz1[TC_FG / 2];
+      if (TC_PARK) {
+        float dt[TC_FG];
+        tmem_ld_triple<TC_FG>(lane_addr + COL_D + f0, lane_addr + COL_D + CRL_H + f0, lane_addr + COL_P + f0, ndh1, ndh1b, dt);
 #pragma unroll
-      for (int i = 0; i < TC_FG / 2; i++) {
-        const float2 h = __fadd2_rn(f2(fh[f_off(f0 + 2 * i, s)], fh[f_off(f0 + 2 * i + 1, s)]),
-                                    f2(fh[f_off(CRL_H + f0 + 2 * i, s)], fh[f_off(CRL_H + f0 + 2 * i + 1, s)]));
-        dz1[i] = __fmul2_rn(__fadd2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), f2(ndh1b[2 * i], ndh1b[2 * i + 1])), __ffma2_rn(h, h, f2s(-1.0f)));
+        for (int i = 0; i < TC_FG / 2; i++)
+          dz1[i] = __fmul2_rn(__fadd2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), f2(ndh1b[2 * i], ndh1b[2 * i + 1])), f2(dt[2 * i], dt[2 * i + 1]));
+      } else {
+        tmem_ld_pair<TC_FG>(lane_addr + COL_D + f0, lane_addr + COL_D + CRL_H + f0, ndh1, ndh1b);
+#pragma unroll
+        for (int i = 0; i < TC_FG / 2; i++) {
+          const float2 h = __fadd2_rn(f2(fh[f_off(f0 + 2 * i, s)], fh[f_off(f0 + 2 * i + 1, s)]),
+                                      f2(fh[f_off(CRL_H + f0 + 2 * i, s)], fh[f_off(CRL_H + f0 + 2 * i + 1, s)]));
+          dz1[i] = __fmul2_rn(__fadd2_rn(f2(ndh1[2 * i], ndh1[2 * i + 1]), f2(ndh1b[2 * i], ndh1b[2 * i + 1])), __ffma2_rn(h, h, f2s(-1.0f)));
+        }
       }
       TR(12);
       mbar_wait(bar2, ph);  // G2 has consumed h1^T and dz2^T
@@ -686,8 +740,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
     float d2[TC_FG], d4[16], d5[16];
     {
       float d2b[TC_FG];
-      tmem_ld_n<TC_FG>(lane_addr + COL_D2 + f0, d2);
-      tmem_ld_n<TC_FG>(lane_addr + COL_D2 + CRL_H + f0, d2b);
+      tmem_ld_pair<TC_FG>(lane_addr + COL_D2 + f0, lane_addr + COL_D2 + CRL_H + f0, d2, d2b);
 #pragma unroll
       for (int i = 0; i < TC_FG; i++) d2[i] += d2b[i];
     }
@@ -837,7 +890,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 template <int ENV>
 __device__ __noinline__ void fused_tail(const UpdateArgs& a, float* scratch, const unsigned long long seq) {
   using E = EnvTraits<ENV>;
-  static_assert(TC_THREADS == 4 * FT_EL, "the fused tail splits the partials over 4 thread groups of 64 elements");
+  static_assert(TC_THREADS >= 4 * FT_EL, "the fused tail splits the partials over 4 thread groups of 64 elements");
   constexpr int P = E::P;
   const AdamArgs& f = a.adam;
   const int tid = threadIdx.x, G = (int)gridDim.x;
@@ -879,7 +932,7 @@ __device__ __noinline__ void fused_tail(const UpdateArgs& a, float* scratch, con
   for (int base = 0; base < ngrad; base += FT_EL) {
     const int e = lo + base + el;
     double s = 0.0;
-    if (base + el < ngrad) {
+    if (g < 4 && base + el < ngrad) {
       int c_lo = 0, c_hi = G;
       const bool critic = e >= a.tc_net_a && e < a.tc_net_a + a.tc_net_c;
       if (critic) c_lo = a.tc_actor_ctas; else c_hi = a.tc_actor_ctas;
@@ -897,7 +950,7 @@ __device__ __noinline__ void fused_tail(const UpdateArgs& a, float* scratch, con
         for (int j = 0; j < 10; j++) s += (double)v[j];
       }
     }
-    sh[g * FT_EL + el] = s;
+    if (g < 4) sh[g * FT_EL + el] = s;
     __syncthreads();
     if (g == 0 && base + el < ngrad) gs[base + el] = (sh[el] + sh[FT_EL + el]) + (sh[2 * FT_EL + el] + sh[3 * FT_EL + el]);
     __syncthreads();
@@ -1172,6 +1225,9 @@ cudaError_t kernels_init_update_tc() {
 
 // Chooses the tensor-core kernel for this minibatch when it applies (parameter image present) and fills
 // in the launch geometry; CRL_NO_TC=1 keeps the FFMA kernel.
+#ifndef TC_ACTOR_COST
+#define TC_ACTOR_COST 1.15
+#endif
 int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   static int disabled = -1, actor_share = -1;
   if (disabled < 0) {
@@ -1188,13 +1244,14 @@ int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   int grid = 2 * n_tiles < sm_count ? 2 * n_tiles : sm_count;
   grid &= ~1;
   if (grid < 2) grid = 2;
-  // An actor tile (two heads, softmax, entropy) costs ~1.15x a critic tile, and every CTA runs a whole number of
-  // tiles: pick the split that minimises the slower side.
+  // An actor tile (two heads, softmax, entropy) costs TC_ACTOR_COST x a critic tile (clock stamps of the -DTC_TRACE
+  // build are perturbed by the stamps and show them equal; the A/B runs of CRL_TC_ACTOR_CTAS say 79 of 148), and every CTA runs a whole number of tiles: pick the split that minimises the
+  // slower side.
   int na = grid / 2;
   {
     double best = 1e30;
     for (int cand = 1; cand < grid; cand++) {
-      const double ta = 1.15 * ((n_tiles + cand - 1) / cand), tc = (double)((n_tiles + (grid - cand) - 1) / (grid - cand));
+      const double ta = TC_ACTOR_COST * ((n_tiles + cand - 1) / cand), tc = (double)((n_tiles + (grid - cand) - 1) / (grid - cand));
       const double cost = ta > tc ? ta : tc;
       if (cost < best - 1e-9) { best = cost; na = cand; }
     }
