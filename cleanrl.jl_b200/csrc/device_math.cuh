@@ -146,13 +146,12 @@ __device__ __forceinline__ double ddiv_const(double a, double c, double y) {
 // but the Float64 literal 4/3 promotes thetaacc, xacc and the velocity updates to Float64
 // (SURVEY §8a row 5u). Explicit _rn intrinsics keep the compiler from contracting mul+add
 // so the arithmetic is the same sequence of roundings as the oracle's.
-__device__ inline void cartpole_step(float s[4], int& t, int action, int max_steps, float& reward, bool& done) {
+// cartpole_dynamics: the state update alone (no counters), so that the rollout kernel can evaluate it for both actions
+// ahead of the sampling; cartpole_outcome: termination and reward from the new state and the already advanced counter.
+__device__ inline void cartpole_dynamics(float s[4], int action) {
   const float gravity = 9.8f, masspole = 0.1f, halflength = 0.5f, forcemag = 10.0f, dt = 0.02f;
   const float totalmass = 1.0f + 0.1f;
   const float polemasslength = 0.1f * 0.5f;
-  const float thetathreshold = (float)(12.0 * 2.0 * 3.141592653589793 / 360.0);
-  const float xthreshold = 2.4f;
-  t += 1;
   const float force = action == 1 ? forcemag : -forcemag;
   const float xdot = s[1], theta = s[2], thetadot = s[3];
   float sintheta, costheta;
@@ -169,8 +168,17 @@ __device__ inline void cartpole_step(float s[4], int& t, int action, int max_ste
   s[1] = (float)__dadd_rn((double)s[1], __dmul_rn((double)dt, xacc));
   s[2] = __fadd_rn(s[2], __fmul_rn(dt, thetadot));
   s[3] = (float)__dadd_rn((double)s[3], __dmul_rn((double)dt, thetaacc));
+}
+__device__ inline void cartpole_outcome(const float s[4], int t, int max_steps, float& reward, bool& done) {
+  const float thetathreshold = (float)(12.0 * 2.0 * 3.141592653589793 / 360.0);
+  const float xthreshold = 2.4f;
   done = fabsf(s[0]) > xthreshold || fabsf(s[2]) > thetathreshold || t > max_steps;
   reward = done ? 0.0f : 1.0f;
+}
+__device__ inline void cartpole_step(float s[4], int& t, int action, int max_steps, float& reward, bool& done) {
+  t += 1;
+  cartpole_dynamics(s, action);
+  cartpole_outcome(s, t, max_steps, reward, done);
 }
 __device__ inline void cartpole_reset(float s[4], int& t, const float u[4]) {
 #pragma unroll

@@ -132,6 +132,69 @@ __device__ __forceinline__ void tile_layer(const ThreadCoord<G>& tc, const float
   }
 }
 
+// The same layer for the rollout's 4 x 4 tiles (EPI_BIAS_TANH), scheduled by hand: the k loop is fully unrolled with the
+// operands of the NEXT four k fetched while the current four are multiplied (the rolled loop stalled on its own loads
+// at the top of every iteration: two warps per scheduler cannot cover them), and the epilogue reads its biases before
+// and stores its outputs after ALL the tanh evaluations (a store between two of them stops the compiler from moving
+// the next bias load up, which serialised the four rows). Every accumulator is still one fma chain over ascending k.
+template <class G, int K>
+__device__ __forceinline__ void tile_layer_fwd4(const ThreadCoord<G>& tc, const float* __restrict__ Wt,
+                                                const float* __restrict__ bias, const float* __restrict__ in,
+                                                float* __restrict__ out) {
+  static_assert(G::TS == 4, "4 x 4 thread tiles");
+  constexpr int SP = G::S_PAD, PF = 4;
+  const float* wp = Wt + tc.jb[0];
+  const float* ap = in + tc.sb[0];
+  const float4 bv = *reinterpret_cast<const float4*>(bias + tc.jb[0]);
+  float2 acc2[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc2[j][0] = acc2[j][1] = make_float2(0.0f, 0.0f);
+  float4 w[PF], a[PF];
+#pragma unroll
+  for (int i = 0; i < PF; i++) {
+    if (i < K) {
+      w[i] = *reinterpret_cast<const float4*>(wp + i * CRL_H);
+      a[i] = *reinterpret_cast<const float4*>(ap + i * SP);
+    }
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += PF) {
+    float4 wn[PF], an[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      if (k0 + PF + i < K) {
+        wn[i] = *reinterpret_cast<const float4*>(wp + (k0 + PF + i) * CRL_H);
+        an[i] = *reinterpret_cast<const float4*>(ap + (k0 + PF + i) * SP);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      if (k0 + i < K) {
+        const float2 a01 = make_float2(a[i].x, a[i].y), a23 = make_float2(a[i].z, a[i].w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float wj = f4_get(w[i], j);
+          const float2 ww = make_float2(wj, wj);
+          acc2[j][0] = __ffma2_rn(ww, a01, acc2[j][0]);
+          acc2[j][1] = __ffma2_rn(ww, a23, acc2[j][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) { w[i] = wn[i]; a[i] = an[i]; }
+  }
+  float4 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float b = f4_get(bv, j);
+    const float2 t0 = tanh_fast2(__fadd2_rn(acc2[j][0], make_float2(b, b)));
+    const float2 t1 = tanh_fast2(__fadd2_rn(acc2[j][1], make_float2(b, b)));
+    o[j] = make_float4(t0.x, t0.y, t1.x, t1.y);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(out + (tc.jb[0] + j) * SP + tc.sb[0]) = o[j];
+}
+
 // Shared-memory image of the parameters: each net copied to a 16-byte aligned base so the
 // float4 weight loads are legal (the flat vector puts the critic at an odd offset).
 template <int ENV> struct SmemParams {

@@ -13,7 +13,13 @@
 
 namespace {
 
-constexpr int RE = 32;  // envs per CTA
+constexpr int RE = 32;            // envs per CTA
+constexpr int ROLL_FWD = CRL_THREADS;   // warps 0-7: the two MLPs; warp 0 also owns the envs (one lane per env)
+constexpr int ROLL_THREADS = ROLL_FWD + 64;   // warps 8, 9: speculation warps (see rollout_kernel)
+constexpr int BAR_FWD = 1, BAR_SPEC = 2;      // named barriers: the 256 forward threads / speculation warps -> warp 0
+
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int ENV> struct RolloutSmem {
   using G = TileGeom<4, 2>;
@@ -24,14 +30,51 @@ template <int ENV> struct RolloutSmem {
   static constexpr int H1 = X + CRL_MAXD * SP;
   static constexpr int H2 = H1 + G::ROWS * SP;
   static constexpr int OUT = H2 + G::ROWS * SP;
-  static constexpr int FLOATS = OUT + 4 * RE;
+  static constexpr int ST = OUT + 4 * RE;          // [4][RE] env state as the speculation warps read it
+  static constexpr int SPEC = ST + 4 * RE;         // [2 actions][4][RE] successor states (CartPole)
+  static constexpr int RST = SPEC + 2 * 4 * RE;    // [4][RE] the state each env takes at its next reset
+  static constexpr int NOISE = RST + 4 * RE;       // double[RE] uniform (Float64, StatsBase) or float[2][RE] normals
+  static constexpr int USED = NOISE + 2 * RE;      // int[RE]: warp 0 consumed the prepared reset state
+  static constexpr int FLOATS = USED + RE;
   static constexpr size_t BYTES = FLOATS * sizeof(float);
+  static_assert((NOISE % 2) == 0, "the Float64 uniforms need 8-byte alignment");
 };
 
+// -DROLL_TRACE: clock stamps of the phases of step 64 of CTA 0 (warps 0 and 5), printed from the kernel (development aid)
+#ifdef ROLL_TRACE
+#define RTR(i) do { if (tr) tr[i] = clock64(); } while (0)
+#else
+#define RTR(i) do { } while (0)
+#endif
+
+// this thread's row of the output layer in registers (threads < RE * (A + 1): output o = tid / RE of env tid % RE):
+// constant during a launch, so the 64 broadcast loads per step become none
+template <int ENV> struct HeadRow { float w[CRL_H]; float b; };
+template <int ENV> __device__ __forceinline__ void load_head_row(const float* sp, HeadRow<ENV>& hr) {
+  using E = EnvTraits<ENV>;
+  const int o = threadIdx.x / RE;
+#pragma unroll
+  for (int k = 0; k < CRL_H; k++) hr.w[k] = 0.0f;
+  hr.b = 0.0f;
+  if (threadIdx.x >= RE * (E::A + 1)) return;
+  if (o < E::A) {
+    const float* a = sp + SmemParams<ENV>::ACTOR;
+#pragma unroll
+    for (int k = 0; k < CRL_H; k++) hr.w[k] = a[NetOff<E::D, E::A>::W3 + k * E::A + o];
+    hr.b = a[NetOff<E::D, E::A>::B3 + o];
+  } else {
+    const float* c = sp + SmemParams<ENV>::CRITIC;
+#pragma unroll
+    for (int k = 0; k < CRL_H; k++) hr.w[k] = c[NetOff<E::D, 1>::W3 + k];
+    hr.b = c[NetOff<E::D, 1>::B3];
+  }
+}
+
 // both nets forward for the 32 samples whose observations sit in xs; heads -> so[o][e]
-// (o < A: actor logits/mean, o == A: critic value)
+// (o < A: actor logits/mean, o == A: critic value). Called by the 256 forward threads only (named barrier BAR_FWD).
 template <int ENV>
-__device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc, float* smem) {
+__device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc, float* smem, const HeadRow<ENV>& hr,
+                                          long long* tr = nullptr) {
   using G = TileGeom<4, 2>;
   using E = EnvTraits<ENV>;
   using SM = RolloutSmem<ENV>;
@@ -43,51 +86,70 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
   float* so = smem + SM::OUT;
   const float* np = sp + net_base<ENV>(tc.net);
   using NO = NetOff<E::D, 1>;  // W1,B1,W2,B2,W3 offsets do not depend on the head width
-  tile_layer<G, E::D, EPI_BIAS_TANH>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
-  __syncthreads();
-  tile_layer<G, CRL_H, EPI_BIAS_TANH>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
-  __syncthreads();
+  RTR(0);
+  tile_layer_fwd4<G, E::D>(tc, np + NO::W1, np + NO::B1, xs, h1 + tc.net * CRL_H * SP);
+  RTR(1);
+  nbar_sync(BAR_FWD, ROLL_FWD);
+  RTR(2);
+  tile_layer_fwd4<G, CRL_H>(tc, np + NO::W2, np + NO::B2, h1 + tc.net * CRL_H * SP, h2 + tc.net * CRL_H * SP);
+  RTR(3);
+  nbar_sync(BAR_FWD, ROLL_FWD);
+  RTR(4);
   if (threadIdx.x < RE * (E::A + 1)) {
     const int o = threadIdx.x / RE, e = threadIdx.x % RE;
+    const float* hrow = h2 + (o < E::A ? 0 : CRL_H) * SP + e;
+    float hv[CRL_H];
+#pragma unroll
+    for (int k = 0; k < CRL_H; k++) hv[k] = hrow[k * SP];   // all 64 loads in flight before the (serial) chain starts
     float acc = 0.0f;
-    if (o < E::A) {
-      const float* a = sp + SmemParams<ENV>::ACTOR;
-      const float* W3 = a + NetOff<E::D, E::A>::W3;
-#pragma unroll 8
-      for (int k = 0; k < CRL_H; k++) acc = fmaf(W3[k * E::A + o], h2[k * SP + e], acc);
-      acc += a[NetOff<E::D, E::A>::B3 + o];
-    } else {
-      const float* c = sp + SmemParams<ENV>::CRITIC;
-      const float* W3 = c + NetOff<E::D, 1>::W3;
-#pragma unroll 8
-      for (int k = 0; k < CRL_H; k++) acc = fmaf(W3[k], h2[(CRL_H + k) * SP + e], acc);
-      acc += c[NetOff<E::D, 1>::B3];
-    }
-    so[o * RE + e] = acc;
+#pragma unroll
+    for (int k = 0; k < CRL_H; k++) acc = fmaf(hr.w[k], hv[k], acc);
+    so[o * RE + e] = acc + hr.b;
   }
-  __syncthreads();
+  RTR(5);
+  nbar_sync(BAR_FWD, ROLL_FWD);
+  RTR(6);
 }
 
+// Persistent rollout. Warps 0-7 evaluate the two MLPs for the CTA's 32 envs; warp 0 (one lane per env) then samples,
+// records and advances its env. Everything that does not depend on the sampled action is taken off that serial
+// phase by two extra warps that work in the shadow of the forward pass:
+//   warp 8   the step's action noise (Philox: the Float64 uniform of StatsBase.sample, or the Gaussian head's normals)
+//            and, CartPole, the successor state for action 0
+//   warp 9   CartPole: the successor state for action 1; both envs: the state every env will take at its NEXT reset
+//            (Philox keyed by the env's reset counter), refreshed after warp 0 consumed it
+// Warp 0 picks the successor of the action it sampled (same device function, same inputs: bit-identical to stepping
+// after the fact). The injected-noise test modes (action_noise / reset_noise) read their draws on warp 0 as before.
 template <int ENV>
-__global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
+__global__ void __launch_bounds__(ROLL_THREADS) rollout_kernel(RolloutArgs a) {
   using G = TileGeom<4, 2>;
   using E = EnvTraits<ENV>;
   using SM = RolloutSmem<ENV>;
   constexpr int SP = G::S_PAD;
   constexpr int D = E::D, A = E::A, S = E::S;
+  constexpr bool CART = ENV == CRL_ENV_CARTPOLE;
   extern __shared__ __align__(16) float smem[];
   float* sp = smem + SM::PARAMS;
   float* xs = smem + SM::X;
   float* so = smem + SM::OUT;
+  float* st_s = smem + SM::ST;
+  float* spec_s = smem + SM::SPEC;
+  float* rst_s = smem + SM::RST;
+  double* noise_d = reinterpret_cast<double*>(smem + SM::NOISE);
+  float* noise_f = smem + SM::NOISE;
+  int* used_s = reinterpret_cast<int*>(smem + SM::USED);
   const ThreadCoord<G> tc;
 
   load_params<ENV>(a.params, sp);
   for (int i = threadIdx.x; i < CRL_MAXD * SP; i += blockDim.x) xs[i] = 0.0f;
 
-  const int e = threadIdx.x;  // env lane, meaningful for warp 0
+  const int warp = threadIdx.x >> 5;
+  const int e = threadIdx.x & 31;  // env lane of warps 0, 8 and 9
   const long long n = (long long)blockIdx.x * RE + e;
+  const bool fwd = threadIdx.x < ROLL_FWD;
   const bool owner = threadIdx.x < RE;
-  const bool valid = owner && n < a.N;
+  const bool in_range = n < a.N;
+  const bool valid = owner && in_range;
   const unsigned long long step0 = a.ds->policy_step;
   const uint32_t gid = (uint32_t)(a.env_id_base + (int)n);
 
@@ -95,11 +157,17 @@ __global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
   float obs[D];
   int env_t = 0, ep_len = 0;
   double ep_ret = 0.0;
-  uint32_t resets = 0;
+  uint32_t resets = 0;  // warp 0: the env's counter; warp 9: the counter the prepared reset state was drawn for
   bool done_flag = false;  // Q3: ppo.jl:170 — is_terminated(env) after reset! is false
   // per-thread episode aggregates
   unsigned long long agg_n = 0;
   double agg_ret = 0.0, agg_len = 0.0, agg_max = -INFINITY;
+  // episode record whose slot is still on its way back from the atomic (stored at the next step: the round trip to L2
+  // would otherwise sit in front of the step barrier)
+  bool rec_pending = false;
+  unsigned int rec_slot = 0;
+  crl_episode rec;
+  rec.step = 0; rec.env = 0; rec.length = 0; rec._pad = 0; rec.episode_return = 0.0;
 
   if (valid) {
 #pragma unroll
@@ -111,129 +179,206 @@ __global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
   } else {
 #pragma unroll
     for (int i = 0; i < S; i++) st[i] = 0.0f;
+    if (warp == 9 && in_range) resets = a.reset_count[n];
   }
   __syncthreads();
+  HeadRow<ENV> hr;
+  load_head_row<ENV>(sp, hr);
   if (owner) {
     env_obs<ENV>(st, obs);  // Q3: ppo.jl:169 — state(env) refreshed (post-reset state)
 #pragma unroll
     for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
+#pragma unroll
+    for (int i = 0; i < S; i++) st_s[i * RE + e] = st[i];
+    used_s[e] = 0;
   }
+  auto prepare_reset = [&]() {   // warp 9: the state env e takes at reset number `resets` (multi_thread_env.jl:105-111)
+    float u4[4], rs[S];
+    int rt;
+    rng_reset_uniforms(a.seed, gid, resets, u4);
+    env_reset<ENV>(rs, rt, u4);
+#pragma unroll
+    for (int i = 0; i < S; i++) rst_s[i * RE + e] = rs[i];
+  };
+  if (warp == 9 && !a.reset_noise) prepare_reset();
   __syncthreads();
 
   for (int t = 0; t < a.T; t++) {
-    forward32<ENV>(tc, smem);  // ends with a barrier; so[] is ready
-    if (owner) {
-      const long long b = (long long)t * a.N + n;
-      ep_len += 1;  // ppo.jl:125
-      const float value = so[A * RE + e];
-      float logprob;
-      int act_i = 0;
-      float act_f = 0.0f;
-      if (!E::CONT) {
-        // get_action, ppo.jl:22-29: softmax / logsoftmax [NNlib], then
-        // StatsBase.sample(Weights(p)): t = rand()*sum(p); walk cw += p[i] while cw < t.
-        float z[A], p[A], lp[A];
-#pragma unroll
-        for (int k = 0; k < A; k++) z[k] = so[k * RE + e];
-        float m = z[0];
-#pragma unroll
-        for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
-        float ex[A], sum = 0.0f;
-#pragma unroll
-        for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
-        const float ls = logf(sum);
-        float psum = 0.0f;
-#pragma unroll
-        for (int k = 0; k < A; k++) {
-          p[k] = __fdiv_rn(ex[k], sum);
-          lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
-          psum = __fadd_rn(psum, p[k]);
-        }
-        double u = 0.0;
-        if (valid) u = a.action_noise ? a.action_noise[b] : rng_action_uniform(a.seed, gid, step0 + (unsigned long long)t);
-        const double tt = __dmul_rn(u, (double)psum);
-        float cw = p[0];
-        int i = 0;
-#pragma unroll
-        for (int k = 1; k < A; k++) {
-          if ((double)cw < tt && i == k - 1) { i = k; cw = __fadd_rn(cw, p[k]); }
-        }
-        act_i = i;
-        logprob = lp[0];
-#pragma unroll
-        for (int k = 1; k < A; k++) logprob = (i == k) ? lp[k] : logprob;
-      } else {
-        // Gaussian head (CleanRL-Python convention; the reference has none)
-        float zn[2] = {0.0f, 0.0f};
-        if (valid) {
-          if (a.action_noise) { for (int k = 0; k < A; k++) zn[k] = (float)a.action_noise[b * A + k]; }
-          else rng_action_normals(a.seed, gid, step0 + (unsigned long long)t, zn);
-        }
-        float lps = 0.0f;
-#pragma unroll
-        for (int k = 0; k < A; k++) {
-          const float mean = so[k * RE + e];
-          const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
-          const float sd = expf(logstd);
-          const float ak = __fadd_rn(mean, __fmul_rn(sd, zn[k]));
-          const float diff = __fsub_rn(ak, mean);
-          const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
-          lps = __fadd_rn(lps, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
-          if (k == 0) act_f = ak;
-          if (valid) reinterpret_cast<float*>(a.action)[b * A + k] = ak;
-        }
-        logprob = lps;
+#ifdef ROLL_TRACE
+    long long trb[12];
+    long long* tr = (blockIdx.x == 0 && t == 64 && (threadIdx.x == 0 || threadIdx.x == 160)) ? trb : nullptr;
+#else
+    long long* tr = nullptr;
+#endif
+    if (!fwd) {
+      // ---- speculation warps, in the shadow of the forward pass
+      if (warp == 9 && !a.reset_noise && used_s[e]) {
+        resets += 1;
+        prepare_reset();
+        used_s[e] = 0;
       }
-      if (valid) {
-        // Buffer.add!, ppo.jl:133-140: state = next_obs, terminal = next_done (previous step)
-        if (D == 4) {
-          reinterpret_cast<float4*>(a.state)[b] = make_float4(obs[0], obs[1], obs[2], obs[3]);
+      if (warp == 8 && !a.action_noise) {
+        if (!E::CONT) {
+          noise_d[e] = in_range ? rng_action_uniform(a.seed, gid, step0 + (unsigned long long)t) : 0.0;
         } else {
-#pragma unroll
-          for (int k = 0; k < D; k++) a.state[b * D + k] = obs[k];
+          float zn[2] = {0.0f, 0.0f};
+          if (in_range) rng_action_normals(a.seed, gid, step0 + (unsigned long long)t, zn);
+          noise_f[e] = zn[0];
+          noise_f[RE + e] = zn[1];
         }
-        if (!E::CONT) reinterpret_cast<int32_t*>(a.action)[b] = act_i;
-        a.logprob[b] = logprob;
-        a.value[b] = value;
-        a.terminal[b] = done_flag ? 1 : 0;
       }
-      // env(action), ppo.jl:130
-      float r;
-      bool dn;
-      if (ENV == CRL_ENV_CARTPOLE) cartpole_step(st, env_t, act_i, a.max_steps, r, dn);
-      else pendulum_step(st, env_t, act_f, a.max_steps, r, dn);
-      env_obs<ENV>(st, obs);  // ppo.jl:143 — copied BEFORE reset! (Q2: stale terminal obs)
-      done_flag = dn;         // ppo.jl:144
-      ep_ret += (double)r;    // ppo.jl:145
-      if (valid) {
-        a.reward[b] = r;  // ppo.jl:132
-        if (dn) {         // ppo.jl:147-165
-          const unsigned int slot = atomicAdd(&a.eb->count, 1u);
-          if (slot < (unsigned int)a.ep_capacity) {
-            crl_episode rec;
-            rec.step = t; rec.env = (int)n; rec.length = ep_len; rec._pad = 0; rec.episode_return = ep_ret;
-            a.records[slot] = rec;
+      if (CART) {
+        float s4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) s4[i] = st_s[i * RE + e];
+        cartpole_dynamics(s4, warp - 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++) spec_s[((warp - 8) * 4 + i) * RE + e] = s4[i];
+      }
+      __threadfence_block();
+      nbar_arrive(BAR_SPEC, RE + 64);
+    } else {
+      forward32<ENV>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
+      if (owner) {
+        if (rec_pending) {   // last step's episode record: its slot has long arrived
+          if (rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
+          rec_pending = false;
+        }
+        const long long b = (long long)t * a.N + n;
+        ep_len += 1;  // ppo.jl:125
+        const float value = so[A * RE + e];
+        float logprob;
+        int act_i = 0;
+        float act_f = 0.0f;
+        if (!E::CONT) {
+          // get_action, ppo.jl:22-29: softmax / logsoftmax [NNlib], then
+          // StatsBase.sample(Weights(p)): t = rand()*sum(p); walk cw += p[i] while cw < t.
+          float z[A], p[A], lp[A];
+#pragma unroll
+          for (int k = 0; k < A; k++) z[k] = so[k * RE + e];
+          float m = z[0];
+#pragma unroll
+          for (int k = 1; k < A; k++) m = fmaxf(m, z[k]);
+          float ex[A], sum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
+          const float ls = logf(sum);
+          float psum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            p[k] = __fdiv_rn(ex[k], sum);
+            lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
+            psum = __fadd_rn(psum, p[k]);
           }
-          agg_n += 1; agg_ret += ep_ret; agg_len += (double)ep_len; agg_max = fmax(agg_max, ep_ret);
-          ep_ret = 0.0;
-          ep_len = 0;
-          float u4[4];
-          if (a.reset_noise) {
-            const float4 v = reinterpret_cast<const float4*>(a.reset_noise)[b];
-            u4[0] = v.x; u4[1] = v.y; u4[2] = v.z; u4[3] = v.w;
+          nbar_sync(BAR_SPEC, RE + 64);   // the speculation warps have delivered this step
+          double u = 0.0;
+          if (valid) u = a.action_noise ? a.action_noise[b] : noise_d[e];
+          const double tt = __dmul_rn(u, (double)psum);
+          float cw = p[0];
+          int i = 0;
+#pragma unroll
+          for (int k = 1; k < A; k++) {
+            if ((double)cw < tt && i == k - 1) { i = k; cw = __fadd_rn(cw, p[k]); }
+          }
+          act_i = i;
+          logprob = lp[0];
+#pragma unroll
+          for (int k = 1; k < A; k++) logprob = (i == k) ? lp[k] : logprob;
+        } else {
+          // Gaussian head (CleanRL-Python convention; the reference has none)
+          nbar_sync(BAR_SPEC, RE + 64);
+          float zn[2] = {0.0f, 0.0f};
+          if (valid) {
+            if (a.action_noise) { for (int k = 0; k < A; k++) zn[k] = (float)a.action_noise[b * A + k]; }
+            else { zn[0] = noise_f[e]; zn[1] = noise_f[RE + e]; }
+          }
+          float lps = 0.0f;
+#pragma unroll
+          for (int k = 0; k < A; k++) {
+            const float mean = so[k * RE + e];
+            const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
+            const float sd = expf(logstd);
+            const float ak = __fadd_rn(mean, __fmul_rn(sd, zn[k]));
+            const float diff = __fsub_rn(ak, mean);
+            const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+            lps = __fadd_rn(lps, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
+            if (k == 0) act_f = ak;
+            if (valid) reinterpret_cast<float*>(a.action)[b * A + k] = ak;
+          }
+          logprob = lps;
+        }
+        if (valid) {
+          // Buffer.add!, ppo.jl:133-140: state = next_obs, terminal = next_done (previous step)
+          if (D == 4) {
+            reinterpret_cast<float4*>(a.state)[b] = make_float4(obs[0], obs[1], obs[2], obs[3]);
           } else {
-            rng_reset_uniforms(a.seed, gid, resets, u4);
-          }
-          resets += 1;
-          env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
-          if (a.fresh_obs_after_reset) env_obs<ENV>(st, obs);  // a2c.jl:108 then :52 (PPO: stale obs, Q2)
-        }
-      }
 #pragma unroll
-      for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
+            for (int k = 0; k < D; k++) a.state[b * D + k] = obs[k];
+          }
+          if (!E::CONT) reinterpret_cast<int32_t*>(a.action)[b] = act_i;
+          a.logprob[b] = logprob;
+          a.value[b] = value;
+          a.terminal[b] = done_flag ? 1 : 0;
+        }
+        RTR(7);
+        // env(action), ppo.jl:130
+        float r;
+        bool dn;
+        if (CART) {
+          // the successor computed by warp 8 + act_i from this very state: cartpole_step without the wait
+#pragma unroll
+          for (int i = 0; i < 4; i++) st[i] = spec_s[(act_i * 4 + i) * RE + e];
+          env_t += 1;
+          cartpole_outcome(st, env_t, a.max_steps, r, dn);
+        } else {
+          pendulum_step(st, env_t, act_f, a.max_steps, r, dn);
+        }
+        env_obs<ENV>(st, obs);  // ppo.jl:143 — copied BEFORE reset! (Q2: stale terminal obs)
+        done_flag = dn;         // ppo.jl:144
+        ep_ret += (double)r;    // ppo.jl:145
+        if (valid) {
+          a.reward[b] = r;  // ppo.jl:132
+          if (dn) {         // ppo.jl:147-165
+            rec_slot = atomicAdd(&a.eb->count, 1u);
+            rec_pending = true;
+            rec.step = t; rec.env = (int)n; rec.length = ep_len; rec._pad = 0; rec.episode_return = ep_ret;
+            agg_n += 1; agg_ret += ep_ret; agg_len += (double)ep_len; agg_max = fmax(agg_max, ep_ret);
+            ep_ret = 0.0;
+            ep_len = 0;
+            if (a.reset_noise) {
+              const float4 v = reinterpret_cast<const float4*>(a.reset_noise)[b];
+              const float u4[4] = {v.x, v.y, v.z, v.w};
+              env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
+            } else {
+#pragma unroll
+              for (int i = 0; i < S; i++) st[i] = rst_s[i * RE + e];   // prepared by warp 9 for this reset counter
+              env_t = 0;
+              used_s[e] = 1;
+            }
+            resets += 1;
+            if (a.fresh_obs_after_reset) env_obs<ENV>(st, obs);  // a2c.jl:108 then :52 (PPO: stale obs, Q2)
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
+#pragma unroll
+        for (int i = 0; i < S; i++) st_s[i * RE + e] = st[i];
+      }
+      RTR(8);
     }
     __syncthreads();
+#ifdef ROLL_TRACE
+    if (tr) {
+      tr[9] = clock64();
+      printf("rollout warp %d: L1 %lld | bar %lld | L2 %lld | bar %lld | head %lld | bar %lld | sample+store %lld | env %lld | bar %lld | total %lld\n",
+             (int)(threadIdx.x >> 5), tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5],
+             threadIdx.x == 0 ? tr[7] - tr[6] : 0ll, threadIdx.x == 0 ? tr[8] - tr[7] : 0ll, tr[9] - tr[8], tr[9] - tr[0]);
+    }
+#endif
   }
+  if (!fwd) return;   // the speculation warps are done; only named barriers among the forward threads follow
+
+  if (owner && rec_pending && rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
 
   // Bootstrap value for GAE: next_values = critic(state(env)) with the refreshed (post-reset)
   // observation, ppo.jl:169-171. The weights cannot change between here and crl_gae.
@@ -246,8 +391,8 @@ __global__ void __launch_bounds__(CRL_THREADS) rollout_kernel(RolloutArgs a) {
 #pragma unroll
     for (int k = 0; k < D; k++) xs[k * SP + e] = fresh[k];
   }
-  __syncthreads();
-  forward32<ENV>(tc, smem);
+  nbar_sync(BAR_FWD, ROLL_FWD);
+  forward32<ENV>(tc, smem, hr);
   if (valid) {
     a.next_value[n] = so[A * RE + e];
 #pragma unroll
@@ -324,7 +469,9 @@ __global__ void __launch_bounds__(CRL_THREADS) policy_forward_raw_kernel(const f
     for (int k = 0; k < D; k++) xs[k * SP + e] = i < n ? obs[i * D + k] : 0.0f;
   }
   __syncthreads();
-  forward32<ENV>(tc, smem);
+  HeadRow<ENV> hr;
+  load_head_row<ENV>(smem + SM::PARAMS, hr);
+  forward32<ENV>(tc, smem, hr);
   if (e < RE && i < n) {
     float z[A];
 #pragma unroll
@@ -346,7 +493,7 @@ __global__ void __launch_bounds__(CRL_THREADS) policy_forward_raw_kernel(const f
 
 template <int ENV> cudaError_t launch_rollout_t(const RolloutArgs& a, cudaStream_t s) {
   const int grid = (a.N + RE - 1) / RE;
-  rollout_kernel<ENV><<<grid, CRL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
+  rollout_kernel<ENV><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 
