@@ -210,6 +210,33 @@ template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float
 }
 
 // ---------------------------------------------------------------- packed FP32 helpers (f2, f2s, tanh_fast2: device_math.cuh)
+// tanh_fast for this kernel: the same rational function, but (a) the argument is clamped to +-sqrt(66) instead of the
+// result being replaced by +-1 beyond it (the rational is 1 - 1.2e-7 there; 4 min/max on the ALU pipe instead of 2
+// compares + 2 selects + 2 sign copies) and (b) the reciprocal is MUFU.RCP without the Newton step (<= 1 ulp). Both are
+// below the 3xTF32 error of the contractions around it (1.2e-6); the rollout and the FFMA kernel keep the exact form.
+// A tanh_fast2 call costs ~35 issue cycles per warp (tools/pipe_probe.cu), 32 calls per thread and tile.
+#ifndef TC_TANH_EXACT
+#define TC_TANH_EXACT 0
+#endif
+__device__ __forceinline__ float2 tanh_upd2(float2 x) {
+  if (TC_TANH_EXACT) return tanh_fast2(x);
+  const float lim = 8.1240384f;   // sqrt(66)
+  x.x = fminf(fmaxf(x.x, -lim), lim);
+  x.y = fminf(fmaxf(x.y, -lim), lim);
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 n = __ffma2_rn(x2, f2s(1.587199e-8f), f2s(2.2332108e-5f));
+  n = __ffma2_rn(x2, n, f2s(0.0035974074f));
+  n = __ffma2_rn(x2, n, f2s(0.1346604f));
+  n = __ffma2_rn(x2, n, f2s(1.0f));
+  float2 d = __ffma2_rn(x2, f2s(8.7767893e-7f), f2s(0.0003453992f));
+  d = __ffma2_rn(x2, d, f2s(0.026262015f));
+  d = __ffma2_rn(x2, d, f2s(0.4679937f));
+  d = __ffma2_rn(x2, d, f2s(1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, __fmul2_rn(n, r));
+}
 // x = hi + lo with hi = TF32(x) (see tf32_hi), two values at once
 __device__ __forceinline__ void split2(float2 v, float2& hi, float2& lo) {
   hi = f2(tf32_hi(v.x), tf32_hi(v.y));
@@ -417,7 +444,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       acc = __ffma2_rn(f2(wa.z, wa.w), xb[1], acc);
       acc = __ffma2_rn(f2(wc.x, wc.y), xb[2], acc);
       if (D == 4) acc = __ffma2_rn(f2(wc.z, wc.w), xb[3], acc);
-      h[i] = tanh_fast2(__fadd2_rn(acc, b1q[p0 + i]));
+      h[i] = tanh_upd2(__fadd2_rn(acc, b1q[p0 + i]));
     }
   };
   // hi/lo of 32 values: TMEM columns (A operand of G1/G3) and rows f0.. / 64+f0.. of a feature-major operand buffer
@@ -518,7 +545,7 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
         for (int o = 0; o < NOUT; o++) part[o] = f2s(0.0f);
 #pragma unroll
         for (int i = 0; i < TC_FG / 2; i++) {
-          h2[i] = tanh_fast2(__fadd2_rn(__fadd2_rn(f2(z2[2 * i], z2[2 * i + 1]), f2(z2b[2 * i], z2b[2 * i + 1])), b2q[p0 + i]));
+          h2[i] = tanh_upd2(__fadd2_rn(__fadd2_rn(f2(z2[2 * i], z2[2 * i + 1]), f2(z2b[2 * i], z2b[2 * i + 1])), b2q[p0 + i]));
 #pragma unroll
           for (int o = 0; o < NOUT; o++) part[o] = __ffma2_rn(w3q[o * (CRL_H / 2) + p0 + i], h2[i], part[o]);
         }
