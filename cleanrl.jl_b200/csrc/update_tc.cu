@@ -501,20 +501,20 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
       float h1h[TC_FG], h1l[TC_FG];
       TR(1);
       split_to_tmem(h1, h1h, h1l);
-      if (TC_PARK) {
+      tmem_st_wait();
+      tc_fence_before();
+      TR(2);
+      handover(BAR_G1, issue_g1);
+      TR(3);
+      if (TC_PARK) {   // not an operand of G1: stored in its shadow (the previous tile's E3 has read its copy: program order)
         float dt[TC_FG];
 #pragma unroll
         for (int i = 0; i < TC_FG / 2; i++) {
           const float2 d = __ffma2_rn(h1[i], h1[i], f2s(-1.0f));
           dt[2 * i] = d.x; dt[2 * i + 1] = d.y;
         }
-        tmem_st_n<TC_FG>(lane_addr + COL_P + f0, dt);   // the previous tile's E3 has read its copy (program order)
+        tmem_st_n<TC_FG>(lane_addr + COL_P + f0, dt);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      TR(2);
-      handover(BAR_G1, issue_g1);
-      TR(3);
       // ---- in the shadow of G1: the shared-memory half (h1^T is the B operand of G2; x~^T), then part of the next
       //      tile's first layer (the rest follows G3 and G4)
       if (it > 0) mbar_wait(bar4, ph ^ 1);  // the previous tile's G4 has read dz1^T (same buffer as h1^T) and x~^T
