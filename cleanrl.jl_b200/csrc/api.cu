@@ -650,7 +650,11 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
   ua.no_vclip = (c->cfg.flags & CRL_FLAG_NO_VCLIP) ? 1 : 0;
   ua.tc_net_a = c->L.critic - c->L.actor; ua.tc_net_c = (c->L.continuous ? c->L.logstd : c->L.P) - c->L.critic;
   ua.values_fresh = spec ? 1 : 0;       // throughput path: the rollout that filled `value` used the current parameters
-  loss_grad_tc_plan(&ua, c->sm_count);  // tensor-core kernel when it applies: sets grid_loss / tc_actor_ctas
+  // Fused tail: the tcgen05 kernel reduces, exchanges and applies clip + Adam itself (one cooperative launch per
+  // minibatch). Needs the peer-memory exchange when there are several ranks; CRL_NO_FUSED_TAIL=1 keeps the 3-kernel chain.
+  static const bool fuse_off = getenv("CRL_NO_FUSED_TAIL") != nullptr;
+  const bool want_fuse = (spec || ua.algo == 1) && !fuse_off && (!multi || c->p2p_on);
+  loss_grad_tc_plan(&ua, c->sm_count, want_fuse);  // tensor-core kernel when it applies: sets grid_loss / tc_actor_ctas
   AdamArgs aa = adam_args(c, M, lr_host, stats_slot);
   if (spec || ua.algo == 1) {  // the A2C losses have no minibatch-global scalars: the 3-kernel chain is already exact
     const bool p2p = multi && c->p2p_on;
@@ -660,10 +664,7 @@ static int enqueue_minibatch(crl_ctx* c, const IdxSrc& ix, int M, double lr_host
       ua.p2p_peers = c->p2p_peers_dev; ua.p2p_flags_off = c->p2p_flags_off; ua.p2p_count = c->p2p_count;
     }
     aa.M_global = (double)M * W; aa.world = W; aa.verify = 1;
-    // Fused tail: the tcgen05 kernel reduces, exchanges and applies clip + Adam itself (one cooperative launch per
-    // minibatch). Needs the peer-memory exchange when there are several ranks; CRL_NO_FUSED_TAIL=1 keeps the 3-kernel chain.
-    static const bool fuse_off = getenv("CRL_NO_FUSED_TAIL") != nullptr;
-    if (ua.tc_actor_ctas > 0 && !fuse_off && (!multi || p2p) && ua.grid_loss <= c->sm_count &&
+    if (ua.tc_actor_ctas > 0 && want_fuse && ua.grid_loss <= c->sm_count &&
         (c->fused_grid == 0 || c->fused_grid == ua.grid_loss)) {
       c->fused_grid = ua.grid_loss;
       ua.fuse_tail = 1;

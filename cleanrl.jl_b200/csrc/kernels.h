@@ -211,7 +211,9 @@ cudaError_t launch_mb_count(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_loss_grad(const UpdateArgs& a, cudaStream_t s);
 // tensor-core variant: loss_grad_tc_plan decides whether it applies and sets grid_loss / tc_actor_ctas
 cudaError_t kernels_init_update_tc();
-int loss_grad_tc_plan(UpdateArgs* a, int sm_count);
+// full_grid: one CTA per SM even when the minibatch has fewer tiles (the fused tail's reduce + Adam work is spread over the
+// grid: with the two CTAs a 32-sample minibatch needs, the tail alone took 100 us)
+int loss_grad_tc_plan(UpdateArgs* a, int sm_count, bool full_grid = false);
 cudaError_t launch_loss_grad_tc(const UpdateArgs& a, cudaStream_t s);
 cudaError_t launch_grad_reduce(const UpdateArgs& a, int P, cudaStream_t s);
 cudaError_t launch_clip_adam(const AdamArgs& a, cudaStream_t s);

@@ -72,7 +72,9 @@ template <int ENV> __device__ __forceinline__ void load_head_row(const float* sp
 
 // both nets forward for the 32 samples whose observations sit in xs; heads -> so[o][e]
 // (o < A: actor logits/mean, o == A: critic value). Called by the 256 forward threads only (named barrier BAR_FWD).
-template <int ENV>
+// HEADREG = false: the output layer reads its weights from shared memory (64 registers fewer: two CTAs per SM when the
+// grid is larger than the GPU)
+template <int ENV, bool HEADREG = true>
 __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc, float* smem, const HeadRow<ENV>& hr,
                                           long long* tr = nullptr) {
   using G = TileGeom<4, 2>;
@@ -102,9 +104,22 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
 #pragma unroll
     for (int k = 0; k < CRL_H; k++) hv[k] = hrow[k * SP];   // all 64 loads in flight before the (serial) chain starts
     float acc = 0.0f;
+    if (HEADREG) {
 #pragma unroll
-    for (int k = 0; k < CRL_H; k++) acc = fmaf(hr.w[k], hv[k], acc);
-    so[o * RE + e] = acc + hr.b;
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(hr.w[k], hv[k], acc);
+      acc += hr.b;
+    } else if (o < E::A) {
+      const float* a = sp + SmemParams<ENV>::ACTOR;
+#pragma unroll
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(a[NetOff<E::D, E::A>::W3 + k * E::A + o], hv[k], acc);
+      acc += a[NetOff<E::D, E::A>::B3 + o];
+    } else {
+      const float* c = sp + SmemParams<ENV>::CRITIC;
+#pragma unroll
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(c[NetOff<E::D, 1>::W3 + k], hv[k], acc);
+      acc += c[NetOff<E::D, 1>::B3];
+    }
+    so[o * RE + e] = acc;
   }
   RTR(5);
   nbar_sync(BAR_FWD, ROLL_FWD);
@@ -120,8 +135,9 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
 //            (Philox keyed by the env's reset counter), refreshed after warp 0 consumed it
 // Warp 0 picks the successor of the action it sampled (same device function, same inputs: bit-identical to stepping
 // after the fact). The injected-noise test modes (action_noise / reset_noise) read their draws on warp 0 as before.
-template <int ENV>
-__global__ void __launch_bounds__(ROLL_THREADS) rollout_kernel(RolloutArgs a) {
+// BIG = true: more CTAs than SMs (N / 32 > SM count): compiled for two resident CTAs per SM.
+template <int ENV, bool BIG>
+__global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(RolloutArgs a) {
   using G = TileGeom<4, 2>;
   using E = EnvTraits<ENV>;
   using SM = RolloutSmem<ENV>;
@@ -183,7 +199,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) rollout_kernel(RolloutArgs a) {
   }
   __syncthreads();
   HeadRow<ENV> hr;
-  load_head_row<ENV>(sp, hr);
+  if (!BIG) load_head_row<ENV>(sp, hr);
   if (owner) {
     env_obs<ENV>(st, obs);  // Q3: ppo.jl:169 — state(env) refreshed (post-reset state)
 #pragma unroll
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) rollout_kernel(RolloutArgs a) {
       __threadfence_block();
       nbar_arrive(BAR_SPEC, RE + 64);
     } else {
-      forward32<ENV>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
+      forward32<ENV, !BIG>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
       if (owner) {
         if (rec_pending) {   // last step's episode record: its slot has long arrived
           if (rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) rollout_kernel(RolloutArgs a) {
     for (int k = 0; k < D; k++) xs[k * SP + e] = fresh[k];
   }
   nbar_sync(BAR_FWD, ROLL_FWD);
-  forward32<ENV>(tc, smem, hr);
+  forward32<ENV, !BIG>(tc, smem, hr);
   if (valid) {
     a.next_value[n] = so[A * RE + e];
 #pragma unroll
@@ -493,7 +509,14 @@ __global__ void __launch_bounds__(CRL_THREADS) policy_forward_raw_kernel(const f
 
 template <int ENV> cudaError_t launch_rollout_t(const RolloutArgs& a, cudaStream_t s) {
   const int grid = (a.N + RE - 1) / RE;
-  rollout_kernel<ENV><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (grid > sms) rollout_kernel<ENV, true><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
+  else rollout_kernel<ENV, false><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -513,8 +536,10 @@ __global__ void episode_buf_init_kernel(EpisodeBuf* eb) {
 }
 
 template <int ENV> cudaError_t init_attrs_t() {
-  cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)RolloutSmem<ENV>::BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(rollout_kernel<ENV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RolloutSmem<ENV>::BYTES);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(policy_forward_raw_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)RolloutSmem<ENV>::BYTES);

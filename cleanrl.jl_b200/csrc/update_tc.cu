@@ -1215,7 +1215,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(const __gri
   const uint32_t tmem = tmem_base_s;
   // this net's four weight images: one elected thread, bulk asynchronous copies completed on an mbarrier
   const uint32_t pbar = smem_u32(&bars.pbar);
-  if (tid == 0) {
+  // (a CTA without tiles -- full grid for the fused tail, small minibatch -- only zero-fills its partials: no images)
+  const bool cta_has_tiles = (net == 0 ? (int)blockIdx.x : (int)blockIdx.x - a.tc_actor_ctas) < (a.M + TC_S - 1) / TC_S;
+  if (tid == 0 && cta_has_tiles) {
     constexpr uint32_t BYTES = 4 * TC_W_FLOATS * 4, CHUNK = 16384;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbar), "r"(BYTES) : "memory");
     const char* src = reinterpret_cast<const char*>(a.image + TcImage<ENV>::BASE + net * TcImage<ENV>::NET_FLOATS);
@@ -1224,7 +1226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loss_grad_tc_kernel(const __gri
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(dst + off), "l"(src + off), "r"(CHUNK), "r"(pbar) : "memory");
   }
-  mbar_wait(pbar, 0);
+  if (cta_has_tiles) mbar_wait(pbar, 0);
 #ifdef TC_TRACE
   const long long k_t1 = clock64();
 #endif
@@ -1255,7 +1257,7 @@ cudaError_t kernels_init_update_tc() {
 #ifndef TC_ACTOR_COST
 #define TC_ACTOR_COST 1.15
 #endif
-int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
+int loss_grad_tc_plan(UpdateArgs* a, int sm_count, bool full_grid) {
   static int disabled = -1, actor_share = -1;
   if (disabled < 0) {
     const char* e = getenv("CRL_NO_TC");
@@ -1268,7 +1270,7 @@ int loss_grad_tc_plan(UpdateArgs* a, int sm_count) {
   // are that output (values_fresh) can the one-net-per-CTA kernel be used
   if (disabled || !a->image || (a->algo == 1 && !a->values_fresh)) return 0;
   const int n_tiles = (a->M + TC_S - 1) / TC_S;
-  int grid = 2 * n_tiles < sm_count ? 2 * n_tiles : sm_count;
+  int grid = (2 * n_tiles < sm_count && !full_grid) ? 2 * n_tiles : sm_count;
   grid &= ~1;
   if (grid < 2) grid = 2;
   // An actor tile (two heads, softmax, entropy) costs TC_ACTOR_COST x a critic tile (clock stamps of the -DTC_TRACE
