@@ -16,6 +16,8 @@ namespace {
 constexpr int RE = 32;            // envs per CTA
 constexpr int ROLL_FWD = CRL_THREADS;   // warps 0-7: the two MLPs; warp 0 also owns the envs (one lane per env)
 constexpr int ROLL_THREADS = ROLL_FWD + 64;   // warps 8, 9: speculation warps (see rollout_kernel)
+// grids larger than the GPU (BIG): 4 forward warps with 8 x 4 register tiles (see fwd_layer_8x4), 2 CTAs per SM
+constexpr int BIG_FWD = 128, BIG_THREADS = BIG_FWD + 64;
 constexpr int BAR_FWD = 1, BAR_SPEC = 2;      // named barriers: the 256 forward threads / speculation warps -> warp 0
 
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -126,6 +128,116 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
   RTR(6);
 }
 
+// The layers for grids larger than the GPU, where the rollout is bound by throughput and not by the latency of one
+// step: 128 forward threads, thread (q, p) owns the 8 neurons 8q.. of net q / 8 and the 4 envs 4p.. (an 8 x 4 register
+// tile: per k two 128-bit weight loads and one 128-bit activation load feed 16 packed FMAs, 1.5 B of shared-memory
+// traffic per FMA instead of the 4 x 4 tile's 2 B; the shared-memory crossbar is what bounds these layers,
+// profiles/r2_pipe_probe.txt). A warp is 4 q x 8 p with the 8 lanes of a quarter-warp on one q: its weight loads are
+// one broadcast address, its activation loads and its stores 128 contiguous bytes. At 4096 envs (one CTA per SM,
+// latency-bound) this variant is SLOWER than 4 x 4 tiles on 8 warps (0.541 vs 0.473 ms) and is not used there.
+// Every accumulator is one fma chain over ascending k, as in tile_layer: same bits.
+struct FwdCoord8x4 {
+  int q, p, net, nb;   // neuron group, sample group, net, first neuron within the net
+  __device__ FwdCoord8x4() {
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 3;
+    q = w * 4 + (lane >> 3);
+    p = lane & 7;
+    net = q >> 3;
+    nb = 8 * (q & 7);
+  }
+};
+template <int K>
+__device__ __forceinline__ void fwd_layer_8x4(const FwdCoord8x4& fc, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                              const float* __restrict__ in, float* __restrict__ out) {
+  constexpr int SP = RE + 4, PF = 2;
+  const float* wp = Wt + fc.nb;
+  const float* ap = in + 4 * fc.p;
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + fc.nb), b1 = *reinterpret_cast<const float4*>(bias + fc.nb + 4);
+  float2 acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = make_float2(0.0f, 0.0f);
+  float4 w0[PF], w1[PF], av[PF];
+#pragma unroll
+  for (int i = 0; i < PF; i++) {
+    if (i < K) {
+      w0[i] = *reinterpret_cast<const float4*>(wp + i * CRL_H);
+      w1[i] = *reinterpret_cast<const float4*>(wp + i * CRL_H + 4);
+      av[i] = *reinterpret_cast<const float4*>(ap + i * SP);
+    }
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += PF) {
+    float4 w0n[PF], w1n[PF], avn[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      if (k0 + PF + i < K) {
+        w0n[i] = *reinterpret_cast<const float4*>(wp + (k0 + PF + i) * CRL_H);
+        w1n[i] = *reinterpret_cast<const float4*>(wp + (k0 + PF + i) * CRL_H + 4);
+        avn[i] = *reinterpret_cast<const float4*>(ap + (k0 + PF + i) * SP);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      if (k0 + i < K) {
+        const float2 a01 = make_float2(av[i].x, av[i].y), a23 = make_float2(av[i].z, av[i].w);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float wj = j < 4 ? f4_get(w0[i], j) : f4_get(w1[i], j - 4);
+          const float2 ww = make_float2(wj, wj);
+          acc[j][0] = __ffma2_rn(ww, a01, acc[j][0]);
+          acc[j][1] = __ffma2_rn(ww, a23, acc[j][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) { w0[i] = w0n[i]; w1[i] = w1n[i]; av[i] = avn[i]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float b = j < 4 ? f4_get(b0, j) : f4_get(b1, j - 4);
+    const float2 t0 = tanh_fast2(__fadd2_rn(acc[j][0], make_float2(b, b)));
+    const float2 t1 = tanh_fast2(__fadd2_rn(acc[j][1], make_float2(b, b)));
+    *reinterpret_cast<float4*>(out + (fc.nb + j) * SP + 4 * fc.p) = make_float4(t0.x, t0.y, t1.x, t1.y);
+  }
+}
+// forward32 for the BIG variant (output layer weights from shared memory)
+template <int ENV>
+__device__ __forceinline__ void forward32_big(const FwdCoord8x4& fc, float* smem) {
+  using E = EnvTraits<ENV>;
+  using SM = RolloutSmem<ENV>;
+  constexpr int SP = RE + 4;
+  static_assert(SP == TileGeom<4, 2>::S_PAD, "both forward variants share one activation layout");
+  float* sp = smem + SM::PARAMS;
+  float* xs = smem + SM::X;
+  float* h1 = smem + SM::H1;
+  float* h2 = smem + SM::H2;
+  float* so = smem + SM::OUT;
+  const float* np = sp + net_base<ENV>(fc.net);
+  using NO = NetOff<E::D, 1>;
+  fwd_layer_8x4<E::D>(fc, np + NO::W1, np + NO::B1, xs, h1 + fc.net * CRL_H * SP);
+  nbar_sync(BAR_FWD, BIG_FWD);
+  fwd_layer_8x4<CRL_H>(fc, np + NO::W2, np + NO::B2, h1 + fc.net * CRL_H * SP, h2 + fc.net * CRL_H * SP);
+  nbar_sync(BAR_FWD, BIG_FWD);
+  if (threadIdx.x < RE * (E::A + 1)) {
+    const int o = threadIdx.x / RE, e = threadIdx.x % RE;
+    const float* hrow = h2 + (o < E::A ? 0 : CRL_H) * SP + e;
+    float acc = 0.0f;
+    if (o < E::A) {
+      const float* a = sp + SmemParams<ENV>::ACTOR;
+#pragma unroll 16
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(a[NetOff<E::D, E::A>::W3 + k * E::A + o], hrow[k * SP], acc);
+      acc += a[NetOff<E::D, E::A>::B3 + o];
+    } else {
+      const float* c = sp + SmemParams<ENV>::CRITIC;
+#pragma unroll 16
+      for (int k = 0; k < CRL_H; k++) acc = fmaf(c[NetOff<E::D, 1>::W3 + k], hrow[k * SP], acc);
+      acc += c[NetOff<E::D, 1>::B3];
+    }
+    so[o * RE + e] = acc;
+  }
+  nbar_sync(BAR_FWD, BIG_FWD);
+}
+
 // Persistent rollout. Warps 0-7 evaluate the two MLPs for the CTA's 32 envs; warp 0 (one lane per env) then samples,
 // records and advances its env. Everything that does not depend on the sampled action is taken off that serial
 // phase by two extra warps that work in the shadow of the forward pass:
@@ -135,9 +247,11 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
 //            (Philox keyed by the env's reset counter), refreshed after warp 0 consumed it
 // Warp 0 picks the successor of the action it sampled (same device function, same inputs: bit-identical to stepping
 // after the fact). The injected-noise test modes (action_noise / reset_noise) read their draws on warp 0 as before.
-// BIG = true: more CTAs than SMs (N / 32 > SM count): compiled for two resident CTAs per SM.
+// BIG = true: more CTAs than SMs (N / 32 > SM count): 4 forward warps with 8 x 4 tiles, two resident CTAs per SM (shared memory: 77 KB each).
 template <int ENV, bool BIG>
-__global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(RolloutArgs a) {
+__global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(RolloutArgs a) {
+  constexpr int FWD = BIG ? BIG_FWD : ROLL_FWD;   // forward threads; the two speculation warps follow them
+  constexpr int SW0 = FWD / 32;
   using G = TileGeom<4, 2>;
   using E = EnvTraits<ENV>;
   using SM = RolloutSmem<ENV>;
@@ -155,6 +269,7 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
   float* noise_f = smem + SM::NOISE;
   int* used_s = reinterpret_cast<int*>(smem + SM::USED);
   const ThreadCoord<G> tc;
+  const FwdCoord8x4 fc;
 
   load_params<ENV>(a.params, sp);
   for (int i = threadIdx.x; i < CRL_MAXD * SP; i += blockDim.x) xs[i] = 0.0f;
@@ -162,7 +277,7 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
   const int warp = threadIdx.x >> 5;
   const int e = threadIdx.x & 31;  // env lane of warps 0, 8 and 9
   const long long n = (long long)blockIdx.x * RE + e;
-  const bool fwd = threadIdx.x < ROLL_FWD;
+  const bool fwd = threadIdx.x < FWD;
   const bool owner = threadIdx.x < RE;
   const bool in_range = n < a.N;
   const bool valid = owner && in_range;
@@ -195,7 +310,7 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
   } else {
 #pragma unroll
     for (int i = 0; i < S; i++) st[i] = 0.0f;
-    if (warp == 9 && in_range) resets = a.reset_count[n];
+    if (warp == SW0 + 1 && in_range) resets = a.reset_count[n];
   }
   __syncthreads();
   HeadRow<ENV> hr;
@@ -216,7 +331,7 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
 #pragma unroll
     for (int i = 0; i < S; i++) rst_s[i * RE + e] = rs[i];
   };
-  if (warp == 9 && !a.reset_noise) prepare_reset();
+  if (warp == SW0 + 1 && !a.reset_noise) prepare_reset();
   __syncthreads();
 
   for (int t = 0; t < a.T; t++) {
@@ -228,12 +343,12 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
 #endif
     if (!fwd) {
       // ---- speculation warps, in the shadow of the forward pass
-      if (warp == 9 && !a.reset_noise && used_s[e]) {
+      if (warp == SW0 + 1 && !a.reset_noise && used_s[e]) {
         resets += 1;
         prepare_reset();
         used_s[e] = 0;
       }
-      if (warp == 8 && !a.action_noise) {
+      if (warp == SW0 && !a.action_noise) {
         if (!E::CONT) {
           noise_d[e] = in_range ? rng_action_uniform(a.seed, gid, step0 + (unsigned long long)t) : 0.0;
         } else {
@@ -247,14 +362,14 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
         float s4[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) s4[i] = st_s[i * RE + e];
-        cartpole_dynamics(s4, warp - 8);
+        cartpole_dynamics(s4, warp - SW0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) spec_s[((warp - 8) * 4 + i) * RE + e] = s4[i];
+        for (int i = 0; i < 4; i++) spec_s[((warp - SW0) * 4 + i) * RE + e] = s4[i];
       }
       __threadfence_block();
       nbar_arrive(BAR_SPEC, RE + 64);
     } else {
-      forward32<ENV, !BIG>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
+      if (BIG) forward32_big<ENV>(fc, smem); else forward32<ENV, true>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
       if (owner) {
         if (rec_pending) {   // last step's episode record: its slot has long arrived
           if (rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
@@ -407,8 +522,8 @@ __global__ void __launch_bounds__(ROLL_THREADS, BIG ? 2 : 1) rollout_kernel(Roll
 #pragma unroll
     for (int k = 0; k < D; k++) xs[k * SP + e] = fresh[k];
   }
-  nbar_sync(BAR_FWD, ROLL_FWD);
-  forward32<ENV, !BIG>(tc, smem, hr);
+  nbar_sync(BAR_FWD, FWD);
+  if (BIG) forward32_big<ENV>(fc, smem); else forward32<ENV, true>(tc, smem, hr);
   if (valid) {
     a.next_value[n] = so[A * RE + e];
 #pragma unroll
@@ -515,7 +630,7 @@ template <int ENV> cudaError_t launch_rollout_t(const RolloutArgs& a, cudaStream
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (grid > sms) rollout_kernel<ENV, true><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
+  if (grid > sms) rollout_kernel<ENV, true><<<grid, BIG_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
   else rollout_kernel<ENV, false><<<grid, ROLL_THREADS, RolloutSmem<ENV>::BYTES, s>>>(a);
   return cudaGetLastError();
 }

@@ -414,6 +414,27 @@ def test_train_update_graph_matches_oracle(crl, olib, abi, torch_cuda, kind):
     h.close()
 
 
+def test_default_config_shape_matches_oracle(crl, olib, abi, torch_cuda):
+    """BASELINE.json configs[0]: PPOConfig() defaults (ppo.jl:2-6): 4 envs x 32 steps, 4 epochs x 4 minibatches of 32
+    samples. One 128-sample tile holds a whole minibatch, so 146 of the update kernel's 148 CTAs have no tile and only
+    take part in the fused tail (reduce, clip, Adam on their slab)."""
+    N, T = 4, 32
+    h, o = make_pair(crl, olib, abi, 0, N=N, T=T, mb=4, epochs=4, seed=1)
+    h.env_reset(); o.env_reset()
+    for u in range(4):
+        lr = float(F(2.5e-4)) * (1 - u / 10)
+        h.train_update(lr)
+        sh, agg = h.fetch_update()
+        so = o.train_update(lr)
+        np.testing.assert_allclose(sh, so, rtol=5e-4, atol=1e-5, err_msg="update %d" % u)
+        np.testing.assert_array_equal(h.read_field(abi.CRL_F_TERMINAL), o.read_field(abi.CRL_F_TERMINAL))
+        np.testing.assert_array_equal(h.read_field(abi.CRL_F_ACTION), o.read_field(abi.CRL_F_ACTION))
+        np.testing.assert_allclose(h.get_params(), o.get_params(), rtol=1e-4, atol=2e-6)
+    assert h.kernel_launches() >= 4 * (4 + 16)   # one fused launch per minibatch
+    assert h.spec_replays() == 0
+    h.close()
+
+
 def test_failed_speculation_is_replayed_exactly(crl, olib, abi, torch_cuda):
     """gamma = lambda = 0 with a critic bias of 1.5: returns are in {0, 1, v}, so the scalar s = mean(v - R^2) of the
     value loss (Q5) exceeds min (clip - R)^2 = 0 and the speculative update fails its on-device verification. The
