@@ -51,7 +51,8 @@ static_assert(DQ_H2 % 4 == 0 && DQ_H1 % 4 == 0 && DQ_W2 % 4 == 0, "128-bit weigh
 constexpr uint32_t STREAM_DQN_ACT = 3u, STREAM_DQN_BATCH = 4u;
 constexpr int ACT_E = 32;           // envs per CTA in dqn_act_kernel
 constexpr int ACT_SP = ACT_E + 4;   // activation row stride (floats): rows stay 16-byte aligned
-constexpr int ACT_T = 256;
+constexpr int ACT_T = 256;          // forward threads of dqn_act_kernel; two speculation warps follow them
+constexpr int ACT_THREADS = ACT_T + 64;
 constexpr int ACT_MAX_STEPS = 16;   // iterations per dqn_act_kernel launch (bounded by the next learning step)
 constexpr int LEARN_B = 128;        // max batch size
 constexpr int LF_S = 16, LF_SP = LF_S + 4, LF_T = 256;   // dqn_learn_fwd_kernel: samples per CTA, row stride, threads
@@ -101,7 +102,13 @@ template <int NT> __device__ __forceinline__ void load_q_params(const float* __r
 // inputs, h1 [120][SP], h2 [84][SP], qo [2][SP] (SP a multiple of 4). A thread owns 4 consecutive samples of one
 // first-layer neuron, then 4 neurons x 4 samples of the second layer (one 128-bit weight load + one 128-bit activation
 // load per k for 16 FMAs), then one (output, sample) chain of the head.
-template <int NS, int SP, int NT>
+// BAR = 0: __syncthreads (all NT threads of the CTA call this); BAR > 0: named barrier BAR over the first NT threads
+// (the acting kernel has two more warps that do not take part)
+template <int BAR, int NT> __device__ __forceinline__ void q_barrier() {
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+template <int NS, int SP, int NT, int BAR = 0>
 __device__ __forceinline__ void q_forward(const float* __restrict__ p, const float* xs, float* h1, float* h2, float* qo, int tid) {
   constexpr int EQ = NS / 4;   // sample quads
   static_assert(NS % 4 == 0 && SP % 4 == 0 && SP >= NS, "tile geometry");
@@ -125,7 +132,7 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 #ifdef DQN_TRACE
   const long long q_t1 = clock64();
 #endif
-  __syncthreads();
+  q_barrier<BAR, NT>();
 #ifdef DQN_TRACE
   const long long q_t2 = clock64();
 #endif
@@ -180,7 +187,7 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 #ifdef DQN_TRACE
   const long long q_t3 = clock64();
 #endif
-  __syncthreads();
+  q_barrier<BAR, NT>();
 #ifdef DQN_TRACE
   const long long q_t4 = clock64();
 #endif
@@ -212,7 +219,7 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 #ifdef DQN_TRACE
   const long long q_t5 = clock64();
 #endif
-  __syncthreads();
+  q_barrier<BAR, NT>();
 #ifdef DQN_TRACE
   if (tid == 0 && blockIdx.x == 0)
     printf("q_forward<%d>: layer1 %lld | barrier %lld | layer2 %lld | barrier %lld | head %lld | barrier %lld\n", NS, q_t1 - q_t0,
@@ -220,24 +227,37 @@ __device__ __forceinline__ void q_forward(const float* __restrict__ p, const flo
 #endif
 }
 
-__global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
+// Warps 0-7 evaluate the Q-network for the CTA's 32 envs; warp 0 (one lane per env) then chooses the action, records the
+// transition and advances its env. As in rollout_kernel, two more warps work in the shadow of the forward pass on what
+// does not depend on the chosen action: warp 8 the step's Philox draw (epsilon test + random action) and the successor
+// state for action 0, warp 9 the successor for action 1 and the state each env takes at its next reset. Warp 0 picks
+// the successor of its action: same device function, same inputs, same bits as stepping afterwards.
+__global__ void __launch_bounds__(ACT_THREADS, 1) dqn_act_kernel(ActArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int SP = ACT_SP;
+  constexpr int BAR_Q = 1, BAR_SPEC = 2;   // named barriers: forward threads | speculation warps -> warp 0
   float* p = smem;                       // [DQ_PP]
   float* h1 = p + DQ_PP;                 // [120][SP]
   float* h2 = h1 + DQ_H1 * SP;           // [84][SP]
   float* qo = h2 + DQ_H2 * SP;           // [2][SP]
   float* xs = qo + DQ_A * SP;            // [4][SP] current observation of the CTA's envs
-  const int tid = threadIdx.x;
-  load_q_params<ACT_T>(a.q, p, tid);
-  const int e = tid;                     // env lane, meaningful for warp 0
+  float* st_s = xs + DQ_D * SP;          // [4][ACT_E] env state for the speculation warps (= xs without the padding)
+  float* spec_s = st_s + 4 * ACT_E;      // [2][4][ACT_E] successor states
+  float* rst_s = spec_s + 8 * ACT_E;     // [4][ACT_E] state at the next reset
+  double* u_s = reinterpret_cast<double*>(rst_s + 4 * ACT_E);          // [ACT_E] uniform of the epsilon test
+  uint32_t* bit_s = reinterpret_cast<uint32_t*>(rst_s + 6 * ACT_E);    // [ACT_E] random action
+  int* used_s = reinterpret_cast<int*>(rst_s + 7 * ACT_E);             // [ACT_E] warp 0 consumed the reset state
+  static_assert(((DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP + 16 * ACT_E) % 2) == 0, "the Float64 uniforms need 8-byte alignment");
+  const int tid = threadIdx.x, warp = tid >> 5;
+  load_q_params<ACT_THREADS>(a.q, p, tid);
+  const int e = tid & 31;                // env lane of warps 0, 8 and 9
   const int n = blockIdx.x * ACT_E + e;
-  const bool owner = tid < ACT_E, valid = owner && n < a.N;   // warp 0: one lane per env, state in registers
+  const bool fwd = tid < ACT_T, owner = tid < ACT_E, in_range = n < a.N, valid = owner && in_range;
   const uint32_t gid = (uint32_t)(a.env_id_base + n);         // Philox is keyed by the global env id
   float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   int t = 0, len = 0;
   double ret = 0.0;
-  uint32_t rc = 0;
+  uint32_t rc = 0;                       // warp 0: the env's reset counter; warp 9: the counter its prepared state was drawn for
   if (owner) {
     if (valid) {
       const float4 s4 = reinterpret_cast<const float4*>(a.env_state)[n];
@@ -248,7 +268,20 @@ __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
       rc = a.resets[n];
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) xs[k * SP + e] = st[k];
+    for (int k = 0; k < 4; k++) { xs[k * SP + e] = st[k]; st_s[k * ACT_E + e] = st[k]; }
+    used_s[e] = 0;
+  }
+  auto prepare_reset = [&]() {           // warp 9
+    float u4[4], rs[4];
+    int rt;
+    rng_reset_uniforms(a.seed, gid, rc, u4);
+    cartpole_reset(rs, rt, u4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) rst_s[k * ACT_E + e] = rs[k];
+  };
+  if (warp == 9) {
+    if (in_range) rc = a.resets[n];
+    prepare_reset();
   }
   __syncthreads();
 #ifdef DQN_TRACE
@@ -259,49 +292,76 @@ __global__ void __launch_bounds__(ACT_T, 1) dqn_act_kernel(ActArgs a) {
     const bool dtrace = blockIdx.x == 0 && s == 5 && (tid == 0 || tid == 5 * 32);
 #endif
     DTR(0);
-    q_forward<ACT_E, SP, ACT_T>(p, xs, h1, h2, qo, tid);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
-    DTR(1);
-    if (valid) {
-      const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
-      uint32_t r[4];
-      philox_draw(a.seed, gid, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
-      const double u = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
-      int action;
-      if (u < a.eps[s]) action = (int)(r[2] & 1u);              // rand(action_space(env)), dqn.jl:54
-      else action = qo[1 * SP + e] > qo[0 * SP + e] ? 1 : 0;    // argmax: first maximum, dqn.jl:56-57
-      DTR(2);
-      float rew;
-      bool done;
-      cartpole_step(st, t, action, a.max_steps, rew, done);
-      DTR(3);
-      const int slot = (int)(((long long)a.ptr + (long long)s * a.N + n) % a.C);   // add!, replay_buffer.jl:23-37, envs in order
-      reinterpret_cast<float4*>(a.b_state)[slot] = obs;
-      reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
-      a.b_action[slot] = action;
-      a.b_reward[slot] = rew;
-      a.b_term[slot] = done ? 1 : 0;
-      ret += (double)rew;
-      len += 1;
-      if (done) {                          // dqn.jl:80-86
-        atomicAdd(&a.dev->episodes, 1ull);
-        atomicAdd(&a.dev->sum_return, ret);
-        atomicAdd(&a.dev->sum_length, (double)len);
-        ret = 0.0;
-        len = 0;
-        float u4[4];
-        rng_reset_uniforms(a.seed, gid, rc, u4);
+    if (!fwd) {
+      // ---- speculation warps
+      if (warp == 9 && used_s[e]) {
         rc += 1;
-        cartpole_reset(st, t, u4);
+        prepare_reset();
+        used_s[e] = 0;
       }
+      if (warp == 8) {
+        uint32_t r[4];
+        philox_draw(a.seed, gid, a.it0 + (unsigned long long)s, STREAM_DQN_ACT, r);
+        u_s[e] = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+        bit_s[e] = r[2] & 1u;
+      }
+      float s4[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) xs[k * SP + e] = st[k];
+      for (int k = 0; k < 4; k++) s4[k] = st_s[k * ACT_E + e];
+      cartpole_dynamics(s4, warp - 8);
+#pragma unroll
+      for (int k = 0; k < 4; k++) spec_s[((warp - 8) * 4 + k) * ACT_E + e] = s4[k];
+      __threadfence_block();
+      asm volatile("bar.arrive %0, %1;" ::"n"(BAR_SPEC), "n"(ACT_E + 64) : "memory");
+    } else {
+      q_forward<ACT_E, SP, ACT_T, BAR_Q>(p, xs, h1, h2, qo, tid);   // q_net(obs), dqn.jl:56 (used only where the epsilon test fails)
+      DTR(1);
+      if (owner) {
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_SPEC), "n"(ACT_E + 64) : "memory");   // this step's speculation has arrived
+        if (valid) {
+          const float4 obs = make_float4(st[0], st[1], st[2], st[3]);   // deepcopy(state(env)), dqn.jl:50
+          int action;
+          if (u_s[e] < a.eps[s]) action = (int)bit_s[e];              // rand(action_space(env)), dqn.jl:54
+          else action = qo[1 * SP + e] > qo[0 * SP + e] ? 1 : 0;     // argmax: first maximum, dqn.jl:56-57
+          DTR(2);
+          float rew;
+          bool done;
+#pragma unroll
+          for (int k = 0; k < 4; k++) st[k] = spec_s[(action * 4 + k) * ACT_E + e];   // cartpole_step, evaluated ahead
+          t += 1;
+          cartpole_outcome(st, t, a.max_steps, rew, done);
+          DTR(3);
+          const int slot = (int)(((long long)a.ptr + (long long)s * a.N + n) % a.C);   // add!, replay_buffer.jl:23-37, envs in order
+          reinterpret_cast<float4*>(a.b_state)[slot] = obs;
+          reinterpret_cast<float4*>(a.b_next)[slot] = make_float4(st[0], st[1], st[2], st[3]);
+          a.b_action[slot] = action;
+          a.b_reward[slot] = rew;
+          a.b_term[slot] = done ? 1 : 0;
+          ret += (double)rew;
+          len += 1;
+          if (done) {                          // dqn.jl:80-86
+            atomicAdd(&a.dev->episodes, 1ull);
+            atomicAdd(&a.dev->sum_return, ret);
+            atomicAdd(&a.dev->sum_length, (double)len);
+            ret = 0.0;
+            len = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) st[k] = rst_s[k * ACT_E + e];   // cartpole_reset with this env's next draw (warp 9)
+            t = 0;
+            rc += 1;
+            used_s[e] = 1;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { xs[k * SP + e] = st[k]; st_s[k * ACT_E + e] = st[k]; }
+        }
+      }
     }
     DTR(4);
     __syncthreads();
     DTR(5);
 #ifdef DQN_TRACE
     if (dtrace)
-      printf("act warp %d: forward %lld | philox+choice %lld | cartpole %lld | store+reset %lld | barrier %lld | step %lld\n",
+      printf("act warp %d: forward %lld | choice %lld | outcome %lld | store+reset %lld | barrier %lld | step %lld\n",
              tid >> 5, dtr[1] - dtr[0], dtr[2] - dtr[1], dtr[3] - dtr[2], dtr[4] - dtr[3], dtr[5] - dtr[4], dtr[5] - dtr[0]);
 #endif
   }
@@ -722,7 +782,8 @@ __global__ void __launch_bounds__(256) dqn_adam_kernel(LearnArgs a) {
   dqn_adam<1>(a, idx, g, ok);
 }
 
-constexpr size_t ACT_SMEM = (DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP) * sizeof(float);
+constexpr int ACT_SPEC_FLOATS = (4 + 2 * 4 + 4 + 2 + 1 + 1) * ACT_E;   // state | 2 successors | reset state | uniform (double) | random bit | used flag
+constexpr size_t ACT_SMEM = (DQ_PP + (DQ_H1 + DQ_H2 + DQ_A + DQ_D) * ACT_SP + ACT_SPEC_FLOATS) * sizeof(float);
 constexpr size_t LF_SMEM = (2 * DQ_PP + (DQ_H1 + DQ_H2 + 2 * DQ_A + 2 * DQ_D) * LF_SP) * sizeof(float);
 constexpr size_t LU_SMEM = ((size_t)LEARN_B * (DQ_H2 + LU_KA) + DQ_H2 * LU_KA) * sizeof(float);   // kind (A) is the largest
 static_assert(LEARN_B * (LU_JB + DQ_D) <= LEARN_B * (DQ_H2 + LU_KA) && LEARN_B * (2 * LU_KC + DQ_A) <= LEARN_B * (DQ_H2 + LU_KA), "upd smem");
@@ -982,7 +1043,7 @@ extern "C" CRL_API int crl_dqn_run(crl_dqn_ctx* c, int64_t iterations, crl_dqn_s
     }
     for (int i = ns; i < ACT_MAX_STEPS; i++) a.eps[i] = 0.0;
     a.n_steps = ns;
-    dqn_act_kernel<<<(N + ACT_E - 1) / ACT_E, ACT_T, ACT_SMEM, c->stream>>>(a);
+    dqn_act_kernel<<<(N + ACT_E - 1) / ACT_E, ACT_THREADS, ACT_SMEM, c->stream>>>(a);
     DCK(cudaGetLastError());
     c->launches += 1;
     if (learn) {
