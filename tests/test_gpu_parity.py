@@ -271,6 +271,43 @@ def test_rollout_injected_noise_matches_oracle(crl, olib, abi, torch_cuda, kind)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("N", [100, 148 * 32 + 20])
+def test_rollout_ragged_env_counts(crl, olib, abi, torch_cuda, kind, N):
+    """env counts that are not a multiple of the 32 envs a CTA owns: one grid smaller than the GPU (100 envs, last CTA 4
+    of 32 lanes) and one larger (4756 envs: the two-CTAs-per-SM variant of the rollout kernel, last CTA 20 lanes).
+    Device RNG on both sides, short horizon, high pole velocity so that episodes end and reset inside the rollout."""
+    T = 8
+    h, o = make_pair(crl, olib, abi, kind, N=N, T=T, mb=4, seed=29)
+    rng = np.random.default_rng(5)
+    if kind == 0:
+        st = (rng.random((N, 4)) * 0.1 - 0.05).astype(F)
+        st[::3, 2] = 0.19
+        st[::3, 3] = 2.0
+        t0 = np.zeros(N, np.int32)
+    else:
+        st = np.stack([rng.uniform(-3, 3, N), rng.uniform(-1, 1, N)], 1).astype(F)
+        t0 = np.zeros(N, np.int32)
+        t0[::2] = 196  # done at t >= 200
+    for x in (h, o):
+        x.env_set_state(st, t0)
+        x.rollout()
+    compare_buffers(h, o, abi, kind, rtol=1e-4, atol=2e-5)
+    term = o.read_field(abi.CRL_F_TERMINAL)
+    assert term[1:].sum() > N // 8
+    for f in (abi.CRL_F_ENV_T, abi.CRL_F_RESET_COUNT, abi.CRL_F_NEXT_DONE, abi.CRL_F_EP_LENGTH):
+        np.testing.assert_array_equal(h.read_field(f), o.read_field(f))
+    for f in (abi.CRL_F_ENV_STATE, abi.CRL_F_NEXT_OBS, abi.CRL_F_EP_RETURN):
+        np.testing.assert_allclose(h.read_field(f), o.read_field(f), rtol=1e-4, atol=2e-5)
+    rh, ah = h.pop_episodes()
+    ro, ao = o.pop_episodes()
+    assert [(r[0], r[1], r[2]) for r in rh] == [(r[0], r[1], r[2]) for r in ro]
+    for x in (h, o):
+        x.gae()
+    np.testing.assert_allclose(h.read_field(abi.CRL_F_NEXT_VALUE), o.read_field(abi.CRL_F_NEXT_VALUE), rtol=1e-4, atol=2e-5)
+    h.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
 def test_rollout_philox_teacher_forced(crl, olib, abi, torch_cuda, kind):
     """device RNG, long horizon: every stored step is re-derived by the oracle from the GPU's own
     previous state (per-step parity, immune to chaotic divergence)"""

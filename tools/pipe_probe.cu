@@ -83,8 +83,36 @@ template <int MODE> __global__ void probe(float* out, long long* cyc, int sel) {
         for (int s = 0; s < 4; s++) acc_s[j * 4 + s] = fmaf(ww[j], aa[s], acc_s[j * 4 + s]);
     }
   }
+  double dacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) dacc[i] = 1.0 + i + lane * 1e-3;
+  if (MODE == 9) {          // 8 independent DFMA chains (throughput)
+    for (int it = 0; it < IT; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dacc[i] = fma(dacc[i], 1.0000001, 1e-9);
+    }
+  } else if (MODE == 10) {  // one dependent DFMA chain (latency)
+    for (int it = 0; it < IT; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dacc[0] = fma(dacc[0], 1.0000001, 1e-9);
+    }
+  } else if (MODE == 11) {  // dependent float -> double -> float round trips with a DADD in between
+    float f = acc_s[0];
+    for (int it = 0; it < IT; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f = (float)((double)f + 1e-9);
+    }
+    acc_s[0] = f;
+  } else if (MODE == 12) {  // Float64 division, dependent
+    for (int it = 0; it < IT / 8; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dacc[0] = 1.0000001 / (dacc[0] + 1e-9);
+    }
+  }
   const long long t1 = clock64();
   float r = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += (float)dacc[i];
 #pragma unroll
   for (int i = 0; i < 8; i++) r += a[i].x + a[i].y;
 #pragma unroll
@@ -97,13 +125,14 @@ int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 1024 * sizeof(float));
   cudaMallocManaged(&cyc, 64 * sizeof(long long));
-  const char* names[9] = {"8 FFMA2 chains", "16 FFMA chains", "8 MUFU.RCP", "8 tanh_fast2 (per pair-call)", "LDS.128 8x16B + broadcast quarters",
-                          "LDS.128 32 distinct", "LDS.128 one address", "4x4 tile k-step (2 LDS.128 + 8 FFMA2)", "4x4 tile k-step scalar (2 LDS.128 + 16 FFMA)"};
-  const int per_it[9] = {8, 16, 8, 1, 1, 1, 1, 1, 1};
-  const int its[9] = {IT, IT, IT, IT, IT, IT, IT, IT, IT};
+  const char* names[13] = {"8 FFMA2 chains", "16 FFMA chains", "8 MUFU.RCP", "8 tanh_fast2 (per pair-call)", "LDS.128 8x16B + broadcast quarters",
+                          "LDS.128 32 distinct", "LDS.128 one address", "4x4 tile k-step (2 LDS.128 + 8 FFMA2)", "4x4 tile k-step scalar (2 LDS.128 + 16 FFMA)",
+                          "8 independent DFMA chains", "1 dependent DFMA chain", "f32->f64, DADD, f64->f32 (dependent)", "Float64 division (dependent)"};
+  const int per_it[13] = {8, 16, 8, 1, 1, 1, 1, 1, 1, 8, 8, 8, 1};
+  const int its[13] = {IT, IT, IT, IT, IT, IT, IT, IT, IT, IT, IT, IT, IT};
   for (int threads : {32, 128, 256, 512}) {
     printf("threads per SM = %d (%d warp(s) per scheduler)\n", threads, threads / 128 ? threads / 128 : 1);
-    for (int m = 0; m < 9; m++) {
+    for (int m = 0; m < 13; m++) {
       switch (m) {
         case 0: probe<0><<<1, threads>>>(out, cyc, m); break;
         case 1: probe<1><<<1, threads>>>(out, cyc, m); break;
@@ -114,6 +143,10 @@ int main() {
         case 6: probe<6><<<1, threads>>>(out, cyc, m); break;
         case 7: probe<7><<<1, threads>>>(out, cyc, m); break;
         case 8: probe<8><<<1, threads>>>(out, cyc, m); break;
+        case 9: probe<9><<<1, threads>>>(out, cyc, m); break;
+        case 10: probe<10><<<1, threads>>>(out, cyc, m); break;
+        case 11: probe<11><<<1, threads>>>(out, cyc, m); break;
+        case 12: probe<12><<<1, threads>>>(out, cyc, m); break;
       }
       cudaDeviceSynchronize();
       printf("  %-46s %8.2f cycles per warp-level op (warp 0's clock)\n", names[m], (double)cyc[m] / ((double)its[m] * per_it[m]));
