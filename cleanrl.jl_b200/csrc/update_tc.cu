@@ -138,21 +138,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// two 16-column loads in flight, one wait
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  __syncwarp();  // the lanes may arrive from a divergent mbarrier poll; the load is .sync.aligned
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr + 16));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   __syncwarp();
@@ -203,10 +188,6 @@ template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const
   static_assert(N == 16 || N == 32, "");
   tmem_st16(taddr, v);
   if (N == 32) tmem_st16(taddr + 16, v + 16);
-}
-template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
-  static_assert(N == 16 || N == 32, "");
-  if (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 
 // ---------------------------------------------------------------- packed FP32 helpers (f2, f2s, tanh_fast2: device_math.cuh)
