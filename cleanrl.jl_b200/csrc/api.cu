@@ -571,8 +571,42 @@ static std::vector<SnapItem> snap_items(crl_ctx* c) {
           {c->adam_v, 4 * P}, {c->beta_pow, 16 * (size_t)CRL_MAX_ARRAYS}, {c->env_state, 4 * N * c->L.S}, {c->env_t, 4 * N},
           {c->ep_return, 8 * N}, {c->ep_length, 4 * N}, {c->reset_count, 4 * N}, {c->ds, sizeof(DevState)}};
 }
+// The snapshot taken before every speculative update: one launch instead of eleven device-to-device copies (the items
+// are all multiples of 4 bytes; 330 KB at BASELINE configs[1]).
+constexpr int SNAP_MAX = 12;
+struct SnapCopy { const uint32_t* src[SNAP_MAX]; uint32_t* dst[SNAP_MAX]; unsigned words[SNAP_MAX]; int n; };
+__global__ void snapshot_kernel(SnapCopy sc) {
+  const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = 0; i < sc.n; i++) {
+    const uint32_t* __restrict__ s = sc.src[i];
+    uint32_t* __restrict__ d = sc.dst[i];
+    const unsigned w = sc.words[i], w4 = w / 4;   // sources and destinations are 16-byte aligned
+    for (unsigned k = t0; k < w4; k += stride) reinterpret_cast<uint4*>(d)[k] = reinterpret_cast<const uint4*>(s)[k];
+    for (unsigned k = 4 * w4 + t0; k < w; k += stride) d[k] = s[k];
+  }
+}
 static int snapshot_copy(crl_ctx* c, int slot, bool restore) {
   size_t off = 0;
+  if (!restore) {
+    SnapCopy sc;
+    sc.n = 0;
+    bool ok = true;
+    for (auto& it : snap_items(c)) {
+      if (sc.n >= SNAP_MAX || (it.bytes & 3) || (reinterpret_cast<uintptr_t>(it.ptr) & 15)) { ok = false; break; }
+      sc.src[sc.n] = reinterpret_cast<const uint32_t*>(it.ptr);
+      sc.dst[sc.n] = reinterpret_cast<uint32_t*>(c->snap[slot] + off);
+      sc.words[sc.n] = (unsigned)(it.bytes / 4);
+      sc.n++;
+      off += (it.bytes + 15) & ~size_t(15);
+    }
+    if (ok) {
+      KernelScope ks(c, CRL_K_OTHER);
+      snapshot_kernel<<<64, 256, 0, c->stream>>>(sc);
+      CK(cudaGetLastError());
+      return CRL_OK;
+    }
+    off = 0;
+  }
   for (auto& it : snap_items(c)) {
     const size_t b = (it.bytes + 15) & ~size_t(15);
     if (restore) CK(cudaMemcpyAsync(it.ptr, c->snap[slot] + off, it.bytes, cudaMemcpyDeviceToDevice, c->stream));
