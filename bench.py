@@ -672,8 +672,17 @@ def run_ours(args):
                                     "TF32 dense peak = MEASURED_PEAKS.json bf16_tflops x 1.1/2.25 (nominal TF32:bf16 ratio; tools/tf32_peak "
                                     "not built)" if bf16 else "nominal 1.1 PFLOP/s TF32 dense (no MEASURED_PEAKS.json)"),
                     "tf32_peak_probe": tf32_meas,
-                    "note": "the kernel is bound by its CUDA-core work (tanh_fast on 2x64 activations per sample and layer, "
-                            "hi/lo splitting, feature-major operand stores), not by the tensor pipe: see DESIGN.md section 5"}
+                    "scope": "one launch = forward + loss + backward of a minibatch AND, since round 2, the deterministic "
+                             "gradient reduction, the peer exchange, per-array ClipNorm and Adam (the fused tail, ~9 us of the "
+                             "launch; round 1 ran them as two more kernels, 0.022 ms per minibatch, outside this figure)",
+                    "frac_vs_round1_denominator": (ach / ((bf16 or 2250.0) * 1.1 / 2.25)) if ach else None,
+                    "round1": "round 1 reported frac 0.083 = 66.7 TFLOP/s over the nominal-ratio peak 801.2 (bf16 measurement x "
+                              "1.1/2.25) for a 0.1049 ms launch without the tail; frac_vs_round1_denominator is this run over that "
+                              "same denominator",
+                    "note": "the kernel is bound by its CUDA-core work (tanh on 2x64 activations per sample and layer, hi/lo "
+                            "splitting, feature-major operand stores: 2.1 k instructions per warp and tile, a packed FMA holds "
+                            "the issue port for 2 cycles) and by the thread that issues the MMAs being held while they execute, "
+                            "not by the tensor pipe: see DESIGN.md sections 5 and 9"}
     else:
         roofline = {"kernel": "loss_grad_kernel", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": ach / fp32_peak if ach else None, "traffic": None,
@@ -693,8 +702,10 @@ def run_ours(args):
                             "frac": ro_tf / fp32_peak, "avg_launch_ms": ro["ms_per_update"],
                             "algorithmic": "%d FLOP per env-step x %d env-steps per launch" % (FWD_FLOP, B_local),
                             "buffer_write_gbs": bytes_per_step * B_local / ro_s / 1e9,
-                            "note": "a %d-step serial chain over %d envs per GPU: latency-bound (one CTA of 32 envs per SM), "
-                                    "neither the FFMA pipe nor HBM is the limit at this batch size" % (NUM_STEPS, args.envs_per_gpu)}
+                            "note": "a %d-step serial chain over %d envs per GPU (one CTA of 32 envs per SM): per step ~7.0 k cycles, "
+                                    "of which ~4.3 k are shared-memory crossbar time of the two 64x64 layers (2 B loaded per FMA with "
+                                    "4x4 register tiles, 128 B/clk) and ~1.2 k the serial per-env phase; neither the FFMA pipe nor "
+                                    "HBM is the limit at this batch size" % (NUM_STEPS, args.envs_per_gpu)}
 
     # ---- GAE HBM roofline (the metric's second half) on rank 0
     roofline_gae = None
