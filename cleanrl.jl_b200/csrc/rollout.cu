@@ -18,7 +18,7 @@ constexpr int ROLL_FWD = CRL_THREADS;   // warps 0-7: the two MLPs; warp 0 also 
 constexpr int ROLL_THREADS = ROLL_FWD + 64;   // warps 8, 9: speculation warps (see rollout_kernel)
 // grids larger than the GPU (BIG): 4 forward warps with 8 x 4 register tiles (see fwd_layer_8x4), 2 CTAs per SM
 constexpr int BIG_FWD = 128, BIG_THREADS = BIG_FWD + 64;
-constexpr int BAR_FWD = 1, BAR_SPEC = 2;      // named barriers: the 256 forward threads / speculation warps -> warp 0
+constexpr int BAR_FWD = 1, BAR_SPEC = 2, BAR_BOOK = 3;      // named barriers: the forward threads / speculation warps -> warp 0 / bookkeeping warp -> output-layer threads
 
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -37,7 +37,8 @@ template <int ENV> struct RolloutSmem {
   static constexpr int RST = SPEC + 2 * 4 * RE;    // [4][RE] the state each env takes at its next reset
   static constexpr int NOISE = RST + 4 * RE;       // double[RE] uniform (Float64, StatsBase) or float[2][RE] normals
   static constexpr int USED = NOISE + 2 * RE;      // int[RE]: warp 0 consumed the prepared reset state
-  static constexpr int FLOATS = USED + RE;
+  static constexpr int BOOK = USED + RE;           // per env: action (int), action (float, Gaussian head), reward, done
+  static constexpr int FLOATS = BOOK + 4 * RE;
   static constexpr size_t BYTES = FLOATS * sizeof(float);
   static_assert((NOISE % 2) == 0, "the Float64 uniforms need 8-byte alignment");
 };
@@ -76,7 +77,7 @@ template <int ENV> __device__ __forceinline__ void load_head_row(const float* sp
 // (o < A: actor logits/mean, o == A: critic value). Called by the 256 forward threads only (named barrier BAR_FWD).
 // HEADREG = false: the output layer reads its weights from shared memory (64 registers fewer: two CTAs per SM when the
 // grid is larger than the GPU)
-template <int ENV, bool HEADREG = true>
+template <int ENV, bool HEADREG = true, bool BOOKSYNC = false>
 __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc, float* smem, const HeadRow<ENV>& hr,
                                           long long* tr = nullptr) {
   using G = TileGeom<4, 2>;
@@ -105,6 +106,7 @@ __device__ __forceinline__ void forward32(const ThreadCoord<TileGeom<4, 2>>& tc,
     float hv[CRL_H];
 #pragma unroll
     for (int k = 0; k < CRL_H; k++) hv[k] = hrow[k * SP];   // all 64 loads in flight before the (serial) chain starts
+    if (BOOKSYNC) nbar_sync(BAR_BOOK, RE * (E::A + 1) + 32);   // the bookkeeping warp has read the previous step's outputs
     float acc = 0.0f;
     if (HEADREG) {
 #pragma unroll
@@ -201,7 +203,7 @@ __device__ __forceinline__ void fwd_layer_8x4(const FwdCoord8x4& fc, const float
   }
 }
 // forward32 for the BIG variant (output layer weights from shared memory)
-template <int ENV>
+template <int ENV, bool BOOKSYNC = false>
 __device__ __forceinline__ void forward32_big(const FwdCoord8x4& fc, float* smem) {
   using E = EnvTraits<ENV>;
   using SM = RolloutSmem<ENV>;
@@ -221,6 +223,7 @@ __device__ __forceinline__ void forward32_big(const FwdCoord8x4& fc, float* smem
   if (threadIdx.x < RE * (E::A + 1)) {
     const int o = threadIdx.x / RE, e = threadIdx.x % RE;
     const float* hrow = h2 + (o < E::A ? 0 : CRL_H) * SP + e;
+    if (BOOKSYNC) nbar_sync(BAR_BOOK, RE * (E::A + 1) + 32);
     float acc = 0.0f;
     if (o < E::A) {
       const float* a = sp + SmemParams<ENV>::ACTOR;
@@ -238,13 +241,17 @@ __device__ __forceinline__ void forward32_big(const FwdCoord8x4& fc, float* smem
   nbar_sync(BAR_FWD, BIG_FWD);
 }
 
-// Persistent rollout. Warps 0-7 evaluate the two MLPs for the CTA's 32 envs; warp 0 (one lane per env) then samples,
-// records and advances its env. Everything that does not depend on the sampled action is taken off that serial
-// phase by two extra warps that work in the shadow of the forward pass:
+// Persistent rollout. Warps 0-7 evaluate the two MLPs for the CTA's 32 envs; warp 0 (one lane per env) then samples
+// the action and advances its env. Only what the NEXT observation depends on stays on that serial phase (softmax
+// probabilities, the inverse-CDF sample, picking the successor state, termination, reset): everything else is done by
+// two extra warps in the shadow of the forward pass:
 //   warp 8   the step's action noise (Philox: the Float64 uniform of StatsBase.sample, or the Gaussian head's normals)
 //            and, CartPole, the successor state for action 0
-//   warp 9   CartPole: the successor state for action 1; both envs: the state every env will take at its NEXT reset
-//            (Philox keyed by the env's reset counter), refreshed after warp 0 consumed it
+//   warp 9   CartPole: the successor state for action 1; the state every env will take at its NEXT reset (Philox keyed
+//            by the env's reset counter), refreshed after warp 0 consumed it; and the BOOKKEEPING of the previous step:
+//            log-probability, the [T][N] buffer stores (Buffer.add!), episode length / return, episode records and
+//            aggregates. Warp 0 hands it (action, reward, done) through shared memory; logits and value it reads from
+//            the forward pass's outputs, the observation it read itself one step earlier.
 // Warp 0 picks the successor of the action it sampled (same device function, same inputs: bit-identical to stepping
 // after the fact). The injected-noise test modes (action_noise / reset_noise) read their draws on warp 0 as before.
 // BIG = true: more CTAs than SMs (N / 32 > SM count): 4 forward warps with 8 x 4 tiles, two resident CTAs per SM (shared memory: 77 KB each).
@@ -268,6 +275,10 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
   double* noise_d = reinterpret_cast<double*>(smem + SM::NOISE);
   float* noise_f = smem + SM::NOISE;
   int* used_s = reinterpret_cast<int*>(smem + SM::USED);
+  int* act_s = reinterpret_cast<int*>(smem + SM::BOOK);
+  float* actf_s = smem + SM::BOOK + RE;
+  float* rew_s = smem + SM::BOOK + 2 * RE;
+  int* done_s = reinterpret_cast<int*>(smem + SM::BOOK + 3 * RE);
   const ThreadCoord<G> tc;
   const FwdCoord8x4 fc;
 
@@ -279,38 +290,45 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
   const long long n = (long long)blockIdx.x * RE + e;
   const bool fwd = threadIdx.x < FWD;
   const bool owner = threadIdx.x < RE;
+  const bool booker = warp == SW0 + 1;
   const bool in_range = n < a.N;
   const bool valid = owner && in_range;
   const unsigned long long step0 = a.ds->policy_step;
   const uint32_t gid = (uint32_t)(a.env_id_base + (int)n);
 
+  // warp 0: the env itself
   float st[S];
   float obs[D];
-  int env_t = 0, ep_len = 0;
-  double ep_ret = 0.0;
+  int env_t = 0;
   uint32_t resets = 0;  // warp 0: the env's counter; warp 9: the counter the prepared reset state was drawn for
   bool done_flag = false;  // Q3: ppo.jl:170 — is_terminated(env) after reset! is false
-  // per-thread episode aggregates
+  // warp 9: the episode bookkeeping of the env
+  int ep_len = 0;
+  double ep_ret = 0.0;
+  bool prev_done = false;   // next_done of the step being recorded (terminal[t], ppo.jl:139)
+  float obs_b[D];           // the observation the step being recorded acted on
   unsigned long long agg_n = 0;
   double agg_ret = 0.0, agg_len = 0.0, agg_max = -INFINITY;
-  // episode record whose slot is still on its way back from the atomic (stored at the next step: the round trip to L2
-  // would otherwise sit in front of the step barrier)
+  // episode record whose slot is still on its way back from the atomic (stored one step later)
   bool rec_pending = false;
   unsigned int rec_slot = 0;
   crl_episode rec;
   rec.step = 0; rec.env = 0; rec.length = 0; rec._pad = 0; rec.episode_return = 0.0;
 
+#pragma unroll
+  for (int i = 0; i < S; i++) st[i] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D; k++) obs_b[k] = 0.0f;
   if (valid) {
 #pragma unroll
     for (int i = 0; i < S; i++) st[i] = a.env_state[n * S + i];
     env_t = a.env_t[n];
+    resets = a.reset_count[n];
+  }
+  if (booker && in_range) {
     ep_len = a.ep_length[n];
     ep_ret = a.ep_return[n];
     resets = a.reset_count[n];
-  } else {
-#pragma unroll
-    for (int i = 0; i < S; i++) st[i] = 0.0f;
-    if (warp == SW0 + 1 && in_range) resets = a.reset_count[n];
   }
   __syncthreads();
   HeadRow<ENV> hr;
@@ -331,22 +349,91 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
 #pragma unroll
     for (int i = 0; i < S; i++) rst_s[i * RE + e] = rs[i];
   };
-  if (warp == SW0 + 1 && !a.reset_noise) prepare_reset();
+  if (booker && !a.reset_noise) prepare_reset();
+
+  // warp 9: everything of step tb that the next observation does not depend on (ppo.jl:125, 133-140, 145-165)
+  auto book = [&](int tb, const float (&zv)[A + 1], int act_i, float act_f, float r, bool dn) {
+    const long long b = (long long)tb * a.N + n;
+    ep_len += 1;  // ppo.jl:125
+    float logprob;
+    if (!E::CONT) {
+      // logsoftmax [NNlib], the same operations warp 0 ran for the probabilities
+      float m = zv[0];
+#pragma unroll
+      for (int k = 1; k < A; k++) m = fmaxf(m, zv[k]);
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < A; k++) sum = __fadd_rn(sum, expf(__fsub_rn(zv[k], m)));
+      const float ls = logf(sum);
+      logprob = __fsub_rn(__fsub_rn(zv[0], m), ls);
+#pragma unroll
+      for (int k = 1; k < A; k++) logprob = (act_i == k) ? __fsub_rn(__fsub_rn(zv[k], m), ls) : logprob;
+    } else {
+      float lps = 0.0f;
+#pragma unroll
+      for (int k = 0; k < A; k++) {
+        const float mean = zv[k];
+        const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
+        const float sd = expf(logstd);
+        const float diff = __fsub_rn(act_f, mean);   // A = 1
+        const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+        lps = __fadd_rn(lps, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
+      }
+      logprob = lps;
+    }
+    if (rec_pending) {   // the previous record: its slot has long arrived
+      if (rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
+      rec_pending = false;
+    }
+    ep_ret += (double)r;    // ppo.jl:145
+    if (in_range) {
+      // Buffer.add!, ppo.jl:133-140: state = next_obs, terminal = next_done (previous step)
+      if (D == 4) {
+        reinterpret_cast<float4*>(a.state)[b] = make_float4(obs_b[0], obs_b[1], obs_b[2], obs_b[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) a.state[b * D + k] = obs_b[k];
+      }
+      if (!E::CONT) reinterpret_cast<int32_t*>(a.action)[b] = act_i;
+      else reinterpret_cast<float*>(a.action)[b * A] = act_f;
+      a.logprob[b] = logprob;
+      a.value[b] = zv[A];
+      a.terminal[b] = prev_done ? 1 : 0;
+      a.reward[b] = r;  // ppo.jl:132
+      if (dn) {         // ppo.jl:147-165
+        rec_slot = atomicAdd(&a.eb->count, 1u);
+        rec_pending = true;
+        rec.step = tb; rec.env = (int)n; rec.length = ep_len; rec._pad = 0; rec.episode_return = ep_ret;
+        agg_n += 1; agg_ret += ep_ret; agg_len += (double)ep_len; agg_max = fmax(agg_max, ep_ret);
+        ep_ret = 0.0;
+        ep_len = 0;
+      }
+    }
+    prev_done = dn;
+  };
+  static_assert(!E::CONT || A == 1, "the Gaussian head hands one action per env to the bookkeeping warp");
   __syncthreads();
 
   for (int t = 0; t < a.T; t++) {
-#ifdef ROLL_TRACE
-    long long trb[12];
-    long long* tr = (blockIdx.x == 0 && t == 64 && (threadIdx.x == 0 || threadIdx.x == 160)) ? trb : nullptr;
-#else
-    long long* tr = nullptr;
-#endif
     if (!fwd) {
-      // ---- speculation warps, in the shadow of the forward pass
-      if (warp == SW0 + 1 && !a.reset_noise && used_s[e]) {
-        resets += 1;
-        prepare_reset();
-        used_s[e] = 0;
+      // ---- speculation / bookkeeping warps, in the shadow of the forward pass
+      if (booker) {
+        // what step t - 1 left behind: copied to registers before the output layer of this step may overwrite so[]
+        float zv[A + 1];
+#pragma unroll
+        for (int k = 0; k <= A; k++) zv[k] = so[k * RE + e];
+        const int act_i = act_s[e];
+        const float act_f = actf_s[e], r = rew_s[e];
+        const bool dn = done_s[e] != 0;
+        nbar_arrive(BAR_BOOK, RE * (A + 1) + 32);
+        if (t > 0) book(t - 1, zv, act_i, act_f, r, dn);
+#pragma unroll
+        for (int k = 0; k < D; k++) obs_b[k] = xs[k * SP + e];   // the observation step t acts on
+        if (!a.reset_noise && used_s[e]) {
+          resets += 1;
+          prepare_reset();
+          used_s[e] = 0;
+        }
       }
       if (warp == SW0 && !a.action_noise) {
         if (!E::CONT) {
@@ -369,22 +456,16 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
       __threadfence_block();
       nbar_arrive(BAR_SPEC, RE + 64);
     } else {
-      if (BIG) forward32_big<ENV>(fc, smem); else forward32<ENV, true>(tc, smem, hr, tr);  // ends with a barrier of the forward threads; so[] is ready
+      // ends with a barrier of the forward threads; so[] is ready
+      if (BIG) forward32_big<ENV, true>(fc, smem); else forward32<ENV, true, true>(tc, smem, hr);
       if (owner) {
-        if (rec_pending) {   // last step's episode record: its slot has long arrived
-          if (rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
-          rec_pending = false;
-        }
         const long long b = (long long)t * a.N + n;
-        ep_len += 1;  // ppo.jl:125
-        const float value = so[A * RE + e];
-        float logprob;
         int act_i = 0;
         float act_f = 0.0f;
         if (!E::CONT) {
-          // get_action, ppo.jl:22-29: softmax / logsoftmax [NNlib], then
+          // get_action, ppo.jl:22-29: softmax [NNlib], then
           // StatsBase.sample(Weights(p)): t = rand()*sum(p); walk cw += p[i] while cw < t.
-          float z[A], p[A], lp[A];
+          float z[A], p[A];
 #pragma unroll
           for (int k = 0; k < A; k++) z[k] = so[k * RE + e];
           float m = z[0];
@@ -393,15 +474,13 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
           float ex[A], sum = 0.0f;
 #pragma unroll
           for (int k = 0; k < A; k++) { ex[k] = expf(__fsub_rn(z[k], m)); sum = __fadd_rn(sum, ex[k]); }
-          const float ls = logf(sum);
           float psum = 0.0f;
 #pragma unroll
           for (int k = 0; k < A; k++) {
             p[k] = __fdiv_rn(ex[k], sum);
-            lp[k] = __fsub_rn(__fsub_rn(z[k], m), ls);
             psum = __fadd_rn(psum, p[k]);
           }
-          nbar_sync(BAR_SPEC, RE + 64);   // the speculation warps have delivered this step
+          nbar_sync(BAR_SPEC, RE + 64);   // the speculation warps have delivered this step (and recorded the last one)
           double u = 0.0;
           if (valid) u = a.action_noise ? a.action_noise[b] : noise_d[e];
           const double tt = __dmul_rn(u, (double)psum);
@@ -412,46 +491,15 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
             if ((double)cw < tt && i == k - 1) { i = k; cw = __fadd_rn(cw, p[k]); }
           }
           act_i = i;
-          logprob = lp[0];
-#pragma unroll
-          for (int k = 1; k < A; k++) logprob = (i == k) ? lp[k] : logprob;
         } else {
           // Gaussian head (CleanRL-Python convention; the reference has none)
           nbar_sync(BAR_SPEC, RE + 64);
-          float zn[2] = {0.0f, 0.0f};
-          if (valid) {
-            if (a.action_noise) { for (int k = 0; k < A; k++) zn[k] = (float)a.action_noise[b * A + k]; }
-            else { zn[0] = noise_f[e]; zn[1] = noise_f[RE + e]; }
-          }
-          float lps = 0.0f;
-#pragma unroll
-          for (int k = 0; k < A; k++) {
-            const float mean = so[k * RE + e];
-            const float logstd = sp[SmemParams<ENV>::LOGSTD + k];
-            const float sd = expf(logstd);
-            const float ak = __fadd_rn(mean, __fmul_rn(sd, zn[k]));
-            const float diff = __fsub_rn(ak, mean);
-            const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(2.0f, sd), sd));
-            lps = __fadd_rn(lps, __fsub_rn(__fsub_rn(q, logstd), 0.9189385332046727f));
-            if (k == 0) act_f = ak;
-            if (valid) reinterpret_cast<float*>(a.action)[b * A + k] = ak;
-          }
-          logprob = lps;
+          float zn = 0.0f;
+          if (valid) zn = a.action_noise ? (float)a.action_noise[b * A] : noise_f[e];
+          const float mean = so[e];
+          const float sd = expf(sp[SmemParams<ENV>::LOGSTD]);
+          act_f = __fadd_rn(mean, __fmul_rn(sd, zn));
         }
-        if (valid) {
-          // Buffer.add!, ppo.jl:133-140: state = next_obs, terminal = next_done (previous step)
-          if (D == 4) {
-            reinterpret_cast<float4*>(a.state)[b] = make_float4(obs[0], obs[1], obs[2], obs[3]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < D; k++) a.state[b * D + k] = obs[k];
-          }
-          if (!E::CONT) reinterpret_cast<int32_t*>(a.action)[b] = act_i;
-          a.logprob[b] = logprob;
-          a.value[b] = value;
-          a.terminal[b] = done_flag ? 1 : 0;
-        }
-        RTR(7);
         // env(action), ppo.jl:130
         float r;
         bool dn;
@@ -466,50 +514,64 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
         }
         env_obs<ENV>(st, obs);  // ppo.jl:143 — copied BEFORE reset! (Q2: stale terminal obs)
         done_flag = dn;         // ppo.jl:144
-        ep_ret += (double)r;    // ppo.jl:145
-        if (valid) {
-          a.reward[b] = r;  // ppo.jl:132
-          if (dn) {         // ppo.jl:147-165
-            rec_slot = atomicAdd(&a.eb->count, 1u);
-            rec_pending = true;
-            rec.step = t; rec.env = (int)n; rec.length = ep_len; rec._pad = 0; rec.episode_return = ep_ret;
-            agg_n += 1; agg_ret += ep_ret; agg_len += (double)ep_len; agg_max = fmax(agg_max, ep_ret);
-            ep_ret = 0.0;
-            ep_len = 0;
-            if (a.reset_noise) {
-              const float4 v = reinterpret_cast<const float4*>(a.reset_noise)[b];
-              const float u4[4] = {v.x, v.y, v.z, v.w};
-              env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
-            } else {
+        act_s[e] = act_i; actf_s[e] = act_f; rew_s[e] = r; done_s[e] = dn ? 1 : 0;   // for the bookkeeping warp
+        if (valid && dn) {      // ppo.jl:147-165
+          if (a.reset_noise) {
+            const float4 v = reinterpret_cast<const float4*>(a.reset_noise)[b];
+            const float u4[4] = {v.x, v.y, v.z, v.w};
+            env_reset<ENV>(st, env_t, u4);  // only terminated envs, multi_thread_env.jl:105-111
+          } else {
 #pragma unroll
-              for (int i = 0; i < S; i++) st[i] = rst_s[i * RE + e];   // prepared by warp 9 for this reset counter
-              env_t = 0;
-              used_s[e] = 1;
-            }
-            resets += 1;
-            if (a.fresh_obs_after_reset) env_obs<ENV>(st, obs);  // a2c.jl:108 then :52 (PPO: stale obs, Q2)
+            for (int i = 0; i < S; i++) st[i] = rst_s[i * RE + e];   // prepared by warp 9 for this reset counter
+            env_t = 0;
+            used_s[e] = 1;
           }
+          resets += 1;
+          if (a.fresh_obs_after_reset) env_obs<ENV>(st, obs);  // a2c.jl:108 then :52 (PPO: stale obs, Q2)
         }
 #pragma unroll
         for (int k = 0; k < D; k++) xs[k * SP + e] = obs[k];
 #pragma unroll
         for (int i = 0; i < S; i++) st_s[i * RE + e] = st[i];
       }
-      RTR(8);
     }
     __syncthreads();
-#ifdef ROLL_TRACE
-    if (tr) {
-      tr[9] = clock64();
-      printf("rollout warp %d: L1 %lld | bar %lld | L2 %lld | bar %lld | head %lld | bar %lld | sample+store %lld | env %lld | bar %lld | total %lld\n",
-             (int)(threadIdx.x >> 5), tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5],
-             threadIdx.x == 0 ? tr[7] - tr[6] : 0ll, threadIdx.x == 0 ? tr[8] - tr[7] : 0ll, tr[9] - tr[8], tr[9] - tr[0]);
-    }
-#endif
   }
-  if (!fwd) return;   // the speculation warps are done; only named barriers among the forward threads follow
-
-  if (owner && rec_pending && rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
+  if (!fwd) {
+    // the last step's bookkeeping, then the episode state and aggregates go back
+    if (booker) {
+      float zv[A + 1];
+#pragma unroll
+      for (int k = 0; k <= A; k++) zv[k] = so[k * RE + e];
+      const int act_i = act_s[e];
+      const float act_f = actf_s[e], r = rew_s[e];
+      const bool dn = done_s[e] != 0;
+      nbar_arrive(BAR_BOOK, RE * (A + 1) + 32);   // the bootstrap pass may overwrite so[] now
+      book(a.T - 1, zv, act_i, act_f, r, dn);
+      if (rec_pending && rec_slot < (unsigned int)a.ep_capacity) a.records[rec_slot] = rec;
+      if (in_range) {
+        a.ep_length[n] = ep_len;
+        a.ep_return[n] = ep_ret;
+      }
+      const double sr = warp_sum(agg_ret), sl = warp_sum(agg_len), mx = warp_max(agg_max);
+      unsigned long long cn = agg_n;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      if (e == 0 && cn > 0) {
+        atomicAdd(&a.eb->n_episodes, cn);
+        atomicAdd(&a.eb->sum_return, sr);
+        atomicAdd(&a.eb->sum_length, sl);
+        unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.eb->max_return);
+        unsigned long long old = *addr, assumed;
+        do {
+          assumed = old;
+          if (__longlong_as_double((long long)assumed) >= mx) break;
+          old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
+        } while (assumed != old);
+      }
+    }
+    return;   // only named barriers among the forward threads follow
+  }
 
   // Bootstrap value for GAE: next_values = critic(state(env)) with the refreshed (post-reset)
   // observation, ppo.jl:169-171. The weights cannot change between here and crl_gae.
@@ -523,36 +585,16 @@ __global__ void __launch_bounds__(BIG ? BIG_THREADS : ROLL_THREADS, BIG ? 2 : 1)
     for (int k = 0; k < D; k++) xs[k * SP + e] = fresh[k];
   }
   nbar_sync(BAR_FWD, FWD);
-  if (BIG) forward32_big<ENV>(fc, smem); else forward32<ENV, true>(tc, smem, hr);
+  if (BIG) forward32_big<ENV, true>(fc, smem); else forward32<ENV, true, true>(tc, smem, hr);
   if (valid) {
     a.next_value[n] = so[A * RE + e];
 #pragma unroll
     for (int i = 0; i < S; i++) a.env_state[n * S + i] = st[i];
     a.env_t[n] = env_t;
-    a.ep_length[n] = ep_len;
-    a.ep_return[n] = ep_ret;
     a.reset_count[n] = resets;
 #pragma unroll
     for (int k = 0; k < D; k++) a.next_obs[n * D + k] = obs_last[k];
     a.next_done[n] = done_flag ? 1 : 0;
-  }
-  if (threadIdx.x < 32) {
-    const double sr = warp_sum(agg_ret), sl = warp_sum(agg_len), mx = warp_max(agg_max);
-    unsigned long long cn = agg_n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
-    if (threadIdx.x == 0 && cn > 0) {
-      atomicAdd(&a.eb->n_episodes, cn);
-      atomicAdd(&a.eb->sum_return, sr);
-      atomicAdd(&a.eb->sum_length, sl);
-      unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.eb->max_return);
-      unsigned long long old = *addr, assumed;
-      do {
-        assumed = old;
-        if (__longlong_as_double((long long)assumed) >= mx) break;
-        old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
-      } while (assumed != old);
-    }
   }
 }
 
