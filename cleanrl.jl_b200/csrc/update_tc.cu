@@ -74,7 +74,8 @@ constexpr uint32_t COL_D = 0, COL_AH = 128, COL_AL = 192, COL_D2 = 256, COL_D4 =
 #ifndef TC_PARK
 #define TC_PARK 1
 #endif
-// named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4 = head exchange
+// named barriers: 1-3 hand an operand set to the issuing warp (it syncs, the other warps only arrive), 4-7 = head exchange
+// of lane quadrant 0-3
 constexpr int BAR_G1 = 1, BAR_G3 = 2, BAR_G4 = 3, BAR_X = 4;
 template <int ENV> struct TcSmem {
   static constexpr int WB = 0;                      // [4][4096] weight images of this CTA's net
@@ -534,7 +535,9 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
         for (int o = 0; o < NOUT; o++) exch[(g * 2 + o) * TC_S + s] = part[o].x + part[o].y;
       }
       TR(6);
-      bar_sync(BAR_X, TC_COMPUTE);
+      // only the TC_NG warps that share this lane quadrant exchange anything: one named barrier per quadrant instead of a
+      // CTA-wide one, so that the quadrants do not wait for each other here (2.126 -> 2.115 ms per update)
+      bar_sync(BAR_X + q, 32 * TC_NG);
       TR(7);
       float dl[NOUT];
 #pragma unroll
@@ -944,18 +947,21 @@ __device__ __noinline__ void fused_tail(const UpdateArgs& a, float* scratch, con
       int c_lo = 0, c_hi = G;
       const bool critic = e >= a.tc_net_a && e < a.tc_net_a + a.tc_net_c;
       if (critic) c_lo = a.tc_actor_ctas; else c_hi = a.tc_actor_ctas;
-      // ten partials requested before the first is added (one L2 round trip per batch); same summation order as the
+      // FT_BATCH partials requested before the first is added (one L2 round trip per batch); same summation order as the
       // plain loop: adding the +0.0f of a padded slot changes nothing
-      for (int c0 = c_lo + g; c0 < c_hi; c0 += 40) {
-        float v[10];
+#ifndef FT_BATCH
+#define FT_BATCH 10
+#endif
+      for (int c0 = c_lo + g; c0 < c_hi; c0 += 4 * FT_BATCH) {
+        float v[FT_BATCH];
 #pragma unroll
-        for (int j = 0; j < 10; j++) {   // unconditional (clamped) loads: a predicated load would be a branch, i.e. serialised
+        for (int j = 0; j < FT_BATCH; j++) {   // unconditional (clamped) loads: a predicated load would be a branch, i.e. serialised
           const int c = c0 + 4 * j;
           const float x = __ldcg(a.gpart + (long long)min(c, c_hi - 1) * P + e);
           v[j] = c < c_hi ? x : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 10; j++) s += (double)v[j];
+        for (int j = 0; j < FT_BATCH; j++) s += (double)v[j];
       }
     }
     if (g < 4) sh[g * FT_EL + el] = s;
