@@ -55,7 +55,6 @@ constexpr int TC_S = 128;        // samples per tile = TMEM lanes
                                  // 128 registers) measured 7 % slower on B200 and is not validated
 #endif
 constexpr int TC_THREADS = 128 * TC_NG;  // 4 lane quadrants x TC_NG feature groups
-constexpr int TC_COMPUTE = TC_THREADS;
 constexpr int TC_WARPS = TC_THREADS / 32;
 constexpr int TC_FG = CRL_H / TC_NG;     // features per thread
 static_assert(TC_NG == 2 || TC_NG == 4, "feature groups per sample");
