@@ -448,7 +448,11 @@ __device__ __forceinline__ void tc_body(const UpdateArgs& a, float* smem, TcBars
   };
 
   // the next tile's first layer is spread over the shadows of G1, G3/G2 and G4 (pairs [0,A), [A,B), [B,end))
+#if defined(TC_L1A) && defined(TC_L1B)
+  constexpr int L1_A = TC_L1A, L1_B = TC_L1B;   // A/B builds
+#else
   constexpr int L1_A = TC_FG / 2 * 3 / 8, L1_B = TC_FG / 2 * 3 / 4;
+#endif
   int it = 0;
   {
     Sample<ENV> cur, nxt;
